@@ -1,0 +1,371 @@
+"""Shared test harness: uniform Python wrappers over the three implementations of the mix path.
+
+  * ``RefBackend``     -- the compiled reference (oracle/_ref/libsubstrata_ref.so: real Resonance Audio +
+                           real AudioResampler + restated feeder).  Optional: present where it was built.
+  * ``OracleBackend``  -- the plain-C restatement (oracle/libmix_oracle.so).
+  * ``substrata_b200.MixEngine`` -- the product (CUDA, through the C ABI of include/sbm_audio.h).
+
+All three expose the same methods, so one scenario (``Scenario``) can be replayed on each and the
+interleaved stereo outputs compared.  Everything under oracle/ is test infrastructure only.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+KIND_PAN = 0       # vraudio::RenderingMode::kStereoPanning
+KIND_HRTF = 3      # vraudio::RenderingMode::kBinauralHighQuality (what AudioEngine.cpp:857 uses)
+KIND_STEREO = 100  # non-spatial stereo source (AudioEngine.cpp:867)
+
+_vp, _i, _f, _sz, _u64, _i64, _d = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_uint64, C.c_int64, C.c_double
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def build_oracle():
+    so = os.path.join(ORACLE_DIR, "libmix_oracle.so")
+    src = os.path.join(ORACLE_DIR, "mix_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+    return so
+
+
+def ref_library_path():
+    p = os.path.join(ORACLE_DIR, "_ref", "libsubstrata_ref.so")
+    return p if os.path.exists(p) else None
+
+
+def load_sh_hrir():
+    """Order-3 SADIE SH-HRIRs [16][256] as the reference decoder receives them (dumped by make_golden.py)."""
+    a = np.fromfile(os.path.join(ROOT, "substrata_b200", "data", "sh_hrir_order3_48k.f32"), dtype=np.float32)
+    return a.reshape(16, -1)
+
+
+class _CBackend:
+    """Common ctypes plumbing for the ref_/orc_ entry points (identical signatures after the handle)."""
+
+    prefix = None
+
+    def _bind(self, lib):
+        p = self.prefix
+        sig = {
+            "buffer_create": (_i, [_vp, _vp, _sz]),
+            "source_create": (_i, [_vp, _i]),
+            "source_attach_buffer": (None, [_vp, _i, _i, _u64, _i, _i, _i]),
+            "source_attach_ring": (None, [_vp, _i, _i]),
+            "source_ring_push": (None, [_vp, _i, _vp, _sz]),
+            "source_attach_mix": (None, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+            "source_set_mix_params": (None, [_vp, _i, _i, _d, _f]),
+            "source_set_eof_marker": (None, [_vp, _i, _i64]),
+            "source_set_looping": (None, [_vp, _i, _i]),
+            "set_source_positions": (None, [_vp, _i, _vp, _vp]),
+            "set_source_volumes": (None, [_vp, _i, _vp, _vp]),
+            "set_source_occlusions": (None, [_vp, _i, _vp, _vp]),
+            "set_head": (None, [_vp, _vp, _vp]),
+            "set_master_volume": (None, [_vp, _f]),
+            "source_destroy": (None, [_vp, _i]),
+            "mix": (_i, [_vp, _vp]),
+            "get_ambisonic_bus": (_i, [_vp, _vp]),
+            "poll_finished": (_i, [_vp, _vp, _i]),
+            "source_query": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+            "destroy": (None, [_vp]),
+        }
+        self._fn = {}
+        for name, (res, args) in sig.items():
+            f = getattr(lib, p + name)
+            f.restype, f.argtypes = res, args
+            self._fn[name] = f
+
+    # -- uniform API -------------------------------------------------------------------------------
+    def buffer_create(self, samples):
+        s = _f32(samples)
+        return self._fn["buffer_create"](self.h, _ptr(s), s.size)
+
+    def source_create(self, kind):
+        return self._fn["source_create"](self.h, kind)
+
+    def source_attach_buffer(self, sid, buf, cur_read_i=0, sampling_rate=48000, looping=True, remove_on_finish=False):
+        self._fn["source_attach_buffer"](self.h, sid, buf, int(cur_read_i), int(sampling_rate), int(looping), int(remove_on_finish))
+
+    def source_attach_ring(self, sid, sampling_rate=48000):
+        self._fn["source_attach_ring"](self.h, sid, int(sampling_rate))
+
+    def source_ring_push(self, sid, samples):
+        s = _f32(samples)
+        self._fn["source_ring_push"](self.h, sid, _ptr(s), s.size)
+
+    def source_attach_mix(self, sid, sampling_rate, bufs, sound_file_i, source_delta, mix_factor):
+        b = np.ascontiguousarray(bufs, dtype=np.int32)
+        p = np.ascontiguousarray(sound_file_i, dtype=np.float64)
+        d = np.ascontiguousarray(source_delta, dtype=np.float64)
+        m = _f32(mix_factor)
+        self._fn["source_attach_mix"](self.h, sid, int(sampling_rate), b.size, _ptr(b), _ptr(p), _ptr(d), _ptr(m))
+
+    def source_set_mix_params(self, sid, z, source_delta, mix_factor):
+        self._fn["source_set_mix_params"](self.h, sid, z, float(source_delta), float(mix_factor))
+
+    def source_set_eof_marker(self, sid, n):
+        self._fn["source_set_eof_marker"](self.h, sid, int(n))
+
+    def source_set_looping(self, sid, looping):
+        self._fn["source_set_looping"](self.h, sid, int(looping))
+
+    def set_source_positions(self, ids, xyz):
+        i = np.ascontiguousarray(ids, dtype=np.int32)
+        x = _f32(xyz)
+        self._fn["set_source_positions"](self.h, i.size, _ptr(i), _ptr(x))
+
+    def set_source_volumes(self, ids, vol):
+        i = np.ascontiguousarray(ids, dtype=np.int32)
+        v = _f32(vol)
+        self._fn["set_source_volumes"](self.h, i.size, _ptr(i), _ptr(v))
+
+    def set_source_occlusions(self, ids, occ):
+        i = np.ascontiguousarray(ids, dtype=np.int32)
+        v = _f32(occ)
+        self._fn["set_source_occlusions"](self.h, i.size, _ptr(i), _ptr(v))
+
+    def set_head(self, pos, quat_xyzw):
+        p, q = _f32(pos), _f32(quat_xyzw)
+        self._fn["set_head"](self.h, _ptr(p), _ptr(q))
+
+    def set_master_volume(self, v):
+        self._fn["set_master_volume"](self.h, float(v))
+
+    def source_destroy(self, sid):
+        self._fn["source_destroy"](self.h, sid)
+
+    def mix(self):
+        out = np.zeros(2 * self.frames, dtype=np.float32)
+        valid = self._fn["mix"](self.h, _ptr(out))
+        return valid, out
+
+    def ambisonic_bus(self):
+        out = np.zeros((16, self.frames), dtype=np.float32)
+        ok = self._fn["get_ambisonic_bus"](self.h, _ptr(out))
+        return out if ok else None
+
+    def poll_finished(self, cap=1024):
+        ids = np.zeros(cap, dtype=np.int32)
+        n = self._fn["poll_finished"](self.h, _ptr(ids), cap)
+        return ids[:n].tolist()
+
+    def source_query(self, sid):
+        cur, eof, ring, pos = _u64(0), _i64(0), _u64(0), _d(0)
+        ok = self._fn["source_query"](self.h, sid, C.byref(cur), C.byref(eof), C.byref(ring), C.byref(pos))
+        if not ok:
+            return None
+        return {"cur_read_i": cur.value, "eof_marker": eof.value, "ring_size": ring.value, "mix_pos0": pos.value}
+
+    def close(self):
+        if self.h:
+            self._fn["destroy"](self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_oracle_lib = None
+_ref_lib = None
+
+
+def oracle_lib():
+    global _oracle_lib
+    if _oracle_lib is None:
+        _oracle_lib = C.CDLL(build_oracle())
+    return _oracle_lib
+
+
+def ref_lib():
+    global _ref_lib
+    if _ref_lib is None:
+        p = ref_library_path()
+        if p is None:
+            return None
+        _ref_lib = C.CDLL(p)
+    return _ref_lib
+
+
+class OracleBackend(_CBackend):
+    prefix = "orc_"
+    name = "oracle"
+
+    def __init__(self, frames, rate=48000, sh_hrir=None, double_bus=False):
+        lib = oracle_lib()
+        self._bind(lib)
+        lib.orc_create.restype, lib.orc_create.argtypes = _vp, [_i, _i, _vp, _i]
+        self.frames = frames
+        if sh_hrir is None:
+            self.h = lib.orc_create(frames, rate, None, 0)
+        else:
+            hr = _f32(sh_hrir)
+            self.h = lib.orc_create(frames, rate, _ptr(hr), hr.shape[1])
+        if double_bus:
+            lib.orc_set_bus_precision.argtypes = [_vp, _i]
+            lib.orc_set_bus_precision(self.h, 1)
+
+
+class RefBackend(_CBackend):
+    prefix = "ref_"
+    name = "reference"
+
+    def __init__(self, frames, rate=48000, hrir_taps=0):
+        lib = ref_lib()
+        if lib is None:
+            raise RuntimeError("oracle/_ref/libsubstrata_ref.so not built")
+        self._bind(lib)
+        lib.ref_create.restype, lib.ref_create.argtypes = _vp, [_i, _i, _i]
+        self.frames = frames
+        self.h = lib.ref_create(frames, rate, hrir_taps)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Scenario: one deterministic workload description that can be replayed on any backend.
+# ---------------------------------------------------------------------------------------------------
+def quat_yaw(yaw_rad):
+    """Rotation about +y (up in Resonance's world convention, RA/base/misc_math.h:82-87), xyzw order."""
+    return np.array([0.0, np.sin(yaw_rad / 2), 0.0, np.cos(yaw_rad / 2)], dtype=np.float32)
+
+
+def synth_pcm(rng, n, f_lo=100.0, f_hi=4000.0, rate=48000):
+    """0.5 sin(2 pi f t) + 0.1 noise."""
+    f = rng.uniform(f_lo, f_hi)
+    t = np.arange(n, dtype=np.float64) / rate
+    return (0.5 * np.sin(2 * np.pi * f * t) + 0.1 * rng.uniform(-1, 1, n)).astype(np.float32)
+
+
+def positions(rng, n, boundary_safe=False):
+    """Uniform in [-40,40]x[-10,10]x[-40,40] m rejecting d < 1.05 m; the boundary-safe variant draws
+    (azimuth, elevation) at k+0.5 degrees so that no direction sits near a lookup-table cell edge at t = 0."""
+    if boundary_safe:
+        az = np.deg2rad(rng.integers(-180, 180, n) + 0.5)
+        el = np.deg2rad(rng.integers(-80, 80, n) + 0.5)
+        d = rng.uniform(1.5, 40.0, n)
+        x = -d * np.cos(el) * np.sin(az)
+        y = d * np.sin(el)
+        z = -d * np.cos(el) * np.cos(az)
+        return np.stack([x, y, z], 1).astype(np.float32)
+    out = np.zeros((n, 3), dtype=np.float32)
+    k = 0
+    while k < n:
+        p = rng.uniform([-40, -10, -40], [40, 10, 40], (n, 3))
+        p = p[np.linalg.norm(p, axis=1) >= 1.05]
+        m = min(n - k, len(p))
+        out[k:k + m] = p[:m]
+        k += m
+    return out
+
+
+class Scenario:
+    """A seeded source set + per-buffer event script.
+
+    kinds:      per-source KIND_*.
+    feeder:     per-source "native" | "resample" (rate != 48000) | "doppler" (one mix_source) | "ring".
+    The listener starts at the origin and, when `moving`, translates 1 m/s along +x and yaws 30 deg/s,
+    updated once per buffer -- which exercises the 1/2048-per-sample gain ramps.
+    """
+
+    def __init__(self, n_sources, frames, seed=12345, kind=KIND_PAN, feeder="native", loop_len=16384, moving=True,
+                 rates=(44100, 24000, 16000, 48000), rate_probs=(0.5, 0.2, 0.15, 0.15), boundary_safe=False,
+                 volume_toggle=False, occlusion_toggle=False, mixed_kinds=False, n_shared_buffers=0):
+        self.n, self.F, self.seed = n_sources, frames, seed
+        rng = np.random.default_rng(seed)
+        self.moving = moving
+        self.volume_toggle, self.occlusion_toggle = volume_toggle, occlusion_toggle
+        self.pos = positions(rng, n_sources, boundary_safe)
+        self.vol = rng.uniform(0.25, 1.0, n_sources).astype(np.float32)
+        if mixed_kinds:
+            self.kinds = rng.choice([KIND_PAN, KIND_HRTF, KIND_STEREO], n_sources, p=[0.45, 0.45, 0.1])
+        else:
+            self.kinds = np.full(n_sources, kind)
+        self.feeder = feeder
+        nb = n_shared_buffers if n_shared_buffers else n_sources
+        self.pcm = [synth_pcm(rng, loop_len) for _ in range(nb)]
+        self.buf_of = np.arange(n_sources) % nb
+        self.start = rng.integers(0, loop_len, n_sources)
+        self.rates = rng.choice(rates, n_sources, p=rate_probs) if feeder == "resample" else np.full(n_sources, 48000)
+        v = rng.uniform(-30, 30, (n_sources, 2))
+        self.delta = (343.0 - v[:, 0]) / (343.0 - v[:, 1])  # doppler_factor, AudioEngine.cpp:140-145
+        self.mixf = rng.uniform(0.5, 1.0, n_sources).astype(np.float32)
+        self.ring_rng_seed = seed + 1
+
+    def build(self, be):
+        bufs = [be.buffer_create(p) for p in self.pcm]
+        ids = []
+        for s in range(self.n):
+            sid = be.source_create(int(self.kinds[s]))
+            ids.append(sid)
+            b = bufs[self.buf_of[s]]
+            if self.feeder in ("native", "resample"):
+                be.source_attach_buffer(sid, b, int(self.start[s]), int(self.rates[s]), True, False)
+            elif self.feeder == "doppler":
+                be.source_attach_mix(sid, 48000, [b], [float(self.start[s])], [float(self.delta[s])], [float(self.mixf[s])])
+            elif self.feeder == "ring":
+                be.source_attach_ring(sid, int(self.rates[s]))
+            else:
+                raise ValueError(self.feeder)
+        self.ids = np.array(ids, dtype=np.int32)
+        be.set_source_positions(self.ids, self.pos)
+        be.set_source_volumes(self.ids, self.vol)
+        return self.ids
+
+    def step(self, be, b):
+        """Events before buffer `b`."""
+        if self.moving:
+            t = b * self.F / 48000.0
+            be.set_head([1.0 * t, 0.0, 0.0], quat_yaw(np.deg2rad(30.0) * t))
+        if self.volume_toggle:
+            sel = self.ids[::4]
+            if b % 6 == 2:
+                be.set_source_volumes(sel, np.zeros(len(sel), np.float32))
+            elif b % 6 == 4:
+                be.set_source_volumes(sel, self.vol[::4])
+        if self.occlusion_toggle:
+            sel = self.ids[1::3]
+            if b % 5 == 1:
+                be.set_source_occlusions(sel, np.ones(len(sel), np.float32))
+            elif b % 5 == 3:
+                be.set_source_occlusions(sel, np.zeros(len(sel), np.float32))
+        if self.feeder == "ring":
+            # 480-sample packets every 10 ms as opus delivers them (ClientUDPHandlerThread.cpp:196); an occasional
+            # dropped packet exercises the underflow zero-pad (AudioEngine.cpp:466-473).
+            rng = np.random.default_rng(self.ring_rng_seed + b)
+            n_pk = int(np.ceil(self.F / 480.0)) + (1 if b == 0 else 0)
+            for s in range(self.n):
+                if b % 7 == 5 and s % 3 == 0:
+                    continue
+                scale = self.rates[s] / 48000.0
+                m = int(n_pk * 480 * scale)
+                be.source_ring_push(int(self.ids[s]), (0.3 * rng.uniform(-1, 1, m)).astype(np.float32))
+
+    def run(self, be, n_buffers):
+        self.build(be)
+        outs, valids = [], []
+        for b in range(n_buffers):
+            self.step(be, b)
+            v, o = be.mix()
+            outs.append(o)
+            valids.append(v)
+        return np.stack(outs), valids
+
+
+def rel_rms(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    den = np.sqrt(np.sum(b * b))
+    return float(np.sqrt(np.sum((a - b) ** 2)) / den) if den > 0 else float(np.sqrt(np.sum(a * a)))
