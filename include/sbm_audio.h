@@ -1,0 +1,186 @@
+/* sbm_audio.h -- C ABI of the B200 spatial-audio mixer ("sbm" = Substrata B200 Mixer).
+ *
+ * This library replaces, for Substrata's glare::AudioEngine, the per-buffer body of ResonanceThread::doRun
+ * (audio/AudioEngine.cpp:367-537 in the reference tree) together with everything the vendored Resonance Audio
+ * library does for it (resonance-audio/resonance_audio/api/resonance_audio_api.h: the subset AudioEngine calls).
+ * One sbm_mix() call == "for every active source: gather/resample its sample window, SetPlanarBuffer; then
+ * FillInterleavedOutputBuffer".  All arithmetic runs in hand-written sm_100a CUDA kernels; there is no CPU
+ * fallback: every entry point that needs the device returns SBM_ERR_CUDA if the device or the kernels are
+ * unavailable.
+ *
+ * Conventions: plain C, opaque handle, int status codes (0 = OK, < 0 = error), no exceptions cross the boundary;
+ * pointers are HOST pointers unless the name says `device`.  Setters may be called from any thread and take effect
+ * at the next sbm_mix() (like Resonance's task queue, resonance_audio_api_impl.cc:462,538); sbm_mix() itself must be
+ * called from one thread at a time (the reference holds AudioEngine::mutex around it, AudioEngine.cpp:367).
+ *
+ * "file:line" notes name the reference interface each entry point stands in for.
+ */
+#ifndef SBM_AUDIO_H_
+#define SBM_AUDIO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SBM_API __declspec(dllexport)
+#else
+#define SBM_API __attribute__((visibility("default")))
+#endif
+
+typedef struct sbm_engine sbm_engine;
+
+enum {
+	SBM_OK = 0,
+	SBM_ERR_INVALID_ARG = -1,
+	SBM_ERR_CUDA = -2,         /* CUDA runtime / kernel failure; sbm_last_error() has the message */
+	SBM_ERR_NO_MEMORY = -3,
+	SBM_ERR_UNKNOWN_ID = -4,   /* Resonance ignores unknown ids silently (resonance_audio_api_impl.cc:551-554); we report it */
+	SBM_ERR_CAPACITY = -5,     /* more sources / buffers / ring samples than configured */
+	SBM_ERR_UNSUPPORTED = -6   /* room effects etc.: rows marked "next" in SURVEY.md 8(f) */
+};
+
+/* Source kinds.  Values match vraudio::RenderingMode (resonance_audio_api.h:35-45) for sound objects. */
+enum {
+	SBM_SOURCE_STEREO_PANNING = 0,  /* CreateSoundObjectSource(kStereoPanning): distance attenuation + L/R pan law */
+	SBM_SOURCE_BINAURAL_HQ = 3,     /* CreateSoundObjectSource(kBinauralHighQuality), AudioEngine.cpp:857: 3rd-order ambisonic encode + SH-HRIR decode */
+	SBM_SOURCE_NONSPATIAL = 100     /* CreateStereoSource(2), AudioEngine.cpp:867: mono duplicated to L/R, volume only */
+};
+
+typedef struct sbm_config {
+	int frames_per_buffer;      /* Resonance accepts 32..16384 (resonance_audio_api_impl.cc:78-94); this build: 32..1024 */
+	int sample_rate_hz;         /* engine rate; AudioEngine uses 48000 (AudioEngine.cpp:580) */
+	int device;                 /* CUDA device ordinal */
+	int max_sources;            /* slot capacity (sources alive at once) */
+	int max_mix_sources;        /* total MixSource entries (AudioEngine.h:61-69) across all sources */
+	const float* sh_hrir;       /* planar [16][sh_hrir_taps] SH-domain HRIRs (what CreateShHrirsFromAssets returns,
+	                               sh_hrir_creator.cc:60-70); NULL => SBM_SOURCE_BINAURAL_HQ sources are rejected */
+	int sh_hrir_taps;           /* 1..1024 (stock SADIE assets: 256) */
+} sbm_config;
+
+/* vraudio::CreateResonanceAudioApi(2, frames, rate) -- AudioEngine.cpp:676, resonance_audio_api.h:133-134. */
+SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine);
+/* `delete resonance` -- AudioEngine.cpp:837. */
+SBM_API void sbm_destroy(sbm_engine* e);
+SBM_API const char* sbm_last_error(const sbm_engine* e);
+
+/* ---- PCM buffers: glare::AudioBuffer / SoundFile::buf shared between sources (AudioEngine.h:39-57,122,253) ---- */
+/* Uploads n mono f32 samples once; many sources may reference the returned buffer id. */
+SBM_API int sbm_buffer_create(sbm_engine* e, const float* samples, size_t n, int* out_buffer);
+/* Adopts PCM already resident in device memory (not owned, must outlive the engine): `count` buffers of `n`
+ * samples each, buffer k starting at device_base + k*stride_samples.  Ids out_first_buffer .. +count-1. */
+SBM_API int sbm_buffer_adopt_device(sbm_engine* e, const float* device_base, size_t n, size_t stride_samples, int count, int* out_first_buffer);
+
+/* ---- sources ---- */
+/* CreateSoundObjectSource / CreateStereoSource (AudioEngine.cpp:857,867).  Ids increase monotonically like
+ * Resonance's source_id_counter_ (resonance_audio_api_impl.cc:209).  `count` sources are created; ids are
+ * out_first_id .. out_first_id+count-1.  New sources are active, volume 1, at the origin. */
+SBM_API int sbm_source_create(sbm_engine* e, int kind, int count, int* out_first_id);
+/* DestroySource (AudioEngine.cpp:511,908). */
+SBM_API int sbm_source_destroy(sbm_engine* e, int n, const int* ids);
+
+/* Feeder attachment = the AudioSource fields the feeder reads (AudioEngine.h:114-131).  Arrays of length n. */
+/* SourceType_NonStreaming reading shared_buffer from cur_read_i (AudioEngine.cpp:389-426); resampler.init(rate, engine rate) (:875). */
+SBM_API int sbm_source_attach_buffer(sbm_engine* e, int n, const int* ids, const int* buffers, const uint64_t* cur_read_i,
+                                     const int* sampling_rate, const uint8_t* looping, const uint8_t* remove_on_finish);
+/* SourceType_Streaming fed through the circular buffer (AudioEngine.cpp:459-474). */
+SBM_API int sbm_source_attach_ring(sbm_engine* e, int id, int sampling_rate, int capacity_samples);
+/* CircularBuffer::pushBackNItems by StreamerThread / ClientUDPHandlerThread (StreamerThread.cpp:53-80, ClientUDPHandlerThread.cpp:239). */
+SBM_API int sbm_source_ring_push(sbm_engine* e, int id, const float* samples, size_t n);
+/* CircularBuffer::size() as of the last sbm_mix() plus pushes since (StreamerThread.cpp:53 polls it). */
+SBM_API int sbm_source_ring_size(sbm_engine* e, int id, uint64_t* out_size);
+/* SourceType_Streaming with mix_sources: pitch/doppler mixer (AudioEngine.cpp:435-458). */
+SBM_API int sbm_source_attach_mix(sbm_engine* e, int id, int sampling_rate, int nz, const int* buffers, const double* sound_file_i,
+                                  const double* source_delta, const float* mix_factor);
+/* Batched form for one MixSource per source (doppler_factor pitch shift of a looping buffer). */
+SBM_API int sbm_source_attach_mix1(sbm_engine* e, int n, const int* ids, const int* buffers, const double* sound_file_i,
+                                   const double* source_delta, const float* mix_factor);
+/* mix_sources[z].source_delta / mix_factor updates by the game thread (gui_client/BikePhysics.cpp:712-740). */
+SBM_API int sbm_source_set_mix_params(sbm_engine* e, int n, const int* ids, const int* z, const double* source_delta, const float* mix_factor);
+/* AudioSource::EOF_marker_position (AudioEngine.h:120), AudioSource::looping. */
+SBM_API int sbm_source_set_eof_marker(sbm_engine* e, int id, int64_t samples_to_eof);
+SBM_API int sbm_source_set_looping(sbm_engine* e, int id, int looping);
+
+/* ---- per-frame setters (AudioEngine.cpp:946-990) ---- */
+SBM_API int sbm_set_source_positions(sbm_engine* e, int n, const int* ids, const float* xyz);  /* SetSourcePosition, :955 */
+SBM_API int sbm_set_source_volumes(sbm_engine* e, int n, const int* ids, const float* volume); /* SetSourceVolume(volume*mute factor), :965 */
+SBM_API int sbm_set_source_occlusions(sbm_engine* e, int n, const int* ids, const float* occ); /* SetSoundObjectOcclusionIntensity, :974 */
+SBM_API int sbm_set_head(sbm_engine* e, const float* pos_xyz, const float* quat_xyzw);          /* SetHeadPosition/Rotation, :987-988 */
+SBM_API int sbm_set_master_volume(sbm_engine* e, float volume);                                  /* SetMasterVolume, :810 */
+SBM_API int sbm_enable_room_effects(sbm_engine* e, int enable);                                  /* EnableRoomEffects, :742; only 0 supported */
+
+/* ---- the per-buffer call ---- */
+/* SetPlanarBuffer for every active source + FillInterleavedOutputBuffer(2, frames, out) (AudioEngine.cpp:370-526).
+ * out_interleaved: 2*frames floats (LRLR...).  *out_valid = what Fill... returns: 0 when no source reached the stereo
+ * mixer this buffer (out is zero-filled), else 1. */
+SBM_API int sbm_mix(sbm_engine* e, float* out_interleaved, int* out_valid);
+
+/* The same call split for multi-GPU use and for device-resident benchmarking:
+ *   sbm_mix_begin   uploads pending setters and launches the per-source kernels on the engine's stream; when it
+ *                   returns, the partial bus of this rank is (asynchronously) in sbm_bus_device().
+ *   (caller may now sum the bus across ranks, e.g. ncclAllReduce on sbm_stream())
+ *   sbm_mix_finish  launches SH decode + stereo mix + interleave, copies 2*frames floats to out_interleaved (host)
+ *                   and synchronises.  Pass NULL to leave the result on the device (sbm_out_device()).
+ * Bus layout: [18][frames] f32: rows 0-15 ambisonic (ACN), 16-17 the stereo bus (panned + non-spatial sources),
+ * followed by 4 floats of flags {ambisonic bus used, stereo bus used, 0, 0} that sum across ranks like the audio. */
+SBM_API int sbm_mix_begin(sbm_engine* e);
+SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid);
+SBM_API int sbm_bus_device(sbm_engine* e, float** out_device_ptr, size_t* out_num_floats);
+SBM_API int sbm_out_device(sbm_engine* e, float** out_device_ptr);
+SBM_API void* sbm_stream(sbm_engine* e);   /* cudaStream_t */
+
+/* ---- feeder bookkeeping read-back (AudioEngine.cpp:496-517) ---- */
+/* Sources the feeder stopped (non-looping source reached its end / EOF marker): they were destroyed exactly like
+ * `resonance->DestroySource` + erase from active_audio_sources.  Returns the number written to ids (<= cap). */
+SBM_API int sbm_poll_finished(sbm_engine* e, int* ids, int cap, int* out_n);
+
+typedef struct sbm_source_state {
+	uint64_t cur_read_i;      /* AudioSource::cur_read_i */
+	int64_t eof_marker;       /* AudioSource::EOF_marker_position */
+	uint64_t ring_size;       /* CircularBuffer::size() */
+	double mix_pos0;          /* mix_sources[0].sound_file_i */
+	float direct_gain;        /* GainNode's current gain */
+	float occlusion;          /* OcclusionNode::current_occlusion_ */
+	int alive;
+} sbm_source_state;
+SBM_API int sbm_source_query(sbm_engine* e, int id, sbm_source_state* out);
+
+/* ---- statistics (the reference has none; SURVEY.md section 5 "metrics") ---- */
+typedef struct sbm_stats {
+	uint64_t buffers_mixed;
+	uint64_t kernel_launches;        /* kernels launched by this library so far */
+	uint32_t active_sources;
+	float last_params_kernel_ms;     /* CUDA-event times of the last sbm_mix_begin/finish on the engine stream */
+	float last_mix_kernel_ms;
+	float last_finish_kernel_ms;
+	uint64_t last_algorithmic_bytes; /* sum over sources of 4*n_src + per-source state bytes */
+	uint64_t last_h2d_bytes, last_d2h_bytes;
+} sbm_stats;
+SBM_API int sbm_get_stats(sbm_engine* e, sbm_stats* out);
+/* Enables CUDA-event timing of the kernels inside mix_begin/finish (off by default). */
+SBM_API int sbm_set_profiling(sbm_engine* e, int enable);
+
+/* ---- AudioResampler drop-in (audio/AudioResampler.h:23-42) for callers that resample outside the engine.
+ * Batched: `count` independent streams, each converting src_rate -> dst_rate with the reference's linear
+ * interpolation and carried state.  All pointers are HOST memory; work runs on the GPU. ---- */
+typedef struct sbm_resampler sbm_resampler;
+SBM_API int sbm_resampler_create(int device, int count, const int* src_rate, int dst_rate, sbm_resampler** out);
+SBM_API void sbm_resampler_destroy(sbm_resampler* r);
+/* numSrcSamplesNeeded(dest_num_samples) for every stream (AudioResampler.cpp:77-86). */
+SBM_API int sbm_resampler_num_src_needed(sbm_resampler* r, size_t n_dst, size_t* out_needed);
+/* resample(): stream k reads src + src_offsets[k] .. +needed[k], writes dst + k*n_dst (AudioResampler.cpp:89-113). */
+SBM_API int sbm_resampler_resample(sbm_resampler* r, float* dst, size_t n_dst, const float* src, const size_t* src_offsets, size_t src_total);
+
+/* ---- debugging / test hooks (host-side exact-arithmetic helpers shared with the kernels) ---- */
+SBM_API float sbm_debug_ramp_advance(float g, float inc, uint32_t n);   /* value after n float adds g += inc, closed form */
+SBM_API float sbm_debug_atan2f(float y, float x);                        /* bit-exact restatement of glibc 2.39 atan2f */
+SBM_API const float* sbm_debug_encoder_table(void);                      /* 91*91*15 floats */
+SBM_API int sbm_debug_get_ambisonic_bus(sbm_engine* e, float* out16xF);  /* this rank's 16 x frames bus of the last mix */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBM_AUDIO_H_ */

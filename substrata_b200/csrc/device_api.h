@@ -1,0 +1,100 @@
+// device_api.h -- the narrow seam between the engine's host logic (engine.cc) and the device.
+//
+// The product implements it with CUDA (device_cuda.cu + k*.cu).  tests/native/device_emu.cc implements the same
+// functions on the host for the no-GPU CPU test suite (host emulation of the kernels' semantics; test
+// infrastructure that is never part of libsubstrata_b200.so).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "sbm_core.h"
+
+namespace sbm {
+
+struct SlotPatch {              // state (re)initialisation of one slot, applied by k_patch before K1
+	uint32_t slot;
+	uint32_t what;              // kPatch*
+	unsigned long long read_i;
+	long long eof;
+	int32_t rate;               // resampler src rate (init)
+	int32_t pad;
+};
+constexpr uint32_t kPatchReset = 1;      // fresh source: all DSP state cleared, live = 1
+constexpr uint32_t kPatchReadI = 2;      // cur_read_i / ring read counter
+constexpr uint32_t kPatchEof = 4;
+constexpr uint32_t kPatchResampler = 8;  // AudioResampler::init (AR.cpp:24-36)
+constexpr uint32_t kPatchKill = 16;      // live = 0
+
+struct MixPatch { uint32_t index; uint32_t pad; double pos; };
+
+struct MixArgs {
+	const WorkRec* rec;
+	const ShGains* shg;
+	const ShRamps* shr;
+	const MixZ* mixz;
+	const double* mix_pos0;
+	Resamp* rs;                 // K2 stores prev_samples of resampled sources
+	float* lpf_prev;            // K2 stores the occlusion filter memory
+	const uint32_t* list_pan;   // slots rendered by the 2-channel kernel (panned + non-spatial sources)
+	uint32_t n_pan;
+	const uint32_t* list_sh;    // slots rendered by the 16-channel kernel
+	uint32_t n_sh;
+	uint32_t frames;
+	int32_t rate;
+	float* partials;            // scratch of per-CTA partial buses: [max_ctas(pan)][2][frames] then [max_ctas(sh)][16][frames]
+	size_t partials_floats;
+	float* bus;                 // [18][frames] + 4 flag floats: this rank's bus
+	const DevFlags* flags;
+	uint32_t parity;
+};
+
+struct FinishArgs {
+	const float* bus;           // (possibly all-reduced) [18][frames] + 4 flags
+	const float* hrir;          // [16][taps] or null
+	uint32_t taps;
+	float* hist;                // [16][taps-1] FIR history (the decoder's overlap state), updated in place
+	DevFlags* flags;
+	uint32_t parity;
+	uint32_t frames;
+	float* out;                 // [2*frames] interleaved, followed by OutTail
+	const uint32_t* list_ring;  // ring-fed slots whose read counters are reported back
+	uint32_t n_ring;
+	const unsigned long long* read_i;
+	int* finished_count_reset;  // unused
+};
+
+struct OutTail {                // follows the 2*frames output floats in the D2H staging buffer
+	int valid;
+	int n_finished;
+	unsigned int n_rendered;
+	int pad;
+	unsigned long long algo_bytes;
+};
+
+namespace dev {
+int init(int device, void** stream_out);
+int use(int device);                             // make `device` current on the calling thread
+void shutdown(void* stream);
+const char* last_error();
+void* alloc(size_t bytes);                       // zero-initialised device memory; nullptr on failure
+void release(void* p);
+void* alloc_pinned(size_t bytes);
+void release_pinned(void* p);
+int h2d(void* dst, const void* src, size_t bytes, void* stream);
+int d2h(void* dst, const void* src, size_t bytes, void* stream);
+int zero(void* dst, size_t bytes, void* stream);
+int sync(void* stream);
+int num_mix_ctas(uint32_t frames, int sh);       // largest grid K2 will use (sizes the partials buffer)
+size_t partials_floats(uint32_t frames);         // floats needed for MixArgs::partials
+// kernels
+int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, const MixPatch* mp, uint32_t nmp, void* stream);
+int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t n_slots, void* stream);
+int launch_mix(const MixArgs& a, void* stream);  // K2 (both lists) + K3 (partials -> bus)
+int launch_finish(const FinishArgs& a, void* stream);
+// timing
+void* event_create();
+void event_destroy(void* ev);
+void event_record(void* ev, void* stream);
+float event_elapsed_ms(void* a, void* b);
+unsigned long long launches();                   // kernels launched so far by this library
+}  // namespace dev
+}  // namespace sbm

@@ -1,0 +1,251 @@
+// k1_core.h -- the per-source, per-buffer scalar work ("K1"): feeder bookkeeping + Resonance's per-source
+// parameter logic, condensed into one WorkRec for the mix kernel.  One call per slot per buffer.
+//
+// Follows, in order: ResonanceThread::doRun's per-source body (AE.cpp:375-517), AudioResampler::numSrcSamplesNeeded /
+// resample's coordinate bookkeeping (AR.cpp:77-113), UpdateAttenuationParameters (RA/dsp/distance_attenuation.cc:82-119),
+// GainNode::AudioProcess (RA/graph/gain_node.cc:38-80), OcclusionNode::AudioProcess (RA/graph/occlusion_node.cc:53-99),
+// StereoMixingPannerNode / AmbisonicMixingEncoderNode (RA/graph/stereo_mixing_panner_node.cc:33-63,
+// RA/graph/ambisonic_mixing_encoder_node.cc:36-67) and GainMixer's processor bookkeeping (RA/dsp/gain_mixer.cc:53-113).
+// Host + device: see sbm_core.h.
+#pragma once
+#include "sbm_core.h"
+
+namespace sbm {
+
+SBM_HD int finished_push(DevFlags* f) {
+#if defined(__CUDA_ARCH__)
+	return atomicAdd(&f->n_finished, 1);
+#else
+	return f->n_finished++;
+#endif
+}
+// Bits returned by update_source (OR-reduced per block by the caller into DevFlags::*_used[parity]).
+constexpr uint32_t kUsedPan = 1, kUsedSh = 2, kUsedStereo = 4;
+
+// StereoPanner gains (RA/dsp/stereo_panner.cc:28-44).  cosf is continuous here (no truncation follows), so the
+// device's cosf (<= 2 ulp) is as good as libm's.
+SBM_HD void stereo_pan_gains(float az, float el, float* gl, float* gr) {
+	const float kRadFromDeg = (float)(3.14159265358979323846 / 180.0);
+	const float left = fmul(kRadFromDeg, 90.0f), right = fmul(kRadFromDeg, -90.0f);
+	const float ce = cosf(el);
+	*gl = fmul(0.5f, fadd(1.0f, fmul(cosf(fsub(left, az)), ce)));
+	*gr = fmul(0.5f, fadd(1.0f, fmul(cosf(fsub(right, az)), ce)));
+}
+
+// AmbisonicLookupTable::GetEncodingCoeffs, order 3, spread 0 (RA/ambisonics/ambisonic_lookup_table.cc:88-161).
+// `table` = 91*91*15 floats built on the host (sh_table.cc).  Symmetry signs (:200-216) in closed form:
+//   left/right flip (azimuth < 0): -1 for m < 0;   up/down (elevation < 0): (-1)^(n+m);
+//   front/back (|azimuth| > 90): m < 0 ? -(-1)^|m| : (-1)^m.
+SBM_HD void encoding_coeffs(const float* table, float az, float el, float* out16) {
+	const float kPi = (float)3.14159265358979323846;
+	const float kDegFromRad = (float)(180.0 / 3.14159265358979323846);
+	const int az_deg = az < kPi ? (int)fmul(az, kDegFromRad) : (int)fmul(az, kDegFromRad) - 360;
+	const int el_deg = (int)fmul(el, kDegFromRad);
+	const int abs_az = az_deg < 0 ? -az_deg : az_deg;
+	const int az_idx = abs_az > 90 ? 180 - abs_az : abs_az;
+	const int el_idx = el_deg < 0 ? -el_deg : el_deg;
+	const float* cell = table + (az_idx * kTableEl + el_idx) * kShRaw;
+	out16[0] = 1.0f;
+	int raw = 0;
+	for (int n = 1; n <= 3; ++n)
+		for (int m = -n; m <= n; ++m, ++raw) {
+			const int am = m < 0 ? -m : m;
+			float flip = 1.0f;
+			if (az_deg < 0 && m < 0) flip = -1.0f;
+			if (el_deg < 0 && ((n + m) & 1)) flip = -flip;
+			if (abs_az > 90) { const float fb = (am & 1) ? -1.0f : 1.0f; flip = fmul(flip, m < 0 ? -fb : fb); }
+			out16[raw + 1] = fmul(cell[raw], flip);
+		}
+}
+
+// Returns kUsed* bits; *rendered_src = PCM samples a rendered source reads this buffer (0 when skipped / stopped).
+SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot,
+                              uint32_t* rendered_src) {
+	*rendered_src = 0;
+	const SrcStatic st = A.stat[slot];
+	WorkRec rec;
+	rec.pcm = st.pcm; rec.len = st.len; rec.start = 0; rec.n_src = 0; rec.avail = 0; rec.flags = kRecSkip;
+	rec.mix_first = st.mix_first; rec.x0 = 0.0; rec.prev0 = 0.0f; rec.prev1 = 0.0f; rec.lpf_coef = 0.0f; rec.lpf_prev = 0.0f;
+	rec.rate = st.rate; rec.nz = st.nz; rec.ch_ramp_mask = 0; rec.slot = slot; rec.pad[0] = 0; rec.pad[1] = 0;
+	rec.direct.konst = 0.0f; rec.direct.start = 0.0f; rec.direct.inc = 0.0f; rec.direct.n = 0;
+	rec.ch[0] = rec.direct; rec.ch[1] = rec.direct;
+	if (!(st.flags & kFlagAlive) || !A.live[slot]) { A.rec[slot] = rec; return 0; }
+
+	const uint32_t F = G.frames;
+	const uint32_t kind = (st.flags >> kFlagKindShift) & 0xff;
+	const uint32_t feed = (st.flags >> kFlagFeedShift) & 3;
+	const bool looping = (st.flags & kFlagLooping) != 0;
+	uint32_t rflags = 0;
+
+	// ---------------- feeder: how many source samples, from where (AE.cpp:378-474) ----------------
+	Resamp rs = A.rs[slot];
+	uint32_t n_src = F;
+	uint32_t alg_samples = 0;       // PCM samples this buffer has to read (accounting only)
+	const bool resample = st.rate != G.rate;
+	if (resample) {
+		// AudioResampler::numSrcSamplesNeeded (AR.cpp:77-86)
+		const int64_t max_dest = rs.prev_dest_dst_coords + (int64_t)F;
+		const double max_dest_src = (double)max_dest * (double)st.rate / (double)G.rate;
+		const int64_t prev1 = rs.prev_samples_0_src_coords + 1;
+		n_src = (uint32_t)(int)((uint64_t)ceil(max_dest_src) - (uint64_t)prev1);
+		// AudioResampler::resample coordinates (AR.cpp:101-103)
+		const int64_t dest0 = rs.prev_dest_dst_coords + 1;
+		const double dest0_src = (double)dest0 * (double)st.rate / (double)G.rate;
+		rec.x0 = dest0_src - (double)rs.prev_samples_0_src_coords;
+		rec.prev0 = rs.prev_samples[0]; rec.prev1 = rs.prev_samples[1];
+		rs.prev_dest_dst_coords += (int64_t)F;
+		rs.prev_samples_0_src_coords += (int64_t)n_src;
+		// prev_samples[] for the next buffer are the last two samples of {prev0, prev1, window}: written by K2.
+		A.rs[slot].prev_dest_dst_coords = rs.prev_dest_dst_coords;
+		A.rs[slot].prev_samples_0_src_coords = rs.prev_samples_0_src_coords;
+		rflags |= kRecResample;
+	}
+	bool remove_source = false;
+	if (feed == kFeedBuffer) {
+		// AE.cpp:389-426
+		uint64_t cur = A.read_i[slot];
+		const uint64_t len = st.len;
+		rec.start = (uint32_t)(cur < len ? cur : len);
+		if (cur + n_src <= len) {
+			rec.avail = n_src;
+			cur += n_src;
+			if (looping && cur == len) cur = 0;
+		} else if (cur < len) {
+			if (looping) { rec.avail = n_src; rflags |= kRecWrap; cur = (cur + n_src) % len; }
+			else { rec.avail = (uint32_t)(len - cur); cur = len; }
+			remove_source = (st.flags & kFlagRemoveOnFinish) && cur >= len;
+		} else {
+			rec.avail = 0;                                   // read index parked at/after the end: zeros
+			remove_source = (st.flags & kFlagRemoveOnFinish) != 0;
+		}
+		A.read_i[slot] = cur;
+	} else if (feed == kFeedRing) {
+		// AE.cpp:459-474: pop what is there, zero-pad the rest.  read_i counts samples popped so far.
+		const uint64_t rd = A.read_i[slot];
+		const uint64_t wr = A.ring_write[slot];
+		const uint64_t have = wr - rd < (uint64_t)n_src ? wr - rd : (uint64_t)n_src;
+		rec.start = (uint32_t)(rd % st.len);
+		rec.avail = (uint32_t)have;
+		rflags |= kRecWrap;
+		A.read_i[slot] = rd + have;
+	} else {
+		// AE.cpp:435-458: K2 evaluates pos0 + (i+1)*delta per mix source; advance the read heads here.
+		rflags |= kRecMix;
+		for (uint32_t z = 0; z < st.nz; ++z) {
+			const uint32_t k = st.mix_first + z;
+			const double p0 = A.mix_pos[k];
+			A.mix_pos0[k] = p0;
+			// The reference adds delta n_src times in double; one fma differs by < n_src ulps of pos (continuous).
+			A.mix_pos[k] = fma((double)n_src, A.mixz[k].delta, p0);
+			alg_samples += (uint32_t)((double)n_src * A.mixz[k].delta) + 2u;
+		}
+	}
+	if (feed != kFeedMix) alg_samples = rec.avail;
+	rec.n_src = n_src;
+
+	// ---------------- EOF bookkeeping (AE.cpp:496-517) ----------------
+	long long eof = A.eof[slot];
+	eof -= (long long)n_src;
+	A.eof[slot] = eof;
+	if (remove_source || (!looping && eof <= 0)) {
+		// DestroySource runs from the task queue before the graph is processed: the last buffer is not rendered.
+		A.live[slot] = 0;
+		A.finished[finished_push(flags)] = (int)st.id;
+		A.rec[slot] = rec;
+		return 0;
+	}
+
+	// ---------------- attenuation + GainNode (distance_attenuation.cc:82-119, gain_node.cc:38-80) ----------------
+	const F4 pv = A.posvol[slot];
+	const float src_pos[3] = {pv.x, pv.y, pv.z};
+	const float input_gain = fmul(G.master, pv.w);
+	uint8_t bits = A.bits[slot];
+	const bool hrtf = kind == kKindHrtf;
+	if (kind != kKindStereo) {
+		// GainMixer::Reset sweep (gain_mixer.cc:80-96): it runs once between two non-empty buffers of that mixer and
+		// touches every source that owns processors, whether or not the source reaches the mixer this buffer.
+		const int prev_used = hrtf ? flags->sh_used[G.parity ^ 1] : flags->pan_used[G.parity ^ 1];
+		if (prev_used) {
+			if (bits & kBitMixActive) bits &= (uint8_t)~kBitMixActive;
+			else bits &= (uint8_t)~kBitMixExists;
+		}
+	}
+	float dg = A.dgain[slot];
+	float target;
+	if (kind == kKindStereo) target = input_gain;                                        // AttenuationType::kInput
+	else target = fmul(input_gain, log_distance_attenuation(G.head_pos, src_pos));        // kDirect
+	if (near_zero(target) && near_zero(dg)) {
+		A.dgain[slot] = 0.0f; A.bits[slot] = bits | kBitDirectInit;
+		// skip: nothing downstream runs, but the feeder still resampled this buffer (AE.cpp:485-494 precede the graph), so
+		// K2 must still carry AudioResampler::prev_samples forward.
+		rec.flags = kRecSkip | (rflags & (kRecResample | kRecWrap));
+		A.rec[slot] = rec;
+		return 0;
+	}
+	if (near_unity(target) && near_unity(dg)) {
+		dg = 1.0f;
+		rec.direct.konst = 1.0f; rec.direct.start = 1.0f; rec.direct.inc = 0.0f; rec.direct.n = 0;
+	} else {
+		rec.direct = plan_gain(&dg, (bits & kBitDirectInit) != 0, target, F, /*accumulate=*/false);
+	}
+	bits |= kBitDirectInit;
+	A.dgain[slot] = dg;
+	*rendered_src = alg_samples ? alg_samples : 1u;
+
+	if (kind == kKindStereo) {
+		rflags |= kRecStereo;
+		rec.ch[0].konst = 1.0f; rec.ch[1].konst = 1.0f;
+		A.bits[slot] = bits;
+		rec.flags = rflags;
+		A.rec[slot] = rec;
+		return kUsedStereo;
+	}
+
+	// ---------------- OcclusionNode (occlusion_node.cc:53-99) ----------------
+	const float occ_t = A.occl[slot];
+	float occ = A.occ_cur[slot];
+	occ = fadd(occ_t, fmul(kOcclusionSmoothing, fsub(occ, occ_t)));
+	A.occ_cur[slot] = occ;
+	rec.lpf_coef = occlusion_coefficient(occ);
+	rec.lpf_prev = A.lpf_prev[slot];
+	if (!(rec.lpf_coef < kEpsilonFloat)) rflags |= kRecLpf;
+
+	// ---------------- direction + mixer gains ----------------
+	float az, el;
+	source_direction(G.head_pos, G.head_q, src_pos, &az, &el);
+	const bool chan_init = (bits & kBitMixExists) != 0;     // processors exist => already initialised by an ApplyGain
+	bits |= kBitMixExists | kBitMixActive;
+	A.bits[slot] = bits;
+	float* cg = A.cgain + (size_t)slot * (size_t)A.cstride;
+	if (!hrtf) {
+		float g[2];
+		stereo_pan_gains(az, el, &g[0], &g[1]);
+		for (int c = 0; c < 2; ++c) {
+			float cur = cg[c];
+			rec.ch[c] = plan_gain(&cur, chan_init, g[c], F, /*accumulate=*/true);
+			cg[c] = cur;
+			if (rec.ch[c].n) rec.ch_ramp_mask |= 1u << c;
+		}
+	} else {
+		float g[kNumSh];
+		encoding_coeffs(table, az, el, g);
+		ShGains sg;
+		for (int c = 0; c < kNumSh; ++c) {
+			float cur = cg[c];
+			const RampDesc d = plan_gain(&cur, chan_init, g[c], F, /*accumulate=*/true);
+			cg[c] = cur;
+			sg.konst[c] = d.konst;
+			if (d.n) {
+				rec.ch_ramp_mask |= 1u << c;
+				A.shr[slot].start[c] = d.start; A.shr[slot].inc[c] = d.inc; A.shr[slot].n[c] = d.n;
+			}
+		}
+		A.shg[slot] = sg;
+		rflags |= kRecHrtf;
+	}
+	rec.flags = rflags;
+	A.rec[slot] = rec;
+	return hrtf ? kUsedSh : kUsedPan;
+}
+
+}  // namespace sbm

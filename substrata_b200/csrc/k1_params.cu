@@ -1,0 +1,75 @@
+// k1_params.cu -- "K1": one thread per source slot runs the feeder bookkeeping and Resonance's per-source parameter
+// logic for this buffer (k1_core.h: update_source) and condenses the slot into one WorkRec for the mix kernel; plus
+// k_patch, which applies host-requested state (re)initialisations before K1.
+//
+// Compiled with -fmad=false: results of this unit feed integer truncations and thresholds (lookup-table cell,
+// -60 dB rules, ramp lengths), so every float operation must round exactly like the reference's SSE build.
+// HBM traffic per slot: SrcStatic 32 B + pos/volume 16 B + ~60 B of state read-modify-write + 128 B WorkRec write.
+#include "device_internal.h"
+#include "k1_core.h"
+
+namespace sbm {
+
+__global__ void __launch_bounds__(256) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table) {
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t used = 0, n_src = 0;
+	if (slot < g.n_slots) used = update_source(g, A, flags, table, slot, &n_src);
+	// Block-level reduction of the "mixer used" bits and the accounting counters: one atomic per warp at most.
+	const unsigned full = 0xffffffffu;
+	uint32_t u = used;
+	unsigned long long bytes = n_src ? 4ull * n_src : 0ull;
+	uint32_t rendered = n_src ? 1u : 0u;
+	for (int o = 16; o > 0; o >>= 1) {
+		u |= __shfl_xor_sync(full, u, o);
+		bytes += __shfl_xor_sync(full, bytes, o);
+		rendered += __shfl_xor_sync(full, rendered, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (u & kUsedPan) atomicOr(&flags->pan_used[g.parity], 1);
+		if (u & kUsedSh) atomicOr(&flags->sh_used[g.parity], 1);
+		if (u & kUsedStereo) atomicOr(&flags->st_used[g.parity], 1);
+		if (rendered) { atomicAdd(&flags->algo_bytes, bytes); atomicAdd(&flags->n_rendered, rendered); }
+	}
+}
+
+__global__ void __launch_bounds__(256) k_patch_kernel(SlotArrays A, const SlotPatch* __restrict__ patches, uint32_t n,
+                                                     const MixPatch* __restrict__ mp, uint32_t nmp) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		const SlotPatch p = patches[i];
+		const uint32_t s = p.slot;
+		if (p.what & kPatchReset) {
+			A.live[s] = 1; A.read_i[s] = 0; A.eof[s] = p.eof;
+			A.dgain[s] = 0.0f; A.occ_cur[s] = 0.0f; A.lpf_prev[s] = 0.0f; A.bits[s] = 0;
+		}
+		if (p.what & kPatchReadI) A.read_i[s] = p.read_i;
+		if (p.what & kPatchEof) A.eof[s] = p.eof;
+		if (p.what & (kPatchResampler | kPatchReset)) {
+			// AudioResampler::init (AR.cpp:24-36)
+			Resamp r; r.prev_dest_dst_coords = -1; r.prev_samples_0_src_coords = -2; r.prev_samples[0] = 0.0f; r.prev_samples[1] = 0.0f;
+			A.rs[s] = r;
+		}
+		if (p.what & kPatchKill) A.live[s] = 0;
+	}
+	if (i < nmp) { A.mix_pos[mp[i].index] = mp[i].pos; A.mix_pos0[mp[i].index] = mp[i].pos; }
+}
+
+namespace dev {
+
+int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, const MixPatch* mp, uint32_t nmp, void* stream) {
+	const uint32_t m = n > nmp ? n : nmp;
+	if (!m) return 0;
+	k_patch_kernel<<<(m + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, patches, n, mp, nmp);
+	note_launch();
+	return check_launch("k_patch");
+}
+
+int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t n_slots, void* stream) {
+	if (!n_slots) return 0;
+	k1_params_kernel<<<(n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, A, flags, table);
+	note_launch();
+	return check_launch("k1_params");
+}
+
+}  // namespace dev
+}  // namespace sbm

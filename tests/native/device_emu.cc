@@ -1,0 +1,162 @@
+// tests/native/device_emu.cc -- TEST INFRASTRUCTURE ONLY.  Never compiled into libsubstrata_b200.so.
+//
+// Host emulation of the device seam (substrata_b200/csrc/device_api.h) so that the no-GPU test suite can drive the
+// REAL host engine (engine.cc: id/slot tables, dirty-range uploads, patch merging, ring bookkeeping, finished-source
+// handling) and the REAL per-source / per-sample arithmetic (k1_core.h, k2_core.h -- the very functions the CUDA
+// kernels call) against the oracle on CPU.  What it does not cover is the kernels' parallel decomposition, which only
+// exists on the GPU and is checked there (`pytest -m gpu`).  Linked into tests/native/libsbm_emu.so only.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "device_api.h"
+#include "k1_core.h"
+#include "k2_core.h"
+
+namespace sbm {
+namespace dev {
+
+static unsigned long long g_launches = 0;
+
+int init(int, void** stream_out) { *stream_out = (void*)1; return 0; }
+int use(int) { return 0; }
+void shutdown(void*) {}
+const char* last_error() { return "emulator"; }
+void* alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+void release(void* p) { free(p); }
+void* alloc_pinned(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+void release_pinned(void* p) { free(p); }
+int h2d(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
+int d2h(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
+int zero(void* dst, size_t bytes, void*) { memset(dst, 0, bytes); return 0; }
+int sync(void*) { return 0; }
+int num_mix_ctas(uint32_t, int) { return 1; }
+size_t partials_floats(uint32_t) { return 1; }
+
+int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, const MixPatch* mp, uint32_t nmp, void*) {
+	++g_launches;
+	for (uint32_t i = 0; i < n; ++i) {
+		const SlotPatch p = patches[i];
+		const uint32_t s = p.slot;
+		if (p.what & kPatchReset) {
+			A.live[s] = 1; A.read_i[s] = 0; A.eof[s] = p.eof;
+			A.dgain[s] = 0.0f; A.occ_cur[s] = 0.0f; A.lpf_prev[s] = 0.0f; A.bits[s] = 0;
+		}
+		if (p.what & kPatchReadI) A.read_i[s] = p.read_i;
+		if (p.what & kPatchEof) A.eof[s] = p.eof;
+		if (p.what & (kPatchResampler | kPatchReset)) {
+			Resamp r; r.prev_dest_dst_coords = -1; r.prev_samples_0_src_coords = -2; r.prev_samples[0] = 0.0f; r.prev_samples[1] = 0.0f;
+			A.rs[s] = r;
+		}
+		if (p.what & kPatchKill) A.live[s] = 0;
+	}
+	for (uint32_t i = 0; i < nmp; ++i) { A.mix_pos[mp[i].index] = mp[i].pos; A.mix_pos0[mp[i].index] = mp[i].pos; }
+	return 0;
+}
+
+int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t n_slots, void*) {
+	++g_launches;
+	uint32_t used = 0;
+	for (uint32_t slot = 0; slot < n_slots; ++slot) {
+		uint32_t n_src = 0;
+		used |= update_source(g, A, flags, table, slot, &n_src);
+		if (n_src) { flags->algo_bytes += 4ull * n_src; flags->n_rendered++; }
+	}
+	if (used & kUsedPan) flags->pan_used[g.parity] = 1;
+	if (used & kUsedSh) flags->sh_used[g.parity] = 1;
+	if (used & kUsedStereo) flags->st_used[g.parity] = 1;
+	return 0;
+}
+
+static void mix_list(const MixArgs& a, const uint32_t* list, uint32_t n, bool sh) {
+	const uint32_t F = a.frames;
+	std::vector<float> y(F);
+	for (uint32_t k = 0; k < n; ++k) {
+		const WorkRec& r = a.rec[list[k]];
+		if (r.flags & kRecSkip) {
+			if (r.flags & kRecResample) resampler_tail(r, &a.rs[r.slot].prev_samples[0], &a.rs[r.slot].prev_samples[1]);
+			continue;
+		}
+		const double w = (double)r.rate / (double)a.rate;
+		for (uint32_t i = 0; i < F; ++i) y[i] = fmul(source_sample(r, a.mixz, a.mix_pos0, w, i), gain_at(r.direct, i));
+		if (r.flags & kRecResample) resampler_tail(r, &a.rs[r.slot].prev_samples[0], &a.rs[r.slot].prev_samples[1]);
+		if (!(r.flags & kRecStereo)) {
+			if (r.flags & kRecLpf) {
+				float p = r.lpf_prev;
+				for (uint32_t i = 0; i < F; ++i) { p = lpf_step(r.lpf_coef, p, y[i]); y[i] = p; }
+				a.lpf_prev[r.slot] = p;
+			} else {
+				a.lpf_prev[r.slot] = y[F - 1];
+			}
+		}
+		if (!sh) {
+			for (int c = 0; c < 2; ++c) {
+				float* row = a.bus + (size_t)(16 + c) * F;
+				for (uint32_t i = 0; i < F; ++i) row[i] = fmaf(gain_at(r.ch[c], i), y[i], row[i]);
+			}
+		} else {
+			for (int c = 0; c < kNumSh; ++c) {
+				RampDesc d; d.konst = a.shg[r.slot].konst[c]; d.n = 0; d.start = 0.0f; d.inc = 0.0f;
+				if (r.ch_ramp_mask & (1u << c)) { d.start = a.shr[r.slot].start[c]; d.inc = a.shr[r.slot].inc[c]; d.n = a.shr[r.slot].n[c]; }
+				float* row = a.bus + (size_t)c * F;
+				for (uint32_t i = 0; i < F; ++i) row[i] = fmaf(gain_at(d, i), y[i], row[i]);
+			}
+		}
+	}
+}
+
+int launch_mix(const MixArgs& a, void*) {
+	g_launches += 2;
+	const uint32_t F = a.frames;
+	memset(a.bus, 0, sizeof(float) * (size_t)kBusRows * F);
+	mix_list(a, a.list_pan, a.n_pan, false);
+	mix_list(a, a.list_sh, a.n_sh, true);
+	float* bf = a.bus + (size_t)kBusRows * F;
+	bf[0] = a.flags->sh_used[a.parity] ? 1.0f : 0.0f;
+	bf[1] = a.flags->pan_used[a.parity] ? 1.0f : 0.0f;
+	bf[2] = a.flags->st_used[a.parity] ? 1.0f : 0.0f;
+	bf[3] = 0.0f;
+	return 0;
+}
+
+int launch_finish(const FinishArgs& a, void*) {
+	++g_launches;
+	const uint32_t F = a.frames;
+	const FinishPlan plan = plan_finish(a.bus + (size_t)kBusRows * F, a.hrir != nullptr, a.flags, a.parity, F);
+	std::vector<float> l(F, 0.0f), r(F, 0.0f);
+	if (plan.decode) {
+		const int H = (int)a.taps - 1;
+		for (uint32_t i = 0; i < F; ++i) decode_frame(a.bus, a.hrir, a.hist, F, a.taps, i, &l[i], &r[i]);
+		if (H > 0) {
+			std::vector<float> nh((size_t)H);
+			for (int c = 0; c < kNumSh; ++c) {
+				float* hc = a.hist + (size_t)c * (size_t)H;
+				for (int q = 0; q < H; ++q) nh[(size_t)q] = decode_input(a.bus + (size_t)c * F, hc, H, (int)F - H + q);
+				memcpy(hc, nh.data(), sizeof(float) * (size_t)H);
+			}
+		}
+	}
+	for (uint32_t i = 0; i < F; ++i) {
+		float lo = l[i], ro = r[i];
+		if (plan.stereo) { lo += a.bus[(size_t)16 * F + i]; ro += a.bus[(size_t)17 * F + i]; }
+		if (!plan.valid) { lo = 0.0f; ro = 0.0f; }
+		a.out[2 * i] = lo; a.out[2 * i + 1] = ro;
+	}
+	OutTail* tail = reinterpret_cast<OutTail*>(a.out + 2 * F);
+	tail->valid = plan.valid; tail->n_finished = a.flags->n_finished; tail->n_rendered = a.flags->n_rendered; tail->pad = 0;
+	tail->algo_bytes = a.flags->algo_bytes;
+	a.flags->n_finished = 0; a.flags->n_rendered = 0; a.flags->algo_bytes = 0;
+	unsigned long long* reads = reinterpret_cast<unsigned long long*>(tail + 1);
+	for (uint32_t q = 0; q < a.n_ring; ++q) reads[q] = a.read_i[a.list_ring[q]];
+	return 0;
+}
+
+void* event_create() { return nullptr; }
+void event_destroy(void*) {}
+void event_record(void*, void*) {}
+float event_elapsed_ms(void*, void*) { return 0.0f; }
+unsigned long long launches() { return g_launches; }
+
+}  // namespace dev
+}  // namespace sbm

@@ -1,0 +1,111 @@
+"""No-GPU tests of the product's HOST side and of the arithmetic the kernels share with it.
+
+The real host engine (substrata_b200/csrc/engine.cc: id/slot tables, patch merging, dirty uploads, rings, finished
+sources) is linked against tests/native/device_emu.cc -- a host emulation of the device seam that calls the same
+per-source (k1_core.h) and per-sample (k2_core.h) functions the CUDA kernels call -- and driven through the C ABI with
+the scenarios whose reference outputs are committed under tests/golden/.  The kernels' parallel decomposition itself is
+only checked on the GPU (tests/test_gpu_parity.py)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import substrata_b200 as sb
+from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, ROOT, OracleBackend, Scenario, load_sh_hrir, rel_rms)
+from golden.make_golden import GOLDEN_SCENARIOS
+
+EMU_DIR = os.path.join(ROOT, "tests", "native")
+EMU = os.path.join(EMU_DIR, "libsbm_emu.so")
+TOL = 1e-5          # the product bar (BASELINE.json north_star)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def build_emu():
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+
+
+def emu_engine(F, hrir=None, max_sources=1024):
+    return sb.MixEngine(F, sh_hrir=hrir, max_sources=max_sources, _lib_path=EMU)
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_SCENARIOS))
+def test_host_engine_matches_reference_golden(name):
+    kw, F, nb, taps = GOLDEN_SCENARIOS[name]
+    g = np.load(os.path.join(GOLDEN_DIR, "scenarios.npz"))
+    hr = load_sh_hrir()
+    out, valid = Scenario(frames=F, **kw).run(emu_engine(F, hr[:, :taps] if taps else hr), nb)
+    assert valid == g[name + "__valid"].tolist()
+    assert rel_rms(out, g[name]) <= TOL
+
+
+def test_feeder_bookkeeping_matches_oracle():
+    """Rows a2/a17 through the C ABI: one-shot removal, EOF marker, looping resampled read index (AudioEngine.cpp:393-425,496-517)."""
+    F = 256
+    rng = np.random.default_rng(3)
+    pcm = [(0.4 * rng.uniform(-1, 1, n)).astype(np.float32) for n in (700, 1024, 5000)]
+    res = {}
+    for be in (OracleBackend(F), emu_engine(F)):
+        bufs = [be.buffer_create(p) for p in pcm]
+        a = be.source_create(KIND_PAN); be.source_attach_buffer(a, bufs[0], 0, 48000, False, True)
+        b = be.source_create(KIND_PAN); be.source_attach_buffer(b, bufs[1], 100, 44100, True, False)
+        c = be.source_create(KIND_PAN); be.source_attach_buffer(c, bufs[2], 0, 48000, False, False); be.source_set_eof_marker(c, 1000)
+        ids = np.array([a, b, c], np.int32)
+        be.set_source_positions(ids, np.array([[2, 0, -3], [-4, 1, 2], [0, 0, -5]], np.float32))
+        outs, fin, q = [], [], []
+        for _ in range(8):
+            v, o = be.mix()
+            outs.append(o); fin.append(be.poll_finished()); q.append(be.source_query(b)["cur_read_i"])
+        res[be.name] = (np.stack(outs), fin, q)
+    oo, of, oq = res["oracle"]
+    eo, ef, eq = res["b200"]
+    assert of == ef and oq == eq
+    assert rel_rms(eo, oo) <= 1e-6
+
+
+def test_slot_reuse_and_destroy():
+    """DestroySource + CreateSoundObjectSource churn (AudioEngine.cpp:900-943, playOneShotSound :1022-1052): ids keep
+    increasing, slots are recycled with clean DSP state."""
+    F = 256
+    rng = np.random.default_rng(5)
+    pcm = (0.3 * rng.uniform(-1, 1, 4096)).astype(np.float32)
+    outs = {}
+    for be in (OracleBackend(F), emu_engine(F, max_sources=4)):
+        buf = be.buffer_create(pcm)
+        o = []
+        ids = []
+        for round_ in range(6):
+            sid = be.source_create(KIND_PAN)
+            ids.append(sid)
+            be.source_attach_buffer(sid, buf, 17 * round_, 48000, True, False)
+            be.set_source_positions([sid], np.array([[1.0 + round_, 0.5, -2.0]], np.float32))
+            for _ in range(2):
+                o.append(be.mix()[1])
+            if round_ % 2 == 1:
+                be.source_destroy(ids[-2]); be.source_destroy(ids[-1])
+        outs[be.name] = (np.stack(o), ids)
+    assert outs["oracle"][1] == outs["b200"][1] == list(range(6))
+    assert rel_rms(outs["b200"][0], outs["oracle"][0]) <= 1e-6
+
+
+def test_capacity_and_argument_errors():
+    e = emu_engine(256, max_sources=2)
+    e.source_create(KIND_PAN, 2)
+    with pytest.raises(sb.SbmError) as ei:
+        e.source_create(KIND_PAN)
+    assert ei.value.code == -5
+    with pytest.raises(sb.SbmError):
+        e.source_create(KIND_HRTF)            # engine created without SH-HRIRs
+    with pytest.raises(sb.SbmError):
+        e.set_source_positions([99], np.zeros((1, 3), np.float32))
+    buf = e.buffer_create(np.zeros(100, np.float32))
+    with pytest.raises(sb.SbmError):          # AudioEngine::addSource rejects rates outside 8000..48000 (AudioEngine.cpp:884-885)
+        e.source_attach_buffer(0, buf, 0, 96000)
+    with pytest.raises(sb.SbmError):
+        sb.MixEngine(16, _lib_path=EMU)       # Resonance accepts 32..16384 frames (resonance_audio_api_impl.cc:78-94)
+
+
+def test_empty_engine_is_invalid_and_silent():
+    e = emu_engine(128)
+    v, o = e.mix()
+    assert v == 0 and not o.any()
