@@ -126,7 +126,9 @@ void shutdown(void* stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream
 void* alloc(size_t bytes) {
 	void* p = nullptr;
 	if (check(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) return nullptr;
-	if (check(cudaMemset(p, 0, bytes ? bytes : 1), "cudaMemset")) { cudaFree(p); return nullptr; }
+	// cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the engine's
+	// non-blocking streams do not wait for: finish it here so that a following upload cannot be overwritten by zeros.
+	if (check(cudaMemset(p, 0, bytes ? bytes : 1), "cudaMemset") || check(cudaStreamSynchronize(0), "cudaMemset(sync)")) { cudaFree(p); return nullptr; }
 	return p;
 }
 void release(void* p) { if (p) cudaFree(p); }
