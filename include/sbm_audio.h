@@ -153,11 +153,13 @@ typedef struct sbm_stats {
 	uint64_t buffers_mixed;
 	uint64_t kernel_launches;        /* kernels launched by this library so far */
 	uint32_t active_sources;
-	float last_params_kernel_ms;     /* CUDA-event times of the last sbm_mix_begin/finish on the engine stream */
-	float last_mix_kernel_ms;
-	float last_finish_kernel_ms;
-	uint64_t last_algorithmic_bytes; /* sum over sources of 4*n_src + per-source state bytes */
+	float last_params_kernel_ms;     /* CUDA-event times of the last buffer on the engine stream (sbm_set_profiling): K1 */
+	float last_mix_kernel_ms;        /*   K2 launches only (the HBM-bound gather/mix kernel) */
+	float last_finish_kernel_ms;     /*   K3 + whatever the caller put between begin and finish + K4 */
+	uint64_t last_algorithmic_bytes; /* PCM bytes the rendered sources had to read: sum of 4 * source samples */
 	uint64_t last_h2d_bytes, last_d2h_bytes;
+	uint32_t last_rendered_sources;  /* sources that reached a bus in the last buffer */
+	uint32_t reserved;
 } sbm_stats;
 SBM_API int sbm_get_stats(sbm_engine* e, sbm_stats* out);
 /* Enables CUDA-event timing of the kernels inside mix_begin/finish (off by default). */

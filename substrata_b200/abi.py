@@ -20,7 +20,7 @@ class SbmSourceState(C.Structure):
 class SbmStats(C.Structure):
     _fields_ = [("buffers_mixed", _u64), ("kernel_launches", _u64), ("active_sources", C.c_uint32), ("last_params_kernel_ms", _f),
                 ("last_mix_kernel_ms", _f), ("last_finish_kernel_ms", _f), ("last_algorithmic_bytes", _u64), ("last_h2d_bytes", _u64),
-                ("last_d2h_bytes", _u64)]
+                ("last_d2h_bytes", _u64), ("last_rendered_sources", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 # name -> (restype, argtypes); every SBM_API symbol of the header.

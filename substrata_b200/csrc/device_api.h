@@ -45,6 +45,7 @@ struct MixArgs {
 	float* bus;                 // [18][frames] + 4 flag floats: this rank's bus
 	const DevFlags* flags;
 	uint32_t parity;
+	void* ev_after_k2;          // optional event recorded between K2 and K3 (profiling)
 };
 
 struct FinishArgs {

@@ -621,8 +621,8 @@ SBM_API int sbm_mix_begin(sbm_engine* e) {
 	m.list_sh = e->dv_list_sh; m.n_sh = (uint32_t)e->list_sh.size();
 	m.frames = e->g.frames; m.rate = e->g.rate; m.partials = e->dv_partials; m.partials_floats = e->partials_floats;
 	m.bus = e->dv_bus; m.flags = e->dv_flags; m.parity = e->g.parity;
+	m.ev_after_k2 = e->profiling ? e->ev[2] : nullptr;
 	if (dev::launch_mix(m, st)) return fail_cuda(e, "k2_mix");
-	if (e->profiling) dev::event_record(e->ev[2], st);
 	e->begun = true;
 	e->stats.active_sources = (uint32_t)(e->list_pan.size() + e->list_sh.size());
 	return SBM_OK;
@@ -669,6 +669,7 @@ SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid
 	e->stats.buffers_mixed++;
 	e->stats.kernel_launches = dev::launches();
 	e->stats.last_algorithmic_bytes = tail.algo_bytes;
+	e->stats.last_rendered_sources = tail.n_rendered;
 	if (e->profiling) {
 		e->stats.last_params_kernel_ms = dev::event_elapsed_ms(e->ev[0], e->ev[1]);
 		e->stats.last_mix_kernel_ms = dev::event_elapsed_ms(e->ev[1], e->ev[2]);

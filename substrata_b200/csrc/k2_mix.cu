@@ -255,6 +255,7 @@ int launch_mix(const MixArgs& a, void* stream) {
 		note_launch();
 		if (check_launch("k2_mix<sh>")) return -1;
 	}
+	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
 	k3_reduce_kernel<<<(kBusRows * F + 255) / 256, 256, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F);
 	note_launch();
 	return check_launch("k3_reduce");
