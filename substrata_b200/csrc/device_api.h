@@ -27,17 +27,15 @@ constexpr uint32_t kPatchKill = 16;      // live = 0
 struct MixPatch { uint32_t index; uint32_t pad; double pos; };
 
 struct MixArgs {
-	const WorkRec* rec;
-	const ShGains* shg;
-	const ShRamps* shr;
+	const WorkRec* rec;         // [n_pan + n_sh] render-list order: stereo-bus sources first, then ambisonic sources
+	const ShGains* shg;         // indexed like rec
+	const ShRamps* shr;         // indexed like rec
 	const MixZ* mixz;
 	const double* mix_pos0;
 	Resamp* rs;                 // K2 stores prev_samples of resampled sources
 	float* lpf_prev;            // K2 stores the occlusion filter memory
-	const uint32_t* list_pan;   // slots rendered by the 2-channel kernel (panned + non-spatial sources)
-	uint32_t n_pan;
-	const uint32_t* list_sh;    // slots rendered by the 16-channel kernel
-	uint32_t n_sh;
+	uint32_t n_pan;             // entries rendered by the 2-channel kernel (panned + non-spatial sources)
+	uint32_t n_sh;              // entries rendered by the 16-channel kernel
 	uint32_t frames;
 	int32_t rate;
 	float* partials;            // scratch of per-CTA partial buses: [max_ctas(pan)][2][frames] then [max_ctas(sh)][16][frames]
@@ -88,7 +86,7 @@ int num_mix_ctas(uint32_t frames, int sh);       // largest grid K2 will use (si
 size_t partials_floats(uint32_t frames);         // floats needed for MixArgs::partials
 // kernels
 int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, const MixPatch* mp, uint32_t nmp, void* stream);
-int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t n_slots, void* stream);
+int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, const uint32_t* lists, uint32_t n_slots, void* stream);   // lists: [n_pan + n_sh] slots in render order
 int launch_mix(const MixArgs& a, void* stream);  // K2 (both lists) + K3 (partials -> bus)
 int launch_finish(const FinishArgs& a, void* stream);
 // timing

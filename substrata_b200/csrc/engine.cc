@@ -73,7 +73,7 @@ struct sbm_engine {
 	MixZ* dv_mixz = nullptr;
 	DevFlags* dv_flags = nullptr;
 	float* dv_table = nullptr;
-	uint32_t *dv_list_pan = nullptr, *dv_list_sh = nullptr, *dv_list_ring = nullptr;
+	uint32_t *dv_lists = nullptr, *dv_list_ring = nullptr;   // dv_lists: pan list followed by the ambisonic list
 	SlotPatch* dv_patches = nullptr; uint32_t dv_patches_cap = 0;
 	MixPatch* dv_mix_patches = nullptr; uint32_t dv_mix_patches_cap = 0;
 	float* dv_partials = nullptr; size_t partials_floats = 0;
@@ -211,7 +211,7 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	const bool hrtf = cfg->sh_hrir != nullptr;
 	if (hrtf) ok = ok && dalloc(A.shg, cap) && dalloc(A.shr, cap); else { A.shg = nullptr; A.shr = nullptr; }
 	ok = ok && dalloc(e->dv_flags, 1) && dalloc(e->dv_table, (size_t)kTableAz * kTableEl * kShRaw);
-	ok = ok && dalloc(e->dv_list_pan, cap) && dalloc(e->dv_list_sh, cap) && dalloc(e->dv_list_ring, cap);
+	ok = ok && dalloc(e->dv_lists, cap) && dalloc(e->dv_list_ring, cap);
 	e->bus_floats = (size_t)kBusRows * F + 4;
 	ok = ok && dalloc(e->dv_bus, e->bus_floats);
 	e->partials_floats = dev::partials_floats(F);
@@ -246,7 +246,7 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	SlotArrays& A = e->A;
 	void* ptrs[] = {e->dv_stat, e->dv_posvol, e->dv_occl, e->dv_ring_write, e->dv_mixz, A.live, A.read_i, A.eof, A.rs, A.dgain, A.occ_cur,
 	                A.lpf_prev, A.bits, A.rec, A.finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
-	                e->dv_table, e->dv_list_pan, e->dv_list_sh, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
+	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
 	                e->dv_hist, e->dv_patches, e->dv_mix_patches};
 	for (void* p : ptrs) if (p) dev::release(p);
 	for (auto& b : e->buffers) if (b.owned && b.dptr) dev::release(b.dptr);
@@ -594,8 +594,8 @@ SBM_API int sbm_mix_begin(sbm_engine* e) {
 		return fail_cuda(e, "sbm_mix_begin(upload)");
 	if (e->lists_dirty) {
 		rebuild_lists(e);
-		if ((!e->list_pan.empty() && dev::h2d(e->dv_list_pan, e->list_pan.data(), 4 * e->list_pan.size(), st)) ||
-		    (!e->list_sh.empty() && dev::h2d(e->dv_list_sh, e->list_sh.data(), 4 * e->list_sh.size(), st)) ||
+		if ((!e->list_pan.empty() && dev::h2d(e->dv_lists, e->list_pan.data(), 4 * e->list_pan.size(), st)) ||
+		    (!e->list_sh.empty() && dev::h2d(e->dv_lists + e->list_pan.size(), e->list_sh.data(), 4 * e->list_sh.size(), st)) ||
 		    (!e->list_ring.empty() && dev::h2d(e->dv_list_ring, e->list_ring.data(), 4 * e->list_ring.size(), st)))
 			return fail_cuda(e, "sbm_mix_begin(lists)");
 		e->stats.last_h2d_bytes += 4 * (e->list_pan.size() + e->list_sh.size() + e->list_ring.size());
@@ -611,14 +611,15 @@ SBM_API int sbm_mix_begin(sbm_engine* e) {
 	}
 	e->g.parity = (uint32_t)(e->buffer_index & 1);
 	e->g.n_slots = e->n_slots;
+	e->g.n_pan = (uint32_t)e->list_pan.size(); e->g.n_sh = (uint32_t)e->list_sh.size();
 	// 2. kernels
 	if (e->profiling) dev::event_record(e->ev[0], st);
-	if (e->n_slots && dev::launch_params(e->g, e->A, e->dv_flags, e->dv_table, e->n_slots, st)) return fail_cuda(e, "k1_params");
+	if (e->g.n_pan + e->g.n_sh && dev::launch_params(e->g, e->A, e->dv_flags, e->dv_table, e->dv_lists, e->n_slots, st)) return fail_cuda(e, "k1_params");
 	if (e->profiling) dev::event_record(e->ev[1], st);
 	MixArgs m;
 	m.rec = e->A.rec; m.shg = e->A.shg; m.shr = e->A.shr; m.mixz = e->dv_mixz; m.mix_pos0 = e->A.mix_pos0; m.rs = e->A.rs; m.lpf_prev = e->A.lpf_prev;
-	m.list_pan = e->dv_list_pan; m.n_pan = (uint32_t)e->list_pan.size();
-	m.list_sh = e->dv_list_sh; m.n_sh = (uint32_t)e->list_sh.size();
+	m.n_pan = (uint32_t)e->list_pan.size();
+	m.n_sh = (uint32_t)e->list_sh.size();
 	m.frames = e->g.frames; m.rate = e->g.rate; m.partials = e->dv_partials; m.partials_floats = e->partials_floats;
 	m.bus = e->dv_bus; m.flags = e->dv_flags; m.parity = e->g.parity;
 	m.ev_after_k2 = e->profiling ? e->ev[2] : nullptr;

@@ -58,18 +58,26 @@ SBM_HD void encoding_coeffs(const float* table, float az, float el, float* out16
 		}
 }
 
+// Converts a non-negative coordinate to 32.32 fixed point (floor).
+SBM_HD unsigned long long to_fx(double x) { return (unsigned long long)(x * kFx); }
+
+// Largest window (in samples) the single-mix-source fast form may ask for; longer reads (source_delta >~ 4 at 1024 frames)
+// stay on the generic per-sample path.
+constexpr uint32_t kMaxMix1Window = 4096;
+
 // Returns kUsed* bits; *rendered_src = PCM samples a rendered source reads this buffer (0 when skipped / stopped).
-SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot,
+// `out` = position in the render lists: where this source's WorkRec / ShGains / ShRamps go.
+SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot, uint32_t out,
                               uint32_t* rendered_src) {
 	*rendered_src = 0;
 	const SrcStatic st = A.stat[slot];
 	WorkRec rec;
 	rec.pcm = st.pcm; rec.len = st.len; rec.start = 0; rec.n_src = 0; rec.avail = 0; rec.flags = kRecSkip;
-	rec.mix_first = st.mix_first; rec.x0 = 0.0; rec.prev0 = 0.0f; rec.prev1 = 0.0f; rec.lpf_coef = 0.0f; rec.lpf_prev = 0.0f;
-	rec.rate = st.rate; rec.nz = st.nz; rec.ch_ramp_mask = 0; rec.slot = slot; rec.pad[0] = 0; rec.pad[1] = 0;
+	rec.slot = slot; rec.x0_fx = 0; rec.step_fx = 0; rec.prev0 = 0.0f; rec.prev1 = 0.0f; rec.lpf_coef = 0.0f; rec.lpf_prev = 0.0f;
+	rec.ch_ramp_mask = 0; rec.mix_factor = 1.0f; rec.mix_first = st.mix_first; rec.nz = st.nz;
 	rec.direct.konst = 0.0f; rec.direct.start = 0.0f; rec.direct.inc = 0.0f; rec.direct.n = 0;
 	rec.ch[0] = rec.direct; rec.ch[1] = rec.direct;
-	if (!(st.flags & kFlagAlive) || !A.live[slot]) { A.rec[slot] = rec; return 0; }
+	if (!(st.flags & kFlagAlive) || !A.live[slot]) { A.rec[out] = rec; return 0; }
 
 	const uint32_t F = G.frames;
 	const uint32_t kind = (st.flags >> kFlagKindShift) & 0xff;
@@ -91,7 +99,9 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		// AudioResampler::resample coordinates (AR.cpp:101-103)
 		const int64_t dest0 = rs.prev_dest_dst_coords + 1;
 		const double dest0_src = (double)dest0 * (double)st.rate / (double)G.rate;
-		rec.x0 = dest0_src - (double)rs.prev_samples_0_src_coords;
+		const double x0 = dest0_src - (double)rs.prev_samples_0_src_coords;
+		rec.x0_fx = to_fx(x0 > 0.0 ? x0 : 0.0);
+		rec.step_fx = to_fx((double)st.rate / (double)G.rate);
 		rec.prev0 = rs.prev_samples[0]; rec.prev1 = rs.prev_samples[1];
 		rs.prev_dest_dst_coords += (int64_t)F;
 		rs.prev_samples_0_src_coords += (int64_t)n_src;
@@ -101,6 +111,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		rflags |= kRecResample;
 	}
 	bool remove_source = false;
+	rec.n_src = n_src;
 	if (feed == kFeedBuffer) {
 		// AE.cpp:389-426
 		uint64_t cur = A.read_i[slot];
@@ -119,6 +130,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 			remove_source = (st.flags & kFlagRemoveOnFinish) != 0;
 		}
 		A.read_i[slot] = cur;
+		alg_samples = rec.avail;
 	} else if (feed == kFeedRing) {
 		// AE.cpp:459-474: pop what is there, zero-pad the rest.  read_i counts samples popped so far.
 		const uint64_t rd = A.read_i[slot];
@@ -128,20 +140,40 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		rec.avail = (uint32_t)have;
 		rflags |= kRecWrap;
 		A.read_i[slot] = rd + have;
+		alg_samples = rec.avail;
 	} else {
-		// AE.cpp:435-458: K2 evaluates pos0 + (i+1)*delta per mix source; advance the read heads here.
-		rflags |= kRecMix;
+		// AE.cpp:435-458: every mix source's read head advances by source_delta before each of the n_src reads.
+		bool fast = st.nz == 1;
 		for (uint32_t z = 0; z < st.nz; ++z) {
 			const uint32_t k = st.mix_first + z;
+			const MixZ mz = A.mixz[k];
 			const double p0 = A.mix_pos[k];
 			A.mix_pos0[k] = p0;
 			// The reference adds delta n_src times in double; one fma differs by < n_src ulps of pos (continuous).
-			A.mix_pos[k] = fma((double)n_src, A.mixz[k].delta, p0);
-			alg_samples += (uint32_t)((double)n_src * A.mixz[k].delta) + 2u;
+			const double pend = fma((double)n_src, mz.delta, p0);
+			A.mix_pos[k] = pend;
+			alg_samples += (uint32_t)((double)n_src * mz.delta) + 2u;
+			if (fast) {
+				// Single mix source as a contiguous window: first read at p1 = p0 + delta, last at pend; window sample j is
+				// pcm[(floor(p1) + j) % len], the read head starts at frac(p1) inside it and steps by delta.
+				const double p1 = p0 + mz.delta;
+				const double span = pend - floor(p1);
+				if (!(mz.delta > 0.0) || !(p1 >= 0.0) || !(span < (double)kMaxMix1Window) || !(pend < 9.0e15)) { fast = false; continue; }
+				const unsigned long long base = (unsigned long long)p1;
+				const uint32_t need = (uint32_t)span + 3u;              // +1: the interpolation partner, +1: fixed-point slack
+				if (need > mz.len) { fast = false; continue; }
+				rec.pcm = mz.pcm; rec.len = mz.len;
+				rec.start = (uint32_t)(base % mz.len);
+				rec.n_src = need; rec.avail = need;
+				rec.x0_fx = to_fx(p1 - (double)base);
+				rec.step_fx = to_fx(mz.delta);
+				rec.mix_factor = mz.mix_factor;
+				if (rec.start + need > mz.len) rflags |= kRecWrap;
+			}
 		}
+		rflags |= fast ? kRecMix1 : kRecMix;
+		if (!fast) { rec.n_src = n_src; rec.avail = 0; rflags &= ~kRecWrap; }
 	}
-	if (feed != kFeedMix) alg_samples = rec.avail;
-	rec.n_src = n_src;
 
 	// ---------------- EOF bookkeeping (AE.cpp:496-517) ----------------
 	long long eof = A.eof[slot];
@@ -151,7 +183,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		// DestroySource runs from the task queue before the graph is processed: the last buffer is not rendered.
 		A.live[slot] = 0;
 		A.finished[finished_push(flags)] = (int)st.id;
-		A.rec[slot] = rec;
+		A.rec[out] = rec;
 		return 0;
 	}
 
@@ -179,7 +211,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		// skip: nothing downstream runs, but the feeder still resampled this buffer (AE.cpp:485-494 precede the graph), so
 		// K2 must still carry AudioResampler::prev_samples forward.
 		rec.flags = kRecSkip | (rflags & (kRecResample | kRecWrap));
-		A.rec[slot] = rec;
+		A.rec[out] = rec;
 		return 0;
 	}
 	if (near_unity(target) && near_unity(dg)) {
@@ -197,7 +229,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		rec.ch[0].konst = 1.0f; rec.ch[1].konst = 1.0f;
 		A.bits[slot] = bits;
 		rec.flags = rflags;
-		A.rec[slot] = rec;
+		A.rec[out] = rec;
 		return kUsedStereo;
 	}
 
@@ -237,14 +269,14 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 			sg.konst[c] = d.konst;
 			if (d.n) {
 				rec.ch_ramp_mask |= 1u << c;
-				A.shr[slot].start[c] = d.start; A.shr[slot].inc[c] = d.inc; A.shr[slot].n[c] = d.n;
+				A.shr[out].start[c] = d.start; A.shr[out].inc[c] = d.inc; A.shr[out].n[c] = d.n;
 			}
 		}
-		A.shg[slot] = sg;
+		A.shg[out] = sg;
 		rflags |= kRecHrtf;
 	}
 	rec.flags = rflags;
-	A.rec[slot] = rec;
+	A.rec[out] = rec;
 	return hrtf ? kUsedSh : kUsedPan;
 }
 

@@ -1,4 +1,4 @@
-// k1_params.cu -- "K1": one thread per source slot runs the feeder bookkeeping and Resonance's per-source parameter
+// k1_params.cu -- "K1": one thread per render-list entry (live source) runs the feeder bookkeeping and Resonance's per-source parameter
 // logic for this buffer (k1_core.h: update_source) and condenses the slot into one WorkRec for the mix kernel; plus
 // k_patch, which applies host-requested state (re)initialisations before K1.
 //
@@ -10,10 +10,11 @@
 
 namespace sbm {
 
-__global__ void __launch_bounds__(256) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table) {
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table,
+                                                       const uint32_t* __restrict__ lists) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;    // position in the render lists
 	uint32_t used = 0, n_src = 0;
-	if (slot < g.n_slots) used = update_source(g, A, flags, table, slot, &n_src);
+	if (k < g.n_pan + g.n_sh) used = update_source(g, A, flags, table, lists[k], k, &n_src);
 	// Block-level reduction of the "mixer used" bits and the accounting counters: one atomic per warp at most.
 	const unsigned full = 0xffffffffu;
 	uint32_t u = used;
@@ -64,9 +65,11 @@ int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, cons
 	return check_launch("k_patch");
 }
 
-int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t n_slots, void* stream) {
-	if (!n_slots) return 0;
-	k1_params_kernel<<<(n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, A, flags, table);
+int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, const uint32_t* lists, uint32_t n_slots, void* stream) {
+	(void)n_slots;
+	const uint32_t n = g.n_pan + g.n_sh;
+	if (!n) return 0;
+	k1_params_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists);
 	note_launch();
 	return check_launch("k1_params");
 }

@@ -38,20 +38,37 @@ SBM_HD float resampler_tmp(const WorkRec& r, int j) {
 	return window_sample(r, (uint32_t)(j - 2));
 }
 
-// Output sample i of the linear sample-rate conversion (AR.cpp:57-74).  The reference advances x by repeated
-// addition; x0 + i*w differs from that by < 1e-13 relative, and the interpolant is continuous in x.
-SBM_HD float resampled_sample(const WorkRec& r, double w, uint32_t i) {
-	const double x = fma((double)i, w, r.x0);
-	const int d = (int)x;
-	const float frac = (float)(x - (double)d);
+// Read-head coordinate of output sample i in 32.32 fixed point -> integer sample index d and interpolation fraction.
+// The fraction keeps the top 23 bits (truncation error < 1.2e-7 of a sample; the interpolant is continuous in it).
+SBM_HD void fx_split(unsigned long long x0_fx, unsigned long long step_fx, uint32_t i, int* d, float* frac) {
+	const unsigned long long p = x0_fx + (unsigned long long)i * step_fx;
+	*d = (int)(uint32_t)(p >> 32);
+	*frac = fsub(u2f(0x3f800000u | ((uint32_t)p >> 9)), 1.0f);
+}
+
+// Output sample i of the linear sample-rate conversion (AR.cpp:57-74): out = tmp[d] (1 - frac) + tmp[d + 1] frac with
+// clamped indices.  The reference advances the coordinate by repeated double addition; the fixed-point head differs
+// from it by < 1e-6 of a sample over a buffer.
+SBM_HD float resampled_sample(const WorkRec& r, uint32_t i) {
+	int d; float frac;
+	fx_split(r.x0_fx, r.step_fx, i, &d, &frac);
 	const int max_i = (int)r.n_src + 1;
-	const int d0 = d < 0 ? 0 : (d > max_i ? max_i : d);
-	const int d1 = d + 1 < 0 ? 0 : (d + 1 > max_i ? max_i : d + 1);
+	const int d0 = d > max_i ? max_i : d;
+	const int d1 = d + 1 > max_i ? max_i : d + 1;
 	return fadd(fmul(resampler_tmp(r, d0), fsub(1.0f, frac)), fmul(resampler_tmp(r, d1), frac));
 }
 
-// Output sample i of the pitch / doppler mixer (AE.cpp:435-458): the read head of every mix source advances by
-// source_delta BEFORE each read.
+// Output sample i of a single pitch-shifted mix source in window form (AE.cpp:443-452; K1 turned the read head into
+// window + fixed-point coordinate): sample = w[d] (1 - frac) + w[d + 1] frac, times mix_factor.
+SBM_HD float mix1_sample(const WorkRec& r, uint32_t i) {
+	int d; float frac;
+	fx_split(r.x0_fx, r.step_fx, i, &d, &frac);
+	const float s = fadd(fmul(window_sample(r, (uint32_t)d), fsub(1.0f, frac)), fmul(window_sample(r, (uint32_t)d + 1u), frac));
+	return fmul(s, r.mix_factor);
+}
+
+// Output sample i of the general pitch / doppler mixer (AE.cpp:435-458), any number of mix sources: the read head of
+// every mix source advances by source_delta BEFORE each read.
 SBM_HD float mixed_sample(const WorkRec& r, const MixZ* mixz, const double* mix_pos0, uint32_t i) {
 	float acc = 0.0f;
 	for (uint32_t z = 0; z < r.nz; ++z) {
@@ -68,9 +85,10 @@ SBM_HD float mixed_sample(const WorkRec& r, const MixZ* mixz, const double* mix_
 }
 
 // Engine-rate input sample i of a source (what SetPlanarBuffer receives, AE.cpp:480-494).
-SBM_HD float source_sample(const WorkRec& r, const MixZ* mixz, const double* mix_pos0, double w, uint32_t i) {
+SBM_HD float source_sample(const WorkRec& r, const MixZ* mixz, const double* mix_pos0, uint32_t i) {
+	if (r.flags & kRecMix1) return mix1_sample(r, i);
 	if (r.flags & kRecMix) return mixed_sample(r, mixz, mix_pos0, i);
-	if (r.flags & kRecResample) return resampled_sample(r, w, i);
+	if (r.flags & kRecResample) return resampled_sample(r, i);
 	return window_sample(r, i);
 }
 

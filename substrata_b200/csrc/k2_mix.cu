@@ -4,13 +4,29 @@
 // ramped bus gains and accumulate into the output tile; and "K3", the fixed-order cross-CTA reduction of the partial
 // buses into this rank's bus.
 //
-// Decomposition: a CTA owns ALL frames of the buffer and a contiguous slice of the source list.  Thread t owns frames
-// t, t+T, t+2T, ... (T = blockDim.x), so that for one source a warp reads 32 consecutive samples per load (coalesced
-// 128 B) and every thread keeps its NCH x K partial sums in registers across the CTA's whole slice of sources -- the
-// per-source contributions never leave the register file until the slice is done.  Each CTA then stores one partial
-// bus [NCH][frames]; K3 sums the partial buses in CTA order (deterministic; no atomics on audio).
-// HBM traffic: 4 B per source sample read (PCM) + 128 B WorkRec (+64 B SH gains) per source; writes are O(grid * frames).
-// Roofline: HBM read.  No tensor cores: 2..16 FMA per 4 B loaded, no contraction to feed them.
+// Decomposition.  A CTA owns ALL frames of the buffer and a contiguous slice of the render list, and keeps its partial
+// sums in registers across the whole slice, so per-source contributions never leave the register file; each CTA then
+// stores one partial bus [NCH][frames] and K3 sums the partial buses in CTA order (deterministic; no atomics on audio).
+//   stereo bus (2 channels):  one WARP per source -- lane l owns frames l, l+32, ... (2 x frames/32 accumulators), the
+//                             four math warps of a CTA work on the four sources of a batch independently and combine
+//                             their tiles through shared memory once, at the end of the slice;
+//   ambisonic bus (16 ch):    one CTA per source -- thread t owns frames t, t+T, t+2T, t+3T (16 x 4 accumulators, FFMA2).
+//
+// Data movement.  Source windows are not loaded by the math threads: a dedicated producer warp drives a multi-stage
+// shared-memory ring with the TMA unit -- one cp.async.bulk (UBLKCP) per window segment, completion signalled on an
+// mbarrier per stage, stages handed back through a second mbarrier by the math warps -- kStages batches of kBatch sources
+// ahead of the math, which keeps ~100 KB of reads in flight per SM regardless of how the math is scheduled.  The
+// per-source records (WorkRec, 128 B, render-list order, + 64 B of SH gains) stream through a second, deeper TMA ring
+// so that the producer never waits on a dependent global load; producer lane b condenses record b of a batch into a
+// 64-byte MathDesc (shared-memory window index, fixed-point read head, pre-multiplied gains, mode bits) so that the math
+// threads spend a handful of instructions per source on set-up.
+// Windows start at arbitrary sample offsets; the copy fetches the enclosing 16-byte-aligned span and the math indexes
+// from the sub-offset.  A looping window that crosses the end of its buffer is fetched as two segments.
+// Sources the fast path cannot express (zero-padded ends, ring underflow, multi-source pitch mixes, windows larger
+// than a stage slot, unaligned buffers, occlusion low-pass) take a generic per-sample path that reads global memory.
+//
+// HBM traffic: 4 B per source sample (PCM, + <= 24 B alignment over-fetch per segment) + 128 B WorkRec (+64 B SH gains)
+// per source; writes are O(grid * frames).  Roofline: HBM read.  No tensor cores: 2..16 FMA per 4 B loaded.
 #include "device_internal.h"
 #include "k2_core.h"
 
@@ -18,154 +34,588 @@ namespace sbm {
 
 namespace {
 
-constexpr int kBatch = 16;            // WorkRecs staged in shared memory per step
+constexpr int kBatch = 4;             // sources per pipeline stage
+constexpr int kStages = 5;            // window stages in flight
+constexpr int kRecStages = kStages + 2;
 constexpr int kPanThreads = 128;
 constexpr int kShK = 4;               // frames per thread in the 16-channel kernel
 
-struct MixSmem {
-	WorkRec rec[kBatch];
-	ShGains shg[kBatch];
-	float lpf[kMaxFrames];
-	float lpf_carry;
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA bulk copy (global -> shared), sm_90+ / sm_100a.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+	uint32_t spins = 0;
+	while (!mbar_try_wait(bar, parity)) {
+		if (++spins > (1u << 24)) __trap();    // a lost completion must fail loudly, not hang the device
+	}
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Packed pair of fp32 FMAs (Blackwell FFMA2): acc.xy += g.xy * x.xy in one issue slot.
+__device__ __forceinline__ void ffma2(float2& acc, const float2 g, const float2 x) {
+	unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
+	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(*reinterpret_cast<const unsigned long long*>(&g)), "l"(*reinterpret_cast<const unsigned long long*>(&x)));
+	acc = *reinterpret_cast<float2*>(&a);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// How a source's window is laid out in its stage slot.  Pure function of the record, evaluated identically by the
+// issuing thread and by the math threads.
+//   slot: [4 floats unused][TMA span ...]; span = pcm[a0 .. a1) with a0 = start & ~3.  Window sample j sits at
+//   w[j] for j < n1 and at w[j + wadj] after a loop wrap (second segment placed at the next 16-byte boundary).
+// ---------------------------------------------------------------------------------------------------------------
+struct WinPlan {
+	bool fast;           // window comes through the TMA ring
+	uint32_t off0;       // start & 3
+	uint32_t seg1_floats, seg2_floats;   // 16-byte multiples; seg2 = 0 without wrap
+	uint32_t a0;         // first fetched sample of segment 1
+	uint32_t n1;         // window samples before the wrap (0xffffffff: no wrap)
+	uint32_t wadj;       // index adjustment after the wrap
 };
 
-// Occlusion low-pass over the CTA's staged buffer (rare path: only occluded sources).  y[n] = c (y[n-1] - x[n]) + x[n]
-// is linear in y[n-1]: warp 0 splits the buffer into 32 contiguous chunks, runs each chunk from a zero state while
-// accumulating c^len, chains the 32 chunk states in order, and re-runs each chunk from its true initial state.
-__device__ void lpf_in_smem(float* buf, uint32_t F, float coef, float prev, float* carry_out) {
-	if (threadIdx.x < 32) {
-		const uint32_t lane = threadIdx.x;
-		const uint32_t chunk = (F + 31) / 32;
-		const uint32_t lo = lane * chunk < F ? lane * chunk : F;
-		const uint32_t hi = lo + chunk < F ? lo + chunk : F;
-		float p = 0.0f, apow = 1.0f;
-		for (uint32_t n = lo; n < hi; ++n) { p = lpf_step(coef, p, buf[n]); apow *= coef; }
-		float carry = prev, mine = prev;
-		for (int l = 0; l < 32; ++l) {
-			const float pl = __shfl_sync(0xffffffffu, p, l), al = __shfl_sync(0xffffffffu, apow, l);
-			if ((int)lane == l) mine = carry;
-			carry = fmaf(al, carry, pl);
+__device__ __forceinline__ WinPlan plan_window(const WorkRec& r, uint32_t wslot) {
+	WinPlan p;
+	p.fast = false; p.off0 = r.start & 3u; p.a0 = r.start & ~3u; p.seg1_floats = 0; p.seg2_floats = 0; p.n1 = 0xffffffffu; p.wadj = 0;
+	const uint32_t flags = r.flags;
+	if (flags & (kRecSkip | kRecMix)) return p;
+	if (r.avail != r.n_src || r.n_src == 0 || r.n_src > r.len) return p;
+	if ((reinterpret_cast<unsigned long long>(r.pcm) & 15ull) != 0) return p;
+	const uint32_t end = r.start + r.n_src;
+	if (end <= r.len) {
+		p.seg1_floats = ((end + 3u) & ~3u) - p.a0;
+	} else {
+		if (!(flags & kRecWrap)) return p;
+		const uint32_t len4 = (r.len + 3u) & ~3u;
+		p.n1 = r.len - r.start;
+		p.wadj = len4 - r.len;
+		p.seg1_floats = len4 - p.a0;
+		p.seg2_floats = (r.n_src - p.n1 + 3u) & ~3u;
+	}
+	if (p.seg1_floats + p.seg2_floats + 4u > wslot) return p;
+	p.fast = true;
+	return p;
+}
+
+struct MixSmemHdr {
+	unsigned long long full_w[kStages], empty_w[kStages];        // window ring: TMA landed / math warps done
+	unsigned long long full_r[kRecStages], empty_r[kRecStages];  // record ring
+	float lpf_carry[8];                                          // per math warp (stereo kernel) / [0] (ambisonic kernel)
+};
+static_assert(sizeof(MixSmemHdr) <= 256, "header must fit its 256-byte slot");
+
+// What the math threads need to know about a source, condensed from its WorkRec by the producer (64 B).
+struct __attribute__((aligned(16))) MathDesc {
+	uint32_t mode;              // kMd*
+	uint32_t w_idx;             // float index into the window ring of element 0 of the array the read head indexes:
+	                            // window sample 0, or two before it for the resampler's {prev0, prev1, window...}
+	uint32_t n1b;               // index (same coordinates) from which `wadj` applies (loop wrap), 0xffffffff = never
+	uint32_t wadj;
+	unsigned long long x0, step;   // 32.32 read head
+	float g0, g1;               // stereo kernel: direct gain * mix factor * bus gain (constant parts)
+	float gd;                   // direct gain * mix factor (constant part)
+	uint32_t nramp;             // frames from the start of the buffer in which some gain of this source still ramps
+	uint32_t slot;
+	uint32_t pad[3];
+};
+static_assert(sizeof(MathDesc) == 64, "MathDesc is 64 bytes");
+constexpr uint32_t kMdSkip = 1, kMdGeneric = 2, kMdInterp = 4, kMdAdjust = 8, kMdResample = 16, kMdLpf = 32, kMdStereo = 64,
+                   kMdRamp = 128, kMdShRamp = 256;
+
+// Barrier among the math warps only (the producer warp never joins): named barrier 1.
+__device__ __forceinline__ void math_sync(uint32_t n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+
+__device__ __forceinline__ MathDesc make_desc(const WorkRec& r, const WinPlan& p, uint32_t slot_float0, bool sh) {
+	MathDesc d;
+	const uint32_t f = r.flags;
+	const bool rs = (f & kRecResample) != 0;
+	d.mode = 0;
+	if (f & kRecSkip) d.mode |= kMdSkip;
+	if (!p.fast) d.mode |= kMdGeneric;
+	if (f & (kRecResample | kRecMix1)) d.mode |= kMdInterp;
+	if (rs) d.mode |= kMdResample;
+	if (p.wadj) d.mode |= kMdAdjust;
+	if (f & kRecLpf) d.mode |= kMdLpf;
+	if (f & kRecStereo) d.mode |= kMdStereo;
+	d.w_idx = slot_float0 + 4u + p.off0 - (rs ? 2u : 0u);
+	d.n1b = p.n1 == 0xffffffffu ? 0xffffffffu : p.n1 + (rs ? 2u : 0u);
+	d.wadj = p.wadj;
+	d.x0 = r.x0_fx; d.step = r.step_fx;
+	const float mf = (p.fast && (f & kRecMix1)) ? r.mix_factor : 1.0f;
+	d.gd = mf * r.direct.konst;
+	d.g0 = d.gd * r.ch[0].konst; d.g1 = d.gd * r.ch[1].konst;
+	uint32_t nr = r.direct.n;
+	if (!sh) {
+		if ((r.ch_ramp_mask & 1u) && r.ch[0].n > nr) nr = r.ch[0].n;
+		if ((r.ch_ramp_mask & 2u) && r.ch[1].n > nr) nr = r.ch[1].n;
+	} else if (r.ch_ramp_mask) {
+		d.mode |= kMdShRamp;
+	}
+	d.nramp = nr;
+	if (nr) d.mode |= kMdRamp;
+	d.slot = r.slot;
+	d.pad[0] = d.pad[1] = d.pad[2] = 0;
+	return d;
+}
+
+// Element d of {prev0, prev1, window...} from the staged window, with the reference's index clamp (AR.cpp:68-71).
+__device__ __forceinline__ float staged_tmp(const WorkRec& r, const float* w, const WinPlan& p, int d) {
+	const int max_i = (int)r.n_src + 1;
+	d = d > max_i ? max_i : d;
+	if (d == 0) return r.prev0;
+	if (d == 1) return r.prev1;
+	const uint32_t j = (uint32_t)(d - 2);
+	return w[j + (j >= p.n1 ? p.wadj : 0u)];
+}
+
+// Engine-rate input sample i from the staged window, every case handled (careful path; w = window sample 0).
+__device__ __forceinline__ float staged_sample(const WorkRec& r, const float* w, const WinPlan& p, uint32_t i) {
+	if (!(r.flags & (kRecResample | kRecMix1))) return w[i + (i >= p.n1 ? p.wadj : 0u)];
+	int d; float fr;
+	fx_split(r.x0_fx, r.step_fx, i, &d, &fr);
+	float v0, v1;
+	if (r.flags & kRecResample) { v0 = staged_tmp(r, w, p, d); v1 = staged_tmp(r, w, p, d + 1); }
+	else {
+		const uint32_t j0 = (uint32_t)d, j1 = (uint32_t)d + 1u;
+		v0 = w[j0 + (j0 >= p.n1 ? p.wadj : 0u)]; v1 = w[j1 + (j1 >= p.n1 ? p.wadj : 0u)];
+		return fmaf(fr, v1 - v0, v0) * r.mix_factor;
+	}
+	return fmaf(fr, v1 - v0, v0);
+}
+
+// Occlusion low-pass over `F` samples staged in shared memory, by ONE warp.  y[n] = c (y[n-1] - x[n]) + x[n] is linear
+// in y[n-1]: the warp splits the buffer into 32 contiguous chunks, runs each chunk from a zero state while accumulating
+// c^len, chains the 32 chunk states in order, and re-runs each chunk from its true initial state.  Returns the final state.
+__device__ float lpf_warp(float* buf, uint32_t F, float coef, float prev, uint32_t lane) {
+	const uint32_t chunk = (F + 31) / 32;
+	const uint32_t lo = lane * chunk < F ? lane * chunk : F;
+	const uint32_t hi = lo + chunk < F ? lo + chunk : F;
+	float p = 0.0f, apow = 1.0f;
+	for (uint32_t n = lo; n < hi; ++n) { p = lpf_step(coef, p, buf[n]); apow *= coef; }
+	float carry = prev, mine = prev;
+	for (int l = 0; l < 32; ++l) {
+		const float pl = __shfl_sync(0xffffffffu, p, l), al = __shfl_sync(0xffffffffu, apow, l);
+		if ((int)lane == l) mine = carry;
+		carry = fmaf(al, carry, pl);
+	}
+	float q = mine;
+	for (uint32_t n = lo; n < hi; ++n) { q = lpf_step(coef, q, buf[n]); buf[n] = q; }
+	return carry;
+}
+
+// Shared-memory carve-up (both kernels): header | WorkRec ring | ShGains ring (ambisonic only) | MathDesc ring | window ring.
+template <int NCH>
+struct SmemView {
+	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; MathDesc* descs; float* wring;
+	__device__ explicit SmemView(unsigned char* raw) {
+		hdr = reinterpret_cast<MixSmemHdr*>(raw);
+		recs = reinterpret_cast<WorkRec*>(raw + 256);
+		unsigned char* p = reinterpret_cast<unsigned char*>(recs) + sizeof(WorkRec) * kRecStages * kBatch;
+		shgs = reinterpret_cast<ShGains*>(p);
+		if (NCH == 16) p += sizeof(ShGains) * kRecStages * kBatch;
+		descs = reinterpret_cast<MathDesc*>(p);
+		p += sizeof(MathDesc) * kStages * kBatch;
+		wring = reinterpret_cast<float*>(p);
+	}
+};
+
+// ================= producer warp (both kernels): lane b looks after source b of each batch =================
+template <int NCH>
+__device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane) {
+	MixSmemHdr* hdr = sm.hdr;
+	const WorkRec* __restrict__ grec = a.rec;
+	const ShGains* __restrict__ gshg = a.shg;
+	// records run kRecStages - kStages batches ahead of the windows
+	auto issue_recs = [&](uint32_t jb) {
+		if (jb >= nbatch) return;
+		const uint32_t q = jb % kRecStages;
+		if (jb >= (uint32_t)kRecStages) mbar_wait(&hdr->empty_r[q], ((jb / kRecStages) - 1u) & 1u);
+		if (lane == 0) {
+			const uint32_t b0 = s0 + jb * kBatch;
+			const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
+			const uint32_t bytes = nb * (uint32_t)sizeof(WorkRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u);
+			mbar_expect_tx(&hdr->full_r[q], bytes);
+			bulk_g2s(sm.recs + q * kBatch, grec + b0, nb * (uint32_t)sizeof(WorkRec), &hdr->full_r[q]);
+			if (NCH == 16) bulk_g2s(sm.shgs + q * kBatch, gshg + b0, nb * (uint32_t)sizeof(ShGains), &hdr->full_r[q]);
 		}
-		float q = mine;
-		for (uint32_t n = lo; n < hi; ++n) { q = lpf_step(coef, q, buf[n]); buf[n] = q; }
-		if (lane == 0) *carry_out = carry;
+		__syncwarp();
+	};
+	for (uint32_t jb = 0; jb < (uint32_t)(kRecStages - kStages); ++jb) issue_recs(jb);
+	for (uint32_t jb = 0; jb < nbatch; ++jb) {
+		issue_recs(jb + (uint32_t)(kRecStages - kStages));
+		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
+		if (jb >= (uint32_t)kStages) mbar_wait(&hdr->empty_w[qw], ((jb / kStages) - 1u) & 1u);
+		mbar_wait(&hdr->full_r[qr], (jb / kRecStages) & 1u);
+		const uint32_t b0 = s0 + jb * kBatch;
+		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
+		WinPlan p;
+		p.fast = false; p.seg1_floats = 0; p.seg2_floats = 0; p.a0 = 0;
+		const uint32_t slot_float0 = (qw * kBatch + lane) * wslot;
+		if (lane < nb) {
+			const WorkRec& r = sm.recs[qr * kBatch + lane];
+			p = plan_window(r, wslot);
+			sm.descs[qw * kBatch + lane] = make_desc(r, p, slot_float0, NCH == 16);
+		}
+		uint32_t bytes = p.fast ? 4u * (p.seg1_floats + p.seg2_floats) : 0u;
+		for (int o = kBatch / 2; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+		__syncwarp();
+		// the arrive below releases the descriptors written above (and, transitively, the records) to the math warps
+		if (lane == 0) {
+			if (bytes) mbar_expect_tx(&hdr->full_w[qw], bytes); else mbar_arrive(&hdr->full_w[qw]);
+		}
+		__syncwarp();
+		if (p.fast) {
+			const float* pcm = sm.recs[qr * kBatch + lane].pcm;
+			float* dst = sm.wring + slot_float0 + 4;
+			bulk_g2s(dst, pcm + p.a0, 4u * p.seg1_floats, &hdr->full_w[qw]);
+			if (p.seg2_floats) bulk_g2s(dst + p.seg1_floats, pcm, 4u * p.seg2_floats, &hdr->full_w[qw]);
+		}
+		__syncwarp();
 	}
 }
 
-template <int NCH, int K>
-__global__ void __launch_bounds__(NCH == 2 ? kPanThreads : 256)
-k2_mix_kernel(MixArgs a, const uint32_t* __restrict__ list, uint32_t n, float* __restrict__ partials) {
-	__shared__ MixSmem sm;
-	const uint32_t F = a.frames, T = blockDim.x, t = threadIdx.x;
-	const uint32_t s0 = (uint32_t)((unsigned long long)blockIdx.x * n / gridDim.x);
-	const uint32_t s1 = (uint32_t)((unsigned long long)(blockIdx.x + 1) * n / gridDim.x);
+__device__ __forceinline__ void init_barriers(MixSmemHdr* hdr, uint32_t n_consumers) {
+	for (int q = 0; q < kStages; ++q) { mbar_init(&hdr->full_w[q], 1); mbar_init(&hdr->empty_w[q], n_consumers); }
+	for (int q = 0; q < kRecStages; ++q) { mbar_init(&hdr->full_r[q], 1); mbar_init(&hdr->empty_r[q], n_consumers); }
+	fence_mbar_init();
+}
+
+__device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_as_float(0x3f800000u | ((uint32_t)p >> 9)) - 1.0f; }
+
+// =====================================================================================================================
+// Stereo-bus kernel (panned + non-spatial sources): kBatch math warps, one source per warp, + the producer warp.
+// KF = frames / 32 rounded up to 8, 16 or 32; EXACT = (frames == 32 * KF): no per-frame bounds checks.
+// =====================================================================================================================
+template <int KF, bool EXACT>
+__global__ void __launch_bounds__(kBatch * 32 + 32) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const SmemView<2> sm(smem_raw);
+	MixSmemHdr* hdr = sm.hdr;
+	const uint32_t F = a.frames, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+	const uint32_t s0 = first + (uint32_t)((unsigned long long)blockIdx.x * n / gridDim.x);
+	const uint32_t s1 = first + (uint32_t)((unsigned long long)(blockIdx.x + 1) * n / gridDim.x);
+	const uint32_t nbatch = (s1 - s0 + kBatch - 1) / kBatch;
+	if (t == 0) init_barriers(hdr, kBatch);
+	__syncthreads();
+	if (warp == (uint32_t)kBatch) { producer_warp<2>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+
+	float acc0[KF], acc1[KF];
+#pragma unroll
+	for (int k = 0; k < KF; ++k) { acc0[k] = 0.0f; acc1[k] = 0.0f; }
+
+	for (uint32_t jb = 0; jb < nbatch; ++jb) {
+		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
+		mbar_wait(&hdr->full_w[qw], (jb / kStages) & 1u);
+		const uint32_t b0 = s0 + jb * kBatch;
+		if (b0 + warp < s1) {
+			const MathDesc& d = sm.descs[qw * kBatch + warp];
+			const WorkRec& r = sm.recs[qr * kBatch + warp];
+			const uint32_t mode = d.mode;
+			if (mode & kMdSkip) {
+				// gain-skipped source: the feeder still consumed this buffer; carry the resampler history forward
+				if ((r.flags & kRecResample) && lane == 0) {
+					float p0, p1;
+					resampler_tail(r, &p0, &p1);
+					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
+				}
+			} else if ((mode & (kMdGeneric | kMdLpf | kMdAdjust)) || d.nramp > 32u) {
+				// ---------------- careful path (rare): every case, straightforward arithmetic ----------------
+				const WinPlan wp = plan_window(r, wslot);
+				float* slot = sm.wring + (size_t)(qw * kBatch + warp) * wslot;     // this warp's stage slot
+				const float* w = slot + 4 + wp.off0;
+				float y[KF];
+#pragma unroll
+				for (int k = 0; k < KF; ++k) {
+					const uint32_t i = lane + 32u * k;
+					float x = 0.0f;
+					if (EXACT || i < F) x = wp.fast ? staged_sample(r, w, wp, i) : source_sample(r, a.mixz, a.mix_pos0, i);
+					y[k] = x * gain_at(r.direct, i);
+				}
+				if ((r.flags & kRecResample) && lane == 0) {
+					float p0, p1;
+					if (wp.fast) { p0 = staged_tmp(r, w, wp, (int)r.n_src); p1 = staged_tmp(r, w, wp, (int)r.n_src + 1); }
+					else resampler_tail(r, &p0, &p1);
+					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
+				}
+				if (!(mode & kMdStereo)) {
+					if (mode & kMdLpf) {
+						// the window is in registers now: reuse this warp's stage slot as scratch for the recurrence
+						__syncwarp();
+#pragma unroll
+						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; if (EXACT || i < F) slot[i] = y[k]; }
+						__syncwarp();
+						const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane);
+						__syncwarp();
+#pragma unroll
+						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; if (EXACT || i < F) y[k] = slot[i]; }
+						if (lane == 0) a.lpf_prev[r.slot] = carry;
+						fence_proxy_async();     // generic-proxy writes to the slot precede the TMA refill
+					} else {
+#pragma unroll
+						for (int k = 0; k < KF; ++k) if (lane + 32u * k == F - 1) a.lpf_prev[r.slot] = y[k];
+					}
+				}
+#pragma unroll
+				for (int k = 0; k < KF; ++k) {
+					const uint32_t i = lane + 32u * k;
+					acc0[k] = fmaf(gain_at(r.ch[0], i), y[k], acc0[k]);
+					acc1[k] = fmaf(gain_at(r.ch[1], i), y[k], acc1[k]);
+				}
+			} else {
+				// ---------------- lean path ----------------
+				const float* wb = sm.wring + d.w_idx;
+				const float g0 = d.g0, g1 = d.g1;
+				const bool ramp0 = (mode & kMdRamp) != 0;         // gains still ramp inside the first 32 frames (k = 0)
+				const bool rsmp = (mode & kMdResample) != 0;
+				float x_last = 0.0f;
+				if (mode & kMdInterp) {
+					unsigned long long p = d.x0 + (unsigned long long)lane * d.step;
+					const unsigned long long step32 = d.step << 5;
+#pragma unroll
+					for (int k = 0; k < KF; ++k) {
+						const uint32_t i = lane + 32u * k;
+						float x = 0.0f;
+						if (EXACT || i < F) {
+							const uint32_t di = (uint32_t)(p >> 32);
+							const float fr = frac_of(p);
+							float v0, v1;
+							// only the first frames (resampler history) and the last ones (index clamp) need the careful form
+							if ((k == 0 || k == KF - 1 || !EXACT) && rsmp) {
+								const WinPlan wp = plan_window(r, wslot);
+								const float* w = wb + 2;
+								v0 = staged_tmp(r, w, wp, (int)di); v1 = staged_tmp(r, w, wp, (int)di + 1);
+							} else { v0 = wb[di]; v1 = wb[di + 1]; }
+							x = fmaf(fr, v1 - v0, v0);
+						}
+						if (k == 0 && ramp0) {
+							const float mf = (r.flags & kRecMix1) ? r.mix_factor : 1.0f;
+							const float yv = (x * mf) * gain_at(r.direct, i);
+							acc0[0] = fmaf(gain_at(r.ch[0], i), yv, acc0[0]);
+							acc1[0] = fmaf(gain_at(r.ch[1], i), yv, acc1[0]);
+						} else {
+							acc0[k] = fmaf(g0, x, acc0[k]);
+							acc1[k] = fmaf(g1, x, acc1[k]);
+						}
+						if (k == KF - 1 || !EXACT) { if (i == F - 1) x_last = x; }
+						p += step32;
+					}
+				} else {
+#pragma unroll
+					for (int k = 0; k < KF; ++k) {
+						const uint32_t i = lane + 32u * k;
+						float x = 0.0f;
+						if (EXACT || i < F) x = wb[i];
+						if (k == 0 && ramp0) {
+							const float yv = x * gain_at(r.direct, i);
+							acc0[0] = fmaf(gain_at(r.ch[0], i), yv, acc0[0]);
+							acc1[0] = fmaf(gain_at(r.ch[1], i), yv, acc1[0]);
+						} else {
+							acc0[k] = fmaf(g0, x, acc0[k]);
+							acc1[k] = fmaf(g1, x, acc1[k]);
+						}
+						if (k == KF - 1 || !EXACT) { if (i == F - 1) x_last = x; }
+					}
+				}
+				// bypassed occlusion filter remembers the last input sample (mono_pole_filter.cc:40-44); nramp <= 32 < frames
+				// here, so the direct gain has reached its constant part by then
+				if (!(mode & kMdStereo) && lane == ((F - 1) & 31u)) a.lpf_prev[d.slot] = x_last * d.gd;
+				if (rsmp && lane == 0) {
+					const WinPlan wp = plan_window(r, wslot);
+					const float* w = wb + 2;
+					a.rs[d.slot].prev_samples[0] = staged_tmp(r, w, wp, (int)r.n_src);
+					a.rs[d.slot].prev_samples[1] = staged_tmp(r, w, wp, (int)r.n_src + 1);
+				}
+			}
+		}
+		// this warp is done with window stage qw and record slot qr: hand them back to the producer
+		__syncwarp();
+		if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }
+	}
+	// ---- combine the math warps' tiles (the window ring is idle now: every batch has been consumed) ----
+	math_sync(kBatch * 32);
+	float* tile = sm.wring;     // [kBatch][2][F]
+#pragma unroll
+	for (int k = 0; k < KF; ++k) {
+		const uint32_t i = lane + 32u * k;
+		if (EXACT || i < F) { tile[(warp * 2 + 0) * F + i] = acc0[k]; tile[(warp * 2 + 1) * F + i] = acc1[k]; }
+	}
+	math_sync(kBatch * 32);
+	float* out = partials + (size_t)blockIdx.x * 2 * F;
+	for (uint32_t q = t; q < 2 * F; q += kBatch * 32) {
+		float s = 0.0f;
+#pragma unroll
+		for (int wv = 0; wv < kBatch; ++wv) s += tile[wv * 2 * F + q];
+		out[q] = s;
+	}
+}
+
+// =====================================================================================================================
+// Ambisonic-bus kernel: T math threads (frames / 4) work on one source at a time + the producer warp.
+// =====================================================================================================================
+constexpr int K = kShK;
+__global__ void __launch_bounds__(256 + 32) k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+	constexpr int NCH = 16;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const SmemView<16> sm(smem_raw);
+	MixSmemHdr* hdr = sm.hdr;
+	// blockDim.x = T math threads + one producer warp (the last warp)
+	const uint32_t F = a.frames, T = blockDim.x - 32, t = threadIdx.x, lane = t & 31u;
+	const uint32_t s0 = first + (uint32_t)((unsigned long long)blockIdx.x * n / gridDim.x);
+	const uint32_t s1 = first + (uint32_t)((unsigned long long)(blockIdx.x + 1) * n / gridDim.x);
+	const uint32_t nbatch = (s1 - s0 + kBatch - 1) / kBatch;
+	if (t == 0) init_barriers(hdr, T / 32);
+	__syncthreads();
+	if (t >= T) { producer_warp<16>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+
 	float acc[NCH][K];
 #pragma unroll
 	for (int c = 0; c < NCH; ++c)
 #pragma unroll
 		for (int k = 0; k < K; ++k) acc[c][k] = 0.0f;
+	const uint32_t warp_i0 = t & ~31u;     // first frame of this warp in iteration k = 0
 
-	for (uint32_t base = s0; base < s1; base += kBatch) {
-		const uint32_t nb = s1 - base < (uint32_t)kBatch ? s1 - base : (uint32_t)kBatch;
-		__syncthreads();
-		// stage the batch's WorkRecs (8 x 16 B each) and, for ambisonic sources, their 16 constant gains (4 x 16 B)
-		for (uint32_t q = t; q < nb * 8; q += T) {
-			const uint32_t slot = list[base + (q >> 3)];
-			reinterpret_cast<uint4*>(sm.rec)[q] = __ldg(reinterpret_cast<const uint4*>(a.rec + slot) + (q & 7));
-		}
-		if (NCH == 16)
-			for (uint32_t q = t; q < nb * 4; q += T) {
-				const uint32_t slot = list[base + (q >> 2)];
-				reinterpret_cast<uint4*>(sm.shg)[q] = __ldg(reinterpret_cast<const uint4*>(a.shg + slot) + (q & 3));
-			}
-		__syncthreads();
-
-		for (uint32_t j = 0; j < nb; ++j) {
-			const WorkRec& r = sm.rec[j];
-			const uint32_t flags = r.flags;
-			if (flags & kRecSkip) {
-				// gain-skipped source: the feeder still consumed this buffer; carry the resampler history forward
-				if ((flags & kRecResample) && t == 0) {
+	for (uint32_t jb = 0; jb < nbatch; ++jb) {
+		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
+		mbar_wait(&hdr->full_w[qw], (jb / kStages) & 1u);
+		const uint32_t b0 = s0 + jb * kBatch;
+		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
+		for (uint32_t b = 0; b < nb; ++b) {
+			const MathDesc& d = sm.descs[qw * kBatch + b];
+			const WorkRec& r = sm.recs[qr * kBatch + b];
+			const uint32_t mode = d.mode;
+			if (mode & kMdSkip) {
+				if ((r.flags & kRecResample) && t == 0) {
 					float p0, p1;
 					resampler_tail(r, &p0, &p1);
 					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
 				}
 				continue;
 			}
-			const double w = (double)r.rate / (double)a.rate;
 			float y[K];
-			// ---- gather / resample / pitch-mix, then the direct gain (GainNode) ----
+			if ((mode & (kMdGeneric | kMdLpf | kMdAdjust | kMdRamp)) != 0) {
+				// ---------------- careful path (rare) ----------------
+				const WinPlan wp = plan_window(r, wslot);
+				float* slot = sm.wring + (size_t)(qw * kBatch + b) * wslot;
+				const float* w = slot + 4 + wp.off0;
 #pragma unroll
-			for (int k = 0; k < K; ++k) {
-				const uint32_t i = t + (uint32_t)k * T;
-				y[k] = i < F ? source_sample(r, a.mixz, a.mix_pos0, w, i) : 0.0f;
-			}
-			if (r.direct.n) {
+				for (int k = 0; k < K; ++k) {
+					const uint32_t i = t + (uint32_t)k * T;
+					float x = 0.0f;
+					if (i < F) x = wp.fast ? staged_sample(r, w, wp, i) : source_sample(r, a.mixz, a.mix_pos0, i);
+					y[k] = x * gain_at(r.direct, i);
+				}
+				if ((r.flags & kRecResample) && t == 0) {
+					float p0, p1;
+					if (wp.fast) { p0 = staged_tmp(r, w, wp, (int)r.n_src); p1 = staged_tmp(r, w, wp, (int)r.n_src + 1); }
+					else resampler_tail(r, &p0, &p1);
+					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
+				}
+				if (mode & kMdLpf) {
+					math_sync(T);     // every thread has its window samples in registers: the slot becomes scratch
 #pragma unroll
-				for (int k = 0; k < K; ++k) y[k] *= gain_at(r.direct, t + (uint32_t)k * T);
-			} else {
-				const float g = r.direct.konst;
+					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) slot[i] = y[k]; }
+					math_sync(T);
+					if (t < 32) { const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane); if (lane == 0) a.lpf_prev[r.slot] = carry; }
+					math_sync(T);
 #pragma unroll
-				for (int k = 0; k < K; ++k) y[k] *= g;
-			}
-			if ((flags & kRecResample) && t == 0) {
-				float p0, p1;
-				resampler_tail(r, &p0, &p1);
-				a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
-			}
-			// ---- occlusion low-pass (OcclusionNode) ----
-			if (!(flags & kRecStereo)) {
-				if (flags & kRecLpf) {
-					__syncthreads();
-#pragma unroll
-					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) sm.lpf[i] = y[k]; }
-					__syncthreads();
-					lpf_in_smem(sm.lpf, F, r.lpf_coef, r.lpf_prev, &sm.lpf_carry);
-					__syncthreads();
-#pragma unroll
-					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) y[k] = sm.lpf[i]; }
-					if (t == 0) a.lpf_prev[r.slot] = sm.lpf_carry;
+					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) y[k] = slot[i]; }
+					fence_proxy_async();
 				} else {
-					// bypassed filter remembers the last input sample (mono_pole_filter.cc:40-44)
 #pragma unroll
 					for (int k = 0; k < K; ++k) if (t + (uint32_t)k * T == F - 1) a.lpf_prev[r.slot] = y[k];
 				}
-			}
-			// ---- bus gains (GainMixer, accumulate mode) ----
-			if (NCH == 2) {
-				if (r.ch_ramp_mask) {
+			} else {
+				// ---------------- lean path ----------------
+				const float* wb = sm.wring + d.w_idx;
+				const float gd = d.gd;
+				if (mode & kMdInterp) {
+					const bool rsmp = (mode & kMdResample) != 0;
 #pragma unroll
 					for (int k = 0; k < K; ++k) {
 						const uint32_t i = t + (uint32_t)k * T;
-						acc[0][k] = fmaf(gain_at(r.ch[0], i), y[k], acc[0][k]);
-						acc[1][k] = fmaf(gain_at(r.ch[1], i), y[k], acc[1][k]);
+						const uint32_t wi0 = warp_i0 + (uint32_t)k * T;
+						float x = 0.0f;
+						if (i < F) {
+							const unsigned long long p = d.x0 + (unsigned long long)i * d.step;
+							const uint32_t di = (uint32_t)(p >> 32);
+							const float fr = frac_of(p);
+							float v0, v1;
+							if (rsmp && (wi0 < 16u || wi0 + 32u > F - 1)) {
+								const WinPlan wp = plan_window(r, wslot);
+								v0 = staged_tmp(r, wb + 2, wp, (int)di); v1 = staged_tmp(r, wb + 2, wp, (int)di + 1);
+							} else { v0 = wb[di]; v1 = wb[di + 1]; }
+							x = fmaf(fr, v1 - v0, v0);
+						}
+						y[k] = x * gd;
+					}
+					if (rsmp && t == 0) {
+						const WinPlan wp = plan_window(r, wslot);
+						a.rs[d.slot].prev_samples[0] = staged_tmp(r, wb + 2, wp, (int)r.n_src);
+						a.rs[d.slot].prev_samples[1] = staged_tmp(r, wb + 2, wp, (int)r.n_src + 1);
 					}
 				} else {
-					const float g0 = r.ch[0].konst, g1 = r.ch[1].konst;
 #pragma unroll
-					for (int k = 0; k < K; ++k) { acc[0][k] = fmaf(g0, y[k], acc[0][k]); acc[1][k] = fmaf(g1, y[k], acc[1][k]); }
+					for (int k = 0; k < K; ++k) {
+						const uint32_t i = t + (uint32_t)k * T;
+						y[k] = i < F ? wb[i] * gd : 0.0f;
+					}
+				}
+#pragma unroll
+				for (int k = 0; k < K; ++k) if (t + (uint32_t)k * T == F - 1) a.lpf_prev[d.slot] = y[k];
+			}
+			// ---------------- bus gains (GainMixer, accumulate mode) ----------------
+			const float* gk = sm.shgs[qr * kBatch + b].konst;
+			if (mode & kMdShRamp) {
+				const ShRamps* rp = a.shr + (b0 + b);
+#pragma unroll
+				for (int c = 0; c < NCH; ++c) {
+					RampDesc rd; rd.konst = gk[c]; rd.n = 0; rd.start = 0.0f; rd.inc = 0.0f;
+					if (r.ch_ramp_mask & (1u << c)) { rd.start = rp->start[c]; rd.inc = rp->inc[c]; rd.n = rp->n[c]; }
+#pragma unroll
+					for (int k = 0; k < K; ++k) acc[c][k] = fmaf(gain_at(rd, t + (uint32_t)k * T), y[k], acc[c][k]);
 				}
 			} else {
-				const float* gk = sm.shg[j].konst;
-				if (r.ch_ramp_mask) {
-					const ShRamps* rp = a.shr + r.slot;
 #pragma unroll
-					for (int c = 0; c < NCH; ++c) {
-						RampDesc d; d.konst = gk[c]; d.n = 0; d.start = 0.0f; d.inc = 0.0f;
-						if (r.ch_ramp_mask & (1u << c)) { d.start = rp->start[c]; d.inc = rp->inc[c]; d.n = rp->n[c]; }
+				for (int c = 0; c < NCH; c += 2) {
+					const float2 g = *reinterpret_cast<const float2*>(gk + c);
 #pragma unroll
-						for (int k = 0; k < K; ++k) acc[c][k] = fmaf(gain_at(d, t + (uint32_t)k * T), y[k], acc[c][k]);
-					}
-				} else {
-#pragma unroll
-					for (int c = 0; c < NCH; ++c) {
-						const float g = gk[c];
-#pragma unroll
-						for (int k = 0; k < K; ++k) acc[c][k] = fmaf(g, y[k], acc[c][k]);
+					for (int k = 0; k < K; ++k) {
+						float2 ac = make_float2(acc[c][k], acc[c + 1][k]);
+						ffma2(ac, g, make_float2(y[k], y[k]));
+						acc[c][k] = ac.x; acc[c + 1][k] = ac.y;
 					}
 				}
 			}
 		}
+		// this warp is done with window stage qw and record slot qr: hand them back to the producer
+		__syncwarp();
+		if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }
 	}
 	float* out = partials + (size_t)blockIdx.x * NCH * F;
 #pragma unroll
@@ -212,7 +662,14 @@ int sm_count() {
 }
 
 uint32_t sh_threads(uint32_t F) { return ((F + kShK - 1) / kShK + 31) / 32 * 32; }
-constexpr uint32_t kMinSourcesPerCta = 8;
+// Stage slot per source, in floats: room for a window of frames * 1.25 (sample-rate ratios <= 1, doppler / pitch up
+// to +25 %) plus alignment slack; larger windows take the generic path.
+uint32_t window_slot(uint32_t F) { return (F + F / 4 + 24u + 3u) & ~3u; }
+size_t mix_smem_bytes(uint32_t F, bool sh) {
+	return 256 + sizeof(WorkRec) * kRecStages * kBatch + (sh ? sizeof(ShGains) * kRecStages * kBatch : 0) + sizeof(MathDesc) * kStages * kBatch +
+	       sizeof(float) * (size_t)kStages * kBatch * window_slot(F);
+}
+constexpr uint32_t kMinSourcesPerCta = 16;
 
 uint32_t pick_grid(uint32_t n, uint32_t max_grid) {
 	uint32_t g = (n + kMinSourcesPerCta - 1) / kMinSourcesPerCta;
@@ -220,13 +677,41 @@ uint32_t pick_grid(uint32_t n, uint32_t max_grid) {
 	return g ? g : 1;
 }
 
+template <class Kernel>
+int launch_one(Kernel kernel, size_t* configured, const char* name, const MixArgs& a, uint32_t first, uint32_t n, uint32_t threads, bool sh,
+               uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
+	const uint32_t F = a.frames;
+	const size_t smem = mix_smem_bytes(F, sh);
+	if (smem > *configured) {
+		if (dev::check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
+		*configured = smem;
+	}
+	const uint32_t g = pick_grid(n, max_grid);
+	kernel<<<g, threads, smem, st>>>(a, first, n, window_slot(F), partials);
+	dev::note_launch();
+	*grid_out = g;
+	return dev::check_launch(name);
+}
+
+template <int KF>
+int launch_stereo(const MixArgs& a, uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
+	static size_t conf_exact = 0, conf_any = 0;
+	const uint32_t threads = kBatch * 32 + 32;
+	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true>, &conf_exact, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+	return launch_one(k2_mix_stereo_kernel<KF, false>, &conf_any, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+}
+
 }  // namespace
 
 namespace dev {
 
+// Upper bound of the K2 grid (sizes the partial-bus scratch): SM count x the most CTAs that fit per SM.
 int num_mix_ctas(uint32_t frames, int sh) {
-	(void)frames;
-	return sm_count() * (sh ? 4 : 8);
+	const size_t smem = mix_smem_bytes(frames, sh != 0) + 1024;
+	int per_sm = (int)((227u * 1024u) / smem);
+	if (per_sm < 1) per_sm = 1;
+	if (per_sm > (sh ? 4 : 8)) per_sm = sh ? 4 : 8;
+	return sm_count() * per_sm;
 }
 
 size_t partials_floats(uint32_t frames) {
@@ -240,20 +725,17 @@ int launch_mix(const MixArgs& a, void* stream) {
 	float* part_sh = a.partials + (size_t)num_mix_ctas(F, 0) * 2 * F;
 	uint32_t g_pan = 0, g_sh = 0;
 	if (a.n_pan) {
-		g_pan = pick_grid(a.n_pan, (uint32_t)num_mix_ctas(F, 0));
-		const uint32_t k = (F + kPanThreads - 1) / kPanThreads;
-		if (k <= 1) k2_mix_kernel<2, 1><<<g_pan, kPanThreads, 0, st>>>(a, a.list_pan, a.n_pan, part_pan);
-		else if (k <= 2) k2_mix_kernel<2, 2><<<g_pan, kPanThreads, 0, st>>>(a, a.list_pan, a.n_pan, part_pan);
-		else if (k <= 4) k2_mix_kernel<2, 4><<<g_pan, kPanThreads, 0, st>>>(a, a.list_pan, a.n_pan, part_pan);
-		else k2_mix_kernel<2, 8><<<g_pan, kPanThreads, 0, st>>>(a, a.list_pan, a.n_pan, part_pan);
-		note_launch();
-		if (check_launch("k2_mix<pan>")) return -1;
+		const uint32_t mg = (uint32_t)num_mix_ctas(F, 0);
+		int rc;
+		if (F <= 256) rc = launch_stereo<8>(a, mg, part_pan, st, &g_pan);
+		else if (F <= 512) rc = launch_stereo<16>(a, mg, part_pan, st, &g_pan);
+		else rc = launch_stereo<32>(a, mg, part_pan, st, &g_pan);
+		if (rc) return -1;
 	}
 	if (a.n_sh) {
-		g_sh = pick_grid(a.n_sh, (uint32_t)num_mix_ctas(F, 1));
-		k2_mix_kernel<16, kShK><<<g_sh, sh_threads(F), 0, st>>>(a, a.list_sh, a.n_sh, part_sh);
-		note_launch();
-		if (check_launch("k2_mix<sh>")) return -1;
+		static size_t conf_sh = 0;
+		if (launch_one(k2_mix_ambisonic_kernel, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, sh_threads(F) + 32, true, (uint32_t)num_mix_ctas(F, 1), part_sh, st, &g_sh))
+			return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
 	k3_reduce_kernel<<<(kBusRows * F + 255) / 256, 256, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F);

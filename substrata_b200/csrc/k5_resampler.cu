@@ -16,11 +16,10 @@ using namespace sbm;
 namespace {
 
 __global__ void __launch_bounds__(256) k5_resample_kernel(const WorkRec* __restrict__ recs, float* __restrict__ dst, uint32_t n_dst,
-                                                         int32_t dst_rate, float2* __restrict__ tails) {
+                                                         float2* __restrict__ tails) {
 	const WorkRec r = recs[blockIdx.y];
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	const double w = (double)r.rate / (double)dst_rate;
-	if (i < n_dst) dst[(size_t)blockIdx.y * n_dst + i] = resampled_sample(r, w, i);
+	if (i < n_dst) dst[(size_t)blockIdx.y * n_dst + i] = resampled_sample(r, i);
 	if (i == 0) {
 		float p0, p1;
 		resampler_tail(r, &p0, &p1);
@@ -113,10 +112,12 @@ SBM_API int sbm_resampler_resample(sbm_resampler* r, float* dst, size_t n_dst, c
 		WorkRec& w = r->recs[k];
 		memset(&w, 0, sizeof(w));
 		w.pcm = r->d_src + src_offsets[k]; w.len = (uint32_t)need; w.start = 0; w.n_src = (uint32_t)need; w.avail = (uint32_t)need;
-		w.flags = kRecResample; w.rate = r->src_rate[k];
+		w.flags = kRecResample;
 		// AudioResampler::resample coordinates (AR.cpp:101-103)
 		const int64_t dest0 = s.prev_dest_dst_coords + 1;
-		w.x0 = (double)dest0 * (double)r->src_rate[k] / (double)r->dst_rate - (double)s.prev_samples_0_src_coords;
+		const double x0 = (double)dest0 * (double)r->src_rate[k] / (double)r->dst_rate - (double)s.prev_samples_0_src_coords;
+		w.x0_fx = (unsigned long long)((x0 > 0.0 ? x0 : 0.0) * kFx);
+		w.step_fx = (unsigned long long)((double)r->src_rate[k] / (double)r->dst_rate * kFx);
 		w.prev0 = s.prev_samples[0]; w.prev1 = s.prev_samples[1];
 	}
 	cudaStream_t st = r->stream;
@@ -124,7 +125,7 @@ SBM_API int sbm_resampler_resample(sbm_resampler* r, float* dst, size_t n_dst, c
 	    (src_total && dev::check(cudaMemcpyAsync(r->d_src, src, sizeof(float) * src_total, cudaMemcpyHostToDevice, st), "resampler H2D")))
 		return SBM_ERR_CUDA;
 	const dim3 grid((unsigned)((n_dst + 255) / 256), (unsigned)count);
-	k5_resample_kernel<<<grid, 256, 0, st>>>(r->d_recs, r->d_dst, (uint32_t)n_dst, r->dst_rate, r->d_tails);
+	k5_resample_kernel<<<grid, 256, 0, st>>>(r->d_recs, r->d_dst, (uint32_t)n_dst, r->d_tails);
 	dev::note_launch();
 	if (dev::check_launch("k5_resample") ||
 	    dev::check(cudaMemcpyAsync(dst, r->d_dst, sizeof(float) * count * n_dst, cudaMemcpyDeviceToHost, st), "resampler D2H") ||

@@ -36,6 +36,7 @@ constexpr int kShRaw = 15;
 constexpr int kTableAz = 91, kTableEl = 91;        // RA/ambisonics/ambisonic_lookup_table.cc:31-35
 constexpr int kBusRows = 18;                       // 16 ambisonic + stereo L/R
 constexpr int kMaxFrames = 1024;
+constexpr double kFx = 4294967296.0;               // 2^32: scale of the 32.32 fixed-point read-head coordinates
 
 // Source kinds (== vraudio::RenderingMode for objects) and feeder types.
 constexpr uint32_t kKindPan = 0, kKindHrtf = 3, kKindStereo = 100;
@@ -56,6 +57,7 @@ constexpr uint32_t kRecLpf = 1u << 3;               // occlusion low-pass active
 constexpr uint32_t kRecStereo = 1u << 4;            // non-spatial: L = R = y
 constexpr uint32_t kRecHrtf = 1u << 5;              // ambisonic encode (16 channels) instead of pan (2)
 constexpr uint32_t kRecWrap = 1u << 6;              // window index wraps modulo len (looping buffer / ring)
+constexpr uint32_t kRecMix1 = 1u << 7;              // exactly one mix source, expressed as a window + fixed-point read head
 
 // ------------------------------------------------------------------------------------------------
 // HBM layout.  One slot per live source; SoA arrays indexed by slot, written by the host (params) or
@@ -96,30 +98,31 @@ struct RampDesc {               // gain over one buffer: i < n ? ramp(start, inc
 	uint32_t n;                 // ramp samples inside this buffer (0 = no ramp)
 };
 
-struct __attribute__((aligned(128))) WorkRec {   // 128 B, K1 -> K2
-	const float* pcm;           //  0
-	uint32_t len;               //  8
-	uint32_t start;             // 12  index of the first window sample
-	uint32_t n_src;             // 16  source samples consumed this buffer
+struct __attribute__((aligned(128))) WorkRec {   // 128 B, K1 -> K2, one per entry of the render lists (list order)
+	const float* pcm;           //  0  window source (shared buffer, ring storage, or the single mix source's buffer)
+	uint32_t len;               //  8  samples in pcm (loop length / ring capacity)
+	uint32_t start;             // 12  index in pcm of window sample 0
+	uint32_t n_src;             // 16  window samples (= source samples consumed this buffer for buffer / ring feeds)
 	uint32_t avail;             // 20  window samples that exist; beyond: zeros (end of buffer / ring underflow)
 	uint32_t flags;             // 24  kRec*
-	uint32_t mix_first;         // 28
-	double x0;                  // 32  resampler: x coordinate of output sample 0 in {prev0, prev1, window...} (AR.cpp:101-103)
-	float prev0, prev1;         // 40  resampler history
-	float lpf_coef, lpf_prev;   // 48
-	int32_t rate;               // 56
-	uint32_t nz;                // 60
+	uint32_t slot;              // 28
+	unsigned long long x0_fx;   // 32  32.32 fixed point: coordinate of output sample 0 in {prev0, prev1, window...} (resample,
+	                            //     AR.cpp:101-103) or in the window (single mix source, AE.cpp:443-452)
+	unsigned long long step_fx; // 40  32.32 fixed point: coordinate step per output sample (src_rate / dst_rate, or source_delta)
+	float prev0, prev1;         // 48  resampler history
+	float lpf_coef, lpf_prev;   // 56
 	RampDesc direct;            // 64  GainNode (kDirect / kInput)
-	RampDesc ch[2];             // 80  pan L/R (pan mode only; HRTF gains live in ShGains)
-	uint32_t ch_ramp_mask;      // 112 bit c set: channel c ramps this buffer (HRTF: see ShRamps)
-	uint32_t slot;              // 116
-	uint32_t pad[2];            // 120
+	RampDesc ch[2];             // 80  pan L/R (pan mode only; ambisonic gains live in ShGains / ShRamps)
+	uint32_t ch_ramp_mask;      // 112 bit c set: bus channel c ramps this buffer
+	float mix_factor;           // 116 kRecMix1: MixSource::mix_factor
+	uint32_t mix_first;         // 120 kRecMix: first entry in the MixZ array
+	uint32_t nz;                // 124 kRecMix: number of mix sources
 };
 
 struct ShGains { float konst[kNumSh]; };                       // 64 B per HRTF source: effective constant gains
 struct ShRamps { float start[kNumSh]; float inc[kNumSh]; uint32_t n[kNumSh]; };   // read only when ch_ramp_mask != 0
 
-// Per-engine scalars that change every buffer (host -> device, 64 B).
+// Per-engine scalars that change every buffer (passed by value to K1).
 struct Globals {
 	float head_pos[3];
 	float master;
@@ -128,6 +131,8 @@ struct Globals {
 	int32_t rate;
 	uint32_t parity;            // buffer index & 1
 	uint32_t n_slots;
+	uint32_t n_pan, n_sh;       // render-list lengths
+	uint32_t pad[2];
 };
 
 // Device-side flags / counters.
@@ -160,9 +165,9 @@ struct SlotArrays {
 	const MixZ* mixz;
 	double* mix_pos;
 	double* mix_pos0;
-	WorkRec* rec;
-	ShGains* shg;
-	ShRamps* shr;
+	WorkRec* rec;               // [n_pan + n_sh] in render-list order (pan list first)
+	ShGains* shg;               // indexed like rec
+	ShRamps* shr;               // indexed like rec
 	int* finished;              // list of public ids stopped by the feeder
 	int cstride;                // 2 or 16
 };

@@ -55,12 +55,13 @@ int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, cons
 	return 0;
 }
 
-int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t n_slots, void*) {
+int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, const uint32_t* lists, uint32_t n_slots, void*) {
 	++g_launches;
 	uint32_t used = 0;
-	for (uint32_t slot = 0; slot < n_slots; ++slot) {
+	(void)n_slots;
+	for (uint32_t k = 0; k < g.n_pan + g.n_sh; ++k) {
 		uint32_t n_src = 0;
-		used |= update_source(g, A, flags, table, slot, &n_src);
+		used |= update_source(g, A, flags, table, lists[k], k, &n_src);
 		if (n_src) { flags->algo_bytes += 4ull * n_src; flags->n_rendered++; }
 	}
 	if (used & kUsedPan) flags->pan_used[g.parity] = 1;
@@ -69,17 +70,16 @@ int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const 
 	return 0;
 }
 
-static void mix_list(const MixArgs& a, const uint32_t* list, uint32_t n, bool sh) {
+static void mix_list(const MixArgs& a, uint32_t first, uint32_t n, bool sh) {
 	const uint32_t F = a.frames;
 	std::vector<float> y(F);
-	for (uint32_t k = 0; k < n; ++k) {
-		const WorkRec& r = a.rec[list[k]];
+	for (uint32_t k = first; k < first + n; ++k) {
+		const WorkRec& r = a.rec[k];
 		if (r.flags & kRecSkip) {
 			if (r.flags & kRecResample) resampler_tail(r, &a.rs[r.slot].prev_samples[0], &a.rs[r.slot].prev_samples[1]);
 			continue;
 		}
-		const double w = (double)r.rate / (double)a.rate;
-		for (uint32_t i = 0; i < F; ++i) y[i] = fmul(source_sample(r, a.mixz, a.mix_pos0, w, i), gain_at(r.direct, i));
+		for (uint32_t i = 0; i < F; ++i) y[i] = fmul(source_sample(r, a.mixz, a.mix_pos0, i), gain_at(r.direct, i));
 		if (r.flags & kRecResample) resampler_tail(r, &a.rs[r.slot].prev_samples[0], &a.rs[r.slot].prev_samples[1]);
 		if (!(r.flags & kRecStereo)) {
 			if (r.flags & kRecLpf) {
@@ -97,8 +97,8 @@ static void mix_list(const MixArgs& a, const uint32_t* list, uint32_t n, bool sh
 			}
 		} else {
 			for (int c = 0; c < kNumSh; ++c) {
-				RampDesc d; d.konst = a.shg[r.slot].konst[c]; d.n = 0; d.start = 0.0f; d.inc = 0.0f;
-				if (r.ch_ramp_mask & (1u << c)) { d.start = a.shr[r.slot].start[c]; d.inc = a.shr[r.slot].inc[c]; d.n = a.shr[r.slot].n[c]; }
+				RampDesc d; d.konst = a.shg[k].konst[c]; d.n = 0; d.start = 0.0f; d.inc = 0.0f;
+				if (r.ch_ramp_mask & (1u << c)) { d.start = a.shr[k].start[c]; d.inc = a.shr[k].inc[c]; d.n = a.shr[k].n[c]; }
 				float* row = a.bus + (size_t)c * F;
 				for (uint32_t i = 0; i < F; ++i) row[i] = fmaf(gain_at(d, i), y[i], row[i]);
 			}
@@ -110,8 +110,8 @@ int launch_mix(const MixArgs& a, void*) {
 	g_launches += 2;
 	const uint32_t F = a.frames;
 	memset(a.bus, 0, sizeof(float) * (size_t)kBusRows * F);
-	mix_list(a, a.list_pan, a.n_pan, false);
-	mix_list(a, a.list_sh, a.n_sh, true);
+	mix_list(a, 0, a.n_pan, false);
+	mix_list(a, a.n_pan, a.n_sh, true);
 	float* bf = a.bus + (size_t)kBusRows * F;
 	bf[0] = a.flags->sh_used[a.parity] ? 1.0f : 0.0f;
 	bf[1] = a.flags->pan_used[a.parity] ? 1.0f : 0.0f;
