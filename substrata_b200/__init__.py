@@ -39,6 +39,10 @@ def lib(path=None):
     if path is not None:
         return bind(C.CDLL(path))
     if _lib is None:
+        override = os.environ.get("SBM_LIB_PATH")      # development: A/B-testing kernel variants on the GPU box
+        if override:
+            _lib = bind(C.CDLL(override))
+            return _lib
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("libsubstrata_b200.so is not built (run `python -m substrata_b200.build`); there is no fallback path")
         _lib = bind(C.CDLL(LIB_PATH))

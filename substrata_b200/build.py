@@ -41,7 +41,12 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """`defines` / `out`: development variants (e.g. ("-DSBM_STAGES=4",) -> another .so for A/B runs on the GPU box)."""
+    global OBJ, LIB
+    if out:
+        OBJ, LIB = out + "_obj", out
+        force = True
     nvcc = find_nvcc()
     cuda_home = os.path.dirname(os.path.dirname(nvcc))
     os.makedirs(OBJ, exist_ok=True)
@@ -54,7 +59,7 @@ def build_library(force=False, verbose=False):
         o = os.path.join(OBJ, src + ".o")
         objs.append(o)
         if force or _newer(o, [s] + headers):
-            cmd = [nvcc] + NVCC_COMMON + extra + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_COMMON + list(defines) + extra + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
             if r.returncode:

@@ -34,8 +34,14 @@ namespace sbm {
 
 namespace {
 
+#ifndef SBM_STAGES
+#define SBM_STAGES 4
+#endif
+#ifndef SBM_MIN_CTAS
+#define SBM_MIN_CTAS 4
+#endif
 constexpr int kBatch = 4;             // sources per pipeline stage
-constexpr int kStages = 5;            // window stages in flight
+constexpr int kStages = SBM_STAGES;   // window stages in flight
 constexpr int kRecStages = kStages + 2;
 constexpr int kPanThreads = 128;
 constexpr int kShK = 4;               // frames per thread in the 16-channel kernel
@@ -313,7 +319,7 @@ __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_a
 // KF = frames / 32 rounded up to 8, 16 or 32; EXACT = (frames == 32 * KF): no per-frame bounds checks.
 // =====================================================================================================================
 template <int KF, bool EXACT>
-__global__ void __launch_bounds__(kBatch * 32 + 32) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+__global__ void __launch_bounds__(kBatch * 32 + 32, SBM_MIN_CTAS) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const SmemView<2> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
@@ -677,16 +683,25 @@ uint32_t pick_grid(uint32_t n, uint32_t max_grid) {
 	return g ? g : 1;
 }
 
+// Launches one K2 kernel as a single wave: grid = SM count x resident CTAs per SM (never more than the sources warrant).
+struct KernelConfig { size_t smem = 0; int ctas_per_sm = 0; };
 template <class Kernel>
-int launch_one(Kernel kernel, size_t* configured, const char* name, const MixArgs& a, uint32_t first, uint32_t n, uint32_t threads, bool sh,
+int launch_one(Kernel kernel, KernelConfig* cfg, const char* name, const MixArgs& a, uint32_t first, uint32_t n, uint32_t threads, bool sh,
                uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
 	const uint32_t F = a.frames;
 	const size_t smem = mix_smem_bytes(F, sh);
-	if (smem > *configured) {
-		if (dev::check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
-		*configured = smem;
+	if (smem != cfg->smem) {
+		if (dev::check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)") ||
+		    dev::check(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
+			return -1;
+		int per_sm = 0;
+		if (dev::check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor")) return -1;
+		cfg->smem = smem;
+		cfg->ctas_per_sm = per_sm > 0 ? per_sm : 1;
 	}
-	const uint32_t g = pick_grid(n, max_grid);
+	uint32_t wave = (uint32_t)(sm_count() * cfg->ctas_per_sm);
+	if (wave > max_grid) wave = max_grid;
+	const uint32_t g = pick_grid(n, wave);
 	kernel<<<g, threads, smem, st>>>(a, first, n, window_slot(F), partials);
 	dev::note_launch();
 	*grid_out = g;
@@ -695,7 +710,7 @@ int launch_one(Kernel kernel, size_t* configured, const char* name, const MixArg
 
 template <int KF>
 int launch_stereo(const MixArgs& a, uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
-	static size_t conf_exact = 0, conf_any = 0;
+	static KernelConfig conf_exact, conf_any;
 	const uint32_t threads = kBatch * 32 + 32;
 	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true>, &conf_exact, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
 	return launch_one(k2_mix_stereo_kernel<KF, false>, &conf_any, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
@@ -733,7 +748,7 @@ int launch_mix(const MixArgs& a, void* stream) {
 		if (rc) return -1;
 	}
 	if (a.n_sh) {
-		static size_t conf_sh = 0;
+		static KernelConfig conf_sh;
 		if (launch_one(k2_mix_ambisonic_kernel, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, sh_threads(F) + 32, true, (uint32_t)num_mix_ctas(F, 1), part_sh, st, &g_sh))
 			return -1;
 	}
