@@ -51,6 +51,7 @@ struct FinishArgs {
 	const float* hrir;          // [16][taps] or null
 	uint32_t taps;
 	float* hist;                // [16][taps-1] FIR history (the decoder's overlap state), updated in place
+	float* dec;                 // [2][frames] scratch: decoder output L / R
 	DevFlags* flags;
 	uint32_t parity;
 	uint32_t frames;

@@ -1,5 +1,6 @@
-// device_cuda.cu -- CUDA implementation of the device seam (device_api.h): memory, copies, events, and "K4", the
-// per-buffer finish kernel (SH-domain HRIR decode of the 16-channel bus + stereo mix + interleave + bookkeeping tail).
+// device_cuda.cu -- CUDA implementation of the device seam (device_api.h): memory, copies, events, and "K4": the
+// SH-domain HRIR decode of the 16-channel bus (K4a) and the per-buffer finish kernel (K4b: stereo mix + interleave +
+// FIR history + bookkeeping tail).
 // There is no host fallback anywhere in this library: every function reports failure when the CUDA call fails.
 #include <stdio.h>
 #include <string.h>
@@ -21,16 +22,59 @@ thread_local std::string t_err_copy;
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-// K4: one CTA.  Thread i handles frame i (frames <= 1024).
+// K4a: SH-domain HRIR decode, 32 frames per CTA, one warp per ambisonic channel (16 warps): thread (c, f) computes
+//   y_c[i] = sum_t h_c[t] * bus_c[i - t]   (double accumulation; history from the previous buffers, k2_core.h)
+// from shared-memory copies of the channel's taps and of the input span [i0 - taps + 1, i0 + 32); the 16 channel results
+// of a frame are then summed in ACN order into L and, sign by ACN degree, into R (ambisonic_binaural_decoder.cc:60-76).
+// Whether this buffer decodes at all is the read-only half of plan_finish (K4b makes the same decision and records it).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDecFrames = 32;
+__global__ void __launch_bounds__(kNumSh * 32) k4a_decode_kernel(FinishArgs a) {
+	extern __shared__ float smem[];   // [16][taps] HRIRs | [16][taps - 1 + 32] inputs | [16][32] channel results
+	const uint32_t F = a.frames, taps = a.taps;
+	const int H = (int)taps - 1;
+	const float* bf = a.bus + (size_t)kBusRows * F;
+	if (!(bf[0] > 0.0f) && !(a.flags->sh_flush_frames < (int)F)) return;      // nothing to decode, no tail to flush
+	const uint32_t c = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t i0 = blockIdx.x * kDecFrames;
+	const uint32_t span = (uint32_t)H + kDecFrames;
+	float* h = smem + (size_t)c * taps;
+	float* x = smem + (size_t)kNumSh * taps + (size_t)c * span;
+	float* ys = smem + (size_t)kNumSh * taps + (size_t)kNumSh * span;
+	const float* bus_c = a.bus + (size_t)c * F;
+	const float* hist_c = a.hist + (size_t)c * (size_t)(H > 0 ? H : 1);
+	for (uint32_t q = lane; q < taps; q += 32) h[q] = a.hrir[(size_t)c * taps + q];
+	for (uint32_t q = lane; q < span; q += 32) {
+		const int j = (int)i0 - H + (int)q;                        // input sample index; negative = history
+		x[q] = j < (int)F ? decode_input(bus_c, hist_c, H, j) : 0.0f;
+	}
+	__syncwarp();
+	double acc = 0.0;
+	const float* xi = x + H + lane;
+	for (uint32_t t = 0; t < taps; ++t) acc = fma((double)h[t], (double)xi[-(int)t], acc);
+	ys[c * kDecFrames + lane] = (float)acc;
+	__syncthreads();
+	if (c == 0 && i0 + lane < F) {
+		float l = 0.0f, r = 0.0f;
+#pragma unroll
+		for (int cc = 0; cc < kNumSh; ++cc) {
+			const float y = ys[cc * kDecFrames + lane];
+			l += y;
+			r = sh_right_ear_negated(cc) ? r - y : r + y;
+		}
+		a.dec[i0 + lane] = l; a.dec[F + i0 + lane] = r;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4b: one CTA.  Thread i handles frame i (frames <= 1024).
 //   1. thread 0 decides what happens this buffer (plan_finish) from the -- possibly cross-rank summed -- bus flags;
-//   2. decode: out_L/R[i] = sum_c (+-) sum_t h_c[t] * bus_c[i - t], history from the previous buffers (k2_core.h);
-//      16 x taps MACs per frame with the taps and the bus staged through shared memory by channel;
-//   3. FIR history <- last taps-1 samples of {history, bus};
-//   4. out[2i], out[2i+1] = stereo bus (panned + non-spatial sources) + decoder output; tail = {valid, finished, counters}
+//   2. FIR history <- last taps-1 samples of {history, bus} (after K4a has read the old history);
+//   3. out[2i], out[2i+1] = stereo bus (panned + non-spatial sources) + decoder output; tail = {valid, finished, counters}
 //      followed by the read counters of ring-fed sources (for CircularBuffer::size(), sbm_source_ring_size).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k4_finish_kernel(FinishArgs a) {
-	extern __shared__ float smem[];   // [taps-1 + frames] input of the current channel, [taps] its HRIR
+__global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
+	extern __shared__ float smem[];   // [taps - 1] new history of the current channel
 	__shared__ FinishPlan plan;
 	const uint32_t F = a.frames, i = threadIdx.x, T = blockDim.x;
 	const uint32_t taps = a.hrir ? a.taps : 0;
@@ -39,26 +83,16 @@ __global__ void __launch_bounds__(1024) k4_finish_kernel(FinishArgs a) {
 	__syncthreads();
 	float l = 0.0f, r = 0.0f;
 	if (plan.decode) {
-		float* x = smem;                       // x[H + j] = bus_c[j], x[0..H) = history
-		float* h = smem + (H > 0 ? H : 0) + F;
-		for (int c = 0; c < kNumSh; ++c) {
-			const float* bus_c = a.bus + (size_t)c * F;
-			float* hist_c = a.hist + (size_t)c * (size_t)(H > 0 ? H : 1);
-			__syncthreads();
-			for (uint32_t q = i; q < (uint32_t)(H > 0 ? H : 0); q += T) x[q] = hist_c[q];
-			for (uint32_t q = i; q < F; q += T) x[(H > 0 ? H : 0) + q] = bus_c[q];
-			for (uint32_t q = i; q < taps; q += T) h[q] = a.hrir[(size_t)c * taps + q];
-			__syncthreads();
-			if (i < F) {
-				double acc = 0.0;
-				const float* xi = x + (H > 0 ? H : 0) + i;
-				for (uint32_t t = 0; t < taps; ++t) acc = fma((double)h[t], (double)xi[-(int)t], acc);
-				const float y = (float)acc;
-				l += y;
-				r = sh_right_ear_negated(c) ? r - y : r + y;
+		if (i < F) { l = a.dec[i]; r = a.dec[F + i]; }
+		if (H > 0) {
+			for (int c = 0; c < kNumSh; ++c) {
+				const float* bus_c = a.bus + (size_t)c * F;
+				float* hist_c = a.hist + (size_t)c * (size_t)H;
+				__syncthreads();
+				for (uint32_t q = i; q < (uint32_t)H; q += T) smem[q] = decode_input(bus_c, hist_c, H, (int)F - H + (int)q);
+				__syncthreads();
+				for (uint32_t q = i; q < (uint32_t)H; q += T) hist_c[q] = smem[q];
 			}
-			// carry the tail: the last H samples of {history, bus}
-			for (uint32_t q = i; q < (uint32_t)(H > 0 ? H : 0); q += T) hist_c[q] = x[F + q];
 		}
 	}
 	if (i < F) {
@@ -150,12 +184,23 @@ int sync(void* stream) { return check(cudaStreamSynchronize((cudaStream_t)stream
 
 int launch_finish(const FinishArgs& a, void* stream) {
 	const uint32_t F = a.frames;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (a.hrir) {
+		const size_t smem = sizeof(float) * ((size_t)kNumSh * a.taps + (size_t)kNumSh * (a.taps - 1 + kDecFrames) + (size_t)kNumSh * kDecFrames);
+		static size_t configured = 48 * 1024;
+		if (smem > configured) {
+			if (check(cudaFuncSetAttribute(k4a_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k4a)")) return -1;
+			configured = smem;
+		}
+		k4a_decode_kernel<<<(F + kDecFrames - 1) / kDecFrames, kNumSh * 32, smem, st>>>(a);
+		note_launch();
+		if (check_launch("k4a_decode")) return -1;
+	}
 	const uint32_t threads = ((F + 31) / 32) * 32;
-	const uint32_t taps = a.hrir ? a.taps : 0;
-	const size_t smem = sizeof(float) * ((size_t)(taps ? taps - 1 : 0) + F + taps);
-	k4_finish_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(a);
+	const size_t smem = sizeof(float) * (size_t)(a.hrir && a.taps > 1 ? a.taps - 1 : 1);
+	k4b_finish_kernel<<<1, threads, smem, st>>>(a);
 	note_launch();
-	return check_launch("k4_finish");
+	return check_launch("k4b_finish");
 }
 
 void* event_create() {

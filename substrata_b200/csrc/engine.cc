@@ -78,7 +78,7 @@ struct sbm_engine {
 	MixPatch* dv_mix_patches = nullptr; uint32_t dv_mix_patches_cap = 0;
 	float* dv_partials = nullptr; size_t partials_floats = 0;
 	float* dv_bus = nullptr; size_t bus_floats = 0;
-	float* dv_hrir = nullptr; float* dv_hist = nullptr;
+	float* dv_hrir = nullptr; float* dv_hist = nullptr; float* dv_dec = nullptr;
 	float* dv_out = nullptr; size_t out_bytes = 0;
 	unsigned char* h_out = nullptr;          // pinned D2H staging: 2F floats + OutTail + ring read counters
 	Globals g;
@@ -222,7 +222,7 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	ok = ok && e->dv_out && e->h_out;
 	if (ok && hrtf) {
 		const size_t T = (size_t)cfg->sh_hrir_taps;
-		ok = dalloc(e->dv_hrir, kNumSh * T) && dalloc(e->dv_hist, kNumSh * T);
+		ok = dalloc(e->dv_hrir, kNumSh * T) && dalloc(e->dv_hist, kNumSh * T) && dalloc(e->dv_dec, 2 * (size_t)F);
 		if (ok) ok = dev::h2d(e->dv_hrir, cfg->sh_hrir, sizeof(float) * kNumSh * T, e->stream) == 0;
 	}
 	if (ok) ok = dev::h2d(e->dv_table, encoder_table(), sizeof(float) * kTableAz * kTableEl * kShRaw, e->stream) == 0;
@@ -247,7 +247,7 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	void* ptrs[] = {e->dv_stat, e->dv_posvol, e->dv_occl, e->dv_ring_write, e->dv_mixz, A.live, A.read_i, A.eof, A.rs, A.dgain, A.occ_cur,
 	                A.lpf_prev, A.bits, A.rec, A.finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
 	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
-	                e->dv_hist, e->dv_patches, e->dv_mix_patches};
+	                e->dv_hist, e->dv_dec, e->dv_patches, e->dv_mix_patches};
 	for (void* p : ptrs) if (p) dev::release(p);
 	for (auto& b : e->buffers) if (b.owned && b.dptr) dev::release(b.dptr);
 	for (auto& r : e->rings) if (r.storage) dev::release(r.storage);
@@ -639,7 +639,7 @@ SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid
 	const uint32_t F = e->g.frames;
 	const uint32_t parity = (uint32_t)(e->buffer_index & 1);
 	FinishArgs f;
-	f.bus = e->dv_bus; f.hrir = e->dv_hrir; f.taps = (uint32_t)e->cfg.sh_hrir_taps; f.hist = e->dv_hist;
+	f.bus = e->dv_bus; f.hrir = e->dv_hrir; f.taps = (uint32_t)e->cfg.sh_hrir_taps; f.hist = e->dv_hist; f.dec = e->dv_dec;
 	f.flags = e->dv_flags; f.parity = parity; f.frames = F; f.out = e->dv_out;
 	f.list_ring = e->dv_list_ring; f.n_ring = (uint32_t)e->list_ring.size(); f.read_i = e->A.read_i; f.finished_count_reset = nullptr;
 	if (dev::launch_finish(f, st)) return fail_cuda(e, "k4_finish");

@@ -270,6 +270,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 			if (d.n) {
 				rec.ch_ramp_mask |= 1u << c;
 				A.shr[out].start[c] = d.start; A.shr[out].inc[c] = d.inc; A.shr[out].n[c] = d.n;
+				if (d.n > rec.ch[0].n) rec.ch[0].n = d.n;       // ambisonic sources: ch[0].n = longest channel ramp (K2's fix-up region)
 			}
 		}
 		A.shg[out] = sg;

@@ -4,7 +4,7 @@
 // ramped bus gains and accumulate into the output tile; and "K3", the fixed-order cross-CTA reduction of the partial
 // buses into this rank's bus.
 //
-// Decomposition.  A CTA owns ALL frames of the buffer and a contiguous slice of the render list, and keeps its partial
+// Decomposition.  A CTA owns ALL frames of the buffer and every grid-th batch of the render list, and keeps its partial
 // sums in registers across the whole slice, so per-source contributions never leave the register file; each CTA then
 // stores one partial bus [NCH][frames] and K3 sums the partial buses in CTA order (deterministic; no atomics on audio).
 //   stereo bus (2 channels):  one WARP per source -- lane l owns frames l, l+32, ... (2 x frames/32 accumulators), the
@@ -34,6 +34,11 @@ namespace sbm {
 
 namespace {
 
+#ifdef SBM_CONTIGUOUS   // development A/B: contiguous slice per CTA instead of round-robin batches
+#define SBM_GLOBAL_BATCH(jb) (blockIdx.x * ((((s1 - s0) + kBatch - 1) / kBatch + gridDim.x - 1) / gridDim.x) + (jb))
+#else
+#define SBM_GLOBAL_BATCH(jb) (blockIdx.x + (jb) * gridDim.x)
+#endif
 #ifndef SBM_STAGES
 #define SBM_STAGES 4
 #endif
@@ -182,6 +187,7 @@ __device__ __forceinline__ MathDesc make_desc(const WorkRec& r, const WinPlan& p
 		if ((r.ch_ramp_mask & 2u) && r.ch[1].n > nr) nr = r.ch[1].n;
 	} else if (r.ch_ramp_mask) {
 		d.mode |= kMdShRamp;
+		if (r.ch[0].n > nr) nr = r.ch[0].n;      // ambisonic sources: K1 leaves the longest channel ramp in ch[0].n
 	}
 	d.nramp = nr;
 	if (nr) d.mode |= kMdRamp;
@@ -235,16 +241,18 @@ __device__ float lpf_warp(float* buf, uint32_t F, float coef, float prev, uint32
 	return carry;
 }
 
-// Shared-memory carve-up (both kernels): header | WorkRec ring | ShGains ring (ambisonic only) | MathDesc ring | window ring.
+// Shared-memory carve-up (both kernels): header | WorkRec ring | ShGains ring, ShRamps ring (ambisonic only) | MathDesc ring | window ring.
 template <int NCH>
 struct SmemView {
-	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; MathDesc* descs; float* wring;
+	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; ShRamps* shrs; MathDesc* descs; float* wring;
 	__device__ explicit SmemView(unsigned char* raw) {
 		hdr = reinterpret_cast<MixSmemHdr*>(raw);
 		recs = reinterpret_cast<WorkRec*>(raw + 256);
 		unsigned char* p = reinterpret_cast<unsigned char*>(recs) + sizeof(WorkRec) * kRecStages * kBatch;
 		shgs = reinterpret_cast<ShGains*>(p);
 		if (NCH == 16) p += sizeof(ShGains) * kRecStages * kBatch;
+		shrs = reinterpret_cast<ShRamps*>(p);       // channel ramps of the sources that have any, staged with the windows
+		if (NCH == 16) p += sizeof(ShRamps) * kStages * kBatch;
 		descs = reinterpret_cast<MathDesc*>(p);
 		p += sizeof(MathDesc) * kStages * kBatch;
 		wring = reinterpret_cast<float*>(p);
@@ -263,7 +271,7 @@ __device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_
 		const uint32_t q = jb % kRecStages;
 		if (jb >= (uint32_t)kRecStages) mbar_wait(&hdr->empty_r[q], ((jb / kRecStages) - 1u) & 1u);
 		if (lane == 0) {
-			const uint32_t b0 = s0 + jb * kBatch;
+			const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 			const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
 			const uint32_t bytes = nb * (uint32_t)sizeof(WorkRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u);
 			mbar_expect_tx(&hdr->full_r[q], bytes);
@@ -278,7 +286,7 @@ __device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_
 		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
 		if (jb >= (uint32_t)kStages) mbar_wait(&hdr->empty_w[qw], ((jb / kStages) - 1u) & 1u);
 		mbar_wait(&hdr->full_r[qr], (jb / kRecStages) & 1u);
-		const uint32_t b0 = s0 + jb * kBatch;
+		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
 		WinPlan p;
 		p.fast = false; p.seg1_floats = 0; p.seg2_floats = 0; p.a0 = 0;
@@ -289,6 +297,12 @@ __device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_
 			sm.descs[qw * kBatch + lane] = make_desc(r, p, slot_float0, NCH == 16);
 		}
 		uint32_t bytes = p.fast ? 4u * (p.seg1_floats + p.seg2_floats) : 0u;
+		bool want_ramps = false;
+		if (NCH == 16 && lane < nb) {
+			const WorkRec& r = sm.recs[qr * kBatch + lane];
+			want_ramps = r.ch_ramp_mask != 0 && !(r.flags & kRecSkip);
+			if (want_ramps) bytes += (uint32_t)sizeof(ShRamps);
+		}
 		for (int o = kBatch / 2; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
 		__syncwarp();
 		// the arrive below releases the descriptors written above (and, transitively, the records) to the math warps
@@ -302,6 +316,7 @@ __device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_
 			bulk_g2s(dst, pcm + p.a0, 4u * p.seg1_floats, &hdr->full_w[qw]);
 			if (p.seg2_floats) bulk_g2s(dst + p.seg1_floats, pcm, 4u * p.seg2_floats, &hdr->full_w[qw]);
 		}
+		if (NCH == 16 && want_ramps) bulk_g2s(sm.shrs + qw * kBatch + lane, a.shr + (b0 + lane), (uint32_t)sizeof(ShRamps), &hdr->full_w[qw]);
 		__syncwarp();
 	}
 }
@@ -312,6 +327,8 @@ __device__ __forceinline__ void init_barriers(MixSmemHdr* hdr, uint32_t n_consum
 	fence_mbar_init();
 }
 
+template <int V> struct IntTag { static constexpr int value = V; };
+
 __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_as_float(0x3f800000u | ((uint32_t)p >> 9)) - 1.0f; }
 
 // =====================================================================================================================
@@ -319,14 +336,21 @@ __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_a
 // KF = frames / 32 rounded up to 8, 16 or 32; EXACT = (frames == 32 * KF): no per-frame bounds checks.
 // =====================================================================================================================
 template <int KF, bool EXACT>
-__global__ void __launch_bounds__(kBatch * 32 + 32, SBM_MIN_CTAS) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+__global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const SmemView<2> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
 	const uint32_t F = a.frames, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-	const uint32_t s0 = first + (uint32_t)((unsigned long long)blockIdx.x * n / gridDim.x);
-	const uint32_t s1 = first + (uint32_t)((unsigned long long)(blockIdx.x + 1) * n / gridDim.x);
-	const uint32_t nbatch = (s1 - s0 + kBatch - 1) / kBatch;
+	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
+	// run of expensive sources (long ramps, occlusion, generic fetches) is spread over the whole grid.
+	const uint32_t s0 = first, s1 = first + n;
+	const uint32_t total_batches = (n + kBatch - 1) / kBatch;
+#ifdef SBM_CONTIGUOUS
+	const uint32_t per_cta = (total_batches + gridDim.x - 1) / gridDim.x;
+	const uint32_t nbatch = blockIdx.x * per_cta < total_batches ? (total_batches - blockIdx.x * per_cta < per_cta ? total_batches - blockIdx.x * per_cta : per_cta) : 0u;
+#else
+	const uint32_t nbatch = blockIdx.x < total_batches ? (total_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+#endif
 	if (t == 0) init_barriers(hdr, kBatch);
 	__syncthreads();
 	if (warp == (uint32_t)kBatch) { producer_warp<2>(sm, a, s0, s1, nbatch, wslot, lane); return; }
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, SBM_MIN_CTAS) k2_mix_stereo_
 	for (uint32_t jb = 0; jb < nbatch; ++jb) {
 		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
 		mbar_wait(&hdr->full_w[qw], (jb / kStages) & 1u);
-		const uint32_t b0 = s0 + jb * kBatch;
+		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		if (b0 + warp < s1) {
 			const MathDesc& d = sm.descs[qw * kBatch + warp];
 			const WorkRec& r = sm.recs[qr * kBatch + warp];
@@ -350,113 +374,107 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, SBM_MIN_CTAS) k2_mix_stereo_
 					resampler_tail(r, &p0, &p1);
 					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
 				}
-			} else if ((mode & (kMdGeneric | kMdLpf | kMdAdjust)) || d.nramp > 32u) {
-				// ---------------- careful path (rare): every case, straightforward arithmetic ----------------
-				const WinPlan wp = plan_window(r, wslot);
-				float* slot = sm.wring + (size_t)(qw * kBatch + warp) * wslot;     // this warp's stage slot
-				const float* w = slot + 4 + wp.off0;
-				float y[KF];
+			} else {
+				float x[KF];           // engine-rate input samples of this lane's frames, before the direct gain
+				float mf = 1.0f;       // MixSource::mix_factor where it is not already inside x
+				bool filtered = false; // x already carries the direct gain and the occlusion low-pass
+				if (mode & (kMdGeneric | kMdLpf | kMdAdjust)) {
+					// ---------------- careful fetch (rare): every case, straightforward arithmetic ----------------
+					const WinPlan wp = plan_window(r, wslot);
+					float* slot = sm.wring + (size_t)(qw * kBatch + warp) * wslot;     // this warp's stage slot
+					const float* w = slot + 4 + wp.off0;
 #pragma unroll
-				for (int k = 0; k < KF; ++k) {
-					const uint32_t i = lane + 32u * k;
-					float x = 0.0f;
-					if (EXACT || i < F) x = wp.fast ? staged_sample(r, w, wp, i) : source_sample(r, a.mixz, a.mix_pos0, i);
-					y[k] = x * gain_at(r.direct, i);
-				}
-				if ((r.flags & kRecResample) && lane == 0) {
-					float p0, p1;
-					if (wp.fast) { p0 = staged_tmp(r, w, wp, (int)r.n_src); p1 = staged_tmp(r, w, wp, (int)r.n_src + 1); }
-					else resampler_tail(r, &p0, &p1);
-					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
-				}
-				if (!(mode & kMdStereo)) {
+					for (int k = 0; k < KF; ++k) {
+						const uint32_t i = lane + 32u * k;
+						x[k] = 0.0f;
+						if (EXACT || i < F) x[k] = wp.fast ? staged_sample(r, w, wp, i) : source_sample(r, a.mixz, a.mix_pos0, i);
+					}
+					if ((r.flags & kRecResample) && lane == 0) {
+						float p0, p1;
+						if (wp.fast) { p0 = staged_tmp(r, w, wp, (int)r.n_src); p1 = staged_tmp(r, w, wp, (int)r.n_src + 1); }
+						else resampler_tail(r, &p0, &p1);
+						a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
+					}
 					if (mode & kMdLpf) {
 						// the window is in registers now: reuse this warp's stage slot as scratch for the recurrence
 						__syncwarp();
 #pragma unroll
-						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; if (EXACT || i < F) slot[i] = y[k]; }
+						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; if (EXACT || i < F) slot[i] = x[k] * gain_at(r.direct, i); }
 						__syncwarp();
 						const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane);
 						__syncwarp();
 #pragma unroll
-						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; if (EXACT || i < F) y[k] = slot[i]; }
+						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; if (EXACT || i < F) x[k] = slot[i]; }
 						if (lane == 0) a.lpf_prev[r.slot] = carry;
 						fence_proxy_async();     // generic-proxy writes to the slot precede the TMA refill
-					} else {
-#pragma unroll
-						for (int k = 0; k < KF; ++k) if (lane + 32u * k == F - 1) a.lpf_prev[r.slot] = y[k];
-					}
-				}
-#pragma unroll
-				for (int k = 0; k < KF; ++k) {
-					const uint32_t i = lane + 32u * k;
-					acc0[k] = fmaf(gain_at(r.ch[0], i), y[k], acc0[k]);
-					acc1[k] = fmaf(gain_at(r.ch[1], i), y[k], acc1[k]);
-				}
-			} else {
-				// ---------------- lean path ----------------
-				const float* wb = sm.wring + d.w_idx;
-				const float g0 = d.g0, g1 = d.g1;
-				const bool ramp0 = (mode & kMdRamp) != 0;         // gains still ramp inside the first 32 frames (k = 0)
-				const bool rsmp = (mode & kMdResample) != 0;
-				float x_last = 0.0f;
-				if (mode & kMdInterp) {
-					unsigned long long p = d.x0 + (unsigned long long)lane * d.step;
-					const unsigned long long step32 = d.step << 5;
-#pragma unroll
-					for (int k = 0; k < KF; ++k) {
-						const uint32_t i = lane + 32u * k;
-						float x = 0.0f;
-						if (EXACT || i < F) {
-							const uint32_t di = (uint32_t)(p >> 32);
-							const float fr = frac_of(p);
-							float v0, v1;
-							// only the first frames (resampler history) and the last ones (index clamp) need the careful form
-							if ((k == 0 || k == KF - 1 || !EXACT) && rsmp) {
-								const WinPlan wp = plan_window(r, wslot);
-								const float* w = wb + 2;
-								v0 = staged_tmp(r, w, wp, (int)di); v1 = staged_tmp(r, w, wp, (int)di + 1);
-							} else { v0 = wb[di]; v1 = wb[di + 1]; }
-							x = fmaf(fr, v1 - v0, v0);
-						}
-						if (k == 0 && ramp0) {
-							const float mf = (r.flags & kRecMix1) ? r.mix_factor : 1.0f;
-							const float yv = (x * mf) * gain_at(r.direct, i);
-							acc0[0] = fmaf(gain_at(r.ch[0], i), yv, acc0[0]);
-							acc1[0] = fmaf(gain_at(r.ch[1], i), yv, acc1[0]);
-						} else {
-							acc0[k] = fmaf(g0, x, acc0[k]);
-							acc1[k] = fmaf(g1, x, acc1[k]);
-						}
-						if (k == KF - 1 || !EXACT) { if (i == F - 1) x_last = x; }
-						p += step32;
+						filtered = true;
 					}
 				} else {
+					// ---------------- lean fetch: window staged in shared memory by the TMA ring ----------------
+					const float* wb = sm.wring + d.w_idx;
+					if (r.flags & kRecMix1) mf = r.mix_factor;
+					if (mode & kMdInterp) {
+						const bool rsmp = (mode & kMdResample) != 0;
+						unsigned long long p = d.x0 + (unsigned long long)lane * d.step;
+						const unsigned long long step32 = d.step << 5;
+#pragma unroll
+						for (int k = 0; k < KF; ++k) {
+							const uint32_t i = lane + 32u * k;
+							float v = 0.0f;
+							if (EXACT || i < F) {
+								const uint32_t di = (uint32_t)(p >> 32);
+								const float fr = frac_of(p);
+								float v0, v1;
+								// only the first frames (resampler history) and the last ones (index clamp) need the careful form
+								if ((k == 0 || k == KF - 1 || !EXACT) && rsmp) {
+									const WinPlan wp = plan_window(r, wslot);
+									v0 = staged_tmp(r, wb + 2, wp, (int)di); v1 = staged_tmp(r, wb + 2, wp, (int)di + 1);
+								} else { v0 = wb[di]; v1 = wb[di + 1]; }
+								v = fmaf(fr, v1 - v0, v0);
+							}
+							x[k] = v;
+							p += step32;
+						}
+						if (rsmp && lane == 0) {
+							const WinPlan wp = plan_window(r, wslot);
+							a.rs[d.slot].prev_samples[0] = staged_tmp(r, wb + 2, wp, (int)r.n_src);
+							a.rs[d.slot].prev_samples[1] = staged_tmp(r, wb + 2, wp, (int)r.n_src + 1);
+						}
+					} else {
+#pragma unroll
+						for (int k = 0; k < KF; ++k) {
+							const uint32_t i = lane + 32u * k;
+							x[k] = (EXACT || i < F) ? wb[i] : 0.0f;
+						}
+					}
+				}
+				// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
+				const float g0 = d.g0, g1 = d.g1;
+				const uint32_t nramp = filtered ? F : d.nramp;     // frames that need per-frame gain evaluation
+				// RAMPS: 0 = no gain ramps in this buffer, 1 = ramps end within the first 32 frames (the usual case while the
+				// listener moves), 2 = anything (long ramps, filtered signal): per-iteration warp-uniform test.
+				auto gains = [&](auto ramps_tag) {
+					constexpr int RAMPS = decltype(ramps_tag)::value;
 #pragma unroll
 					for (int k = 0; k < KF; ++k) {
 						const uint32_t i = lane + 32u * k;
-						float x = 0.0f;
-						if (EXACT || i < F) x = wb[i];
-						if (k == 0 && ramp0) {
-							const float yv = x * gain_at(r.direct, i);
-							acc0[0] = fmaf(gain_at(r.ch[0], i), yv, acc0[0]);
-							acc1[0] = fmaf(gain_at(r.ch[1], i), yv, acc1[0]);
+						const bool per_frame = RAMPS == 2 ? (32u * k < nramp) : (RAMPS == 1 && k == 0);
+						if (per_frame) {
+							const float yv = filtered ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
+							acc0[k] = fmaf(gain_at(r.ch[0], i), yv, acc0[k]);
+							acc1[k] = fmaf(gain_at(r.ch[1], i), yv, acc1[k]);
+							if (!filtered && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[d.slot] = yv;
 						} else {
-							acc0[k] = fmaf(g0, x, acc0[k]);
-							acc1[k] = fmaf(g1, x, acc1[k]);
+							acc0[k] = fmaf(g0, x[k], acc0[k]);
+							acc1[k] = fmaf(g1, x[k], acc1[k]);
+							// bypassed occlusion filter remembers the last input sample (mono_pole_filter.cc:40-44)
+							if ((k == KF - 1 || !EXACT) && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[d.slot] = x[k] * d.gd;
 						}
-						if (k == KF - 1 || !EXACT) { if (i == F - 1) x_last = x; }
 					}
-				}
-				// bypassed occlusion filter remembers the last input sample (mono_pole_filter.cc:40-44); nramp <= 32 < frames
-				// here, so the direct gain has reached its constant part by then
-				if (!(mode & kMdStereo) && lane == ((F - 1) & 31u)) a.lpf_prev[d.slot] = x_last * d.gd;
-				if (rsmp && lane == 0) {
-					const WinPlan wp = plan_window(r, wslot);
-					const float* w = wb + 2;
-					a.rs[d.slot].prev_samples[0] = staged_tmp(r, w, wp, (int)r.n_src);
-					a.rs[d.slot].prev_samples[1] = staged_tmp(r, w, wp, (int)r.n_src + 1);
-				}
+				};
+				if (nramp == 0) gains(IntTag<0>());
+				else if (nramp <= 32u) gains(IntTag<1>());
+				else gains(IntTag<2>());
 			}
 		}
 		// this warp is done with window stage qw and record slot qr: hand them back to the producer
@@ -485,31 +503,40 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, SBM_MIN_CTAS) k2_mix_stereo_
 // Ambisonic-bus kernel: T math threads (frames / 4) work on one source at a time + the producer warp.
 // =====================================================================================================================
 constexpr int K = kShK;
-__global__ void __launch_bounds__(256 + 32) k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+template <int TMAX>     // TMAX = 128 (frames <= 512) or 256 (frames <= 1024): sets the register budget
+__global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : 1)
+k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const SmemView<16> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
 	// blockDim.x = T math threads + one producer warp (the last warp)
 	const uint32_t F = a.frames, T = blockDim.x - 32, t = threadIdx.x, lane = t & 31u;
-	const uint32_t s0 = first + (uint32_t)((unsigned long long)blockIdx.x * n / gridDim.x);
-	const uint32_t s1 = first + (uint32_t)((unsigned long long)(blockIdx.x + 1) * n / gridDim.x);
-	const uint32_t nbatch = (s1 - s0 + kBatch - 1) / kBatch;
+	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
+	// run of expensive sources (long ramps, occlusion, generic fetches) is spread over the whole grid.
+	const uint32_t s0 = first, s1 = first + n;
+	const uint32_t total_batches = (n + kBatch - 1) / kBatch;
+#ifdef SBM_CONTIGUOUS
+	const uint32_t per_cta = (total_batches + gridDim.x - 1) / gridDim.x;
+	const uint32_t nbatch = blockIdx.x * per_cta < total_batches ? (total_batches - blockIdx.x * per_cta < per_cta ? total_batches - blockIdx.x * per_cta : per_cta) : 0u;
+#else
+	const uint32_t nbatch = blockIdx.x < total_batches ? (total_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+#endif
 	if (t == 0) init_barriers(hdr, T / 32);
 	__syncthreads();
 	if (t >= T) { producer_warp<16>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
-	float acc[NCH][K];
+	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1): one FFMA2 per pair and frame
 #pragma unroll
-	for (int c = 0; c < NCH; ++c)
+	for (int c = 0; c < NCH / 2; ++c)
 #pragma unroll
-		for (int k = 0; k < K; ++k) acc[c][k] = 0.0f;
+		for (int k = 0; k < K; ++k) acc[c][k] = make_float2(0.0f, 0.0f);
 	const uint32_t warp_i0 = t & ~31u;     // first frame of this warp in iteration k = 0
 
 	for (uint32_t jb = 0; jb < nbatch; ++jb) {
 		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
 		mbar_wait(&hdr->full_w[qw], (jb / kStages) & 1u);
-		const uint32_t b0 = s0 + jb * kBatch;
+		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
 		for (uint32_t b = 0; b < nb; ++b) {
 			const MathDesc& d = sm.descs[qw * kBatch + b];
@@ -523,8 +550,10 @@ __global__ void __launch_bounds__(256 + 32) k2_mix_ambisonic_kernel(MixArgs a, u
 				}
 				continue;
 			}
-			float y[K];
-			if ((mode & (kMdGeneric | kMdLpf | kMdAdjust | kMdRamp)) != 0) {
+			float x[K];          // engine-rate input samples of this thread's frames (before any gain)
+			float mf = 1.0f;     // MixSource::mix_factor where it is not already inside x
+			bool lpf_done = false;
+			if ((mode & (kMdGeneric | kMdLpf | kMdAdjust)) != 0) {
 				// ---------------- careful path (rare) ----------------
 				const WinPlan wp = plan_window(r, wslot);
 				float* slot = sm.wring + (size_t)(qw * kBatch + b) * wslot;
@@ -532,9 +561,8 @@ __global__ void __launch_bounds__(256 + 32) k2_mix_ambisonic_kernel(MixArgs a, u
 #pragma unroll
 				for (int k = 0; k < K; ++k) {
 					const uint32_t i = t + (uint32_t)k * T;
-					float x = 0.0f;
-					if (i < F) x = wp.fast ? staged_sample(r, w, wp, i) : source_sample(r, a.mixz, a.mix_pos0, i);
-					y[k] = x * gain_at(r.direct, i);
+					x[k] = 0.0f;
+					if (i < F) x[k] = wp.fast ? staged_sample(r, w, wp, i) : source_sample(r, a.mixz, a.mix_pos0, i);
 				}
 				if ((r.flags & kRecResample) && t == 0) {
 					float p0, p1;
@@ -543,30 +571,29 @@ __global__ void __launch_bounds__(256 + 32) k2_mix_ambisonic_kernel(MixArgs a, u
 					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
 				}
 				if (mode & kMdLpf) {
-					math_sync(T);     // every thread has its window samples in registers: the slot becomes scratch
+					// direct gain, then the recurrence in the (now free) stage slot; x becomes the filtered, gained signal
+					math_sync(T);
 #pragma unroll
-					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) slot[i] = y[k]; }
+					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) slot[i] = x[k] * gain_at(r.direct, i); }
 					math_sync(T);
 					if (t < 32) { const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane); if (lane == 0) a.lpf_prev[r.slot] = carry; }
 					math_sync(T);
 #pragma unroll
-					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) y[k] = slot[i]; }
+					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) x[k] = slot[i]; }
 					fence_proxy_async();
-				} else {
-#pragma unroll
-					for (int k = 0; k < K; ++k) if (t + (uint32_t)k * T == F - 1) a.lpf_prev[r.slot] = y[k];
+					lpf_done = true;
 				}
 			} else {
 				// ---------------- lean path ----------------
 				const float* wb = sm.wring + d.w_idx;
-				const float gd = d.gd;
+				if (r.flags & kRecMix1) mf = r.mix_factor;
 				if (mode & kMdInterp) {
 					const bool rsmp = (mode & kMdResample) != 0;
 #pragma unroll
 					for (int k = 0; k < K; ++k) {
 						const uint32_t i = t + (uint32_t)k * T;
 						const uint32_t wi0 = warp_i0 + (uint32_t)k * T;
-						float x = 0.0f;
+						float v = 0.0f;
 						if (i < F) {
 							const unsigned long long p = d.x0 + (unsigned long long)i * d.step;
 							const uint32_t di = (uint32_t)(p >> 32);
@@ -576,9 +603,9 @@ __global__ void __launch_bounds__(256 + 32) k2_mix_ambisonic_kernel(MixArgs a, u
 								const WinPlan wp = plan_window(r, wslot);
 								v0 = staged_tmp(r, wb + 2, wp, (int)di); v1 = staged_tmp(r, wb + 2, wp, (int)di + 1);
 							} else { v0 = wb[di]; v1 = wb[di + 1]; }
-							x = fmaf(fr, v1 - v0, v0);
+							v = fmaf(fr, v1 - v0, v0);
 						}
-						y[k] = x * gd;
+						x[k] = v;
 					}
 					if (rsmp && t == 0) {
 						const WinPlan wp = plan_window(r, wslot);
@@ -589,33 +616,35 @@ __global__ void __launch_bounds__(256 + 32) k2_mix_ambisonic_kernel(MixArgs a, u
 #pragma unroll
 					for (int k = 0; k < K; ++k) {
 						const uint32_t i = t + (uint32_t)k * T;
-						y[k] = i < F ? wb[i] * gd : 0.0f;
+						x[k] = i < F ? wb[i] : 0.0f;
 					}
 				}
-#pragma unroll
-				for (int k = 0; k < K; ++k) if (t + (uint32_t)k * T == F - 1) a.lpf_prev[d.slot] = y[k];
 			}
-			// ---------------- bus gains (GainMixer, accumulate mode) ----------------
+			// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
 			const float* gk = sm.shgs[qr * kBatch + b].konst;
-			if (mode & kMdShRamp) {
-				const ShRamps* rp = a.shr + (b0 + b);
+			const ShRamps& rp = sm.shrs[qw * kBatch + b];
+			const float gd = d.gd;
+			const uint32_t nramp = d.nramp;     // frames in which the direct gain or a channel gain still ramps
+			const uint32_t mask = r.ch_ramp_mask;
 #pragma unroll
-				for (int c = 0; c < NCH; ++c) {
-					RampDesc rd; rd.konst = gk[c]; rd.n = 0; rd.start = 0.0f; rd.inc = 0.0f;
-					if (r.ch_ramp_mask & (1u << c)) { rd.start = rp->start[c]; rd.inc = rp->inc[c]; rd.n = rp->n[c]; }
+			for (int k = 0; k < K; ++k) {
+				const uint32_t i = t + (uint32_t)k * T;
+				if (warp_i0 + (uint32_t)k * T < nramp) {
+					// warp-uniform: only the warps whose frames lie inside a ramp evaluate ramps
+					const float yv = lpf_done ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
+					if (!lpf_done && i == F - 1) a.lpf_prev[d.slot] = yv;
 #pragma unroll
-					for (int k = 0; k < K; ++k) acc[c][k] = fmaf(gain_at(rd, t + (uint32_t)k * T), y[k], acc[c][k]);
-				}
-			} else {
-#pragma unroll
-				for (int c = 0; c < NCH; c += 2) {
-					const float2 g = *reinterpret_cast<const float2*>(gk + c);
-#pragma unroll
-					for (int k = 0; k < K; ++k) {
-						float2 ac = make_float2(acc[c][k], acc[c + 1][k]);
-						ffma2(ac, g, make_float2(y[k], y[k]));
-						acc[c][k] = ac.x; acc[c + 1][k] = ac.y;
+					for (int c = 0; c < NCH; c += 2) {
+						float g0 = gk[c], g1 = gk[c + 1];
+						if ((mask >> c) & 1u) { if (i < rp.n[c]) g0 = fmaf((float)i, rp.inc[c], rp.start[c]); }
+						if ((mask >> (c + 1)) & 1u) { if (i < rp.n[c + 1]) g1 = fmaf((float)i, rp.inc[c + 1], rp.start[c + 1]); }
+						ffma2(acc[c / 2][k], make_float2(g0, g1), make_float2(yv, yv));
 					}
+				} else {
+					const float yv = lpf_done ? x[k] : x[k] * gd;
+					if (!lpf_done && i == F - 1) a.lpf_prev[d.slot] = yv;
+#pragma unroll
+					for (int c = 0; c < NCH; c += 2) ffma2(acc[c / 2][k], *reinterpret_cast<const float2*>(gk + c), make_float2(yv, yv));
 				}
 			}
 		}
@@ -625,11 +654,11 @@ __global__ void __launch_bounds__(256 + 32) k2_mix_ambisonic_kernel(MixArgs a, u
 	}
 	float* out = partials + (size_t)blockIdx.x * NCH * F;
 #pragma unroll
-	for (int c = 0; c < NCH; ++c)
+	for (int c = 0; c < NCH / 2; ++c)
 #pragma unroll
 		for (int k = 0; k < K; ++k) {
 			const uint32_t i = t + (uint32_t)k * T;
-			if (i < F) out[(size_t)c * F + i] = acc[c][k];
+			if (i < F) { out[(size_t)(2 * c) * F + i] = acc[c][k].x; out[(size_t)(2 * c + 1) * F + i] = acc[c][k].y; }
 		}
 }
 
@@ -672,7 +701,8 @@ uint32_t sh_threads(uint32_t F) { return ((F + kShK - 1) / kShK + 31) / 32 * 32;
 // to +25 %) plus alignment slack; larger windows take the generic path.
 uint32_t window_slot(uint32_t F) { return (F + F / 4 + 24u + 3u) & ~3u; }
 size_t mix_smem_bytes(uint32_t F, bool sh) {
-	return 256 + sizeof(WorkRec) * kRecStages * kBatch + (sh ? sizeof(ShGains) * kRecStages * kBatch : 0) + sizeof(MathDesc) * kStages * kBatch +
+	return 256 + sizeof(WorkRec) * kRecStages * kBatch + (sh ? sizeof(ShGains) * kRecStages * kBatch + sizeof(ShRamps) * kStages * kBatch : 0) +
+	       sizeof(MathDesc) * kStages * kBatch +
 	       sizeof(float) * (size_t)kStages * kBatch * window_slot(F);
 }
 constexpr uint32_t kMinSourcesPerCta = 16;
@@ -749,8 +779,11 @@ int launch_mix(const MixArgs& a, void* stream) {
 	}
 	if (a.n_sh) {
 		static KernelConfig conf_sh;
-		if (launch_one(k2_mix_ambisonic_kernel, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, sh_threads(F) + 32, true, (uint32_t)num_mix_ctas(F, 1), part_sh, st, &g_sh))
-			return -1;
+		static KernelConfig conf_sh_big;
+		const uint32_t tm = sh_threads(F);
+		const int rc = tm <= 128 ? launch_one(k2_mix_ambisonic_kernel<128>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, (uint32_t)num_mix_ctas(F, 1), part_sh, st, &g_sh)
+		                         : launch_one(k2_mix_ambisonic_kernel<256>, &conf_sh_big, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, (uint32_t)num_mix_ctas(F, 1), part_sh, st, &g_sh);
+		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
 	k3_reduce_kernel<<<(kBusRows * F + 255) / 256, 256, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F);
