@@ -82,11 +82,31 @@ def build_library(force=False, verbose=False, defines=(), out=None):
         log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError("link failed:\n" + log[-1])
+    host_lib = build_host_library(objs_dir=OBJ, lib=LIB, force=force, log=log)
     with open(os.path.join(OBJ, "build.log"), "a") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
     return LIB
+
+
+HOST_DIR = os.path.join(HERE, "host")
+
+
+def build_host_library(objs_dir, lib, force=False, log=None):
+    """libsubstrata_b200_host.so: the glare::AudioEngine / glare::AudioResampler mirror (host/*.cpp) above the C ABI."""
+    out = os.path.join(os.path.dirname(lib), "libsubstrata_b200_host.so")
+    srcs = [os.path.join(HOST_DIR, f) for f in ("AudioEngine.cpp", "AudioResampler.cpp")]
+    deps = srcs + [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith(".h")] + [lib]
+    if force or _newer(out, deps):
+        cmd = ["g++"] + HOST_FLAGS + ["-fvisibility=default", "-shared", "-o", out] + srcs + [
+            "-L" + os.path.dirname(lib), "-l:" + os.path.basename(lib), "-Wl,-rpath,$ORIGIN", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if log is not None:
+            log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("host library build failed:\n" + r.stdout + r.stderr)
+    return out
 
 
 if __name__ == "__main__":

@@ -70,14 +70,26 @@ constexpr uint32_t kMaxMix1Window = 4096;
 SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot, uint32_t out,
                               uint32_t* rendered_src) {
 	*rendered_src = 0;
+	// All per-slot state is loaded up front, unconditionally: the loads are independent of each other, so the memory
+	// system sees them as one batch instead of a chain of dependent round trips behind the branches below.
 	const SrcStatic st = A.stat[slot];
+	const uint32_t live = A.live[slot];
+	const F4 pv = A.posvol[slot];
+	const float occ_t = A.occl[slot];
+	const unsigned long long read_i0 = A.read_i[slot];
+	long long eof = A.eof[slot];
+	Resamp rs = A.rs[slot];
+	float dg = A.dgain[slot];
+	float occ = A.occ_cur[slot];
+	const float lpf_prev0 = A.lpf_prev[slot];
+	uint8_t bits = A.bits[slot];
 	WorkRec rec;
 	rec.pcm = st.pcm; rec.len = st.len; rec.start = 0; rec.n_src = 0; rec.avail = 0; rec.flags = kRecSkip;
 	rec.slot = slot; rec.x0_fx = 0; rec.step_fx = 0; rec.prev0 = 0.0f; rec.prev1 = 0.0f; rec.lpf_coef = 0.0f; rec.lpf_prev = 0.0f;
 	rec.ch_ramp_mask = 0; rec.mix_factor = 1.0f; rec.mix_first = st.mix_first; rec.nz = st.nz;
 	rec.direct.konst = 0.0f; rec.direct.start = 0.0f; rec.direct.inc = 0.0f; rec.direct.n = 0;
 	rec.ch[0] = rec.direct; rec.ch[1] = rec.direct;
-	if (!(st.flags & kFlagAlive) || !A.live[slot]) { A.rec[out] = rec; return 0; }
+	if (!(st.flags & kFlagAlive) || !live) { A.rec[out] = rec; return 0; }
 
 	const uint32_t F = G.frames;
 	const uint32_t kind = (st.flags >> kFlagKindShift) & 0xff;
@@ -86,7 +98,6 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	uint32_t rflags = 0;
 
 	// ---------------- feeder: how many source samples, from where (AE.cpp:378-474) ----------------
-	Resamp rs = A.rs[slot];
 	uint32_t n_src = F;
 	uint32_t alg_samples = 0;       // PCM samples this buffer has to read (accounting only)
 	const bool resample = st.rate != G.rate;
@@ -114,7 +125,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	rec.n_src = n_src;
 	if (feed == kFeedBuffer) {
 		// AE.cpp:389-426
-		uint64_t cur = A.read_i[slot];
+		uint64_t cur = read_i0;
 		const uint64_t len = st.len;
 		rec.start = (uint32_t)(cur < len ? cur : len);
 		if (cur + n_src <= len) {
@@ -133,7 +144,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		alg_samples = rec.avail;
 	} else if (feed == kFeedRing) {
 		// AE.cpp:459-474: pop what is there, zero-pad the rest.  read_i counts samples popped so far.
-		const uint64_t rd = A.read_i[slot];
+		const uint64_t rd = read_i0;
 		const uint64_t wr = A.ring_write[slot];
 		const uint64_t have = wr - rd < (uint64_t)n_src ? wr - rd : (uint64_t)n_src;
 		rec.start = (uint32_t)(rd % st.len);
@@ -176,7 +187,6 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	}
 
 	// ---------------- EOF bookkeeping (AE.cpp:496-517) ----------------
-	long long eof = A.eof[slot];
 	eof -= (long long)n_src;
 	A.eof[slot] = eof;
 	if (remove_source || (!looping && eof <= 0)) {
@@ -188,10 +198,8 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	}
 
 	// ---------------- attenuation + GainNode (distance_attenuation.cc:82-119, gain_node.cc:38-80) ----------------
-	const F4 pv = A.posvol[slot];
 	const float src_pos[3] = {pv.x, pv.y, pv.z};
 	const float input_gain = fmul(G.master, pv.w);
-	uint8_t bits = A.bits[slot];
 	const bool hrtf = kind == kKindHrtf;
 	if (kind != kKindStereo) {
 		// GainMixer::Reset sweep (gain_mixer.cc:80-96): it runs once between two non-empty buffers of that mixer and
@@ -202,7 +210,6 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 			else bits &= (uint8_t)~kBitMixExists;
 		}
 	}
-	float dg = A.dgain[slot];
 	float target;
 	if (kind == kKindStereo) target = input_gain;                                        // AttenuationType::kInput
 	else target = fmul(input_gain, log_distance_attenuation(G.head_pos, src_pos));        // kDirect
@@ -234,12 +241,10 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	}
 
 	// ---------------- OcclusionNode (occlusion_node.cc:53-99) ----------------
-	const float occ_t = A.occl[slot];
-	float occ = A.occ_cur[slot];
 	occ = fadd(occ_t, fmul(kOcclusionSmoothing, fsub(occ, occ_t)));
 	A.occ_cur[slot] = occ;
 	rec.lpf_coef = occlusion_coefficient(occ);
-	rec.lpf_prev = A.lpf_prev[slot];
+	rec.lpf_prev = lpf_prev0;
 	if (!(rec.lpf_coef < kEpsilonFloat)) rflags |= kRecLpf;
 
 	// ---------------- direction + mixer gains ----------------

@@ -503,7 +503,8 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 // Ambisonic-bus kernel: T math threads (frames / 4) work on one source at a time + the producer warp.
 // =====================================================================================================================
 constexpr int K = kShK;
-template <int TMAX>     // TMAX = 128 (frames <= 512) or 256 (frames <= 1024): sets the register budget
+template <int TMAX, bool EXACT>     // TMAX = 128 (frames <= 512) or 256 (frames <= 1024): sets the register budget;
+                                    // EXACT: frames == 4 * T, no per-frame bounds checks
 __global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : 1)
 k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
@@ -594,7 +595,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 						const uint32_t i = t + (uint32_t)k * T;
 						const uint32_t wi0 = warp_i0 + (uint32_t)k * T;
 						float v = 0.0f;
-						if (i < F) {
+						if (EXACT || i < F) {
 							const unsigned long long p = d.x0 + (unsigned long long)i * d.step;
 							const uint32_t di = (uint32_t)(p >> 32);
 							const float fr = frac_of(p);
@@ -616,35 +617,51 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 #pragma unroll
 					for (int k = 0; k < K; ++k) {
 						const uint32_t i = t + (uint32_t)k * T;
-						x[k] = i < F ? wb[i] : 0.0f;
+						x[k] = (EXACT || i < F) ? wb[i] : 0.0f;
 					}
 				}
 			}
 			// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
-			const float* gk = sm.shgs[qr * kBatch + b].konst;
-			const ShRamps& rp = sm.shrs[qw * kBatch + b];
+			float2 g2[NCH / 2];      // the 16 constant channel gains, as FFMA2 operand pairs
+			{
+				const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
+#pragma unroll
+				for (int q = 0; q < NCH / 4; ++q) { const float4 v = gk4[q]; g2[2 * q] = make_float2(v.x, v.y); g2[2 * q + 1] = make_float2(v.z, v.w); }
+			}
 			const float gd = d.gd;
 			const uint32_t nramp = d.nramp;     // frames in which the direct gain or a channel gain still ramps
-			const uint32_t mask = r.ch_ramp_mask;
+			if (nramp == 0) {
+				// no ramp anywhere in this buffer (the common case)
 #pragma unroll
-			for (int k = 0; k < K; ++k) {
-				const uint32_t i = t + (uint32_t)k * T;
-				if (warp_i0 + (uint32_t)k * T < nramp) {
-					// warp-uniform: only the warps whose frames lie inside a ramp evaluate ramps
-					const float yv = lpf_done ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
-					if (!lpf_done && i == F - 1) a.lpf_prev[d.slot] = yv;
-#pragma unroll
-					for (int c = 0; c < NCH; c += 2) {
-						float g0 = gk[c], g1 = gk[c + 1];
-						if ((mask >> c) & 1u) { if (i < rp.n[c]) g0 = fmaf((float)i, rp.inc[c], rp.start[c]); }
-						if ((mask >> (c + 1)) & 1u) { if (i < rp.n[c + 1]) g1 = fmaf((float)i, rp.inc[c + 1], rp.start[c + 1]); }
-						ffma2(acc[c / 2][k], make_float2(g0, g1), make_float2(yv, yv));
-					}
-				} else {
+				for (int k = 0; k < K; ++k) {
 					const float yv = lpf_done ? x[k] : x[k] * gd;
-					if (!lpf_done && i == F - 1) a.lpf_prev[d.slot] = yv;
+					if (k == K - 1 || !EXACT) { if (!lpf_done && t + (uint32_t)k * T == F - 1) a.lpf_prev[d.slot] = yv; }
 #pragma unroll
-					for (int c = 0; c < NCH; c += 2) ffma2(acc[c / 2][k], *reinterpret_cast<const float2*>(gk + c), make_float2(yv, yv));
+					for (int c = 0; c < NCH / 2; ++c) ffma2(acc[c][k], g2[c], make_float2(yv, yv));
+				}
+			} else {
+				const ShRamps& rp = sm.shrs[qw * kBatch + b];
+				const uint32_t mask = r.ch_ramp_mask;
+#pragma unroll
+				for (int k = 0; k < K; ++k) {
+					const uint32_t i = t + (uint32_t)k * T;
+					if (warp_i0 + (uint32_t)k * T < nramp) {
+						// warp-uniform: only the warps whose frames lie inside a ramp evaluate ramps
+						const float yv = lpf_done ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
+						if (!lpf_done && i == F - 1) a.lpf_prev[d.slot] = yv;
+#pragma unroll
+						for (int c = 0; c < NCH / 2; ++c) {
+							float2 g = g2[c];
+							if ((mask >> (2 * c)) & 1u) { if (i < rp.n[2 * c]) g.x = fmaf((float)i, rp.inc[2 * c], rp.start[2 * c]); }
+							if ((mask >> (2 * c + 1)) & 1u) { if (i < rp.n[2 * c + 1]) g.y = fmaf((float)i, rp.inc[2 * c + 1], rp.start[2 * c + 1]); }
+							ffma2(acc[c][k], g, make_float2(yv, yv));
+						}
+					} else {
+						const float yv = lpf_done ? x[k] : x[k] * gd;
+						if (!lpf_done && i == F - 1) a.lpf_prev[d.slot] = yv;
+#pragma unroll
+						for (int c = 0; c < NCH / 2; ++c) ffma2(acc[c][k], g2[c], make_float2(yv, yv));
+					}
 				}
 			}
 		}
@@ -779,10 +796,15 @@ int launch_mix(const MixArgs& a, void* stream) {
 	}
 	if (a.n_sh) {
 		static KernelConfig conf_sh;
-		static KernelConfig conf_sh_big;
+		static KernelConfig conf_sh_big, conf_sh_x, conf_sh_big_x;
 		const uint32_t tm = sh_threads(F);
-		const int rc = tm <= 128 ? launch_one(k2_mix_ambisonic_kernel<128>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, (uint32_t)num_mix_ctas(F, 1), part_sh, st, &g_sh)
-		                         : launch_one(k2_mix_ambisonic_kernel<256>, &conf_sh_big, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, (uint32_t)num_mix_ctas(F, 1), part_sh, st, &g_sh);
+		const uint32_t mg = (uint32_t)num_mix_ctas(F, 1);
+		const bool exact = F == tm * kShK;
+		int rc;
+		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<128, true>, &conf_sh_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
+		                         : launch_one(k2_mix_ambisonic_kernel<128, false>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
+		else rc = exact ? launch_one(k2_mix_ambisonic_kernel<256, true>, &conf_sh_big_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
+		                : launch_one(k2_mix_ambisonic_kernel<256, false>, &conf_sh_big, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);

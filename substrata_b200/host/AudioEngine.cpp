@@ -1,0 +1,417 @@
+// AudioEngine.cpp -- host side of the glare::AudioEngine mirror (see AudioEngine.h).  Follows audio/AudioEngine.cpp of
+// the reference tree function by function; "AE.cpp:n" cites its lines.  No sample arithmetic happens here: the only
+// per-sample host work is the device-callback clamp (AE.cpp:215-216), which the reference also does on the host.
+#include "AudioEngine.h"
+
+#include <chrono>
+#include <limits>
+
+static const int INVALID_RESONANCE_HANDLE = std::numeric_limits<int>::max();   // AE.cpp:62
+
+namespace glare {
+
+// ------------------------------------------------------------------------------------------------------------------
+// AudioSource (AE.cpp:68-163)
+// ------------------------------------------------------------------------------------------------------------------
+AudioSource::AudioSource()
+    : resonance_handle(INVALID_RESONANCE_HANDLE), sampling_rate(44100), EOF_marker_position(std::numeric_limits<int64>::max()), cur_read_i(0),
+      type(SourceType_NonStreaming), spatial_type(SourceSpatialType_Spatial), paused(false), looping(true), remove_on_finish(false), volume(1.f),
+      mute_volume_factor(1.f), mute_change_start_time(-2), mute_change_end_time(-1), mute_vol_fac_start(1.f), mute_vol_fac_end(1.f),
+      doppler_factor(1), pos(0, 0, 0, 1), num_occlusions(0), userdata_1(0), smoothed_cur_level(0), feed_prev_dest_dst_coords(-1),
+      feed_prev_samples_0_src_coords(-2) {}
+
+AudioSource::~AudioSource() {}
+
+void AudioSource::startMuting(double cur_time, double transition_period) {
+	if (mute_vol_fac_end != 0) {   // If we have not already started muting, and are not already muted
+		mute_change_start_time = cur_time;
+		mute_change_end_time = cur_time + transition_period * mute_volume_factor;
+		mute_vol_fac_start = mute_volume_factor;
+		mute_vol_fac_end = 0;
+	}
+}
+
+void AudioSource::startUnmuting(double cur_time, double transition_period) {
+	if (mute_vol_fac_end != 1) {
+		mute_change_start_time = cur_time;
+		mute_change_end_time = cur_time + transition_period * (1.f - mute_volume_factor);
+		mute_vol_fac_start = mute_volume_factor;
+		mute_vol_fac_end = 1;
+	}
+}
+
+void AudioSource::updateCurrentMuteVolumeFactor(double cur_time) {
+	if ((cur_time < mute_change_end_time) && ((mute_change_end_time - mute_change_start_time) > 1.0e-4)) {
+		const double frac = (cur_time - mute_change_start_time) / (mute_change_end_time - mute_change_start_time);
+		mute_volume_factor = mute_vol_fac_start + (float)frac * (mute_vol_fac_end - mute_vol_fac_start);
+	} else {
+		mute_volume_factor = mute_vol_fac_end;
+	}
+}
+
+void AudioSource::setMuteVolumeFactorImmediately(float factor) {
+	mute_change_end_time = -1;
+	mute_volume_factor = factor;
+}
+
+void AudioSource::updateDopplerEffectFactor(const Vec4f& source_linear_vel, const Vec4f& listener_linear_vel, const Vec4f& listener_pos) {
+	const Vec4f source_to_listener = listener_pos - pos;
+	const Vec4f projected_source_vel = projectOntoDir(source_linear_vel, source_to_listener);
+	const Vec4f projected_listener_vel = projectOntoDir(listener_linear_vel, source_to_listener);
+	const float v_s = projected_source_vel.length() * Maths::sign(dot(projected_source_vel, source_to_listener));
+	const float v_l = projected_listener_vel.length() * Maths::sign(dot(projected_listener_vel, source_to_listener));
+	const float c = 343.f;   // Speed of sound in air.
+	this->doppler_factor = (c - v_l) / (c - v_s);
+}
+
+bool AudioSource::isPlaying() { return !paused && (looping || (EOF_marker_position > 0)); }
+
+float SoundFile::maxVal() const {
+	float m = -std::numeric_limits<float>::infinity();
+	for (float x : buf->buffer) m = myMax(m, x);
+	return m;
+}
+float SoundFile::minVal() const {
+	float m = std::numeric_limits<float>::infinity();
+	for (float x : buf->buffer) m = myMin(m, x);
+	return m;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// AudioEngine
+// ------------------------------------------------------------------------------------------------------------------
+AudioEngine::AudioEngine() : engine(nullptr), initialised(false), die(false), frames_mixed(0), sample_rate(48000) { callback_data.engine = this; }
+
+AudioEngine::~AudioEngine() { shutdown(); }
+
+// AE.cpp:576-735 without the OS device: create the mixer (CreateResonanceAudioApi, :676), start the mixing thread (:711-718).
+void AudioEngine::init() {
+	if (initialised) return;
+	sample_rate = (uint32)options.sample_rate;
+	sbm_config cfg;
+	cfg.frames_per_buffer = options.frames_per_buffer;
+	cfg.sample_rate_hz = options.sample_rate;
+	cfg.device = options.cuda_device;
+	cfg.max_sources = options.max_sources;
+	cfg.max_mix_sources = options.max_mix_sources;
+	cfg.sh_hrir = options.binaural && !options.sh_hrir.empty() ? options.sh_hrir.data() : nullptr;
+	cfg.sh_hrir_taps = options.sh_hrir_taps;
+	if (options.binaural && !cfg.sh_hrir) throw glare::Exception("AudioEngine::init: binaural rendering needs the SH-HRIR taps (Options::sh_hrir)");
+	const int rc = sbm_create(&cfg, &engine);
+	if (rc != SBM_OK) {
+		engine = nullptr;
+		throw glare::Exception("Failed to initialise the B200 audio mixer (sbm_create returned " + std::to_string(rc) + "); there is no CPU fallback");
+	}
+	sbm_enable_room_effects(engine, 0);   // AE.cpp:742 / GUIClient.cpp:6896: room effects off outside parcels
+	frames_mixed = 0;
+	die = false;
+	initialised = true;
+	if (options.start_mix_thread) mix_thread = std::thread(&AudioEngine::mixThreadMain, this);
+}
+
+void AudioEngine::shutdown() {
+	if (mix_thread.joinable()) { die = true; mix_thread.join(); }   // thread_manager.killThreadsBlocking(), AE.cpp:816
+	{
+		Lock lock(mutex);
+		active_audio_sources.clear();
+		audio_sources.clear();
+		source_of_handle.clear();
+	}
+	if (engine) { sbm_destroy(engine); engine = nullptr; }          // delete resonance, AE.cpp:837
+	device_buffers.clear();
+	device_buffer_refs.clear();
+	initialised = false;
+}
+
+// Uploads an AudioBuffer once; sources sharing it (sound_files cache, AE.h:122,253) share the device copy.
+int AudioEngine::deviceBufferFor(const AudioBufferRef& buf) {
+	auto it = device_buffers.find(buf.ptr());
+	if (it != device_buffers.end()) return it->second;
+	int id = -1;
+	const int rc = sbm_buffer_create(engine, buf->buffer.data(), buf->buffer.size(), &id);
+	if (rc != SBM_OK) throw glare::Exception(std::string("sbm_buffer_create failed: ") + sbm_last_error(engine));
+	device_buffers[buf.ptr()] = id;
+	device_buffer_refs.push_back(buf);
+	return id;
+}
+
+// AE.cpp:848-876
+void AudioEngine::createResonanceObAndResamplerForSource(AudioSource& source_) {
+	if (!initialised) return;
+	AudioSource* source = &source_;
+	int id = -1;
+	if (source->spatial_type == AudioSource::SourceSpatialType_Spatial) {
+		if (sbm_source_create(engine, options.binaural ? SBM_SOURCE_BINAURAL_HQ : SBM_SOURCE_STEREO_PANNING, 1, &id) != SBM_OK)
+			throw glare::Exception(std::string("sbm_source_create failed: ") + sbm_last_error(engine));
+		source->resonance_handle = id;
+		if (source->pos.isFinite()) {   // Avoid NaN or Inf position coords.
+			const float xyz[3] = {source->pos[0], source->pos[1], source->pos[2]};
+			sbm_set_source_positions(engine, 1, &id, xyz);
+			const float v = source->volume * source->getMuteVolumeFactor();
+			sbm_set_source_volumes(engine, 1, &id, &v);
+		}
+	} else {
+		if (sbm_source_create(engine, SBM_SOURCE_NONSPATIAL, 1, &id) != SBM_OK)
+			throw glare::Exception(std::string("sbm_source_create failed: ") + sbm_last_error(engine));
+		source->resonance_handle = id;
+		const float v = source->volume * source->getMuteVolumeFactor();
+		sbm_set_source_volumes(engine, 1, &id, &v);
+	}
+	// Feeder attachment: what ResonanceThread reads from the AudioSource every buffer (AE.cpp:389-474); resampler.init (:875).
+	int rc = SBM_OK;
+	if (source->type == AudioSource::SourceType_NonStreaming) {
+		if (source->shared_buffer.isNull()) throw glare::Exception("AudioSource of type NonStreaming has no shared_buffer");
+		const int buf = deviceBufferFor(source->shared_buffer);
+		const uint64_t cur = source->cur_read_i;
+		const uint8_t looping = source->looping, rem = source->remove_on_finish;
+		rc = sbm_source_attach_buffer(engine, 1, &id, &buf, &cur, &source->sampling_rate, &looping, &rem);
+	} else if (!source->mix_sources.empty()) {
+		std::vector<int> bufs; std::vector<double> pos, delta; std::vector<float> mixf;
+		for (MixSource& m : source->mix_sources) {
+			bufs.push_back(deviceBufferFor(m.soundfile->buf));
+			pos.push_back(m.sound_file_i); delta.push_back(m.source_delta); mixf.push_back(m.mix_factor);
+		}
+		rc = sbm_source_attach_mix(engine, id, source->sampling_rate, (int)bufs.size(), bufs.data(), pos.data(), delta.data(), mixf.data());
+	} else {
+		rc = sbm_source_attach_ring(engine, id, source->sampling_rate, 4 * 48000);
+		source->feed_prev_dest_dst_coords = -1; source->feed_prev_samples_0_src_coords = -2;
+	}
+	if (rc != SBM_OK) {
+		const std::string msg = sbm_last_error(engine);
+		sbm_source_destroy(engine, 1, &id);
+		source->resonance_handle = INVALID_RESONANCE_HANDLE;
+		throw glare::Exception("attaching audio data to the source failed: " + msg);
+	}
+	if (source->EOF_marker_position != std::numeric_limits<int64>::max()) sbm_source_set_eof_marker(engine, id, source->EOF_marker_position);
+	if (source->num_occlusions != 0) sbm_set_source_occlusions(engine, 1, &id, &source->num_occlusions);
+}
+
+// AE.cpp:879-897
+void AudioEngine::addSource(AudioSourceRef source) {
+	if (!initialised) return;
+	if (source->sampling_rate < 8000 || source->sampling_rate > 48000)
+		throw glare::Exception("Unsupported sampling rate for audio source: " + std::to_string(source->sampling_rate));
+	Lock lock(mutex);   // the mixing thread must not run between creating the source and registering it
+	if (!source->paused) createResonanceObAndResamplerForSource(*source);
+	audio_sources.insert(source);
+	if (!source->paused) {
+		active_audio_sources.insert(source);
+		source_of_handle[source->resonance_handle] = source;
+	}
+}
+
+// AE.cpp:900-943 (the MP3 streamer maps are out of scope)
+void AudioEngine::removeSource(AudioSourceRef source) {
+	if (!initialised) return;
+	Lock lock(mutex);
+	if (source->resonance_handle != INVALID_RESONANCE_HANDLE) {
+		sbm_source_destroy(engine, 1, &source->resonance_handle);
+		source_of_handle.erase(source->resonance_handle);
+		source->resonance_handle = INVALID_RESONANCE_HANDLE;
+	}
+	audio_sources.erase(source);
+	active_audio_sources.erase(source);
+}
+
+// AE.cpp:946-956
+void AudioEngine::sourcePositionUpdated(AudioSource& source) {
+	if (!initialised) return;
+	if (!source.pos.isFinite()) return;
+	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) {
+		const float xyz[3] = {source.pos[0], source.pos[1], source.pos[2]};
+		sbm_set_source_positions(engine, 1, &source.resonance_handle, xyz);
+	}
+}
+
+// AE.cpp:959-966
+void AudioEngine::sourceVolumeUpdated(AudioSource& source) {
+	if (!initialised) return;
+	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) {
+		const float v = source.volume * source.getMuteVolumeFactor();
+		sbm_set_source_volumes(engine, 1, &source.resonance_handle, &v);
+	}
+}
+
+// AE.cpp:969-975
+void AudioEngine::sourceNumOcclusionsUpdated(AudioSource& source) {
+	if (!initialised) return;
+	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) sbm_set_source_occlusions(engine, 1, &source.resonance_handle, &source.num_occlusions);
+}
+
+// AE.cpp:978-990
+void AudioEngine::setHeadTransform(const Vec4f& head_pos, const Quatf& head_rot) {
+	if (!initialised) return;
+	if (head_pos.isFinite() && head_rot.v.isFinite()) {
+		const float p[3] = {head_pos[0], head_pos[1], head_pos[2]};
+		const float q[4] = {head_rot.v[0], head_rot.v[1], head_rot.v[2], head_rot.v[3]};
+		sbm_set_head(engine, p, q);
+	}
+}
+
+void AudioEngine::setMasterVolume(float volume) {   // AE.cpp:806-811
+	if (!initialised) return;
+	sbm_set_master_volume(engine, volume);
+}
+
+void AudioEngine::setRoomEffectsEnabled(bool enabled) {   // AE.cpp:738-743
+	if (!initialised) return;
+	if (enabled) throw glare::Exception("room effects are not on the accelerated path yet (SURVEY.md 8f)");
+	sbm_enable_room_effects(engine, 0);
+}
+
+void AudioEngine::setCurentRoomDimensions(const js::AABBox& /*room_aabb*/) {}   // AE.cpp:746-768: only meaningful with room effects on
+
+void AudioEngine::insertSoundFile(const std::string& sound_file_path, SoundFileRef sound) { sound_files.insert(std::make_pair(sound_file_path, sound)); }   // AE.cpp:999-1002
+
+SoundFileRef AudioEngine::getOrLoadSoundFile(const std::string& sound_file_path) {   // AE.cpp:1005-1019, cache part
+	auto res = sound_files.find(sound_file_path);
+	if (res == sound_files.end()) throw glare::Exception("sound file not in the cache and file decoding is out of scope here: " + sound_file_path);
+	return res->second;
+}
+
+// AE.cpp:1022-1052
+void AudioEngine::playOneShotSound(const std::string& sound_file_path, const Vec4f& pos) {
+	if (!initialised) return;
+	if (!pos.isFinite()) return;
+	try {
+		SoundFileRef sound = getOrLoadSoundFile(sound_file_path);
+		AudioSourceRef source = new AudioSource();
+		source->type = AudioSource::SourceType_NonStreaming;
+		source->sampling_rate = (int)sound->sample_rate;
+		source->shared_buffer = sound->buf;
+		source->paused = false;
+		source->looping = false;
+		source->remove_on_finish = true;
+		source->pos = pos;
+		addSource(source);
+	} catch (glare::Exception&) {
+		// the reference prints a warning and carries on
+	}
+}
+
+// AE.cpp:1143-1159: (re)start a paused or finished source from the beginning.
+void AudioEngine::seekToStartAndUnpauseAudio(AudioSource& source) {
+	if (!initialised) return;
+	Lock lock(mutex);
+	AudioSourceRef ref(&source);
+	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) {
+		sbm_source_destroy(engine, 1, &source.resonance_handle);
+		source_of_handle.erase(source.resonance_handle);
+		source.resonance_handle = INVALID_RESONANCE_HANDLE;
+	}
+	source.cur_read_i = 0;
+	source.paused = false;
+	for (MixSource& m : source.mix_sources) m.sound_file_i = 0;
+	createResonanceObAndResamplerForSource(source);
+	active_audio_sources.insert(ref);
+	source_of_handle[source.resonance_handle] = ref;
+}
+
+// Moves exactly the samples the next buffer will consume from the source's host CircularBuffer to its device ring
+// (what `source->buffer.popFrontNItems(...)` does in AE.cpp:459-474), so that buffer.size() keeps the meaning the
+// StreamerThread relies on (StreamerThread.cpp:53).  numSrcSamplesNeeded is a pure function of two integer counters.
+void AudioEngine::feedStreamingSource(AudioSource& source) {
+	const int64 F = options.frames_per_buffer;
+	size_t n_src = (size_t)F;
+	if (source.sampling_rate != (int)sample_rate) {
+		const int64 max_dest = source.feed_prev_dest_dst_coords + F;
+		const double max_dest_src = (double)max_dest * (double)source.sampling_rate / (double)sample_rate;
+		n_src = (size_t)ceil(max_dest_src) - (size_t)(source.feed_prev_samples_0_src_coords + 1);   // AudioResampler.cpp:77-86
+		source.feed_prev_dest_dst_coords += F;
+		source.feed_prev_samples_0_src_coords += (int64)n_src;
+	}
+	const size_t have = myMin(n_src, source.buffer.size());
+	if (have) {
+		temp_buf.resize(have);
+		source.buffer.popFrontNItems(temp_buf.data(), have);
+		sbm_source_ring_push(engine, source.resonance_handle, temp_buf.data(), have);
+	}
+}
+
+// The body of ResonanceThread::doRun's inner loop (AE.cpp:367-545).
+bool AudioEngine::mixOneBuffer() {
+	if (!initialised) return false;
+	const size_t F = (size_t)options.frames_per_buffer;
+	std::vector<float> out(2 * F);
+	int valid = 0;
+	{
+		Lock lock(mutex);
+		for (auto it = active_audio_sources.begin(); it != active_audio_sources.end(); ++it) {
+			AudioSource& source = **it;
+			if (source.resonance_handle == INVALID_RESONANCE_HANDLE) continue;
+			if (source.type == AudioSource::SourceType_Streaming) {
+				if (source.mix_sources.empty()) feedStreamingSource(source);
+				else {
+					// the game thread edits source_delta / mix_factor in place under `mutex` (BikePhysics.cpp:712-740)
+					for (size_t z = 0; z < source.mix_sources.size(); ++z) {
+						const int zi = (int)z;
+						sbm_source_set_mix_params(engine, 1, &source.resonance_handle, &zi, &source.mix_sources[z].source_delta, &source.mix_sources[z].mix_factor);
+					}
+				}
+			}
+		}
+		const int rc = sbm_mix(engine, out.data(), &valid);
+		if (rc != SBM_OK) throw glare::Exception(std::string("sbm_mix failed: ") + sbm_last_error(engine));
+		// Sources the feeder stopped (AE.cpp:496-517): already destroyed on the device; mirror the registry bookkeeping.
+		int ids[256], n = 0;
+		do {
+			sbm_poll_finished(engine, ids, 256, &n);
+			for (int i = 0; i < n; ++i) {
+				auto f = source_of_handle.find(ids[i]);
+				if (f == source_of_handle.end()) continue;
+				AudioSourceRef s = f->second;
+				s->resonance_handle = INVALID_RESONANCE_HANDLE;
+				active_audio_sources.erase(s);
+				if (s->remove_on_finish) audio_sources.erase(s);
+				source_of_handle.erase(f);
+			}
+		} while (n == 256);
+	}
+	frames_mixed += (int64)F;
+	if (!valid) return false;                                           // AE.cpp:535-536
+	if (frames_mixed <= (int64)options.initial_mute_frames) return true;   // AE.cpp:532-533: the first second is discarded
+	{
+		Lock lock(callback_data.buffer_mutex);
+		callback_data.buffer.pushBackNItems(out.data(), 2 * F);         // AE.cpp:540-545
+	}
+	return true;
+}
+
+// ResonanceThread::doRun (AE.cpp:345-555): keep 4 buffers queued ahead of the device.
+void AudioEngine::mixThreadMain() {
+	const size_t F = (size_t)options.frames_per_buffer;
+	try {
+		while (!die) {
+			for (;;) {
+				size_t queued;
+				{ Lock lock(callback_data.buffer_mutex); queued = callback_data.buffer.size(); }
+				if (die || queued >= 4 * 2 * F) break;                  // AE.cpp:363
+				if (!mixOneBuffer()) break;
+			}
+			std::this_thread::sleep_for(std::chrono::milliseconds(1));     // AE.cpp:548
+		}
+	} catch (glare::Exception&) {
+		// AE.cpp:551-554: the thread exits on an exception
+	}
+}
+
+// miniAudioCallBack (AE.cpp:191-226)
+void AudioEngine::fillOutputBuffer(float* output_buffer_f, size_t frame_count) {
+	const size_t num_samples_needed = frame_count * 2;   // We always use stereo output so each frame is 2 samples.
+	Lock lock(callback_data.buffer_mutex);
+	const size_t num_samples_to_dequeue = myMin(num_samples_needed, callback_data.buffer.size());
+	callback_data.buffer.popFrontNItems(output_buffer_f, num_samples_to_dequeue);
+	for (size_t z = 0; z < num_samples_to_dequeue; ++z) output_buffer_f[z] = myClamp(output_buffer_f[z], -1.f, 1.f);
+	for (size_t i = num_samples_to_dequeue; i < num_samples_needed; ++i) output_buffer_f[i] = 0.f;   // Pad with zeroes
+}
+
+void AudioEngine::syncSourceState(AudioSource& source) {
+	if (!initialised || source.resonance_handle == INVALID_RESONANCE_HANDLE) return;
+	sbm_source_state st;
+	if (sbm_source_query(engine, source.resonance_handle, &st) != SBM_OK) return;
+	source.cur_read_i = (size_t)st.cur_read_i;
+	source.EOF_marker_position = st.eof_marker;
+	if (!source.mix_sources.empty()) source.mix_sources[0].sound_file_i = st.mix_pos0;
+}
+
+}  // namespace glare

@@ -1,0 +1,195 @@
+// AudioEngine.h -- host-side mirror of glare::AudioEngine / glare::AudioSource (audio/AudioEngine.h:39-261 in the
+// reference tree): same class and member names, same argument meaning, same error behaviour (init failure and bad
+// sampling rates throw glare::Exception; everything else is a silent no-op until initialised).  What changed is
+// behind it: where the reference's ResonanceThread gathers every source's window on the CPU and hands it to Resonance
+// Audio (AudioEngine.cpp:367-537), this class keeps the sources' PCM resident on the GPU and calls sbm_mix() once per
+// buffer (include/sbm_audio.h); `resonance_handle` holds the sbm source id.
+//
+// Not carried over (out of the hot path): the OS audio device (miniaudio / RtAudio) -- the device
+// callback body is exposed as fillOutputBuffer() for whoever owns the device --, the MP3 streamer
+// (addSourceFromStreamingSoundFile) and the audio file readers (getOrLoadSoundFile only consults the cache).
+#pragma once
+#ifndef SBM_USE_GLARE_CORE
+#include "glare_core_min.h"
+#endif
+#include <map>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sbm_audio.h"
+#include "AudioResampler.h"
+
+namespace glare {
+
+class AudioEngine;
+
+struct AudioBuffer : public ThreadSafeRefCounted {
+	js::Vector<float, 16> buffer;
+};
+typedef Reference<AudioBuffer> AudioBufferRef;
+typedef VRef<AudioBuffer> AudioBufferVRef;
+
+struct SoundFile : public ThreadSafeRefCounted {
+	SoundFile() : buf(new AudioBuffer()), num_channels(1), sample_rate(48000) {}
+	float maxVal() const;
+	float minVal() const;
+	AudioBufferVRef buf;
+	uint32 num_channels;
+	uint32 sample_rate;  // in hz
+};
+typedef Reference<SoundFile> SoundFileRef;
+
+struct MixSource {
+	MixSource() : sound_file_i(0), source_delta(1), mix_factor(1) {}
+	Reference<SoundFile> soundfile;
+	double sound_file_i;  // Current (floating-point) index into soundfile buffer.  Advanced on the GPU; refreshed by AudioEngine::syncSourceState().
+	double source_delta;  // Every sample, we advance this much in the soundfile buffer.
+	float mix_factor;     // Volume mixing factor.
+};
+
+class AudioSource : public ThreadSafeRefCounted {
+public:
+	GLARE_ALIGNED_16_NEW_DELETE
+
+	enum SourceType {
+		SourceType_NonStreaming,  // Audio is played from an audio buffer fully present in RAM (shared_buffer).
+		SourceType_Streaming      // Audio data is streamed into the circular buffer, or mixed from mix_sources.
+	};
+	enum SourceSpatialType { SourceSpatialType_Spatial, SourceSpatialType_NonSpatial };
+
+	AudioSource();
+	~AudioSource();
+
+	void startMuting(double cur_time, double transition_period);
+	void startUnmuting(double cur_time, double transition_period);
+	void updateCurrentMuteVolumeFactor(double cur_time);
+	void setMuteVolumeFactorImmediately(float factor);
+	inline float getMuteVolumeFactor() const { return mute_volume_factor; }
+	void updateDopplerEffectFactor(const Vec4f& source_linear_vel, const Vec4f& listener_linear_vel, const Vec4f& listener_pos);
+	bool isPlaying();
+
+	int resonance_handle;  // Set in AudioEngine::addSource(): the sbm source id (INT_MAX = none).
+	int sampling_rate;
+	CircularBuffer<float> buffer;  // Read from front, enqueue to back.  Used for type SourceType_Streaming only.
+	int64 EOF_marker_position;     // Number of samples still to play in buffer before EOF is reached.
+	AudioBufferRef shared_buffer;  // Used for SourceType_NonStreaming type only.
+	size_t cur_read_i;             // Read index in shared_buffer at addSource(); refreshed by AudioEngine::syncSourceState().
+	std::vector<MixSource> mix_sources;
+	SourceType type;
+	SourceSpatialType spatial_type;
+	bool paused;
+	bool looping;
+	bool remove_on_finish;
+	float volume;
+
+private:
+	float mute_volume_factor;
+	double mute_change_start_time;
+	double mute_change_end_time;
+	float mute_vol_fac_start;
+	float mute_vol_fac_end;
+
+public:
+	float doppler_factor;
+	Vec4f pos;
+	float num_occlusions;
+	uint32 userdata_1;
+	std::string debugname;
+	float smoothed_cur_level;
+
+private:
+	friend class AudioEngine;
+	// Host mirror of the AudioResampler counters of a ring-fed source (AudioResampler.h:37-39): how many source samples
+	// the next buffer consumes is a pure function of these, so the feeder can move exactly that many to the device ring.
+	int64 feed_prev_dest_dst_coords, feed_prev_samples_0_src_coords;
+};
+typedef Reference<AudioSource> AudioSourceRef;
+
+struct AudioCallbackData {
+	Mutex buffer_mutex;             // protects buffer
+	CircularBuffer<float> buffer GUARDED_BY(buffer_mutex);
+	AudioEngine* engine;
+};
+
+class AudioEngine {
+public:
+	AudioEngine();
+	~AudioEngine();
+
+	// Extra knobs the reference hard-codes (AudioEngine.cpp:580-586,857) or gets from the device.  Set before init().
+	struct Options {
+		Options() : frames_per_buffer(256), sample_rate(48000), cuda_device(0), max_sources(65536), max_mix_sources(4096),
+		            binaural(true), start_mix_thread(true), initial_mute_frames(48000) {}
+		int frames_per_buffer;   // device period (256; 1024 on Emscripten)
+		int sample_rate;
+		int cuda_device;
+		int max_sources, max_mix_sources;
+		bool binaural;           // true: kBinauralHighQuality for spatial sources as the reference; false: kStereoPanning
+		bool start_mix_thread;   // false: the owner calls mixOneBuffer() itself (tests, offline rendering)
+		int initial_mute_frames; // the reference discards the first second of output (AudioEngine.cpp:532-533)
+		std::vector<float> sh_hrir;  // planar [16][taps] SH-HRIRs (CreateShHrirsFromAssets); required when binaural
+		int sh_hrir_taps = 0;
+	};
+	Options options;
+
+	void init();       // throws glare::Exception when no B200 / the library cannot be initialised (no CPU fallback)
+	void shutdown();
+	bool isInitialised() const { return initialised; }
+
+	void addSource(AudioSourceRef source);
+	void removeSource(AudioSourceRef source);
+
+	void sourcePositionUpdated(AudioSource& source);
+	void sourceVolumeUpdated(AudioSource& source);
+	void sourceNumOcclusionsUpdated(AudioSource& source);
+	void setHeadTransform(const Vec4f& head_pos, const Quatf& head_rot);
+	void playOneShotSound(const std::string& sound_file_path, const Vec4f& pos);
+	void setRoomEffectsEnabled(bool enabled);                      // only `false` is on the accelerated path
+	void setCurentRoomDimensions(const js::AABBox& room_aabb);     // accepted and ignored while room effects are off
+	uint32 getSampleRate() const { return sample_rate; }
+	void seekToStartAndUnpauseAudio(AudioSource& source);
+	void setMasterVolume(float volume);
+	void insertSoundFile(const std::string& sound_file_path, SoundFileRef sound);
+	SoundFileRef getOrLoadSoundFile(const std::string& sound_file_path);   // cache only: file decoding is out of scope
+
+	// ---- what the reference does in ResonanceThread::doRun / miniAudioCallBack, exposed for the owner of the device ----
+	// One pass of the mixing loop body (AudioEngine.cpp:367-545): feed streamed sources, mix one buffer on the GPU,
+	// apply feeder bookkeeping (finished sources), push 2 * frames samples to the callback ring.  Returns false when
+	// nothing reached the mixer (nothing pushed), like FillInterleavedOutputBuffer.
+	bool mixOneBuffer();
+	// miniAudioCallBack (AudioEngine.cpp:191-226): pop, clamp to [-1, 1], zero-pad.
+	void fillOutputBuffer(float* output_buffer, size_t frame_count);
+	// Refreshes cur_read_i / EOF_marker_position / mix_sources[].sound_file_i of `source` from the device.
+	void syncSourceState(AudioSource& source);
+	sbm_engine* nativeEngine() { return engine; }
+
+private:
+	void createResonanceObAndResamplerForSource(AudioSource& source);
+	int deviceBufferFor(const AudioBufferRef& buf);
+	void feedStreamingSource(AudioSource& source);
+	void mixThreadMain();
+
+	sbm_engine* engine;
+	AudioCallbackData callback_data;
+	bool initialised;
+	std::thread mix_thread;
+	std::atomic<bool> die;
+	int64 frames_mixed;
+	std::map<const AudioBuffer*, int> device_buffers;   // AudioBuffer -> sbm buffer id (the buffer is kept alive below)
+	std::vector<AudioBufferRef> device_buffer_refs;
+	std::map<int, AudioSourceRef> source_of_handle;
+	std::vector<float> temp_buf;
+
+public:
+	Mutex mutex;  // Guards access to audio_sources
+	std::set<AudioSourceRef> active_audio_sources GUARDED_BY(mutex);
+	std::set<AudioSourceRef> audio_sources GUARDED_BY(mutex);
+	std::map<std::string, SoundFileRef> sound_files;
+
+private:
+	uint32 sample_rate;
+};
+
+}  // namespace glare
