@@ -195,13 +195,6 @@ def run_reference_arm(args, wl, rank, world):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
-class DevPtr:
-    """__cuda_array_interface__ view of device memory owned by the engine (for torch.as_tensor)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
 def build_engine(wl, device, seed):
     import torch
     import substrata_b200 as sb
@@ -258,9 +251,9 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng, pcm, ids, p = build_engine(wl, local_rank, 12345 + rank)
     F, n = wl["frames"], wl["n"]
-    stream = torch.cuda.ExternalStream(eng.stream(), device=local_rank)
-    bus_ptr, bus_n = eng.bus_device()
-    bus_t = torch.as_tensor(DevPtr(bus_ptr, bus_n), device="cuda:%d" % local_rank)
+    from substrata_b200.sharding import ShardedMixer
+    mixer = ShardedMixer(eng, device="cuda:%d" % local_rank)
+    stream = mixer.stream
     out_host = np.zeros(2 * F, np.float32)
     eng.set_profiling(True)
     rng = np.random.default_rng(99 + rank)
@@ -274,13 +267,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
     def step_resident(s):
         hp, hq = listener_pose(s, F)
         eng.set_head(hp, hq)
-        if world > 1:
-            eng.mix_begin()
-            with torch.cuda.stream(stream):
-                dist.all_reduce(bus_t)
-            eng.mix_finish(out_host)
-        else:
-            eng.mix(out_host)
+        mixer.mix(out_host)        # sbm_mix_begin -> (N > 1: NCCL all-reduce of the bus on the engine stream) -> sbm_mix_finish
 
     movers = min(MOVERS_PER_STEP, n)
     mv_ids = [np.ascontiguousarray(ids[(k * movers) % max(1, n - movers + 1):][:movers]) for k in range(8)]
@@ -290,13 +277,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
         hp, hq = listener_pose(s, F)
         eng.set_source_positions(mv_ids[s % 8], mv_pos[s % 8])
         eng.set_head(hp, hq)
-        if world > 1:
-            eng.mix_begin()
-            with torch.cuda.stream(stream):
-                dist.all_reduce(bus_t)
-            eng.mix_finish(out_host)
-        else:
-            eng.mix(out_host)
+        mixer.mix(out_host)
 
     def timed(step_fn, s0):
         for s in range(args.warmup):
