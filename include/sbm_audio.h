@@ -71,7 +71,10 @@ SBM_API const char* sbm_last_error(const sbm_engine* e);
 /* Uploads n mono f32 samples once; many sources may reference the returned buffer id. */
 SBM_API int sbm_buffer_create(sbm_engine* e, const float* samples, size_t n, int* out_buffer);
 /* Adopts PCM already resident in device memory (not owned, must outlive the engine): `count` buffers of `n`
- * samples each, buffer k starting at device_base + k*stride_samples.  Ids out_first_buffer .. +count-1. */
+ * samples each, buffer k starting at device_base + k*stride_samples.  Ids out_first_buffer .. +count-1.
+ * For the fast (TMA) fetch path every buffer must start 16-byte aligned and have >= 3 readable floats after its last
+ * sample (i.e. stride_samples >= n rounded up to 4, stride_samples % 4 == 0); other layouts are rendered identically
+ * through the generic fetch path. */
 SBM_API int sbm_buffer_adopt_device(sbm_engine* e, const float* device_base, size_t n, size_t stride_samples, int count, int* out_first_buffer);
 
 /* ---- sources ---- */
