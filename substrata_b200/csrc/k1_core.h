@@ -174,7 +174,8 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 				const uint32_t need = (uint32_t)span + 3u;              // +1: the interpolation partner, +1: fixed-point slack
 				if (need > mz.len) { fast = false; continue; }
 				rec.pcm = mz.pcm; rec.len = mz.len;
-				rec.start = (uint32_t)(base % mz.len);
+				// 32-bit remainder whenever the read head is below 2^32 samples (a day of audio): 64-bit division is ~5x the cost
+				rec.start = base <= 0xffffffffull ? (uint32_t)base % mz.len : (uint32_t)(base % mz.len);
 				rec.n_src = need; rec.avail = need;
 				rec.x0_fx = to_fx(p1 - (double)base);
 				rec.step_fx = to_fx(mz.delta);

@@ -10,7 +10,10 @@
 
 namespace sbm {
 
-__global__ void __launch_bounds__(256) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table,
+#ifndef SBM_K1_MINB
+#define SBM_K1_MINB 4
+#endif
+__global__ void __launch_bounds__(256, SBM_K1_MINB) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table,
                                                        const uint32_t* __restrict__ lists) {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;    // position in the render lists
 	uint32_t used = 0, n_src = 0;

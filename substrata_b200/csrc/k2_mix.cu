@@ -512,7 +512,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 	const SmemView<16> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
 	// blockDim.x = T math threads + one producer warp (the last warp)
-	const uint32_t F = a.frames, T = blockDim.x - 32, t = threadIdx.x, lane = t & 31u;
+	const uint32_t F = a.frames, T = EXACT ? (uint32_t)TMAX : blockDim.x - 32, t = threadIdx.x, lane = t & 31u;   // EXACT: T is a compile-time constant
 	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
 	// run of expensive sources (long ramps, occlusion, generic fetches) is spread over the whole grid.
 	const uint32_t s0 = first, s1 = first + n;
@@ -549,6 +549,39 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 					resampler_tail(r, &p0, &p1);
 					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
 				}
+				continue;
+			}
+			if (EXACT && (mode & ~kMdInterp) == 0) {
+				// ---------------- fast path: native-rate or single-mix-source window, no ramp, no filter ----------------
+				// (the overwhelmingly common case; kept free of everything the general code below has to consider)
+				const float* wb = sm.wring + d.w_idx;
+				float xs[K];
+				if (mode & kMdInterp) {
+#pragma unroll
+					for (int k = 0; k < K; ++k) {
+						const unsigned long long p = d.x0 + (unsigned long long)(t + (uint32_t)k * T) * d.step;
+						const uint32_t di = (uint32_t)(p >> 32);
+						const float v0 = wb[di], v1 = wb[di + 1];
+						xs[k] = fmaf(frac_of(p), v1 - v0, v0);
+					}
+				} else {
+#pragma unroll
+					for (int k = 0; k < K; ++k) xs[k] = wb[t + (uint32_t)k * T];
+				}
+				const float gdf = d.gd;
+				const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
+#pragma unroll
+				for (int k = 0; k < K; ++k) xs[k] *= gdf;
+#pragma unroll
+				for (int q = 0; q < NCH / 4; ++q) {
+					const float4 g = gk4[q];
+#pragma unroll
+					for (int k = 0; k < K; ++k) {
+						ffma2(acc[2 * q][k], make_float2(g.x, g.y), make_float2(xs[k], xs[k]));
+						ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(xs[k], xs[k]));
+					}
+				}
+				if (t == T - 1) a.lpf_prev[d.slot] = xs[K - 1];     // frame F - 1 = t + (K - 1) T: the bypassed filter's memory
 				continue;
 			}
 			float x[K];          // engine-rate input samples of this thread's frames (before any gain)
@@ -679,21 +712,29 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 		}
 }
 
-// K3: bus[row][f] = sum over CTAs (ascending) of the partial buses; rows 0-15 from the ambisonic kernel's partials,
-// rows 16-17 from the stereo kernel's.  Also publishes this rank's "mixer used" flags as floats behind the audio so
-// that they sum across ranks with it.
+// K3: bus[row][f] = sum over CTAs of the partial buses; rows 0-15 from the ambisonic kernel's partials, rows 16-17 from
+// the stereo kernel's.  One CTA per (row, 32 frames): warp w sums the partials of CTAs w, w+8, w+16, ... and the eight
+// warp sums are added in warp order -- a fixed tree, so the result is bit-stable from run to run (no atomics on audio).
+// Also publishes this rank's "mixer used" flags as floats behind the audio so that they sum across ranks with it.
 __global__ void __launch_bounds__(256) k3_reduce_kernel(const float* __restrict__ part_pan, uint32_t g_pan, const float* __restrict__ part_sh,
                                                        uint32_t g_sh, float* __restrict__ bus, const DevFlags* __restrict__ flags,
                                                        uint32_t parity, uint32_t F) {
-	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx < kBusRows * F) {
-		const uint32_t row = idx / F, f = idx - row * F;
-		float s = 0.0f;
-		if (row < 16) for (uint32_t b = 0; b < g_sh; ++b) s += part_sh[((size_t)b * 16 + row) * F + f];
-		else for (uint32_t b = 0; b < g_pan; ++b) s += part_pan[((size_t)b * 2 + (row - 16)) * F + f];
-		bus[idx] = s;
+	__shared__ float warp_sum[8][32];
+	const uint32_t row = blockIdx.y, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	const uint32_t f = blockIdx.x * 32 + lane;
+	const float* part = row < 16 ? part_sh : part_pan;
+	const uint32_t g = row < 16 ? g_sh : g_pan, rows = row < 16 ? 16u : 2u, r = row < 16 ? row : row - 16;
+	float s = 0.0f;
+	if (f < F) for (uint32_t b = w; b < g; b += 8) s += part[((size_t)b * rows + r) * F + f];
+	warp_sum[w][lane] = s;
+	__syncthreads();
+	if (w == 0 && f < F) {
+		float t = warp_sum[0][lane];
+#pragma unroll
+		for (int q = 1; q < 8; ++q) t += warp_sum[q][lane];
+		bus[(size_t)row * F + f] = t;
 	}
-	if (idx == 0) {
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
 		float* bf = bus + (size_t)kBusRows * F;
 		bf[0] = flags->sh_used[parity] ? 1.0f : 0.0f;
 		bf[1] = flags->pan_used[parity] ? 1.0f : 0.0f;
@@ -799,7 +840,7 @@ int launch_mix(const MixArgs& a, void* stream) {
 		static KernelConfig conf_sh_big, conf_sh_x, conf_sh_big_x;
 		const uint32_t tm = sh_threads(F);
 		const uint32_t mg = (uint32_t)num_mix_ctas(F, 1);
-		const bool exact = F == tm * kShK;
+		const bool exact = (tm == 128 || tm == 256) && F == tm * kShK;     // the EXACT instantiations fix T = TMAX at compile time
 		int rc;
 		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<128, true>, &conf_sh_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
 		                         : launch_one(k2_mix_ambisonic_kernel<128, false>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
@@ -808,7 +849,7 @@ int launch_mix(const MixArgs& a, void* stream) {
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
-	k3_reduce_kernel<<<(kBusRows * F + 255) / 256, 256, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F);
+	k3_reduce_kernel<<<dim3((F + 31) / 32, kBusRows), 256, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F);
 	note_launch();
 	return check_launch("k3_reduce");
 }

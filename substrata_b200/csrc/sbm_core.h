@@ -375,11 +375,14 @@ SBM_HD float log_distance_attenuation(const float* listener, const float* source
 	if (distance > kMaxDistance) return 0.0f;
 	const float min_allowed = kNearFieldThreshold;      // max(min_distance = 0, kNearFieldThreshold)
 	if (distance > min_allowed) {
-		const float interval = fsub(kMaxDistance, min_allowed);
+		// interval = 500 - 1, att_max = 1 / (1 + interval), 1 - att_max: constants of the reference's expression, folded
+		// at compile time with IEEE float arithmetic (identical values)
+		constexpr float interval = kMaxDistance - kNearFieldThreshold;
+		constexpr float att_max = 1.0f / (1.0f + interval);
+		constexpr float one_minus_att_max = 1.0f - att_max;
 		const float relative = fsub(distance, min_allowed);
 		const float att = fdiv(1.0f, fadd(relative, 1.0f));
-		const float att_max = fdiv(1.0f, fadd(1.0f, interval));
-		return fdiv(fsub(att, att_max), fsub(1.0f, att_max));
+		return fdiv(fsub(att, att_max), one_minus_att_max);
 	}
 	return 1.0f;
 }
@@ -426,7 +429,10 @@ SBM_HD RampDesc plan_gain(float* cur, bool initialised, float target, uint32_t F
 	if (ramp > 0) {
 		d.inc = fdiv(fsub(target, c), (float)ramp);
 		d.n = ramp < F ? ramp : F;
-		c = ramp_advance(c, d.inc, d.n);
+		// the value after d.n running additions, bit for bit: literally for short ramps (the usual few frames while the
+		// listener moves), through the closed form for long ones
+		if (d.n <= 48u) { for (uint32_t j = 0; j < d.n; ++j) c = fadd(c, d.inc); }
+		else c = ramp_advance(c, d.inc, d.n);
 	} else {
 		c = target;
 	}
