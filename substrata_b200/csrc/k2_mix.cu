@@ -50,6 +50,7 @@ constexpr int kStages = SBM_STAGES;   // window stages in flight
 constexpr int kRecStages = kStages + 2;
 constexpr int kPanThreads = 128;
 constexpr int kShK = 4;               // frames per thread in the 16-channel kernel
+constexpr int kRampTile = 128;        // ambisonic kernel: frames at the start of the buffer whose gain-ramp corrections go through shared memory
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + TMA bulk copy (global -> shared), sm_90+ / sm_100a.
@@ -244,7 +245,7 @@ __device__ float lpf_warp(float* buf, uint32_t F, float coef, float prev, uint32
 // Shared-memory carve-up (both kernels): header | WorkRec ring | ShGains ring, ShRamps ring (ambisonic only) | MathDesc ring | window ring.
 template <int NCH>
 struct SmemView {
-	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; ShRamps* shrs; MathDesc* descs; float* wring;
+	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; ShRamps* shrs; float* rtile; MathDesc* descs; float* wring;
 	__device__ explicit SmemView(unsigned char* raw) {
 		hdr = reinterpret_cast<MixSmemHdr*>(raw);
 		recs = reinterpret_cast<WorkRec*>(raw + 256);
@@ -253,6 +254,8 @@ struct SmemView {
 		if (NCH == 16) p += sizeof(ShGains) * kRecStages * kBatch;
 		shrs = reinterpret_cast<ShRamps*>(p);       // channel ramps of the sources that have any, staged with the windows
 		if (NCH == 16) p += sizeof(ShRamps) * kStages * kBatch;
+		rtile = reinterpret_cast<float*>(p);        // [16][kRampTile] ramp corrections of the first frames (ambisonic kernel)
+		if (NCH == 16) p += sizeof(float) * 16 * kRampTile;
 		descs = reinterpret_cast<MathDesc*>(p);
 		p += sizeof(MathDesc) * kStages * kBatch;
 		wring = reinterpret_cast<float*>(p);
@@ -499,13 +502,53 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 	}
 }
 
+// Ambisonic fast path, second half: the frames inside a gain ramp (direct gain and / or channel gains; at most kRampTile
+// frames from the start of the buffer) were accumulated with the constant gains like every other frame; this adds
+// (ramping gain x ramping signal - constant gain x constant signal) for them into the CTA's shared-memory correction
+// tile.  The work is split over all math warps by channel: tile element (c, i) is owned by exactly one thread.
+template <int TMAX>
+__device__ __forceinline__ void sh_ramp_fixup(float* rtile, const MathDesc& d, const WorkRec& r, const ShRamps& rp, const float* gk, const float* wb, uint32_t t) {
+	constexpr int CPW = kNumSh / (TMAX / 32);     // channels per warp
+	const uint32_t nr = d.nramp, mask = r.ch_ramp_mask, lane = t & 31u, c0 = (t >> 5) * CPW;
+	const float mfx = (r.flags & kRecMix1) ? r.mix_factor : 1.0f;
+	const float gdf = d.gd;
+	for (uint32_t i = lane; i < nr; i += 32) {
+		float xi;
+		if (d.mode & kMdInterp) {
+			const unsigned long long p = d.x0 + (unsigned long long)i * d.step;
+			const uint32_t di = (uint32_t)(p >> 32);
+			const float v0 = wb[di], v1 = wb[di + 1];
+			xi = fmaf(frac_of(p), v1 - v0, v0);
+		} else xi = wb[i];
+		const float yc = xi * gdf;                               // what the constant-gain pass used
+		const float yr = (xi * mfx) * gain_at(r.direct, i);      // the signal with the ramping direct gain
+		// all shared-memory loads of this frame first, then the arithmetic, then the stores: the tile update is a
+		// read-modify-write the compiler will not reorder other shared loads across
+		float kc[CPW], cur[CPW], st[CPW], inc[CPW];
+		uint32_t nc[CPW];
+#pragma unroll
+		for (int q = 0; q < CPW; ++q) {
+			const uint32_t c = c0 + q;
+			kc[q] = gk[c]; cur[q] = rtile[c * kRampTile + i];
+			nc[q] = ((mask >> c) & 1u) ? rp.n[c] : 0u; st[q] = rp.start[c]; inc[q] = rp.inc[c];
+		}
+#pragma unroll
+		for (int q = 0; q < CPW; ++q) {
+			const float g = i < nc[q] ? fmaf((float)i, inc[q], st[q]) : kc[q];
+			cur[q] += g * yr - kc[q] * yc;
+		}
+#pragma unroll
+		for (int q = 0; q < CPW; ++q) rtile[(c0 + q) * kRampTile + i] = cur[q];     // (c, i) is owned by exactly one thread of the CTA
+	}
+}
+
 // =====================================================================================================================
 // Ambisonic-bus kernel: T math threads (frames / 4) work on one source at a time + the producer warp.
 // =====================================================================================================================
 constexpr int K = kShK;
 template <int TMAX, bool EXACT>     // TMAX = 128 (frames <= 512) or 256 (frames <= 1024): sets the register budget;
                                     // EXACT: frames == 4 * T, no per-frame bounds checks
-__global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : 1)
+__global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : 2)
 k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -524,6 +567,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 	const uint32_t nbatch = blockIdx.x < total_batches ? (total_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 #endif
 	if (t == 0) init_barriers(hdr, T / 32);
+	for (uint32_t q = t; q < 16u * kRampTile; q += blockDim.x) sm.rtile[q] = 0.0f;
 	__syncthreads();
 	if (t >= T) { producer_warp<16>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
@@ -539,7 +583,63 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 		mbar_wait(&hdr->full_w[qw], (jb / kStages) & 1u);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
-		for (uint32_t b = 0; b < nb; ++b) {
+		// ---------------- whole-batch fast path: when all kBatch sources of the stage qualify for the fast form, fetch all
+		// their samples first and run one long independent FFMA2 block, so that the shared-memory latencies of the four
+		// sources overlap instead of adding up ----------------
+		bool batch_done = false;
+		if (EXACT && nb == (uint32_t)kBatch) {
+			bool all_fast = true;
+#pragma unroll
+			for (int b = 0; b < kBatch; ++b) {
+				const MathDesc& d = sm.descs[qw * kBatch + b];
+				all_fast = all_fast && (d.mode & ~(kMdInterp | kMdRamp | kMdShRamp)) == 0 && d.nramp <= (uint32_t)kRampTile;
+			}
+			if (all_fast) {
+				float xs[kBatch][K];
+#pragma unroll
+				for (int b = 0; b < kBatch; ++b) {
+					const MathDesc& d = sm.descs[qw * kBatch + b];
+					const float* wb = sm.wring + d.w_idx;
+					if (d.mode & kMdInterp) {
+#pragma unroll
+						for (int k = 0; k < K; ++k) {
+							const unsigned long long p = d.x0 + (unsigned long long)(t + (uint32_t)k * T) * d.step;
+							const uint32_t di = (uint32_t)(p >> 32);
+							const float v0 = wb[di], v1 = wb[di + 1];
+							xs[b][k] = fmaf(frac_of(p), v1 - v0, v0);
+						}
+					} else {
+#pragma unroll
+						for (int k = 0; k < K; ++k) xs[b][k] = wb[t + (uint32_t)k * T];
+					}
+				}
+#pragma unroll
+				for (int b = 0; b < kBatch; ++b) {
+					const MathDesc& d = sm.descs[qw * kBatch + b];
+					const float gdf = d.gd;
+					const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
+#pragma unroll
+					for (int k = 0; k < K; ++k) xs[b][k] *= gdf;
+#pragma unroll
+					for (int q = 0; q < NCH / 4; ++q) {
+						const float4 g = gk4[q];
+#pragma unroll
+						for (int k = 0; k < K; ++k) {
+							ffma2(acc[2 * q][k], make_float2(g.x, g.y), make_float2(xs[b][k], xs[b][k]));
+							ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(xs[b][k], xs[b][k]));
+						}
+					}
+					if (t == T - 1) a.lpf_prev[d.slot] = xs[b][K - 1];
+				}
+#pragma unroll
+				for (int b = 0; b < kBatch; ++b) {
+					const MathDesc& d = sm.descs[qw * kBatch + b];
+					if (d.nramp) sh_ramp_fixup<TMAX>(sm.rtile, d, sm.recs[qr * kBatch + b], sm.shrs[qw * kBatch + b], sm.shgs[qr * kBatch + b].konst, sm.wring + d.w_idx, t);
+				}
+				batch_done = true;
+			}
+		}
+		for (uint32_t b = 0; b < nb && !batch_done; ++b) {
 			const MathDesc& d = sm.descs[qw * kBatch + b];
 			const WorkRec& r = sm.recs[qr * kBatch + b];
 			const uint32_t mode = d.mode;
@@ -551,9 +651,10 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 				}
 				continue;
 			}
-			if (EXACT && (mode & ~kMdInterp) == 0) {
-				// ---------------- fast path: native-rate or single-mix-source window, no ramp, no filter ----------------
-				// (the overwhelmingly common case; kept free of everything the general code below has to consider)
+			if (EXACT && (mode & ~(kMdInterp | kMdRamp | kMdShRamp)) == 0 && d.nramp <= (uint32_t)kRampTile) {
+				// ---------------- fast path: native-rate or single-mix-source window, no filter; gain ramps (if any) end within
+				// the first kRampTile frames.  Every frame is accumulated with the constant gains; the frames inside a ramp
+				// are then corrected through a small shared-memory tile, the work split over all math warps by channel. ----------------
 				const float* wb = sm.wring + d.w_idx;
 				float xs[K];
 				if (mode & kMdInterp) {
@@ -582,6 +683,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 					}
 				}
 				if (t == T - 1) a.lpf_prev[d.slot] = xs[K - 1];     // frame F - 1 = t + (K - 1) T: the bypassed filter's memory
+				if (d.nramp) sh_ramp_fixup<TMAX>(sm.rtile, d, r, sm.shrs[qw * kBatch + b], sm.shgs[qr * kBatch + b].konst, wb, t);
 				continue;
 			}
 			float x[K];          // engine-rate input samples of this thread's frames (before any gain)
@@ -702,13 +804,18 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 		__syncwarp();
 		if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }
 	}
+	math_sync(T);     // the ramp-correction tile is complete
 	float* out = partials + (size_t)blockIdx.x * NCH * F;
 #pragma unroll
 	for (int c = 0; c < NCH / 2; ++c)
 #pragma unroll
 		for (int k = 0; k < K; ++k) {
 			const uint32_t i = t + (uint32_t)k * T;
-			if (i < F) { out[(size_t)(2 * c) * F + i] = acc[c][k].x; out[(size_t)(2 * c + 1) * F + i] = acc[c][k].y; }
+			if (i < F) {
+				float v0 = acc[c][k].x, v1 = acc[c][k].y;
+				if (k == 0 && i < (uint32_t)kRampTile) { v0 += sm.rtile[(2 * c) * kRampTile + i]; v1 += sm.rtile[(2 * c + 1) * kRampTile + i]; }
+				out[(size_t)(2 * c) * F + i] = v0; out[(size_t)(2 * c + 1) * F + i] = v1;
+			}
 		}
 }
 
@@ -759,7 +866,7 @@ uint32_t sh_threads(uint32_t F) { return ((F + kShK - 1) / kShK + 31) / 32 * 32;
 // to +25 %) plus alignment slack; larger windows take the generic path.
 uint32_t window_slot(uint32_t F) { return (F + F / 4 + 24u + 3u) & ~3u; }
 size_t mix_smem_bytes(uint32_t F, bool sh) {
-	return 256 + sizeof(WorkRec) * kRecStages * kBatch + (sh ? sizeof(ShGains) * kRecStages * kBatch + sizeof(ShRamps) * kStages * kBatch : 0) +
+	return 256 + sizeof(WorkRec) * kRecStages * kBatch + (sh ? sizeof(ShGains) * kRecStages * kBatch + sizeof(ShRamps) * kStages * kBatch + sizeof(float) * 16 * kRampTile : 0) +
 	       sizeof(MathDesc) * kStages * kBatch +
 	       sizeof(float) * (size_t)kStages * kBatch * window_slot(F);
 }
