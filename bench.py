@@ -363,12 +363,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4_1m_doppler_pan", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--sources", type=int, default=0, help="override the workload's sources per GPU (profiling under ncu only; the line says so)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.sources:
+        wl["n"] = args.sources
+        wl["desc"] += " [--sources override: %d sources/GPU, NOT the named configuration]" % args.sources
     if args.impl == "reference":
         run_reference_arm(args, wl, rank, world)
         return

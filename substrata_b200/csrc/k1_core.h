@@ -280,6 +280,10 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 			}
 		}
 		A.shg[out] = sg;
+		// K2 reads n[] of all 16 channels of a source that has any channel ramp: the non-ramping ones must say 0
+		if (rec.ch_ramp_mask)
+			for (int c = 0; c < kNumSh; ++c)
+				if (!((rec.ch_ramp_mask >> c) & 1u)) A.shr[out].n[c] = 0;
 		rflags |= kRecHrtf;
 	}
 	rec.flags = rflags;

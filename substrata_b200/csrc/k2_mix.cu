@@ -45,12 +45,16 @@ namespace {
 #ifndef SBM_MIN_CTAS
 #define SBM_MIN_CTAS 4
 #endif
+#ifndef SBM_PRODUCER_SLEEP_NS
+#define SBM_PRODUCER_SLEEP_NS 200
+#endif
+#ifndef SBM_SH_BIG_CTAS
+#define SBM_SH_BIG_CTAS 1             // resident CTAs per SM the 1024-frame ambisonic kernel's register budget is set for (2 -> 96 registers and spills)
+#endif
 constexpr int kBatch = 4;             // sources per pipeline stage
 constexpr int kStages = SBM_STAGES;   // window stages in flight
 constexpr int kRecStages = kStages + 2;
 constexpr int kPanThreads = 128;
-constexpr int kShK = 4;               // frames per thread in the 16-channel kernel
-constexpr int kRampTile = 128;        // ambisonic kernel: frames at the start of the buffer whose gain-ramp corrections go through shared memory
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + TMA bulk copy (global -> shared), sm_90+ / sm_100a.
@@ -80,6 +84,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 	uint32_t spins = 0;
 	while (!mbar_try_wait(bar, parity)) {
 		if (++spins > (1u << 24)) __trap();    // a lost completion must fail loudly, not hang the device
+	}
+}
+// Producer-side wait: the producer runs several batches ahead of the math warps, so it spends most of its life waiting
+// for a stage to be handed back.  Sleeping between polls keeps it out of the issue slots of the math warps that share
+// its scheduler (a hot spin cost ~70 issue slots per source on that scheduler).
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, uint32_t parity) {
+	uint32_t spins = 0;
+	while (!mbar_try_wait(bar, parity)) {
+		__nanosleep(SBM_PRODUCER_SLEEP_NS);
+		if (++spins > (1u << 22)) __trap();
 	}
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
@@ -144,17 +158,19 @@ static_assert(sizeof(MixSmemHdr) <= 256, "header must fit its 256-byte slot");
 
 // What the math threads need to know about a source, condensed from its WorkRec by the producer (64 B).
 struct __attribute__((aligned(16))) MathDesc {
+	// first 16 bytes: everything the fused fast paths need, one LDS.128
 	uint32_t mode;              // kMd*
 	uint32_t w_idx;             // float index into the window ring of element 0 of the array the read head indexes:
 	                            // window sample 0, or two before it for the resampler's {prev0, prev1, window...}
-	uint32_t n1b;               // index (same coordinates) from which `wadj` applies (loop wrap), 0xffffffff = never
-	uint32_t wadj;
-	unsigned long long x0, step;   // 32.32 read head
-	float g0, g1;               // stereo kernel: direct gain * mix factor * bus gain (constant parts)
 	float gd;                   // direct gain * mix factor (constant part)
 	uint32_t nramp;             // frames from the start of the buffer in which some gain of this source still ramps
+	unsigned long long x0, step;   // 32.32 read head
+	float g0, g1;               // stereo kernel: direct gain * mix factor * bus gain (constant parts)
+	uint32_t n1b;               // index (same coordinates as w_idx) from which `wadj` applies (loop wrap), 0xffffffff = never
+	uint32_t wadj;
 	uint32_t slot;
-	uint32_t pad[3];
+	float mfx;                  // MixSource::mix_factor where the lean paths must apply it to the samples themselves (ramping direct gain), else 1
+	uint32_t pad[2];
 };
 static_assert(sizeof(MathDesc) == 64, "MathDesc is 64 bytes");
 constexpr uint32_t kMdSkip = 1, kMdGeneric = 2, kMdInterp = 4, kMdAdjust = 8, kMdResample = 16, kMdLpf = 32, kMdStereo = 64,
@@ -179,7 +195,8 @@ __device__ __forceinline__ MathDesc make_desc(const WorkRec& r, const WinPlan& p
 	d.n1b = p.n1 == 0xffffffffu ? 0xffffffffu : p.n1 + (rs ? 2u : 0u);
 	d.wadj = p.wadj;
 	d.x0 = r.x0_fx; d.step = r.step_fx;
-	const float mf = (p.fast && (f & kRecMix1)) ? r.mix_factor : 1.0f;
+	// mix_factor: folded into the constant gains on the lean path; the careful paths (staged_sample / source_sample) apply it to the samples
+	const float mf = (p.fast && (f & kRecMix1) && !p.wadj && !(f & kRecLpf)) ? r.mix_factor : 1.0f;
 	d.gd = mf * r.direct.konst;
 	d.g0 = d.gd * r.ch[0].konst; d.g1 = d.gd * r.ch[1].konst;
 	uint32_t nr = r.direct.n;
@@ -193,7 +210,8 @@ __device__ __forceinline__ MathDesc make_desc(const WorkRec& r, const WinPlan& p
 	d.nramp = nr;
 	if (nr) d.mode |= kMdRamp;
 	d.slot = r.slot;
-	d.pad[0] = d.pad[1] = d.pad[2] = 0;
+	d.mfx = (f & kRecMix1) ? r.mix_factor : 1.0f;
+	d.pad[0] = d.pad[1] = 0;
 	return d;
 }
 
@@ -245,7 +263,7 @@ __device__ float lpf_warp(float* buf, uint32_t F, float coef, float prev, uint32
 // Shared-memory carve-up (both kernels): header | WorkRec ring | ShGains ring, ShRamps ring (ambisonic only) | MathDesc ring | window ring.
 template <int NCH>
 struct SmemView {
-	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; ShRamps* shrs; float* rtile; MathDesc* descs; float* wring;
+	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; ShRamps* shrs; MathDesc* descs; float* wring;
 	__device__ explicit SmemView(unsigned char* raw) {
 		hdr = reinterpret_cast<MixSmemHdr*>(raw);
 		recs = reinterpret_cast<WorkRec*>(raw + 256);
@@ -254,8 +272,6 @@ struct SmemView {
 		if (NCH == 16) p += sizeof(ShGains) * kRecStages * kBatch;
 		shrs = reinterpret_cast<ShRamps*>(p);       // channel ramps of the sources that have any, staged with the windows
 		if (NCH == 16) p += sizeof(ShRamps) * kStages * kBatch;
-		rtile = reinterpret_cast<float*>(p);        // [16][kRampTile] ramp corrections of the first frames (ambisonic kernel)
-		if (NCH == 16) p += sizeof(float) * 16 * kRampTile;
 		descs = reinterpret_cast<MathDesc*>(p);
 		p += sizeof(MathDesc) * kStages * kBatch;
 		wring = reinterpret_cast<float*>(p);
@@ -272,7 +288,7 @@ __device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_
 	auto issue_recs = [&](uint32_t jb) {
 		if (jb >= nbatch) return;
 		const uint32_t q = jb % kRecStages;
-		if (jb >= (uint32_t)kRecStages) mbar_wait(&hdr->empty_r[q], ((jb / kRecStages) - 1u) & 1u);
+		if (jb >= (uint32_t)kRecStages) mbar_wait_relaxed(&hdr->empty_r[q], ((jb / kRecStages) - 1u) & 1u);
 		if (lane == 0) {
 			const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 			const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
@@ -287,7 +303,7 @@ __device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_
 	for (uint32_t jb = 0; jb < nbatch; ++jb) {
 		issue_recs(jb + (uint32_t)(kRecStages - kStages));
 		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
-		if (jb >= (uint32_t)kStages) mbar_wait(&hdr->empty_w[qw], ((jb / kStages) - 1u) & 1u);
+		if (jb >= (uint32_t)kStages) mbar_wait_relaxed(&hdr->empty_w[qw], ((jb / kStages) - 1u) & 1u);
 		mbar_wait(&hdr->full_r[qr], (jb / kRecStages) & 1u);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
@@ -502,53 +518,21 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 	}
 }
 
-// Ambisonic fast path, second half: the frames inside a gain ramp (direct gain and / or channel gains; at most kRampTile
-// frames from the start of the buffer) were accumulated with the constant gains like every other frame; this adds
-// (ramping gain x ramping signal - constant gain x constant signal) for them into the CTA's shared-memory correction
-// tile.  The work is split over all math warps by channel: tile element (c, i) is owned by exactly one thread.
-template <int TMAX>
-__device__ __forceinline__ void sh_ramp_fixup(float* rtile, const MathDesc& d, const WorkRec& r, const ShRamps& rp, const float* gk, const float* wb, uint32_t t) {
-	constexpr int CPW = kNumSh / (TMAX / 32);     // channels per warp
-	const uint32_t nr = d.nramp, mask = r.ch_ramp_mask, lane = t & 31u, c0 = (t >> 5) * CPW;
-	const float mfx = (r.flags & kRecMix1) ? r.mix_factor : 1.0f;
-	const float gdf = d.gd;
-	for (uint32_t i = lane; i < nr; i += 32) {
-		float xi;
-		if (d.mode & kMdInterp) {
-			const unsigned long long p = d.x0 + (unsigned long long)i * d.step;
-			const uint32_t di = (uint32_t)(p >> 32);
-			const float v0 = wb[di], v1 = wb[di + 1];
-			xi = fmaf(frac_of(p), v1 - v0, v0);
-		} else xi = wb[i];
-		const float yc = xi * gdf;                               // what the constant-gain pass used
-		const float yr = (xi * mfx) * gain_at(r.direct, i);      // the signal with the ramping direct gain
-		// all shared-memory loads of this frame first, then the arithmetic, then the stores: the tile update is a
-		// read-modify-write the compiler will not reorder other shared loads across
-		float kc[CPW], cur[CPW], st[CPW], inc[CPW];
-		uint32_t nc[CPW];
-#pragma unroll
-		for (int q = 0; q < CPW; ++q) {
-			const uint32_t c = c0 + q;
-			kc[q] = gk[c]; cur[q] = rtile[c * kRampTile + i];
-			nc[q] = ((mask >> c) & 1u) ? rp.n[c] : 0u; st[q] = rp.start[c]; inc[q] = rp.inc[c];
-		}
-#pragma unroll
-		for (int q = 0; q < CPW; ++q) {
-			const float g = i < nc[q] ? fmaf((float)i, inc[q], st[q]) : kc[q];
-			cur[q] += g * yr - kc[q] * yc;
-		}
-#pragma unroll
-		for (int q = 0; q < CPW; ++q) rtile[(c0 + q) * kRampTile + i] = cur[q];     // (c, i) is owned by exactly one thread of the CTA
-	}
-}
-
 // =====================================================================================================================
-// Ambisonic-bus kernel: T math threads (frames / 4) work on one source at a time + the producer warp.
+// Ambisonic-bus kernel: T math threads (frames / 4) work on one batch of sources at a time + the producer warp.
+//   Thread t owns frames t, t + T, t + 2T, t + 3T and all 16 bus channels of them: 64 accumulators as 32 channel PAIRS,
+//   one FFMA2 (gain pair x broadcast sample) per pair and frame; the gains come out of shared memory as LDS.128 = two
+//   ready-made pairs.  A batch whose four sources are all "simple" (native-rate or single read head, no filter, ramps
+//   inside the first T frames) runs as ONE straight-line block -- descriptor and sample loads of all four sources
+//   first, then the arithmetic -- because the per-source dependent chain (load descriptor -> branch -> load samples
+//   -> FMA) is what bounds this kernel, not the issue rate.  The frames inside a gain ramp are the first few of the
+//   buffer = iteration k = 0 of the first warps: those warps evaluate the 16 ramping gains in registers, the others
+//   never see the ramp.
 // =====================================================================================================================
-constexpr int K = kShK;
+constexpr int K = 4;
 template <int TMAX, bool EXACT>     // TMAX = 128 (frames <= 512) or 256 (frames <= 1024): sets the register budget;
-                                    // EXACT: frames == 4 * T, no per-frame bounds checks
-__global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : 2)
+                                    // EXACT: frames == 4 * TMAX, no per-frame bounds checks
+__global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : SBM_SH_BIG_CTAS)
 k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -567,40 +551,66 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 	const uint32_t nbatch = blockIdx.x < total_batches ? (total_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 #endif
 	if (t == 0) init_barriers(hdr, T / 32);
-	for (uint32_t q = t; q < 16u * kRampTile; q += blockDim.x) sm.rtile[q] = 0.0f;
 	__syncthreads();
 	if (t >= T) { producer_warp<16>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
-	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1): one FFMA2 per pair and frame
+	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1) x frames t + k T
 #pragma unroll
 	for (int c = 0; c < NCH / 2; ++c)
 #pragma unroll
 		for (int k = 0; k < K; ++k) acc[c][k] = make_float2(0.0f, 0.0f);
 	const uint32_t warp_i0 = t & ~31u;     // first frame of this warp in iteration k = 0
+	const float ft = (float)t;
+
+	// acc[.][k] += gains (x) yv for one frame, constant gains: 8 FFMA2, gains straight from shared memory
+	auto accumulate_const = [&](const float* gk, float yv, int k) {
+		const float4* gk4 = reinterpret_cast<const float4*>(gk);
+#pragma unroll
+		for (int q = 0; q < NCH / 4; ++q) {
+			const float4 g = gk4[q];
+			ffma2(acc[2 * q][k], make_float2(g.x, g.y), make_float2(yv, yv));
+			ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(yv, yv));
+		}
+	};
+	// same for a frame inside a ramp: channel c ramps while i < n[c] (GainProcessor in accumulate mode, gain.cc:25-92)
+	auto accumulate_ramped = [&](const float* gk, const ShRamps* rp, float yv, uint32_t i, float fi, int k) {
+		const float4* gk4 = reinterpret_cast<const float4*>(gk);
+#pragma unroll
+		for (int q = 0; q < NCH / 4; ++q) {
+			float4 g = gk4[q];
+			if (rp) {     // null: no channel ramps this buffer (only the direct gain ramps), ShRamps was not staged
+				const uint4 nn = reinterpret_cast<const uint4*>(rp->n)[q];
+				const float4 st = reinterpret_cast<const float4*>(rp->start)[q], in = reinterpret_cast<const float4*>(rp->inc)[q];
+				g.x = i < nn.x ? fmaf(fi, in.x, st.x) : g.x; g.y = i < nn.y ? fmaf(fi, in.y, st.y) : g.y;
+				g.z = i < nn.z ? fmaf(fi, in.z, st.z) : g.z; g.w = i < nn.w ? fmaf(fi, in.w, st.w) : g.w;
+			}
+			ffma2(acc[2 * q][k], make_float2(g.x, g.y), make_float2(yv, yv));
+			ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(yv, yv));
+		}
+	};
 
 	for (uint32_t jb = 0; jb < nbatch; ++jb) {
 		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
 		mbar_wait(&hdr->full_w[qw], (jb / kStages) & 1u);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
-		// ---------------- whole-batch fast path: when all kBatch sources of the stage qualify for the fast form, fetch all
-		// their samples first and run one long independent FFMA2 block, so that the shared-memory latencies of the four
-		// sources overlap instead of adding up ----------------
+		// ---------------- whole-batch fast path ----------------
 		bool batch_done = false;
 		if (EXACT && nb == (uint32_t)kBatch) {
-			bool all_fast = true;
+			uint4 dh[kBatch];     // {mode, w_idx, gd, nramp} of the four sources
+			uint32_t any = 0;
 #pragma unroll
 			for (int b = 0; b < kBatch; ++b) {
-				const MathDesc& d = sm.descs[qw * kBatch + b];
-				all_fast = all_fast && (d.mode & ~(kMdInterp | kMdRamp | kMdShRamp)) == 0 && d.nramp <= (uint32_t)kRampTile;
+				dh[b] = *reinterpret_cast<const uint4*>(&sm.descs[qw * kBatch + b]);
+				any |= (dh[b].x & ~(kMdInterp | kMdRamp | kMdShRamp)) | (dh[b].w > (uint32_t)TMAX ? kMdGeneric : 0u);
 			}
-			if (all_fast) {
+			if (any == 0) {
 				float xs[kBatch][K];
 #pragma unroll
 				for (int b = 0; b < kBatch; ++b) {
-					const MathDesc& d = sm.descs[qw * kBatch + b];
-					const float* wb = sm.wring + d.w_idx;
-					if (d.mode & kMdInterp) {
+					const float* wb = sm.wring + dh[b].y;
+					if (dh[b].x & kMdInterp) {
+						const MathDesc& d = sm.descs[qw * kBatch + b];
 #pragma unroll
 						for (int k = 0; k < K; ++k) {
 							const unsigned long long p = d.x0 + (unsigned long long)(t + (uint32_t)k * T) * d.step;
@@ -615,26 +625,20 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 				}
 #pragma unroll
 				for (int b = 0; b < kBatch; ++b) {
-					const MathDesc& d = sm.descs[qw * kBatch + b];
-					const float gdf = d.gd;
-					const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
+					const float gdf = __uint_as_float(dh[b].z);
+					const float* gk = sm.shgs[qr * kBatch + b].konst;
+					const uint32_t nramp = dh[b].w;
 #pragma unroll
-					for (int k = 0; k < K; ++k) xs[b][k] *= gdf;
-#pragma unroll
-					for (int q = 0; q < NCH / 4; ++q) {
-						const float4 g = gk4[q];
-#pragma unroll
-						for (int k = 0; k < K; ++k) {
-							ffma2(acc[2 * q][k], make_float2(g.x, g.y), make_float2(xs[b][k], xs[b][k]));
-							ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(xs[b][k], xs[b][k]));
-						}
-					}
-					if (t == T - 1) a.lpf_prev[d.slot] = xs[b][K - 1];
-				}
-#pragma unroll
-				for (int b = 0; b < kBatch; ++b) {
-					const MathDesc& d = sm.descs[qw * kBatch + b];
-					if (d.nramp) sh_ramp_fixup<TMAX>(sm.rtile, d, sm.recs[qr * kBatch + b], sm.shrs[qw * kBatch + b], sm.shgs[qr * kBatch + b].konst, sm.wring + d.w_idx, t);
+					for (int k = 1; k < K; ++k) accumulate_const(gk, xs[b][k] * gdf, k);
+					if (warp_i0 < nramp) {
+						// this warp's first frames lie inside a ramp of the direct gain and / or of channel gains
+						const MathDesc& d = sm.descs[qw * kBatch + b];
+						const WorkRec& r = sm.recs[qr * kBatch + b];
+						const float yv = (xs[b][0] * d.mfx) * gain_at(r.direct, t);
+						accumulate_ramped(gk, (dh[b].x & kMdShRamp) ? &sm.shrs[qw * kBatch + b] : nullptr, yv, t, ft, 0);
+					} else accumulate_const(gk, xs[b][0] * gdf, 0);
+					// frame F - 1 = t + (K - 1) T of thread T - 1: the bypassed occlusion filter's memory (mono_pole_filter.cc:40-44)
+					if (t == T - 1) a.lpf_prev[sm.descs[qw * kBatch + b].slot] = xs[b][K - 1] * gdf;
 				}
 				batch_done = true;
 			}
@@ -644,6 +648,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 			const WorkRec& r = sm.recs[qr * kBatch + b];
 			const uint32_t mode = d.mode;
 			if (mode & kMdSkip) {
+				// gain-skipped source: the feeder still consumed this buffer; carry the resampler history forward
 				if ((r.flags & kRecResample) && t == 0) {
 					float p0, p1;
 					resampler_tail(r, &p0, &p1);
@@ -651,46 +656,11 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 				}
 				continue;
 			}
-			if (EXACT && (mode & ~(kMdInterp | kMdRamp | kMdShRamp)) == 0 && d.nramp <= (uint32_t)kRampTile) {
-				// ---------------- fast path: native-rate or single-mix-source window, no filter; gain ramps (if any) end within
-				// the first kRampTile frames.  Every frame is accumulated with the constant gains; the frames inside a ramp
-				// are then corrected through a small shared-memory tile, the work split over all math warps by channel. ----------------
-				const float* wb = sm.wring + d.w_idx;
-				float xs[K];
-				if (mode & kMdInterp) {
-#pragma unroll
-					for (int k = 0; k < K; ++k) {
-						const unsigned long long p = d.x0 + (unsigned long long)(t + (uint32_t)k * T) * d.step;
-						const uint32_t di = (uint32_t)(p >> 32);
-						const float v0 = wb[di], v1 = wb[di + 1];
-						xs[k] = fmaf(frac_of(p), v1 - v0, v0);
-					}
-				} else {
-#pragma unroll
-					for (int k = 0; k < K; ++k) xs[k] = wb[t + (uint32_t)k * T];
-				}
-				const float gdf = d.gd;
-				const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
-#pragma unroll
-				for (int k = 0; k < K; ++k) xs[k] *= gdf;
-#pragma unroll
-				for (int q = 0; q < NCH / 4; ++q) {
-					const float4 g = gk4[q];
-#pragma unroll
-					for (int k = 0; k < K; ++k) {
-						ffma2(acc[2 * q][k], make_float2(g.x, g.y), make_float2(xs[k], xs[k]));
-						ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(xs[k], xs[k]));
-					}
-				}
-				if (t == T - 1) a.lpf_prev[d.slot] = xs[K - 1];     // frame F - 1 = t + (K - 1) T: the bypassed filter's memory
-				if (d.nramp) sh_ramp_fixup<TMAX>(sm.rtile, d, r, sm.shrs[qw * kBatch + b], sm.shgs[qr * kBatch + b].konst, wb, t);
-				continue;
-			}
 			float x[K];          // engine-rate input samples of this thread's frames (before any gain)
 			float mf = 1.0f;     // MixSource::mix_factor where it is not already inside x
-			bool lpf_done = false;
+			bool filtered = false;   // x already carries the direct gain and the occlusion low-pass
 			if ((mode & (kMdGeneric | kMdLpf | kMdAdjust)) != 0) {
-				// ---------------- careful path (rare) ----------------
+				// ---------------- careful fetch (rare): every case, straightforward arithmetic ----------------
 				const WinPlan wp = plan_window(r, wslot);
 				float* slot = sm.wring + (size_t)(qw * kBatch + b) * wslot;
 				const float* w = slot + 4 + wp.off0;
@@ -716,13 +686,13 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 					math_sync(T);
 #pragma unroll
 					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) x[k] = slot[i]; }
-					fence_proxy_async();
-					lpf_done = true;
+					fence_proxy_async();     // generic-proxy writes to the slot precede the TMA refill
+					filtered = true;
 				}
 			} else {
-				// ---------------- lean path ----------------
+				// ---------------- lean fetch: window staged in shared memory by the TMA ring ----------------
 				const float* wb = sm.wring + d.w_idx;
-				if (r.flags & kRecMix1) mf = r.mix_factor;
+				mf = d.mfx;
 				if (mode & kMdInterp) {
 					const bool rsmp = (mode & kMdResample) != 0;
 #pragma unroll
@@ -735,6 +705,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 							const uint32_t di = (uint32_t)(p >> 32);
 							const float fr = frac_of(p);
 							float v0, v1;
+							// only the first frames (resampler history) and the last ones (index clamp) need the careful form
 							if (rsmp && (wi0 < 16u || wi0 + 32u > F - 1)) {
 								const WinPlan wp = plan_window(r, wslot);
 								v0 = staged_tmp(r, wb + 2, wp, (int)di); v1 = staged_tmp(r, wb + 2, wp, (int)di + 1);
@@ -757,46 +728,22 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 				}
 			}
 			// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
-			float2 g2[NCH / 2];      // the 16 constant channel gains, as FFMA2 operand pairs
-			{
-				const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
-#pragma unroll
-				for (int q = 0; q < NCH / 4; ++q) { const float4 v = gk4[q]; g2[2 * q] = make_float2(v.x, v.y); g2[2 * q + 1] = make_float2(v.z, v.w); }
-			}
+			const float* gk = sm.shgs[qr * kBatch + b].konst;
 			const float gd = d.gd;
 			const uint32_t nramp = d.nramp;     // frames in which the direct gain or a channel gain still ramps
-			if (nramp == 0) {
-				// no ramp anywhere in this buffer (the common case)
+			const ShRamps* rp = (mode & kMdShRamp) ? &sm.shrs[qw * kBatch + b] : nullptr;
 #pragma unroll
-				for (int k = 0; k < K; ++k) {
-					const float yv = lpf_done ? x[k] : x[k] * gd;
-					if (k == K - 1 || !EXACT) { if (!lpf_done && t + (uint32_t)k * T == F - 1) a.lpf_prev[d.slot] = yv; }
-#pragma unroll
-					for (int c = 0; c < NCH / 2; ++c) ffma2(acc[c][k], g2[c], make_float2(yv, yv));
-				}
-			} else {
-				const ShRamps& rp = sm.shrs[qw * kBatch + b];
-				const uint32_t mask = r.ch_ramp_mask;
-#pragma unroll
-				for (int k = 0; k < K; ++k) {
-					const uint32_t i = t + (uint32_t)k * T;
-					if (warp_i0 + (uint32_t)k * T < nramp) {
-						// warp-uniform: only the warps whose frames lie inside a ramp evaluate ramps
-						const float yv = lpf_done ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
-						if (!lpf_done && i == F - 1) a.lpf_prev[d.slot] = yv;
-#pragma unroll
-						for (int c = 0; c < NCH / 2; ++c) {
-							float2 g = g2[c];
-							if ((mask >> (2 * c)) & 1u) { if (i < rp.n[2 * c]) g.x = fmaf((float)i, rp.inc[2 * c], rp.start[2 * c]); }
-							if ((mask >> (2 * c + 1)) & 1u) { if (i < rp.n[2 * c + 1]) g.y = fmaf((float)i, rp.inc[2 * c + 1], rp.start[2 * c + 1]); }
-							ffma2(acc[c][k], g, make_float2(yv, yv));
-						}
-					} else {
-						const float yv = lpf_done ? x[k] : x[k] * gd;
-						if (!lpf_done && i == F - 1) a.lpf_prev[d.slot] = yv;
-#pragma unroll
-						for (int c = 0; c < NCH / 2; ++c) ffma2(acc[c][k], g2[c], make_float2(yv, yv));
-					}
+			for (int k = 0; k < K; ++k) {
+				const uint32_t i = t + (uint32_t)k * T;
+				if (warp_i0 + (uint32_t)k * T < nramp) {
+					// warp-uniform: only the warps whose frames lie inside a ramp evaluate ramps
+					const float yv = filtered ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
+					if (!filtered && i == F - 1) a.lpf_prev[d.slot] = yv;
+					accumulate_ramped(gk, rp, yv, i, (float)i, k);
+				} else {
+					const float yv = filtered ? x[k] : x[k] * gd;
+					if ((k == K - 1 || !EXACT) && !filtered && i == F - 1) a.lpf_prev[d.slot] = yv;
+					accumulate_const(gk, yv, k);
 				}
 			}
 		}
@@ -804,18 +751,13 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 		__syncwarp();
 		if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }
 	}
-	math_sync(T);     // the ramp-correction tile is complete
 	float* out = partials + (size_t)blockIdx.x * NCH * F;
 #pragma unroll
 	for (int c = 0; c < NCH / 2; ++c)
 #pragma unroll
 		for (int k = 0; k < K; ++k) {
 			const uint32_t i = t + (uint32_t)k * T;
-			if (i < F) {
-				float v0 = acc[c][k].x, v1 = acc[c][k].y;
-				if (k == 0 && i < (uint32_t)kRampTile) { v0 += sm.rtile[(2 * c) * kRampTile + i]; v1 += sm.rtile[(2 * c + 1) * kRampTile + i]; }
-				out[(size_t)(2 * c) * F + i] = v0; out[(size_t)(2 * c + 1) * F + i] = v1;
-			}
+			if (EXACT || i < F) { out[(size_t)(2 * c) * F + i] = acc[c][k].x; out[(size_t)(2 * c + 1) * F + i] = acc[c][k].y; }
 		}
 }
 
@@ -861,12 +803,12 @@ int sm_count() {
 	return n;
 }
 
-uint32_t sh_threads(uint32_t F) { return ((F + kShK - 1) / kShK + 31) / 32 * 32; }
 // Stage slot per source, in floats: room for a window of frames * 1.25 (sample-rate ratios <= 1, doppler / pitch up
 // to +25 %) plus alignment slack; larger windows take the generic path.
 uint32_t window_slot(uint32_t F) { return (F + F / 4 + 24u + 3u) & ~3u; }
+uint32_t sh_threads(uint32_t F) { return ((F + K - 1) / K + 31) / 32 * 32; }
 size_t mix_smem_bytes(uint32_t F, bool sh) {
-	return 256 + sizeof(WorkRec) * kRecStages * kBatch + (sh ? sizeof(ShGains) * kRecStages * kBatch + sizeof(ShRamps) * kStages * kBatch + sizeof(float) * 16 * kRampTile : 0) +
+	return 256 + sizeof(WorkRec) * kRecStages * kBatch + (sh ? sizeof(ShGains) * kRecStages * kBatch + sizeof(ShRamps) * kStages * kBatch : 0) +
 	       sizeof(MathDesc) * kStages * kBatch +
 	       sizeof(float) * (size_t)kStages * kBatch * window_slot(F);
 }
@@ -920,7 +862,7 @@ int num_mix_ctas(uint32_t frames, int sh) {
 	const size_t smem = mix_smem_bytes(frames, sh != 0) + 1024;
 	int per_sm = (int)((227u * 1024u) / smem);
 	if (per_sm < 1) per_sm = 1;
-	if (per_sm > (sh ? 4 : 8)) per_sm = sh ? 4 : 8;
+	if (per_sm > 8) per_sm = 8;
 	return sm_count() * per_sm;
 }
 
@@ -943,11 +885,10 @@ int launch_mix(const MixArgs& a, void* stream) {
 		if (rc) return -1;
 	}
 	if (a.n_sh) {
-		static KernelConfig conf_sh;
-		static KernelConfig conf_sh_big, conf_sh_x, conf_sh_big_x;
+		static KernelConfig conf_sh, conf_sh_big, conf_sh_x, conf_sh_big_x;
 		const uint32_t tm = sh_threads(F);
 		const uint32_t mg = (uint32_t)num_mix_ctas(F, 1);
-		const bool exact = (tm == 128 || tm == 256) && F == tm * kShK;     // the EXACT instantiations fix T = TMAX at compile time
+		const bool exact = (tm == 128 || tm == 256) && F == tm * K;     // the EXACT instantiations fix T = TMAX at compile time
 		int rc;
 		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<128, true>, &conf_sh_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
 		                         : launch_one(k2_mix_ambisonic_kernel<128, false>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);

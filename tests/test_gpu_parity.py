@@ -42,6 +42,12 @@ def test_cuda_matches_reference_golden(name):
     (dict(n_sources=200, kind=KIND_PAN, loop_len=100, feeder="resample", seed=27), 1024, 6, 0),     # loops shorter than a buffer
     (dict(n_sources=100, kind=KIND_HRTF, seed=28), 32, 10, 0),                                      # smallest buffer Resonance accepts
     (dict(n_sources=100, mixed_kinds=True, seed=29), 1000, 5, 0),                                   # frames not a multiple of the tile
+    # loop lengths that are not a multiple of 4 samples: the wrapped window's second TMA segment is re-aligned (kMdAdjust)
+    (dict(n_sources=512, kind=KIND_PAN, feeder="doppler", loop_len=4099, seed=32), 512, 8, 0),
+    (dict(n_sources=512, kind=KIND_HRTF, feeder="doppler", loop_len=4098, seed=33), 512, 8, 0),
+    (dict(n_sources=512, kind=KIND_HRTF, feeder="doppler", loop_len=4096, seed=34, volume_toggle=True), 256, 8, 0),
+    (dict(n_sources=300, mixed_kinds=True, occlusion_toggle=True, volume_toggle=True, seed=35, feeder="resample", loop_len=3001), 1024, 8, 0),
+    (dict(n_sources=300, mixed_kinds=True, occlusion_toggle=True, seed=36, feeder="doppler", loop_len=2049), 480, 8, 0),
 ])
 def test_cuda_matches_oracle(kw, F, nb, taps):
     hr = load_sh_hrir()
