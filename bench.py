@@ -45,6 +45,8 @@ WORKLOADS = {
                                  desc="4 096 sources, linear resample (44.1k/24k/16k/48k mix) + atten + pan, 512-frame @48kHz"),
     "c3_65536_hq_128tap": dict(n=65536, frames=1024, kind="hq", feeder="native", loop=16384, taps=128,
                                desc="65 536 sources, 3rd-order ambisonic encode + 128-tap SH-HRIR decode per ear, 1 024-frame @48kHz"),
+    "c5_voice_ambient": dict(n=33792, frames=256, kind="hq", feeder="c5", loop=16384, taps=256, voices=1024,
+                             desc="1 024 streamed voice sources (rings fed 480-sample packets, batched push) + 32 768 ambient loops, ambisonic encode + 256-tap SH-HRIR decode, 256-frame @48kHz"),
     "c1_16_pan": dict(n=16, frames=512, kind="pan", feeder="native", loop=48000, taps=0,
                       desc="16 mono looping sources, distance atten + stereo pan, 512-frame @48kHz"),
     "1m_native_pan": dict(n=1048576, frames=512, kind="pan", feeder="native", loop=16384, taps=0,
@@ -79,40 +81,64 @@ def listener_pose(step, frames):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every 2 ms from a thread
+    (a timed leg lasts tens of milliseconds, shorter than one nvidia-smi -lms period); nvidia-smi is the fallback."""
+    REASONS = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+               ("hw_power_brake", 0x80)]
 
     def __init__(self, gpu_index):
-        self.rows, self.p, self.idx = [], None, gpu_index
+        self.idx, self.sm, self.mask, self.mx, self.stop_flag, self.t, self.err = gpu_index, [], 0, None, False, None, None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except Exception:
+                return self.idx
+        return self.idx
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:
-            self.p = None
+        except Exception as ex:
+            self.err = "nvml: %s" % ex
+            self.t = None
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception as ex:
+                self.err = "nvml: %s" % ex
+                break
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=2)
-        except Exception:
-            self.p.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 8 for k in range(4) if r[4 + k].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=1)
+        if not self.sm:
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                r = subprocess.run(["nvidia-smi", "-i", str(self._visible_index()), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                return {"sm_mhz": float(r[0]), "sm_max_mhz": float(r[1]), "reasons": [n for n, v in zip(names, r[2:]) if v.strip().lower().startswith("active")],
+                        "samples": 1, "how": "one nvidia-smi query after the timed legs (%s)" % self.err}
+            except Exception as ex:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable: %s / %s" % (self.err, ex)], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.mx,
+                "reasons": [n for n, bit in self.REASONS if self.mask & bit], "samples": len(self.sm), "how": "NVML polled every 2 ms across both timed legs"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -120,7 +146,7 @@ class ClockSampler:
 # restated feeder) when it was built, else the oracle port.  Independent engines on disjoint source subsets, one per
 # host thread (the reference graph itself is single-threaded: RA/api/resonance_audio_api.h:139-141).
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(wl, threads, sources_per_thread, buffers, warmup):
+def cpu_reference_run(wl, threads, sources_per_thread, buffers, warmup, target_seconds=0.0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import harness
     kind = "reference" if harness.ref_library_path() else "port"
@@ -129,6 +155,7 @@ def cpu_reference_run(wl, threads, sources_per_thread, buffers, warmup):
     if wl["taps"]:
         hr = hr[:, :wl["taps"]]
     k = harness.KIND_PAN if wl["kind"] == "pan" else harness.KIND_HRTF
+    feeder = "native" if wl["feeder"] == "c5" else wl["feeder"]      # C5 on the CPU: its ambient loops (32 768 of the 33 792 sources)
 
     def make():
         if kind == "reference":
@@ -137,7 +164,7 @@ def cpu_reference_run(wl, threads, sources_per_thread, buffers, warmup):
 
     engines, scen = [], []
     for t in range(threads):
-        sc = harness.Scenario(n_sources=sources_per_thread, frames=F, seed=1000 + t, kind=k, feeder=wl["feeder"], loop_len=min(wl["loop"], 16384),
+        sc = harness.Scenario(n_sources=sources_per_thread, frames=F, seed=1000 + t, kind=k, feeder=feeder, loop_len=min(wl["loop"], 16384),
                               n_shared_buffers=min(sources_per_thread, 256))
         be = make()
         sc.build(be)
@@ -161,11 +188,17 @@ def cpu_reference_run(wl, threads, sources_per_thread, buffers, warmup):
         return time.perf_counter() - t0
 
     run(0, warmup)
-    wall = run(warmup, buffers)
+    done = warmup
+    if target_seconds:
+        # bounded sample: probe a few buffers, then size the timed run for about `target_seconds` of wall time
+        probe = run(done, 4)
+        done += 4
+        buffers = int(min(20000, max(8, target_seconds / max(probe / 4, 1e-6))))
+    wall = run(done, buffers)
     samples = threads * sources_per_thread * F * buffers
     return dict(value=samples / wall, unit=UNIT, cores=threads, kind=kind,
-                sample="%d threads x %d sources x %d buffers of %d frames (%s), independent engines, wall %.2f s" %
-                       (threads, sources_per_thread, buffers, F, wl["feeder"] + "/" + wl["kind"], wall),
+                sample="%d threads x %d sources x %d buffers of %d frames (%s), independent engines (the reference graph is single-threaded), wall %.2f s" %
+                       (threads, sources_per_thread, buffers, F, feeder + "/" + wl["kind"], wall),
                 ms_per_step=1e3 * wall / buffers)
 
 
@@ -220,6 +253,11 @@ def build_engine(wl, device, seed):
     bufs = np.arange(first_buf, first_buf + n, dtype=np.int32)
     if wl["feeder"] == "doppler":
         eng.sources_attach_mix1(ids, bufs, p["start"].astype(np.float64), p["delta"], p["mixf"])
+    elif wl["feeder"] == "c5":
+        nv = wl["voices"]
+        for sid in ids[:nv]:
+            eng.source_attach_ring(int(sid), 48000, capacity=wl.get("ring_capacity", 96000))
+        eng.sources_attach_buffer(ids[nv:], bufs[nv:], p["start"][nv:], p["rates"][nv:])
     else:
         eng.sources_attach_buffer(ids, bufs, p["start"], p["rates"])
     eng.set_source_positions(ids, p["pos"])
@@ -237,7 +275,8 @@ def parity_sample(wl):
     hr = hr[:, :wl["taps"]] if wl["taps"] else hr
     k = harness.KIND_PAN if wl["kind"] == "pan" else harness.KIND_HRTF
     n = min(wl["n"], 2048)
-    sc = harness.Scenario(n_sources=n, frames=F, seed=4242, kind=k, feeder=wl["feeder"], loop_len=4096)
+    sc = harness.Scenario(n_sources=n, frames=F, seed=4242, kind=k, feeder="ring" if wl["feeder"] == "c5" else wl["feeder"], loop_len=4096,
+                          batched_ring_push=True)
     oo, _ = sc.run(harness.OracleBackend(F, sh_hrir=hr), 4)
     go, _ = sc.run(sb.MixEngine(F, sh_hrir=hr if wl["kind"] == "hq" else None, max_sources=n), 4)
     return {"rel_rms": harness.rel_rms(go, oo), "sample": "%d sources x 4 buffers vs oracle (CPU port pinned to the compiled reference)" % n}
@@ -264,10 +303,27 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize(local_rank)
 
+    # C5: voice rings.  Packets of 480 samples per voice every 10 ms (ClientUDPHandlerThread.cpp:196), all voices in one
+    # sbm_source_ring_push_batch call.  value leg: rings pre-filled before the timed region (inputs resident);
+    # e2e leg: the packets cross PCIe inside the timed region, as they would behind a network thread.
+    voices = wl.get("voices", 0)
+    if voices:
+        v_ids = np.ascontiguousarray(ids[:voices])
+        v_offs = (np.arange(voices + 1, dtype=np.uint64) * np.uint64(480))
+        v_payload = [(0.3 * rng.uniform(-1, 1, voices * 480)).astype(np.float32) for _ in range(4)]
+        ring_state = {"pushed": 0, "consumed": 0}
+
+        def feed_voices(upto_samples):
+            while ring_state["pushed"] < upto_samples:
+                eng.sources_ring_push_flat(v_ids, v_payload[(ring_state["pushed"] // 480) % 4], v_offs)
+                ring_state["pushed"] += 480
+
     def step_resident(s):
         hp, hq = listener_pose(s, F)
         eng.set_head(hp, hq)
         mixer.mix(out_host)        # sbm_mix_begin -> (N > 1: NCCL all-reduce of the bus on the engine stream) -> sbm_mix_finish
+        if voices:
+            ring_state["consumed"] += F
 
     movers = min(MOVERS_PER_STEP, n)
     mv_ids = [np.ascontiguousarray(ids[(k * movers) % max(1, n - movers + 1):][:movers]) for k in range(8)]
@@ -275,11 +331,17 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
 
     def step_e2e(s):
         hp, hq = listener_pose(s, F)
+        if voices:
+            feed_voices(ring_state["consumed"] + F)       # the packets that arrived since the previous buffer
         eng.set_source_positions(mv_ids[s % 8], mv_pos[s % 8])
         eng.set_head(hp, hq)
         mixer.mix(out_host)
+        if voices:
+            ring_state["consumed"] += F
 
     def timed(step_fn, s0):
+        if voices and step_fn is step_resident:
+            feed_voices(ring_state["consumed"] + (args.warmup + args.steps) * F)      # resident inputs: outside the timed region
         for s in range(args.warmup):
             step_fn(s0 + s)
         sync_all()
@@ -335,7 +397,8 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
                        "parallelism": "sources sharded, 1 rank/GPU" + (", NCCL all-reduce of the 18x%d bus" % F if world > 1 else ""),
                        "realtime_budget_ms": 1e3 * F / 48000.0},
             "e2e": {"value": total / (e2e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e2e["ms"], "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                    "what": "%d source positions + listener pose from host arrays per step, stereo buffer back to host, through sbm_set_*/sbm_mix" % movers},
+                    "what": ("%d source positions + listener pose from host arrays per step, stereo buffer back to host, through sbm_set_*/sbm_mix" % movers) +
+                            ("; %d voice packets of 480 samples per 10 ms of audio through sbm_source_ring_push_batch" % voices if voices else "")},
             "gpu_launches": res["launches"],
             "roofline": {"bound": "hbm", "kernel": "k2_mix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": res["k2"], "peak_source": peak_src,
@@ -348,7 +411,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
             except Exception as ex:          # the oracle is test infrastructure; its absence must not hide the GPU numbers
                 line["parity"] = {"error": str(ex)}
             threads = min(host_threads(), 64)
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(wl, threads, min(1024, max(1, wl["n"] // threads)), 6, 2).items() if k != "ms_per_step"}
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(wl, threads, min(1024, max(1, wl["n"] // threads)), 0, 2, target_seconds=12.0).items() if k != "ms_per_step"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -373,6 +436,7 @@ def main():
     if args.sources:
         wl["n"] = args.sources
         wl["desc"] += " [--sources override: %d sources/GPU, NOT the named configuration]" % args.sources
+    wl["ring_capacity"] = max(96000, (args.warmup + args.steps + 8) * wl["frames"] + 960)
     if args.impl == "reference":
         run_reference_arm(args, wl, rank, world)
         return

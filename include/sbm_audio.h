@@ -94,6 +94,12 @@ SBM_API int sbm_source_attach_ring(sbm_engine* e, int id, int sampling_rate, int
 /* CircularBuffer::pushBackNItems by StreamerThread / ClientUDPHandlerThread (StreamerThread.cpp:53-80, ClientUDPHandlerThread.cpp:239). */
 SBM_API int sbm_source_ring_push(sbm_engine* e, int id, const float* samples, size_t n);
 /* CircularBuffer::size() as of the last sbm_mix() plus pushes since (StreamerThread.cpp:53 polls it). */
+/* Batched push for many ring-fed sources at once: packet k = samples[offsets[k] .. offsets[k+1]) goes to source ids[k]
+ * (the same id may appear more than once; packets are appended in order).  One pinned staging copy + one H2D + one
+ * scatter kernel for the whole call -- what glare::AudioEngine's voice / streaming feeders use instead of one
+ * CircularBuffer::pushBackNItems per source (ClientUDPHandlerThread.cpp:239-242, StreamerThread.cpp:33-60).
+ * All-or-nothing: SBM_ERR_CAPACITY (some ring full) or SBM_ERR_UNKNOWN_ID leave every ring untouched. */
+SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, const float* samples, const size_t* offsets /* n + 1 */);
 SBM_API int sbm_source_ring_size(sbm_engine* e, int id, uint64_t* out_size);
 /* SourceType_Streaming with mix_sources: pitch/doppler mixer (AudioEngine.cpp:435-458). */
 SBM_API int sbm_source_attach_mix(sbm_engine* e, int id, int sampling_rate, int nz, const int* buffers, const double* sound_file_i,

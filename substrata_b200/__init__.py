@@ -151,6 +151,18 @@ class MixEngine:
         s = _f32(samples)
         self._ck(self._l.sbm_source_ring_push(self.h, int(sid), _p(s), s.size), "sbm_source_ring_push")
 
+    def sources_ring_push(self, ids, packets):
+        """Batched push: packets[k] (1-D float arrays) is appended to the ring of source ids[k]; one H2D + one scatter kernel."""
+        i = _i32(ids)
+        offs = np.zeros(i.size + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(p) for p in packets])
+        payload = _f32(np.concatenate([np.asarray(p, np.float32).ravel() for p in packets])) if i.size else _f32(np.zeros(1))
+        self._ck(self._l.sbm_source_ring_push_batch(self.h, i.size, _p(i), _p(payload), _p(offs)), "sbm_source_ring_push_batch")
+
+    def sources_ring_push_flat(self, ids, payload, offsets):
+        """Same, for a pre-concatenated payload (float32) and offsets (uint64, len(ids) + 1): no Python-side copies."""
+        self._ck(self._l.sbm_source_ring_push_batch(self.h, len(ids), _p(ids), _p(payload), _p(offsets)), "sbm_source_ring_push_batch")
+
     def source_ring_size(self, sid):
         out = C.c_uint64()
         self._ck(self._l.sbm_source_ring_size(self.h, int(sid), C.byref(out)), "sbm_source_ring_size")

@@ -26,6 +26,14 @@ constexpr uint32_t kPatchKill = 16;      // live = 0
 
 struct MixPatch { uint32_t index; uint32_t pad; double pos; };
 
+struct RingPush {               // one packet of a batched ring push: stage[src_off .. src_off + n) -> ring[(at + i) % capacity]
+	float* ring;
+	uint32_t capacity;
+	uint32_t at;                // write index of the packet's first sample
+	uint32_t src_off;           // offset of the packet in the staged payload, in floats
+	uint32_t n;
+};
+
 struct MixArgs {
 	const WorkRec* rec;         // [n_pan + n_sh] render-list order: stereo-bus sources first, then ambisonic sources
 	const ShGains* shg;         // indexed like rec
@@ -88,6 +96,7 @@ size_t partials_floats(uint32_t frames);         // floats needed for MixArgs::p
 // kernels
 int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, const MixPatch* mp, uint32_t nmp, void* stream);
 int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, const uint32_t* lists, uint32_t n_slots, void* stream);   // lists: [n_pan + n_sh] slots in render order
+int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void* stream);   // batched ring push: one CTA per packet
 int launch_mix(const MixArgs& a, void* stream);  // K2 (both lists) + K3 (partials -> bus)
 int launch_finish(const FinishArgs& a, void* stream);
 // timing

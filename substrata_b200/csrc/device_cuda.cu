@@ -113,6 +113,19 @@ __global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
 	for (uint32_t q = i; q < a.n_ring; q += T) reads[q] = a.read_i[a.list_ring[q]];
 }
 
+// Batched ring push (the streaming feed, AE.cpp:540-545 / ClientUDPHandlerThread.cpp:239-242 for many sources at once):
+// the packets of one call arrive as ONE staged payload (single H2D from pinned memory); one CTA per packet copies it
+// into its source's ring with wrap-around.  Coalesced 4-byte accesses; packets are a few hundred samples.
+__global__ void __launch_bounds__(128) k_ring_scatter_kernel(const RingPush* __restrict__ pk, const float* __restrict__ stage) {
+	const RingPush p = pk[blockIdx.x];
+	for (uint32_t i = threadIdx.x; i < p.n; i += blockDim.x) {
+		uint32_t at = p.at + i;
+		if (at >= p.capacity) at -= p.capacity;
+		if (at >= p.capacity) at %= p.capacity;
+		p.ring[at] = stage[p.src_off + i];
+	}
+}
+
 namespace dev {
 
 void note_launch(unsigned n) { g_launches += n; }
@@ -181,6 +194,13 @@ int d2h(void* dst, const void* src, size_t bytes, void* stream) {
 }
 int zero(void* dst, size_t bytes, void* stream) { return check(cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)stream), "cudaMemsetAsync"); }
 int sync(void* stream) { return check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
+
+int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void* stream) {
+	if (!n) return 0;
+	k_ring_scatter_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(packets, stage);
+	note_launch();
+	return check_launch("k_ring_scatter");
+}
 
 int launch_finish(const FinishArgs& a, void* stream) {
 	const uint32_t F = a.frames;

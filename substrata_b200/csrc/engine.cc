@@ -80,6 +80,11 @@ struct sbm_engine {
 	float* dv_bus = nullptr; size_t bus_floats = 0;
 	float* dv_hrir = nullptr; float* dv_hist = nullptr; float* dv_dec = nullptr;
 	float* dv_out = nullptr; size_t out_bytes = 0;
+	unsigned char* h_ring_stage = nullptr;   // pinned staging of sbm_source_ring_push_batch: packet table + payload
+	unsigned char* d_ring_stage = nullptr;
+	size_t ring_stage_bytes = 0;
+	size_t pending_ring_h2d_bytes = 0;       // ring pushes since the last sbm_mix_begin (reported with the next buffer's stats)
+	bool ring_stage_in_flight = false;       // an H2D from h_ring_stage may still be running (cleared by every stream sync in mix)
 	unsigned char* h_out = nullptr;          // pinned D2H staging: 2F floats + OutTail + ring read counters
 	Globals g;
 	unsigned long long buffer_index = 0;
@@ -252,6 +257,8 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	for (auto& b : e->buffers) if (b.owned && b.dptr) dev::release(b.dptr);
 	for (auto& r : e->rings) if (r.storage) dev::release(r.storage);
 	if (e->h_out) dev::release_pinned(e->h_out);
+	if (e->h_ring_stage) dev::release_pinned(e->h_ring_stage);
+	if (e->d_ring_stage) dev::release(e->d_ring_stage);
 	for (int i = 0; i < 4; ++i) if (e->ev[i]) dev::event_destroy(e->ev[i]);
 	dev::shutdown(e->stream);
 	delete e;
@@ -396,10 +403,65 @@ SBM_API int sbm_source_ring_push(sbm_engine* e, int id, const float* samples, si
 	}
 	// The packet is copied from the caller's memory asynchronously only if it is pinned; make the call safe for any memory.
 	if (dev::sync(e->stream)) return fail_cuda(e, "sbm_source_ring_push");
-	e->stats.last_h2d_bytes += sizeof(float) * n;
+	e->pending_ring_h2d_bytes += sizeof(float) * n;
 	r.written += n;
 	e->h_ring_write[(uint32_t)slot] = r.written;
 	e->d_ring.mark((uint32_t)slot);
+	return SBM_OK;
+}
+
+// Batched form of sbm_source_ring_push: the packets of MANY ring-fed sources in one call (what the voice / streaming threads
+// deliver between two buffers).  All payloads and the packet table are staged in one pinned buffer, cross PCIe as ONE
+// copy, and a scatter kernel writes each packet into its source's ring -- instead of one copy + one stream
+// synchronisation per source.  offsets[k] .. offsets[k + 1] is packet k inside `samples`.  Either every packet is
+// accepted or none (ring full / unknown id -> nothing is written).
+SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, const float* samples, const size_t* offsets) {
+	if (!e || n < 0 || (n && (!ids || !samples || !offsets))) return SBM_ERR_INVALID_ARG;
+	if (!n) return SBM_OK;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	const size_t total = offsets[n] - offsets[0];
+	std::vector<RingPush> pk((size_t)n);
+	std::vector<uint32_t> slots((size_t)n);
+	std::vector<unsigned long long> pending(e->rings.size(), 0);     // samples accepted earlier in this call, per slot
+	for (int k = 0; k < n; ++k) {
+		const int slot = slot_for(e, ids[k]);
+		if (slot < 0) return SBM_ERR_UNKNOWN_ID;
+		if (offsets[k + 1] < offsets[k]) return SBM_ERR_INVALID_ARG;
+		RingInfo& r = e->rings[(uint32_t)slot];
+		if (!r.storage) return fail(e, SBM_ERR_INVALID_ARG, "source is not ring-fed");
+		const size_t m = offsets[k + 1] - offsets[k];
+		unsigned long long& pend = pending[(uint32_t)slot];
+		if (r.written + pend - r.read_known + m > r.capacity) return fail(e, SBM_ERR_CAPACITY, "ring full");
+		pk[(size_t)k] = RingPush{r.storage, r.capacity, (uint32_t)((r.written + pend) % r.capacity), (uint32_t)(offsets[k] - offsets[0]), (uint32_t)m};
+		slots[(size_t)k] = (uint32_t)slot;
+		pend += m;
+	}
+	// staging layout: [packet table, padded to 256 B][payload]
+	const size_t table_bytes = (sizeof(RingPush) * (size_t)n + 255) & ~(size_t)255;
+	const size_t bytes = table_bytes + sizeof(float) * total;
+	if (e->ring_stage_in_flight) { if (dev::sync(e->stream)) return fail_cuda(e, "sbm_source_ring_push_batch"); e->ring_stage_in_flight = false; }
+	if (bytes > e->ring_stage_bytes) {
+		dev::sync(e->stream);
+		dev::release_pinned(e->h_ring_stage); dev::release(e->d_ring_stage);
+		e->ring_stage_bytes = std::max<size_t>(bytes * 2, 1 << 20);
+		e->h_ring_stage = (unsigned char*)dev::alloc_pinned(e->ring_stage_bytes);
+		e->d_ring_stage = (unsigned char*)dev::alloc(e->ring_stage_bytes);
+		if (!e->h_ring_stage || !e->d_ring_stage) { e->ring_stage_bytes = 0; return fail_cuda(e, "sbm_source_ring_push_batch(alloc)"); }
+	}
+	memcpy(e->h_ring_stage, pk.data(), sizeof(RingPush) * (size_t)n);
+	memcpy(e->h_ring_stage + table_bytes, samples + offsets[0], sizeof(float) * total);
+	if (dev::h2d(e->d_ring_stage, e->h_ring_stage, bytes, e->stream) ||
+	    dev::launch_ring_scatter((const RingPush*)e->d_ring_stage, (uint32_t)n, (const float*)(e->d_ring_stage + table_bytes), e->stream))
+		return fail_cuda(e, "sbm_source_ring_push_batch");
+	e->ring_stage_in_flight = true;      // the pinned staging buffer is reused: the next push waits for this copy
+	e->pending_ring_h2d_bytes += bytes;
+	for (int k = 0; k < n; ++k) {
+		RingInfo& r = e->rings[slots[(size_t)k]];
+		r.written += pk[(size_t)k].n;
+		e->h_ring_write[slots[(size_t)k]] = r.written;
+		e->d_ring.mark(slots[(size_t)k]);
+	}
 	return SBM_OK;
 }
 
@@ -585,7 +647,9 @@ SBM_API int sbm_mix_begin(sbm_engine* e) {
 	std::lock_guard<std::mutex> lk(e->mu);
 	dev::use(e->cfg.device);
 	if (e->begun) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_begin called twice without sbm_mix_finish");
-	e->stats.last_h2d_bytes = 0; e->stats.last_d2h_bytes = 0;
+	// bytes pushed into rings since the previous buffer belong to this buffer's host->device traffic
+	e->stats.last_h2d_bytes = e->pending_ring_h2d_bytes; e->stats.last_d2h_bytes = 0;
+	e->pending_ring_h2d_bytes = 0;
 	void* st = e->stream;
 	// 1. pending parameter uploads
 	if (upload_range(e, e->dv_stat, e->h_stat, e->d_stat) || upload_range(e, e->dv_posvol, e->h_posvol, e->d_posvol) ||
@@ -646,6 +710,7 @@ SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid
 	if (e->profiling) dev::event_record(e->ev[3], st);
 	const size_t bytes = sizeof(float) * 2 * F + sizeof(OutTail) + sizeof(unsigned long long) * e->list_ring.size();
 	if (dev::d2h(e->h_out, e->dv_out, bytes, st) || dev::sync(st)) return fail_cuda(e, "sbm_mix_finish(d2h)");
+	e->ring_stage_in_flight = false;
 	e->stats.last_d2h_bytes += bytes;
 	OutTail tail;
 	memcpy(&tail, e->h_out + sizeof(float) * 2 * F, sizeof(tail));

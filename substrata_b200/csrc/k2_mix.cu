@@ -52,8 +52,15 @@ namespace {
 #define SBM_SH_BIG_CTAS 1             // resident CTAs per SM the 1024-frame ambisonic kernel's register budget is set for (2 -> 96 registers and spills)
 #endif
 constexpr int kBatch = 4;             // sources per pipeline stage
-constexpr int kStages = SBM_STAGES;   // window stages in flight
-constexpr int kRecStages = kStages + 2;
+// Window stages in flight per CTA (batches of kBatch sources); the record ring is two batches deeper.
+#ifndef SBM_STAGES_SH
+#define SBM_STAGES_SH 4
+#endif
+#ifndef SBM_STAGES_SH_BIG
+#define SBM_STAGES_SH_BIG 6
+#endif
+constexpr int kStagesPan = SBM_STAGES, kStagesSh = SBM_STAGES_SH, kStagesShBig = SBM_STAGES_SH_BIG;
+constexpr int kMaxStages = 10;
 constexpr int kPanThreads = 128;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -150,11 +157,11 @@ __device__ __forceinline__ WinPlan plan_window(const WorkRec& r, uint32_t wslot)
 }
 
 struct MixSmemHdr {
-	unsigned long long full_w[kStages], empty_w[kStages];        // window ring: TMA landed / math warps done
-	unsigned long long full_r[kRecStages], empty_r[kRecStages];  // record ring
+	unsigned long long full_w[kMaxStages], empty_w[kMaxStages];          // window ring: TMA landed / math warps done
+	unsigned long long full_r[kMaxStages + 2], empty_r[kMaxStages + 2];  // record ring
 	float lpf_carry[8];                                          // per math warp (stereo kernel) / [0] (ambisonic kernel)
 };
-static_assert(sizeof(MixSmemHdr) <= 256, "header must fit its 256-byte slot");
+static_assert(sizeof(MixSmemHdr) <= 512, "header must fit its 512-byte slot");
 
 // What the math threads need to know about a source, condensed from its WorkRec by the producer (64 B).
 struct __attribute__((aligned(16))) MathDesc {
@@ -261,34 +268,38 @@ __device__ float lpf_warp(float* buf, uint32_t F, float coef, float prev, uint32
 }
 
 // Shared-memory carve-up (both kernels): header | WorkRec ring | ShGains ring, ShRamps ring (ambisonic only) | MathDesc ring | window ring.
-template <int NCH>
+template <int NCH, int kStages>
 struct SmemView {
+	static constexpr int kRecStages = kStages + 2;
 	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; ShRamps* shrs; MathDesc* descs; float* wring;
 	__device__ explicit SmemView(unsigned char* raw) {
 		hdr = reinterpret_cast<MixSmemHdr*>(raw);
-		recs = reinterpret_cast<WorkRec*>(raw + 256);
+		recs = reinterpret_cast<WorkRec*>(raw + 512);
 		unsigned char* p = reinterpret_cast<unsigned char*>(recs) + sizeof(WorkRec) * kRecStages * kBatch;
 		shgs = reinterpret_cast<ShGains*>(p);
 		if (NCH == 16) p += sizeof(ShGains) * kRecStages * kBatch;
 		shrs = reinterpret_cast<ShRamps*>(p);       // channel ramps of the sources that have any, staged with the windows
 		if (NCH == 16) p += sizeof(ShRamps) * kStages * kBatch;
 		descs = reinterpret_cast<MathDesc*>(p);
-		p += sizeof(MathDesc) * kStages * kBatch;
+		p += sizeof(MathDesc) * kRecStages * kBatch;
 		wring = reinterpret_cast<float*>(p);
 	}
 };
 
 // ================= producer warp (both kernels): lane b looks after source b of each batch =================
-template <int NCH>
-__device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane) {
+template <int NCH, int kStages>
+__device__ void producer_warp(const SmemView<NCH, kStages>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane) {
+	constexpr int kRecStages = kStages + 2;
 	MixSmemHdr* hdr = sm.hdr;
 	const WorkRec* __restrict__ grec = a.rec;
 	const ShGains* __restrict__ gshg = a.shg;
-	// records run kRecStages - kStages batches ahead of the windows
-	auto issue_recs = [&](uint32_t jb) {
+	// Records run two batches ahead of the windows.  Per batch: (1) wait for its records, plan the windows and write the
+	// MathDescs (desc ring indexed like the record ring, so this needs no free window stage), (2) refill the record slot
+	// two batches ahead, (3) wait for the window stage to be handed back, (4) arm the barrier and issue the copies --
+	// so that between "stage handed back" and "copies issued" there are only a few instructions.
+	auto issue_recs = [&](uint32_t jb, uint32_t q, uint32_t parity_prev) {
 		if (jb >= nbatch) return;
-		const uint32_t q = jb % kRecStages;
-		if (jb >= (uint32_t)kRecStages) mbar_wait_relaxed(&hdr->empty_r[q], ((jb / kRecStages) - 1u) & 1u);
+		if (jb >= (uint32_t)kRecStages) mbar_wait_relaxed(&hdr->empty_r[q], parity_prev);
 		if (lane == 0) {
 			const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 			const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
@@ -299,30 +310,35 @@ __device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_
 		}
 		__syncwarp();
 	};
-	for (uint32_t jb = 0; jb < (uint32_t)(kRecStages - kStages); ++jb) issue_recs(jb);
+	issue_recs(0, 0, 0);
+	issue_recs(1, 1, 0);
+	uint32_t qr = 0, ph_r = 0;        // record slot of batch jb, its full_r parity
+	uint32_t qw = 0, ph_w = 0;        // window stage of batch jb, its full_w parity
+	uint32_t q2 = 2, ph_2 = 0;        // record slot of batch jb + 2, its full_r parity
 	for (uint32_t jb = 0; jb < nbatch; ++jb) {
-		issue_recs(jb + (uint32_t)(kRecStages - kStages));
-		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
-		if (jb >= (uint32_t)kStages) mbar_wait_relaxed(&hdr->empty_w[qw], ((jb / kStages) - 1u) & 1u);
-		mbar_wait(&hdr->full_r[qr], (jb / kRecStages) & 1u);
+		mbar_wait(&hdr->full_r[qr], ph_r);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
 		WinPlan p;
 		p.fast = false; p.seg1_floats = 0; p.seg2_floats = 0; p.a0 = 0;
 		const uint32_t slot_float0 = (qw * kBatch + lane) * wslot;
+		const float* pcm = nullptr;
+		bool want_ramps = false;
+		uint32_t bytes = 0;
 		if (lane < nb) {
 			const WorkRec& r = sm.recs[qr * kBatch + lane];
 			p = plan_window(r, wslot);
-			sm.descs[qw * kBatch + lane] = make_desc(r, p, slot_float0, NCH == 16);
-		}
-		uint32_t bytes = p.fast ? 4u * (p.seg1_floats + p.seg2_floats) : 0u;
-		bool want_ramps = false;
-		if (NCH == 16 && lane < nb) {
-			const WorkRec& r = sm.recs[qr * kBatch + lane];
-			want_ramps = r.ch_ramp_mask != 0 && !(r.flags & kRecSkip);
-			if (want_ramps) bytes += (uint32_t)sizeof(ShRamps);
+			sm.descs[qr * kBatch + lane] = make_desc(r, p, slot_float0, NCH == 16);
+			pcm = r.pcm;
+			if (p.fast) bytes = 4u * (p.seg1_floats + p.seg2_floats);
+			if (NCH == 16) {
+				want_ramps = r.ch_ramp_mask != 0 && !(r.flags & kRecSkip);
+				if (want_ramps) bytes += (uint32_t)sizeof(ShRamps);
+			}
 		}
 		for (int o = kBatch / 2; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+		issue_recs(jb + 2, q2, ph_2 ^ 1u);
+		if (jb >= (uint32_t)kStages) mbar_wait_relaxed(&hdr->empty_w[qw], ph_w ^ 1u);
 		__syncwarp();
 		// the arrive below releases the descriptors written above (and, transitively, the records) to the math warps
 		if (lane == 0) {
@@ -330,17 +346,21 @@ __device__ void producer_warp(const SmemView<NCH>& sm, const MixArgs& a, uint32_
 		}
 		__syncwarp();
 		if (p.fast) {
-			const float* pcm = sm.recs[qr * kBatch + lane].pcm;
 			float* dst = sm.wring + slot_float0 + 4;
 			bulk_g2s(dst, pcm + p.a0, 4u * p.seg1_floats, &hdr->full_w[qw]);
 			if (p.seg2_floats) bulk_g2s(dst + p.seg1_floats, pcm, 4u * p.seg2_floats, &hdr->full_w[qw]);
 		}
 		if (NCH == 16 && want_ramps) bulk_g2s(sm.shrs + qw * kBatch + lane, a.shr + (b0 + lane), (uint32_t)sizeof(ShRamps), &hdr->full_w[qw]);
 		__syncwarp();
+		if (++qr == (uint32_t)kRecStages) { qr = 0; ph_r ^= 1u; }
+		if (++qw == (uint32_t)kStages) { qw = 0; ph_w ^= 1u; }
+		if (++q2 == (uint32_t)kRecStages) { q2 = 0; ph_2 ^= 1u; }
 	}
 }
 
+template <int kStages>
 __device__ __forceinline__ void init_barriers(MixSmemHdr* hdr, uint32_t n_consumers) {
+	constexpr int kRecStages = kStages + 2;
 	for (int q = 0; q < kStages; ++q) { mbar_init(&hdr->full_w[q], 1); mbar_init(&hdr->empty_w[q], n_consumers); }
 	for (int q = 0; q < kRecStages; ++q) { mbar_init(&hdr->full_r[q], 1); mbar_init(&hdr->empty_r[q], n_consumers); }
 	fence_mbar_init();
@@ -357,7 +377,8 @@ __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_a
 template <int KF, bool EXACT>
 __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	const SmemView<2> sm(smem_raw);
+	constexpr int kStages = kStagesPan, kRecStages = kStages + 2;
+	const SmemView<2, kStages> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
 	const uint32_t F = a.frames, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
 	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
@@ -370,20 +391,20 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 #else
 	const uint32_t nbatch = blockIdx.x < total_batches ? (total_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 #endif
-	if (t == 0) init_barriers(hdr, kBatch);
+	if (t == 0) init_barriers<kStages>(hdr, kBatch);
 	__syncthreads();
-	if (warp == (uint32_t)kBatch) { producer_warp<2>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+	if (warp == (uint32_t)kBatch) { producer_warp<2, kStages>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float acc0[KF], acc1[KF];
 #pragma unroll
 	for (int k = 0; k < KF; ++k) { acc0[k] = 0.0f; acc1[k] = 0.0f; }
 
-	for (uint32_t jb = 0; jb < nbatch; ++jb) {
-		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
-		mbar_wait(&hdr->full_w[qw], (jb / kStages) & 1u);
+	uint32_t qr = 0, qw = 0, ph_w = 0;     // record slot / window stage of batch jb, parity of its full_w
+	for (uint32_t jb = 0; jb < nbatch; ++jb, qr = qr + 1 == (uint32_t)kRecStages ? 0u : qr + 1, ph_w ^= (qw + 1 == (uint32_t)kStages), qw = qw + 1 == (uint32_t)kStages ? 0u : qw + 1) {
+		mbar_wait(&hdr->full_w[qw], ph_w);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		if (b0 + warp < s1) {
-			const MathDesc& d = sm.descs[qw * kBatch + warp];
+			const MathDesc& d = sm.descs[qr * kBatch + warp];
 			const WorkRec& r = sm.recs[qr * kBatch + warp];
 			const uint32_t mode = d.mode;
 			if (mode & kMdSkip) {
@@ -536,7 +557,8 @@ __global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : SBM_SH_BIG_CTAS)
 k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	const SmemView<16> sm(smem_raw);
+	constexpr int kStages = TMAX == 128 ? kStagesSh : kStagesShBig, kRecStages = kStages + 2;
+	const SmemView<16, kStages> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
 	// blockDim.x = T math threads + one producer warp (the last warp)
 	const uint32_t F = a.frames, T = EXACT ? (uint32_t)TMAX : blockDim.x - 32, t = threadIdx.x, lane = t & 31u;   // EXACT: T is a compile-time constant
@@ -550,9 +572,9 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 #else
 	const uint32_t nbatch = blockIdx.x < total_batches ? (total_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 #endif
-	if (t == 0) init_barriers(hdr, T / 32);
+	if (t == 0) init_barriers<kStages>(hdr, T / 32);
 	__syncthreads();
-	if (t >= T) { producer_warp<16>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+	if (t >= T) { producer_warp<16, kStages>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1) x frames t + k T
 #pragma unroll
@@ -589,9 +611,9 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 		}
 	};
 
-	for (uint32_t jb = 0; jb < nbatch; ++jb) {
-		const uint32_t qr = jb % kRecStages, qw = jb % kStages;
-		mbar_wait(&hdr->full_w[qw], (jb / kStages) & 1u);
+	uint32_t qr = 0, qw = 0, ph_w = 0;     // record slot / window stage of batch jb, parity of its full_w
+	for (uint32_t jb = 0; jb < nbatch; ++jb, qr = qr + 1 == (uint32_t)kRecStages ? 0u : qr + 1, ph_w ^= (qw + 1 == (uint32_t)kStages), qw = qw + 1 == (uint32_t)kStages ? 0u : qw + 1) {
+		mbar_wait(&hdr->full_w[qw], ph_w);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
 		// ---------------- whole-batch fast path ----------------
@@ -601,7 +623,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 			uint32_t any = 0;
 #pragma unroll
 			for (int b = 0; b < kBatch; ++b) {
-				dh[b] = *reinterpret_cast<const uint4*>(&sm.descs[qw * kBatch + b]);
+				dh[b] = *reinterpret_cast<const uint4*>(&sm.descs[qr * kBatch + b]);
 				any |= (dh[b].x & ~(kMdInterp | kMdRamp | kMdShRamp)) | (dh[b].w > (uint32_t)TMAX ? kMdGeneric : 0u);
 			}
 			if (any == 0) {
@@ -610,7 +632,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 				for (int b = 0; b < kBatch; ++b) {
 					const float* wb = sm.wring + dh[b].y;
 					if (dh[b].x & kMdInterp) {
-						const MathDesc& d = sm.descs[qw * kBatch + b];
+						const MathDesc& d = sm.descs[qr * kBatch + b];
 #pragma unroll
 						for (int k = 0; k < K; ++k) {
 							const unsigned long long p = d.x0 + (unsigned long long)(t + (uint32_t)k * T) * d.step;
@@ -632,19 +654,19 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 					for (int k = 1; k < K; ++k) accumulate_const(gk, xs[b][k] * gdf, k);
 					if (warp_i0 < nramp) {
 						// this warp's first frames lie inside a ramp of the direct gain and / or of channel gains
-						const MathDesc& d = sm.descs[qw * kBatch + b];
+						const MathDesc& d = sm.descs[qr * kBatch + b];
 						const WorkRec& r = sm.recs[qr * kBatch + b];
 						const float yv = (xs[b][0] * d.mfx) * gain_at(r.direct, t);
 						accumulate_ramped(gk, (dh[b].x & kMdShRamp) ? &sm.shrs[qw * kBatch + b] : nullptr, yv, t, ft, 0);
 					} else accumulate_const(gk, xs[b][0] * gdf, 0);
 					// frame F - 1 = t + (K - 1) T of thread T - 1: the bypassed occlusion filter's memory (mono_pole_filter.cc:40-44)
-					if (t == T - 1) a.lpf_prev[sm.descs[qw * kBatch + b].slot] = xs[b][K - 1] * gdf;
+					if (t == T - 1) a.lpf_prev[sm.descs[qr * kBatch + b].slot] = xs[b][K - 1] * gdf;
 				}
 				batch_done = true;
 			}
 		}
 		for (uint32_t b = 0; b < nb && !batch_done; ++b) {
-			const MathDesc& d = sm.descs[qw * kBatch + b];
+			const MathDesc& d = sm.descs[qr * kBatch + b];
 			const WorkRec& r = sm.recs[qr * kBatch + b];
 			const uint32_t mode = d.mode;
 			if (mode & kMdSkip) {
@@ -807,10 +829,12 @@ int sm_count() {
 // to +25 %) plus alignment slack; larger windows take the generic path.
 uint32_t window_slot(uint32_t F) { return (F + F / 4 + 24u + 3u) & ~3u; }
 uint32_t sh_threads(uint32_t F) { return ((F + K - 1) / K + 31) / 32 * 32; }
+int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig); }
 size_t mix_smem_bytes(uint32_t F, bool sh) {
-	return 256 + sizeof(WorkRec) * kRecStages * kBatch + (sh ? sizeof(ShGains) * kRecStages * kBatch + sizeof(ShRamps) * kStages * kBatch : 0) +
-	       sizeof(MathDesc) * kStages * kBatch +
-	       sizeof(float) * (size_t)kStages * kBatch * window_slot(F);
+	const size_t st = (size_t)mix_stages(F, sh), rst = st + 2;
+	return 512 + sizeof(WorkRec) * rst * kBatch + (sh ? sizeof(ShGains) * rst * kBatch + sizeof(ShRamps) * st * kBatch : 0) +
+	       sizeof(MathDesc) * rst * kBatch +
+	       sizeof(float) * st * kBatch * window_slot(F);
 }
 constexpr uint32_t kMinSourcesPerCta = 16;
 

@@ -282,7 +282,7 @@ class Scenario:
 
     def __init__(self, n_sources, frames, seed=12345, kind=KIND_PAN, feeder="native", loop_len=16384, moving=True,
                  rates=(44100, 24000, 16000, 48000), rate_probs=(0.5, 0.2, 0.15, 0.15), boundary_safe=False,
-                 volume_toggle=False, occlusion_toggle=False, mixed_kinds=False, n_shared_buffers=0):
+                 volume_toggle=False, occlusion_toggle=False, mixed_kinds=False, n_shared_buffers=0, batched_ring_push=False):
         self.n, self.F, self.seed = n_sources, frames, seed
         rng = np.random.default_rng(seed)
         self.moving = moving
@@ -303,6 +303,7 @@ class Scenario:
         self.delta = (343.0 - v[:, 0]) / (343.0 - v[:, 1])  # doppler_factor, AudioEngine.cpp:140-145
         self.mixf = rng.uniform(0.5, 1.0, n_sources).astype(np.float32)
         self.ring_rng_seed = seed + 1
+        self.batched_ring_push = batched_ring_push
 
     def build(self, be):
         bufs = [be.buffer_create(p) for p in self.pcm]
@@ -346,12 +347,18 @@ class Scenario:
             # dropped packet exercises the underflow zero-pad (AudioEngine.cpp:466-473).
             rng = np.random.default_rng(self.ring_rng_seed + b)
             n_pk = int(np.ceil(self.F / 480.0)) + (1 if b == 0 else 0)
+            ids, packets = [], []
             for s in range(self.n):
                 if b % 7 == 5 and s % 3 == 0:
                     continue
                 scale = self.rates[s] / 48000.0
                 m = int(n_pk * 480 * scale)
-                be.source_ring_push(int(self.ids[s]), (0.3 * rng.uniform(-1, 1, m)).astype(np.float32))
+                ids.append(int(self.ids[s])); packets.append((0.3 * rng.uniform(-1, 1, m)).astype(np.float32))
+            if self.batched_ring_push and hasattr(be, "sources_ring_push"):
+                be.sources_ring_push(ids, packets)       # sbm_source_ring_push_batch: one H2D + scatter kernel
+            else:
+                for sid, pk in zip(ids, packets):
+                    be.source_ring_push(sid, pk)
 
     def run(self, be, n_buffers):
         self.build(be)

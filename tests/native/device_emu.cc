@@ -120,6 +120,16 @@ int launch_mix(const MixArgs& a, void*) {
 	return 0;
 }
 
+int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void*) {
+	if (!n) return 0;
+	++g_launches;
+	for (uint32_t k = 0; k < n; ++k) {
+		const RingPush& p = packets[k];
+		for (uint32_t i = 0; i < p.n; ++i) p.ring[(p.at + i) % p.capacity] = stage[p.src_off + i];
+	}
+	return 0;
+}
+
 int launch_finish(const FinishArgs& a, void*) {
 	++g_launches;
 	const uint32_t F = a.frames;

@@ -109,3 +109,33 @@ def test_empty_engine_is_invalid_and_silent():
     e = emu_engine(128)
     v, o = e.mix()
     assert v == 0 and not o.any()
+
+
+def test_batched_ring_push_equals_per_source_pushes():
+    """sbm_source_ring_push_batch (one staged H2D + scatter) must leave every ring exactly as the
+    per-source sbm_source_ring_push calls do -- including ring wrap, dropped packets (underflow) and mixed rates."""
+    F, nb = 256, 12
+    hr = load_sh_hrir()
+    kw = dict(n_sources=24, frames=F, kind=KIND_HRTF, feeder="ring", rates=(48000, 24000), rate_probs=(0.5, 0.5), seed=91)
+    a, va = Scenario(**kw).run(emu_engine(F, hr), nb)
+    b, vb = Scenario(batched_ring_push=True, **kw).run(emu_engine(F, hr), nb)
+    o, vo = Scenario(**kw).run(OracleBackend(F, sh_hrir=hr), nb)
+    assert va == vb == vo
+    assert np.array_equal(a, b)
+    assert rel_rms(b, o) <= TOL
+
+
+def test_batched_ring_push_is_all_or_nothing():
+    e = emu_engine(256)
+    ids = [e.source_create(KIND_PAN) for _ in range(2)]
+    for sid in ids:
+        e.source_attach_ring(sid, 48000, capacity=1000)
+    e.sources_ring_push(ids, [np.ones(600, np.float32), np.ones(300, np.float32)])
+    with pytest.raises(sb.SbmError) as ei:      # the first ring would overflow: neither packet is accepted
+        e.sources_ring_push([ids[1], ids[0]], [np.ones(100, np.float32), np.ones(500, np.float32)])
+    assert ei.value.code == -5
+    assert e.source_ring_size(ids[0]) == 600 and e.source_ring_size(ids[1]) == 300
+    e.sources_ring_push([ids[1], ids[1]], [np.ones(100, np.float32), np.ones(50, np.float32)])      # the same id twice appends in order
+    assert e.source_ring_size(ids[1]) == 450
+    with pytest.raises(sb.SbmError):
+        e.sources_ring_push([12345], [np.ones(4, np.float32)])

@@ -39,6 +39,7 @@ def test_cuda_matches_reference_golden(name):
     (dict(n_sources=1024, kind=KIND_HRTF, feeder="resample", loop_len=4096, seed=24, volume_toggle=True), 512, 12, 0),
     (dict(n_sources=300, mixed_kinds=True, occlusion_toggle=True, volume_toggle=True, seed=25, n_shared_buffers=7, feeder="resample"), 256, 12, 0),
     (dict(n_sources=64, kind=KIND_PAN, feeder="ring", seed=26, rates=(48000, 44100), rate_probs=(0.5, 0.5)), 256, 10, 0),
+    (dict(n_sources=256, kind=KIND_HRTF, feeder="ring", seed=37, rates=(48000, 24000), rate_probs=(0.7, 0.3), batched_ring_push=True), 256, 12, 0),
     (dict(n_sources=200, kind=KIND_PAN, loop_len=100, feeder="resample", seed=27), 1024, 6, 0),     # loops shorter than a buffer
     (dict(n_sources=100, kind=KIND_HRTF, seed=28), 32, 10, 0),                                      # smallest buffer Resonance accepts
     (dict(n_sources=100, mixed_kinds=True, seed=29), 1000, 5, 0),                                   # frames not a multiple of the tile
