@@ -291,7 +291,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
     eng, pcm, ids, p = build_engine(wl, local_rank, 12345 + rank)
     F, n = wl["frames"], wl["n"]
     from substrata_b200.sharding import ShardedMixer
-    mixer = ShardedMixer(eng, device="cuda:%d" % local_rank)
+    mixer = ShardedMixer(eng, device="cuda:%d" % local_rank, exchange=args.exchange)
     stream = mixer.stream
     out_host = np.zeros(2 * F, np.float32)
     eng.set_profiling(True)
@@ -394,7 +394,8 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
             "config": {"workload": args.workload, "description": wl["desc"], "sources_per_gpu": n, "frames": F, "sample_rate": 48000,
                        "pcm": "private %d-sample f32 loops resident in HBM (%.1f GiB/GPU)" % (wl["loop"], n * (wl["loop"] + 16) * 4 / 2**30),
                        "l2": "per-step PCM windows %.0f MB >> 126 MB L2: inputs larger than L2, no flush" % (res["algo"] / 1e6),
-                       "parallelism": "sources sharded, 1 rank/GPU" + (", NCCL all-reduce of the 18x%d bus" % F if world > 1 else ""),
+                       "parallelism": "sources sharded, 1 rank/GPU" + ((", 18x%d bus exchanged over NVLink peer memory inside K3 / the gather kernel" % F if args.exchange == "peer"
+                                                                        else ", NCCL all-reduce of the 18x%d bus" % F) if world > 1 else ""),
                        "realtime_budget_ms": 1e3 * F / 48000.0},
             "e2e": {"value": total / (e2e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e2e["ms"], "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "what": ("%d source positions + listener pose from host arrays per step, stereo buffer back to host, through sbm_set_*/sbm_mix" % movers) +
@@ -426,6 +427,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4_1m_doppler_pan", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "allreduce"],
+                    help="N > 1: bus exchange inside the kernels over NVLink peer memory (default) or an NCCL all-reduce between mix_begin and mix_finish")
     ap.add_argument("--sources", type=int, default=0, help="override the workload's sources per GPU (profiling under ncu only; the line says so)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -137,6 +137,17 @@ SBM_API int sbm_mix(sbm_engine* e, float* out_interleaved, int* out_valid);
  * followed by 4 floats of flags {ambisonic bus used, stereo bus used, 0, 0} that sum across ranks like the audio. */
 SBM_API int sbm_mix_begin(sbm_engine* e);
 SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid);
+/* Multi-GPU (one engine per GPU, one process per GPU, sources sharded by the caller): the only exchange of
+ * the path -- the sum of the ranks' [18][frames] buses -- runs over NVLink peer memory inside the kernels: K3 stores
+ * its bus into every rank's gather area and signals, a gather kernel in front of K4 waits and sums in rank order.
+ *   sbm_peer_export : allocates this engine's gather area and returns its 64-byte CUDA IPC handle;
+ *   sbm_peer_connect: after the ranks exchanged their handles (any host transport; handles + p * handle_stride is rank
+ *                     p's), maps the peers.  From then on every sbm_mix / sbm_mix_begin+finish is a collective: all
+ *                     ranks must call it for every buffer.  world == 1 is allowed (no peers).
+ * Without these calls an engine is single-GPU; a caller may also sum buses itself between sbm_mix_begin and
+ * sbm_mix_finish (sbm_bus_device), which is what the CPU-only tests do over gloo. */
+SBM_API int sbm_peer_export(sbm_engine* e, void* handle_out, size_t handle_bytes /* >= 64 */);
+SBM_API int sbm_peer_connect(sbm_engine* e, int rank, int world, const void* handles, size_t handle_stride);
 SBM_API int sbm_bus_device(sbm_engine* e, float** out_device_ptr, size_t* out_num_floats);
 SBM_API int sbm_out_device(sbm_engine* e, float** out_device_ptr);
 SBM_API void* sbm_stream(sbm_engine* e);   /* cudaStream_t */

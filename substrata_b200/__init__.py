@@ -233,6 +233,19 @@ class MixEngine:
         self._ck(self._l.sbm_mix_finish(self.h, _p(out) if copy_out else None, C.byref(valid)), "sbm_mix_finish")
         return valid.value, out
 
+    def peer_export(self):
+        """64-byte CUDA IPC handle of this engine's gather area (multi-GPU bus exchange over peer memory)."""
+        h = (C.c_ubyte * 64)()
+        self._ck(self._l.sbm_peer_export(self.h, h, 64), "sbm_peer_export")
+        return bytes(h)
+
+    def peer_connect(self, rank, world, handles):
+        """handles: the ranks' peer_export() results in rank order (exchanged by any host transport)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._ck(self._l.sbm_peer_connect(self.h, int(rank), int(world), buf, 64), "sbm_peer_connect")
+
     def bus_device(self):
         ptr, n = C.c_void_p(), C.c_size_t()
         self._ck(self._l.sbm_bus_device(self.h, C.byref(ptr), C.byref(n)), "sbm_bus_device")

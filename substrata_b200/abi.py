@@ -51,6 +51,8 @@ SIGNATURES = {
     "sbm_mix": (_i, [_vp, _vp, _vp]),
     "sbm_mix_begin": (_i, [_vp]),
     "sbm_mix_finish": (_i, [_vp, _vp, _vp]),
+    "sbm_peer_export": (_i, [_vp, _vp, _sz]),
+    "sbm_peer_connect": (_i, [_vp, _i, _i, _vp, _sz]),
     "sbm_bus_device": (_i, [_vp, _vp, _vp]),
     "sbm_out_device": (_i, [_vp, _vp]),
     "sbm_stream": (_vp, [_vp]),

@@ -34,6 +34,18 @@ struct RingPush {               // one packet of a batched ring push: stage[src_
 	uint32_t n;
 };
 
+constexpr int kMaxPeers = 8;
+// Cross-GPU exchange of the bus over NVLink peer memory (world == 0: single GPU, nothing is exchanged).
+// Every rank owns one gather area [2 buffer parities][world][bus_floats] plus two arrival counters; K3 of rank r stores
+// its reduced bus straight into slot r of EVERY rank's area (peer stores) and then bumps every rank's counter; the gather
+// kernel in front of K4 waits for `world` arrivals and sums the slots in rank order (identical result on all ranks).
+struct PeerArgs {
+	uint32_t rank, world;
+	float* gather[kMaxPeers];           // gather[p]: rank p's area (own memory for p == rank, peer-mapped otherwise)
+	unsigned int* arrive[kMaxPeers];    // arrive[p]: rank p's two monotonic arrival counters
+	unsigned int* done;                 // local: K3 CTAs finished (last-CTA election)
+};
+
 struct MixArgs {
 	const WorkRec* rec;         // [n_pan + n_sh] render-list order: stereo-bus sources first, then ambisonic sources
 	const ShGains* shg;         // indexed like rec
@@ -52,6 +64,8 @@ struct MixArgs {
 	const DevFlags* flags;
 	uint32_t parity;
 	void* ev_after_k2;          // optional event recorded between K2 and K3 (profiling)
+	PeerArgs peer;
+	size_t bus_floats;
 };
 
 struct FinishArgs {
@@ -99,6 +113,11 @@ int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const 
 int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void* stream);   // batched ring push: one CTA per packet
 int launch_mix(const MixArgs& a, void* stream);  // K2 (both lists) + K3 (partials -> bus)
 int launch_finish(const FinishArgs& a, void* stream);
+// peer exchange (multi-GPU): IPC plumbing + the gather kernel
+int peer_export(void* device_ptr, void* handle_out64);             // cudaIpcGetMemHandle
+void* peer_open(const void* handle64);                             // cudaIpcOpenMemHandle (other process, any GPU of the node)
+void peer_close(void* mapped);
+int launch_peer_gather(const PeerArgs& pa, float* bus_sum, size_t bus_floats, uint32_t parity, unsigned int target, void* stream);
 // timing
 void* event_create();
 void event_destroy(void* ev);

@@ -195,6 +195,22 @@ int d2h(void* dst, const void* src, size_t bytes, void* stream) {
 int zero(void* dst, size_t bytes, void* stream) { return check(cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)stream), "cudaMemsetAsync"); }
 int sync(void* stream) { return check(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
 
+int peer_export(void* device_ptr, void* handle_out64) {
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+	cudaIpcMemHandle_t h;
+	if (check(cudaIpcGetMemHandle(&h, device_ptr), "cudaIpcGetMemHandle")) return -1;
+	memcpy(handle_out64, &h, sizeof(h));
+	return 0;
+}
+void* peer_open(const void* handle64) {
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof(h));
+	void* p = nullptr;
+	if (check(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return nullptr;
+	return p;
+}
+void peer_close(void* mapped) { if (mapped) cudaIpcCloseMemHandle(mapped); }
+
 int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void* stream) {
 	if (!n) return 0;
 	k_ring_scatter_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(packets, stage);

@@ -80,9 +80,15 @@ struct sbm_engine {
 	float* dv_bus = nullptr; size_t bus_floats = 0;
 	float* dv_hrir = nullptr; float* dv_hist = nullptr; float* dv_dec = nullptr;
 	float* dv_out = nullptr; size_t out_bytes = 0;
+	// multi-GPU bus exchange over peer memory (sbm_peer_export / sbm_peer_connect)
+	PeerArgs peer{};                         // world == 0 until connected
+	float* dv_gather = nullptr;              // own gather area [2][kMaxPeers][bus_floats] followed by the counters
+	float* dv_bus_sum = nullptr;             // bus summed over ranks (what K4 reads when connected)
+	void* peer_mapped[kMaxPeers] = {};       // IPC mappings of the other ranks' areas
 	unsigned char* h_ring_stage = nullptr;   // pinned staging of sbm_source_ring_push_batch: packet table + payload
 	unsigned char* d_ring_stage = nullptr;
 	size_t ring_stage_bytes = 0;
+	unsigned long long peer_epoch = 0;       // buffer_index at which the peers were connected (arrival counters count from there)
 	size_t pending_ring_h2d_bytes = 0;       // ring pushes since the last sbm_mix_begin (reported with the next buffer's stats)
 	bool ring_stage_in_flight = false;       // an H2D from h_ring_stage may still be running (cleared by every stream sync in mix)
 	unsigned char* h_out = nullptr;          // pinned D2H staging: 2F floats + OutTail + ring read counters
@@ -257,6 +263,9 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	for (auto& b : e->buffers) if (b.owned && b.dptr) dev::release(b.dptr);
 	for (auto& r : e->rings) if (r.storage) dev::release(r.storage);
 	if (e->h_out) dev::release_pinned(e->h_out);
+	for (void* m : e->peer_mapped) dev::peer_close(m);
+	if (e->dv_gather) dev::release(e->dv_gather);
+	if (e->dv_bus_sum) dev::release(e->dv_bus_sum);
 	if (e->h_ring_stage) dev::release_pinned(e->h_ring_stage);
 	if (e->d_ring_stage) dev::release(e->d_ring_stage);
 	for (int i = 0; i < 4; ++i) if (e->ev[i]) dev::event_destroy(e->ev[i]);
@@ -687,6 +696,7 @@ SBM_API int sbm_mix_begin(sbm_engine* e) {
 	m.frames = e->g.frames; m.rate = e->g.rate; m.partials = e->dv_partials; m.partials_floats = e->partials_floats;
 	m.bus = e->dv_bus; m.flags = e->dv_flags; m.parity = e->g.parity;
 	m.ev_after_k2 = e->profiling ? e->ev[2] : nullptr;
+	m.peer = e->peer; m.bus_floats = e->bus_floats;
 	if (dev::launch_mix(m, st)) return fail_cuda(e, "k2_mix");
 	e->begun = true;
 	e->stats.active_sources = (uint32_t)(e->list_pan.size() + e->list_sh.size());
@@ -702,8 +712,13 @@ SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid
 	void* st = e->stream;
 	const uint32_t F = e->g.frames;
 	const uint32_t parity = (uint32_t)(e->buffer_index & 1);
+	if (e->peer.world) {
+		// wait for every rank's bus of this buffer (K3 stored them into our gather area) and sum them in rank order
+		const unsigned int target = (unsigned int)(e->peer.world * ((e->buffer_index >> 1) - (e->peer_epoch >> 1) + 1));
+		if (dev::launch_peer_gather(e->peer, e->dv_bus_sum, e->bus_floats, parity, target, st)) return fail_cuda(e, "k_peer_gather");
+	}
 	FinishArgs f;
-	f.bus = e->dv_bus; f.hrir = e->dv_hrir; f.taps = (uint32_t)e->cfg.sh_hrir_taps; f.hist = e->dv_hist; f.dec = e->dv_dec;
+	f.bus = e->peer.world ? e->dv_bus_sum : e->dv_bus; f.hrir = e->dv_hrir; f.taps = (uint32_t)e->cfg.sh_hrir_taps; f.hist = e->dv_hist; f.dec = e->dv_dec;
 	f.flags = e->dv_flags; f.parity = parity; f.frames = F; f.out = e->dv_out;
 	f.list_ring = e->dv_list_ring; f.n_ring = (uint32_t)e->list_ring.size(); f.read_i = e->A.read_i; f.finished_count_reset = nullptr;
 	if (dev::launch_finish(f, st)) return fail_cuda(e, "k4_finish");
@@ -750,6 +765,52 @@ SBM_API int sbm_mix(sbm_engine* e, float* out_interleaved, int* out_valid) {
 	const int rc = sbm_mix_begin(e);
 	if (rc) return rc;
 	return sbm_mix_finish(e, out_interleaved, out_valid);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// multi-GPU: one engine per GPU / process, sources sharded, buses exchanged over NVLink peer memory
+// ---------------------------------------------------------------------------------------------------------------
+static size_t gather_area_floats(const sbm_engine* e) { return 2 * (size_t)kMaxPeers * e->bus_floats; }
+
+SBM_API int sbm_peer_export(sbm_engine* e, void* handle_out, size_t handle_bytes) {
+	if (!e || !handle_out || handle_bytes < 64) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	if (!e->dv_gather) {
+		// area + 16 counters' worth of padding: [2 arrival counters][done counter]
+		e->dv_gather = (float*)dev::alloc(sizeof(float) * (gather_area_floats(e) + 16));
+		e->dv_bus_sum = (float*)dev::alloc(sizeof(float) * e->bus_floats);
+		if (!e->dv_gather || !e->dv_bus_sum) return fail_cuda(e, "sbm_peer_export(alloc)");
+	}
+	if (dev::peer_export(e->dv_gather, handle_out)) return fail_cuda(e, "sbm_peer_export");
+	return SBM_OK;
+}
+
+SBM_API int sbm_peer_connect(sbm_engine* e, int rank, int world, const void* handles, size_t handle_stride) {
+	if (!e || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || (world > 1 && (!handles || handle_stride < 64))) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	if (!e->dv_gather) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect before sbm_peer_export");
+	if (e->begun) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect between sbm_mix_begin and sbm_mix_finish");
+	if (e->peer.world) return fail(e, SBM_ERR_INVALID_ARG, "already connected");
+	// the arrival counters count buffers per parity from now on: all ranks must connect at the same, even, buffer index
+	if (e->buffer_index & 1) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect needs an even number of buffers mixed so far (all ranks alike)");
+	PeerArgs pa{};
+	pa.rank = (uint32_t)rank; pa.world = (uint32_t)world;
+	for (int p = 0; p < world; ++p) {
+		float* base = e->dv_gather;
+		if (p != rank) {
+			e->peer_mapped[p] = dev::peer_open((const unsigned char*)handles + (size_t)p * handle_stride);
+			if (!e->peer_mapped[p]) return fail_cuda(e, "sbm_peer_connect");
+			base = (float*)e->peer_mapped[p];
+		}
+		pa.gather[p] = base;
+		pa.arrive[p] = (unsigned int*)(base + gather_area_floats(e));
+	}
+	pa.done = (unsigned int*)(e->dv_gather + gather_area_floats(e)) + 4;
+	e->peer = pa;
+	e->peer_epoch = e->buffer_index;
+	return SBM_OK;
 }
 
 SBM_API int sbm_bus_device(sbm_engine* e, float** out_device_ptr, size_t* out_num_floats) {

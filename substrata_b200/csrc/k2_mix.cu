@@ -789,7 +789,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 // Also publishes this rank's "mixer used" flags as floats behind the audio so that they sum across ranks with it.
 __global__ void __launch_bounds__(256) k3_reduce_kernel(const float* __restrict__ part_pan, uint32_t g_pan, const float* __restrict__ part_sh,
                                                        uint32_t g_sh, float* __restrict__ bus, const DevFlags* __restrict__ flags,
-                                                       uint32_t parity, uint32_t F) {
+                                                       uint32_t parity, uint32_t F, PeerArgs pa, size_t bus_floats) {
 	__shared__ float warp_sum[8][32];
 	const uint32_t row = blockIdx.y, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	const uint32_t f = blockIdx.x * 32 + lane;
@@ -799,18 +799,61 @@ __global__ void __launch_bounds__(256) k3_reduce_kernel(const float* __restrict_
 	if (f < F) for (uint32_t b = w; b < g; b += 8) s += part[((size_t)b * rows + r) * F + f];
 	warp_sum[w][lane] = s;
 	__syncthreads();
+	// multi-GPU: this rank's slot in rank p's gather area
+	const size_t slot_off = ((size_t)parity * pa.world + pa.rank) * bus_floats;
 	if (w == 0 && f < F) {
 		float t = warp_sum[0][lane];
 #pragma unroll
 		for (int q = 1; q < 8; ++q) t += warp_sum[q][lane];
 		bus[(size_t)row * F + f] = t;
+		for (uint32_t p = 0; p < pa.world; ++p) pa.gather[p][slot_off + (size_t)row * F + f] = t;     // NVLink peer stores (local for p == rank)
 	}
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-		float* bf = bus + (size_t)kBusRows * F;
+		float bf[4];
 		bf[0] = flags->sh_used[parity] ? 1.0f : 0.0f;
 		bf[1] = flags->pan_used[parity] ? 1.0f : 0.0f;
 		bf[2] = flags->st_used[parity] ? 1.0f : 0.0f;
 		bf[3] = 0.0f;
+		for (int q = 0; q < 4; ++q) {
+			bus[(size_t)kBusRows * F + q] = bf[q];
+			for (uint32_t p = 0; p < pa.world; ++p) pa.gather[p][slot_off + (size_t)kBusRows * F + q] = bf[q];
+		}
+	}
+	if (pa.world) {
+		// Last-CTA election: every CTA makes its peer stores visible system-wide, then counts itself; the CTA that completes
+		// the count signals one arrival to every rank (system-scope atomics on peer memory).
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			const unsigned int total = gridDim.x * gridDim.y;
+			if (atomicAdd(pa.done, 1u) == total - 1u) {
+				*pa.done = 0u;
+				__threadfence_system();
+				for (uint32_t p = 0; p < pa.world; ++p) atomicAdd_system(pa.arrive[p] + parity, 1u);
+			}
+		}
+	}
+}
+
+// Gather kernel in front of K4 (multi-GPU): waits until all `world` ranks have delivered this buffer's bus into the
+// local gather area, then sums the slots in rank order -- every rank computes the identical sum.  A peer that never
+// arrives (crashed rank) trips the trap after ~2 s instead of hanging the device.
+__global__ void __launch_bounds__(256) k_peer_gather_kernel(PeerArgs pa, float* __restrict__ bus_sum, size_t bus_floats, uint32_t parity, unsigned int target) {
+	if (threadIdx.x == 0) {
+		const volatile unsigned int* cnt = pa.arrive[pa.rank] + parity;
+		unsigned int spins = 0;
+		while ((int)(*cnt - target) < 0) {
+			__nanosleep(256);
+			if (++spins > (1u << 23)) __trap();
+		}
+		__threadfence_system();
+	}
+	__syncthreads();
+	const float* area = pa.gather[pa.rank] + (size_t)parity * pa.world * bus_floats;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bus_floats; i += (size_t)gridDim.x * blockDim.x) {
+		float s = 0.0f;
+		for (uint32_t p = 0; p < pa.world; ++p) s += __ldcg(area + (size_t)p * bus_floats + i);
+		bus_sum[i] = s;
 	}
 }
 
@@ -921,9 +964,16 @@ int launch_mix(const MixArgs& a, void* stream) {
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
-	k3_reduce_kernel<<<dim3((F + 31) / 32, kBusRows), 256, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F);
+	k3_reduce_kernel<<<dim3((F + 31) / 32, kBusRows), 256, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F, a.peer, a.bus_floats);
 	note_launch();
 	return check_launch("k3_reduce");
+}
+
+int launch_peer_gather(const PeerArgs& pa, float* bus_sum, size_t bus_floats, uint32_t parity, unsigned int target, void* stream) {
+	const uint32_t grid = (uint32_t)((bus_floats + 255) / 256);
+	k_peer_gather_kernel<<<grid < 148u ? grid : 148u, 256, 0, (cudaStream_t)stream>>>(pa, bus_sum, bus_floats, parity, target);
+	note_launch();
+	return check_launch("k_peer_gather");
 }
 
 }  // namespace dev

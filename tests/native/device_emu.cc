@@ -120,6 +120,12 @@ int launch_mix(const MixArgs& a, void*) {
 	return 0;
 }
 
+// The host emulation has no peer GPUs: multi-rank CPU tests sum the buses with a gloo all-reduce instead (sharding.py).
+int peer_export(void*, void*) { return -1; }
+void* peer_open(const void*) { return nullptr; }
+void peer_close(void*) {}
+int launch_peer_gather(const PeerArgs&, float*, size_t, uint32_t, unsigned int, void*) { return -1; }
+
 int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void*) {
 	if (!n) return 0;
 	++g_launches;
