@@ -45,6 +45,9 @@ namespace {
 #ifndef SBM_MIN_CTAS
 #define SBM_MIN_CTAS 4
 #endif
+#ifndef SBM_PACKED_LERP
+#define SBM_PACKED_LERP 1             // stereo kernel: interpolate frame pairs with packed f32x2 instructions
+#endif
 #ifndef SBM_PRODUCER_SLEEP_NS
 #define SBM_PRODUCER_SLEEP_NS 200
 #endif
@@ -116,6 +119,12 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2 g, const float2 
 	unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
 	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(*reinterpret_cast<const unsigned long long*>(&g)), "l"(*reinterpret_cast<const unsigned long long*>(&x)));
 	acc = *reinterpret_cast<float2*>(&a);
+}
+
+__device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
+	unsigned long long r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+	return *reinterpret_cast<float2*>(&r);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -395,9 +404,9 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 	__syncthreads();
 	if (warp == (uint32_t)kBatch) { producer_warp<2, kStages>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
-	float acc0[KF], acc1[KF];
+	float2 acc[KF];     // (L, R) of frame lane + 32 k: one FFMA2 (gain pair x broadcast sample) per frame on the constant-gain path
 #pragma unroll
-	for (int k = 0; k < KF; ++k) { acc0[k] = 0.0f; acc1[k] = 0.0f; }
+	for (int k = 0; k < KF; ++k) acc[k] = make_float2(0.0f, 0.0f);
 
 	uint32_t qr = 0, qw = 0, ph_w = 0;     // record slot / window stage of batch jb, parity of its full_w
 	for (uint32_t jb = 0; jb < nbatch; ++jb, qr = qr + 1 == (uint32_t)kRecStages ? 0u : qr + 1, ph_w ^= (qw + 1 == (uint32_t)kStages), qw = qw + 1 == (uint32_t)kStages ? 0u : qw + 1) {
@@ -457,8 +466,7 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 						const bool rsmp = (mode & kMdResample) != 0;
 						unsigned long long p = d.x0 + (unsigned long long)lane * d.step;
 						const unsigned long long step32 = d.step << 5;
-#pragma unroll
-						for (int k = 0; k < KF; ++k) {
+						auto lerp1 = [&](int k) {
 							const uint32_t i = lane + 32u * k;
 							float v = 0.0f;
 							if (EXACT || i < F) {
@@ -474,6 +482,28 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 							}
 							x[k] = v;
 							p += step32;
+						};
+						if (EXACT && SBM_PACKED_LERP) {
+							// frames 1 .. KF-2 in pairs: the two interpolations of a pair share packed f32x2 instructions
+							lerp1(0);
+#pragma unroll
+							for (int k = 1; k + 1 < KF - 1; k += 2) {
+								const unsigned long long pa = p, pb = p + step32;
+								const uint32_t da = (uint32_t)(pa >> 32), db = (uint32_t)(pb >> 32);
+								const float2 v0 = make_float2(wb[da], wb[db]), v1 = make_float2(wb[da + 1], wb[db + 1]);
+								const float2 fb = make_float2(__uint_as_float(0x3f800000u | ((uint32_t)pa >> 9)), __uint_as_float(0x3f800000u | ((uint32_t)pb >> 9)));
+								const float2 fr = fadd2(fb, make_float2(-1.0f, -1.0f));
+								float2 dv = v1;
+								ffma2(dv, v0, make_float2(-1.0f, -1.0f));     // v1 - v0
+								float2 v = v0;
+								ffma2(v, fr, dv);                              // v0 + fr (v1 - v0)
+								x[k] = v.x; x[k + 1] = v.y;
+								p += step32 << 1;
+							}
+							lerp1(KF - 1);
+						} else {
+#pragma unroll
+							for (int k = 0; k < KF; ++k) lerp1(k);
 						}
 						if (rsmp && lane == 0) {
 							const WinPlan wp = plan_window(r, wslot);
@@ -489,7 +519,7 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 					}
 				}
 				// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
-				const float g0 = d.g0, g1 = d.g1;
+				const float2 g01 = make_float2(d.g0, d.g1);
 				const uint32_t nramp = filtered ? F : d.nramp;     // frames that need per-frame gain evaluation
 				// RAMPS: 0 = no gain ramps in this buffer, 1 = ramps end within the first 32 frames (the usual case while the
 				// listener moves), 2 = anything (long ramps, filtered signal): per-iteration warp-uniform test.
@@ -501,12 +531,11 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 						const bool per_frame = RAMPS == 2 ? (32u * k < nramp) : (RAMPS == 1 && k == 0);
 						if (per_frame) {
 							const float yv = filtered ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
-							acc0[k] = fmaf(gain_at(r.ch[0], i), yv, acc0[k]);
-							acc1[k] = fmaf(gain_at(r.ch[1], i), yv, acc1[k]);
+							acc[k].x = fmaf(gain_at(r.ch[0], i), yv, acc[k].x);
+							acc[k].y = fmaf(gain_at(r.ch[1], i), yv, acc[k].y);
 							if (!filtered && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[d.slot] = yv;
 						} else {
-							acc0[k] = fmaf(g0, x[k], acc0[k]);
-							acc1[k] = fmaf(g1, x[k], acc1[k]);
+							ffma2(acc[k], g01, make_float2(x[k], x[k]));
 							// bypassed occlusion filter remembers the last input sample (mono_pole_filter.cc:40-44)
 							if ((k == KF - 1 || !EXACT) && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[d.slot] = x[k] * d.gd;
 						}
@@ -527,7 +556,7 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 #pragma unroll
 	for (int k = 0; k < KF; ++k) {
 		const uint32_t i = lane + 32u * k;
-		if (EXACT || i < F) { tile[(warp * 2 + 0) * F + i] = acc0[k]; tile[(warp * 2 + 1) * F + i] = acc1[k]; }
+		if (EXACT || i < F) { tile[(warp * 2 + 0) * F + i] = acc[k].x; tile[(warp * 2 + 1) * F + i] = acc[k].y; }
 	}
 	math_sync(kBatch * 32);
 	float* out = partials + (size_t)blockIdx.x * 2 * F;
