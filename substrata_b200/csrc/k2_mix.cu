@@ -40,7 +40,7 @@ namespace {
 #define SBM_GLOBAL_BATCH(jb) (blockIdx.x + (jb) * gridDim.x)
 #endif
 #ifndef SBM_STAGES
-#define SBM_STAGES 4
+#define SBM_STAGES 2
 #endif
 #ifndef SBM_MIN_CTAS
 #define SBM_MIN_CTAS 4
@@ -54,7 +54,13 @@ namespace {
 #ifndef SBM_SH_BIG_CTAS
 #define SBM_SH_BIG_CTAS 1             // resident CTAs per SM the 1024-frame ambisonic kernel's register budget is set for (2 -> 96 registers and spills)
 #endif
-constexpr int kBatch = 4;             // sources per pipeline stage
+#ifndef SBM_BATCH_PAN
+#define SBM_BATCH_PAN 8
+#endif
+// Sources per pipeline stage.  The producer warp plans one source per LANE, so its (latency-bound, serial) cost per batch
+// is the same for 4 or 8 sources: the stereo kernel, whose math warps take a source each, uses batches of 8 (two rounds
+// of its four warps) to halve the producer's cost per source -- it was the producer, not HBM, the math warps waited for.
+constexpr int kBatchSh = 4, kBatchPan = SBM_BATCH_PAN, kPanWarps = 4;
 // Window stages in flight per CTA (batches of kBatch sources); the record ring is two batches deeper.
 #ifndef SBM_STAGES_SH
 #define SBM_STAGES_SH 4
@@ -277,7 +283,7 @@ __device__ float lpf_warp(float* buf, uint32_t F, float coef, float prev, uint32
 }
 
 // Shared-memory carve-up (both kernels): header | WorkRec ring | ShGains ring, ShRamps ring (ambisonic only) | MathDesc ring | window ring.
-template <int NCH, int kStages>
+template <int NCH, int kStages, int kBatch>
 struct SmemView {
 	static constexpr int kRecStages = kStages + 2;
 	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; ShRamps* shrs; MathDesc* descs; float* wring;
@@ -296,8 +302,8 @@ struct SmemView {
 };
 
 // ================= producer warp (both kernels): lane b looks after source b of each batch =================
-template <int NCH, int kStages>
-__device__ void producer_warp(const SmemView<NCH, kStages>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane) {
+template <int NCH, int kStages, int kBatch>
+__device__ void producer_warp(const SmemView<NCH, kStages, kBatch>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane) {
 	constexpr int kRecStages = kStages + 2;
 	MixSmemHdr* hdr = sm.hdr;
 	const WorkRec* __restrict__ grec = a.rec;
@@ -384,10 +390,10 @@ __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_a
 // KF = frames / 32 rounded up to 8, 16 or 32; EXACT = (frames == 32 * KF): no per-frame bounds checks.
 // =====================================================================================================================
 template <int KF, bool EXACT>
-__global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+__global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	constexpr int kStages = kStagesPan, kRecStages = kStages + 2;
-	const SmemView<2, kStages> sm(smem_raw);
+	constexpr int kStages = kStagesPan, kRecStages = kStages + 2, kBatch = kBatchPan;
+	const SmemView<2, kStages, kBatch> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
 	const uint32_t F = a.frames, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
 	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
@@ -400,9 +406,9 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 #else
 	const uint32_t nbatch = blockIdx.x < total_batches ? (total_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 #endif
-	if (t == 0) init_barriers<kStages>(hdr, kBatch);
+	if (t == 0) init_barriers<kStages>(hdr, kPanWarps);
 	__syncthreads();
-	if (warp == (uint32_t)kBatch) { producer_warp<2, kStages>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+	if (warp == (uint32_t)kPanWarps) { producer_warp<2, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[KF];     // (L, R) of frame lane + 32 k: one FFMA2 (gain pair x broadcast sample) per frame on the constant-gain path
 #pragma unroll
@@ -412,9 +418,11 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 	for (uint32_t jb = 0; jb < nbatch; ++jb, qr = qr + 1 == (uint32_t)kRecStages ? 0u : qr + 1, ph_w ^= (qw + 1 == (uint32_t)kStages), qw = qw + 1 == (uint32_t)kStages ? 0u : qw + 1) {
 		mbar_wait(&hdr->full_w[qw], ph_w);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
-		if (b0 + warp < s1) {
-			const MathDesc& d = sm.descs[qr * kBatch + warp];
-			const WorkRec& r = sm.recs[qr * kBatch + warp];
+#pragma unroll 1
+		for (uint32_t src = warp; src < (uint32_t)kBatch; src += kPanWarps)     // this warp's sources of the batch
+		if (b0 + src < s1) {
+			const MathDesc& d = sm.descs[qr * kBatch + src];
+			const WorkRec& r = sm.recs[qr * kBatch + src];
 			const uint32_t mode = d.mode;
 			if (mode & kMdSkip) {
 				// gain-skipped source: the feeder still consumed this buffer; carry the resampler history forward
@@ -430,7 +438,7 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 				if (mode & (kMdGeneric | kMdLpf | kMdAdjust)) {
 					// ---------------- careful fetch (rare): every case, straightforward arithmetic ----------------
 					const WinPlan wp = plan_window(r, wslot);
-					float* slot = sm.wring + (size_t)(qw * kBatch + warp) * wslot;     // this warp's stage slot
+					float* slot = sm.wring + (size_t)(qw * kBatch + src) * wslot;     // this source's stage slot
 					const float* w = slot + 4 + wp.off0;
 #pragma unroll
 					for (int k = 0; k < KF; ++k) {
@@ -551,19 +559,19 @@ __global__ void __launch_bounds__(kBatch * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS)
 		if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }
 	}
 	// ---- combine the math warps' tiles (the window ring is idle now: every batch has been consumed) ----
-	math_sync(kBatch * 32);
-	float* tile = sm.wring;     // [kBatch][2][F]
+	math_sync(kPanWarps * 32);
+	float* tile = sm.wring;     // [kPanWarps][2][F]
 #pragma unroll
 	for (int k = 0; k < KF; ++k) {
 		const uint32_t i = lane + 32u * k;
 		if (EXACT || i < F) { tile[(warp * 2 + 0) * F + i] = acc[k].x; tile[(warp * 2 + 1) * F + i] = acc[k].y; }
 	}
-	math_sync(kBatch * 32);
+	math_sync(kPanWarps * 32);
 	float* out = partials + (size_t)blockIdx.x * 2 * F;
-	for (uint32_t q = t; q < 2 * F; q += kBatch * 32) {
+	for (uint32_t q = t; q < 2 * F; q += kPanWarps * 32) {
 		float s = 0.0f;
 #pragma unroll
-		for (int wv = 0; wv < kBatch; ++wv) s += tile[wv * 2 * F + q];
+		for (int wv = 0; wv < kPanWarps; ++wv) s += tile[wv * 2 * F + q];
 		out[q] = s;
 	}
 }
@@ -586,8 +594,8 @@ __global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : SBM_SH_BIG_CTAS)
 k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	constexpr int kStages = TMAX == 128 ? kStagesSh : kStagesShBig, kRecStages = kStages + 2;
-	const SmemView<16, kStages> sm(smem_raw);
+	constexpr int kStages = TMAX == 128 ? kStagesSh : kStagesShBig, kRecStages = kStages + 2, kBatch = kBatchSh;
+	const SmemView<16, kStages, kBatch> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
 	// blockDim.x = T math threads + one producer warp (the last warp)
 	const uint32_t F = a.frames, T = EXACT ? (uint32_t)TMAX : blockDim.x - 32, t = threadIdx.x, lane = t & 31u;   // EXACT: T is a compile-time constant
@@ -603,7 +611,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 #endif
 	if (t == 0) init_barriers<kStages>(hdr, T / 32);
 	__syncthreads();
-	if (t >= T) { producer_warp<16, kStages>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+	if (t >= T) { producer_warp<16, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1) x frames t + k T
 #pragma unroll
@@ -903,7 +911,7 @@ uint32_t window_slot(uint32_t F) { return (F + F / 4 + 24u + 3u) & ~3u; }
 uint32_t sh_threads(uint32_t F) { return ((F + K - 1) / K + 31) / 32 * 32; }
 int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig); }
 size_t mix_smem_bytes(uint32_t F, bool sh) {
-	const size_t st = (size_t)mix_stages(F, sh), rst = st + 2;
+	const size_t st = (size_t)mix_stages(F, sh), rst = st + 2, kBatch = sh ? kBatchSh : kBatchPan;
 	return 512 + sizeof(WorkRec) * rst * kBatch + (sh ? sizeof(ShGains) * rst * kBatch + sizeof(ShRamps) * st * kBatch : 0) +
 	       sizeof(MathDesc) * rst * kBatch +
 	       sizeof(float) * st * kBatch * window_slot(F);
@@ -944,7 +952,7 @@ int launch_one(Kernel kernel, KernelConfig* cfg, const char* name, const MixArgs
 template <int KF>
 int launch_stereo(const MixArgs& a, uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
 	static KernelConfig conf_exact, conf_any;
-	const uint32_t threads = kBatch * 32 + 32;
+	const uint32_t threads = kPanWarps * 32 + 32;
 	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true>, &conf_exact, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
 	return launch_one(k2_mix_stereo_kernel<KF, false>, &conf_any, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
 }
