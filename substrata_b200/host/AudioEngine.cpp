@@ -322,9 +322,12 @@ void AudioEngine::feedStreamingSource(AudioSource& source) {
 	}
 	const size_t have = myMin(n_src, source.buffer.size());
 	if (have) {
-		temp_buf.resize(have);
-		source.buffer.popFrontNItems(temp_buf.data(), have);
-		sbm_source_ring_push(engine, source.resonance_handle, temp_buf.data(), have);
+		// appended to this buffer's batch: all streaming sources cross PCIe in ONE sbm_source_ring_push_batch call
+		const size_t at = feed_payload.size();
+		feed_payload.resize(at + have);
+		source.buffer.popFrontNItems(feed_payload.data() + at, have);
+		feed_ids.push_back(source.resonance_handle);
+		feed_offsets.push_back(feed_payload.size());
 	}
 }
 
@@ -336,6 +339,7 @@ bool AudioEngine::mixOneBuffer() {
 	int valid = 0;
 	{
 		Lock lock(mutex);
+		feed_ids.clear(); feed_payload.clear(); feed_offsets.assign(1, 0);
 		for (auto it = active_audio_sources.begin(); it != active_audio_sources.end(); ++it) {
 			AudioSource& source = **it;
 			if (source.resonance_handle == INVALID_RESONANCE_HANDLE) continue;
@@ -350,6 +354,8 @@ bool AudioEngine::mixOneBuffer() {
 				}
 			}
 		}
+		if (!feed_ids.empty() && sbm_source_ring_push_batch(engine, (int)feed_ids.size(), feed_ids.data(), feed_payload.data(), feed_offsets.data()) != SBM_OK)
+			throw glare::Exception(std::string("sbm_source_ring_push_batch failed: ") + sbm_last_error(engine));
 		const int rc = sbm_mix(engine, out.data(), &valid);
 		if (rc != SBM_OK) throw glare::Exception(std::string("sbm_mix failed: ") + sbm_last_error(engine));
 		// Sources the feeder stopped (AE.cpp:496-517): already destroyed on the device; mirror the registry bookkeeping.

@@ -181,6 +181,10 @@ private:
 	std::vector<AudioBufferRef> device_buffer_refs;
 	std::map<int, AudioSourceRef> source_of_handle;
 	std::vector<float> temp_buf;
+	// this buffer's streaming feed, pushed to the device rings in one batched call (sbm_source_ring_push_batch)
+	std::vector<int> feed_ids;
+	std::vector<float> feed_payload;
+	std::vector<size_t> feed_offsets;
 
 public:
 	Mutex mutex;  // Guards access to audio_sources

@@ -35,9 +35,12 @@ int main(int argc, char** argv) {
 	} catch (glare::Exception& e) { fprintf(stderr, "init failed: %s\n", e.what()); return 3; }
 
 	std::vector<AudioSourceRef> sources;
+	std::vector<std::vector<float>> streams;     // content of the streamed sources
+	std::vector<int> stream_src;
 	for (int s = 0; s < n; ++s) {
 		AudioSourceRef src = new AudioSource();
 		const int nonspatial = rd<int>(f);
+		const int streaming = rd<int>(f);
 		src->sampling_rate = rd<int>(f);
 		src->looping = rd<int>(f) != 0;
 		src->cur_read_i = (size_t)rd<uint64_t>(f);
@@ -45,10 +48,18 @@ int main(int argc, char** argv) {
 		const float x = rd<float>(f), y = rd<float>(f), z = rd<float>(f);
 		src->pos = Vec4f(x, y, z, 1.f);
 		src->spatial_type = nonspatial ? AudioSource::SourceSpatialType_NonSpatial : AudioSource::SourceSpatialType_Spatial;
-		src->type = AudioSource::SourceType_NonStreaming;
-		src->shared_buffer = new AudioBuffer();
-		src->shared_buffer->buffer.resize((size_t)loop_len);
-		rdv(f, src->shared_buffer->buffer.data(), (size_t)loop_len);
+		std::vector<float> pcm((size_t)loop_len);
+		rdv(f, pcm.data(), (size_t)loop_len);
+		if (streaming) {
+			// a voice / streamed source: other threads push packets into AudioSource::buffer (ClientUDPHandlerThread.cpp:239-242)
+			src->type = AudioSource::SourceType_Streaming;
+			streams.push_back(pcm); stream_src.push_back(s);
+		} else {
+			src->type = AudioSource::SourceType_NonStreaming;
+			src->shared_buffer = new AudioBuffer();
+			src->shared_buffer->buffer.resize((size_t)loop_len);
+			memcpy(src->shared_buffer->buffer.data(), pcm.data(), sizeof(float) * (size_t)loop_len);
+		}
 		engine.addSource(src);
 		sources.push_back(src);
 	}
@@ -62,6 +73,17 @@ int main(int argc, char** argv) {
 		float hp[3], hq[4];
 		rdv(f, hp, 3); rdv(f, hq, 4);
 		engine.setHeadTransform(Vec4f(hp[0], hp[1], hp[2], 1.f), Quatf(hq[0], hq[1], hq[2], hq[3]));
+		// packets of the streamed sources for this buffer (480 samples per 10 ms at 48 kHz, scaled by the source rate); one
+		// buffer in five delivers nothing (underflow -> the mixer zero-pads, AudioEngine.cpp:466-473)
+		if (b % 5 != 3) {
+			Lock lock(engine.mutex);
+			for (size_t k = 0; k < streams.size(); ++k) {
+				AudioSource& src = *sources[(size_t)stream_src[k]];
+				const size_t m = (size_t)(480 * ((F + 479) / 480) * (double)src.sampling_rate / 48000.0);
+				const size_t at = (size_t)b * m;
+				if (at + m <= streams[k].size()) src.buffer.pushBackNItems(streams[k].data() + at, m);
+			}
+		}
 		if (!threaded) engine.mixOneBuffer();
 		else std::this_thread::sleep_for(std::chrono::milliseconds(20));
 		engine.fillOutputBuffer(out.data() + (size_t)b * 2 * F, (size_t)F);

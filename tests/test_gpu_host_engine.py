@@ -41,8 +41,9 @@ def scenario(n, F, nb, binaural, seed):
     rates = rng.choice([48000, 44100, 24000], n).astype(np.int32)
     start = rng.integers(0, L, n)
     nonspatial = (rng.uniform(size=n) < 0.1).astype(np.int32)
+    streaming = ((rng.uniform(size=n) < 0.25) & (nonspatial == 0)).astype(np.int32)     # voice-like sources fed packet by packet
     heads = [(np.array([b * F / 48000.0, 0, 0], np.float32), quat_yaw(np.deg2rad(30.0) * b * F / 48000.0)) for b in range(nb)]
-    return dict(n=n, F=F, nb=nb, L=L, pcm=pcm, pos=pos, vol=vol, rates=rates, start=start, nonspatial=nonspatial, heads=heads, binaural=binaural)
+    return dict(n=n, F=F, nb=nb, L=L, pcm=pcm, pos=pos, vol=vol, rates=rates, start=start, nonspatial=nonspatial, streaming=streaming, heads=heads, binaural=binaural)
 
 
 def write_scenario(path, sc, hr):
@@ -51,7 +52,7 @@ def write_scenario(path, sc, hr):
         if sc["binaural"]:
             f.write(np.ascontiguousarray(hr, np.float32).tobytes())
         for s in range(sc["n"]):
-            f.write(struct.pack("<3iQ4f", int(sc["nonspatial"][s]), int(sc["rates"][s]), 1, int(sc["start"][s]), float(sc["vol"][s]), *[float(v) for v in sc["pos"][s]]))
+            f.write(struct.pack("<4iQ4f", int(sc["nonspatial"][s]), int(sc["streaming"][s]), int(sc["rates"][s]), 1, int(sc["start"][s]), float(sc["vol"][s]), *[float(v) for v in sc["pos"][s]]))
             f.write(sc["pcm"][s].tobytes())
         for hp, hq in sc["heads"]:
             f.write(np.concatenate([hp, hq]).astype(np.float32).tobytes())
@@ -63,13 +64,23 @@ def oracle_run(sc, hr):
     for s in range(sc["n"]):
         kind = KIND_STEREO if sc["nonspatial"][s] else (KIND_HRTF if sc["binaural"] else KIND_PAN)
         sid = be.source_create(kind)
-        be.source_attach_buffer(sid, be.buffer_create(sc["pcm"][s]), int(sc["start"][s]), int(sc["rates"][s]), True, False)
+        if sc["streaming"][s]:
+            be.source_attach_ring(sid, int(sc["rates"][s]))
+        else:
+            be.source_attach_buffer(sid, be.buffer_create(sc["pcm"][s]), int(sc["start"][s]), int(sc["rates"][s]), True, False)
         ids.append(sid)
     ids = np.array(ids, np.int32)
     be.set_source_positions(ids, sc["pos"]); be.set_source_volumes(ids, sc["vol"])
     outs = []
-    for hp, hq in sc["heads"]:
+    F = sc["F"]
+    for b, (hp, hq) in enumerate(sc["heads"]):
         be.set_head(hp, hq)
+        if b % 5 != 3:      # the driver's packet schedule (tests/native/test_audio_engine.cc)
+            for s in range(sc["n"]):
+                if sc["streaming"][s]:
+                    m = int(480 * ((F + 479) // 480) * float(sc["rates"][s]) / 48000.0)
+                    if b * m + m <= sc["L"]:
+                        be.source_ring_push(int(ids[s]), sc["pcm"][s][b * m:(b + 1) * m])
         outs.append(np.clip(be.mix()[1], -1.0, 1.0))          # the device callback clamps (AudioEngine.cpp:215-216)
     return np.stack(outs)
 
