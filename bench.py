@@ -318,44 +318,58 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
                 eng.sources_ring_push_flat(v_ids, v_payload[(ring_state["pushed"] // 480) % 4], v_offs)
                 ring_state["pushed"] += 480
 
-    def step_resident(s):
+    def prep_resident(s):
         hp, hq = listener_pose(s, F)
         eng.set_head(hp, hq)
-        mixer.mix(out_host)        # sbm_mix_begin -> (N > 1: NCCL all-reduce of the bus on the engine stream) -> sbm_mix_finish
-        if voices:
-            ring_state["consumed"] += F
 
     movers = min(MOVERS_PER_STEP, n)
     mv_ids = [np.ascontiguousarray(ids[(k * movers) % max(1, n - movers + 1):][:movers]) for k in range(8)]
     mv_pos = [rng.uniform([-40, -10, -40], [40, 10, 40], (movers, 3)).astype(np.float32) + np.float32(1.5) for _ in range(8)]
 
-    def step_e2e(s):
+    def prep_e2e(s):
         hp, hq = listener_pose(s, F)
         if voices:
             feed_voices(ring_state["consumed"] + F)       # the packets that arrived since the previous buffer
         eng.set_source_positions(mv_ids[s % 8], mv_pos[s % 8])
         eng.set_head(hp, hq)
-        mixer.mix(out_host)
-        if voices:
-            ring_state["consumed"] += F
 
-    def timed(step_fn, s0):
-        if voices and step_fn is step_resident:
+    pipelined = args.pipeline >= 2 and (args.exchange == "peer" or world == 1)
+
+    def timed(prep_fn, s0, resident):
+        """W warm-up + K timed buffers.  prep_fn(s) = the host-side events of buffer s (pose / position / packet updates);
+        the buffer itself goes through sbm_mix, or -- pipelined -- sbm_mix_submit with the previous buffer collected
+        afterwards (two buffers in flight: the host's launch latency hides behind the previous buffer's kernels)."""
+        if voices and resident:
             feed_voices(ring_state["consumed"] + (args.warmup + args.steps) * F)      # resident inputs: outside the timed region
         for s in range(args.warmup):
-            step_fn(s0 + s)
+            prep_fn(s0 + s)
+            mixer.mix(out_host)
+            if voices:
+                ring_state["consumed"] += F
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k1 = k2 = k3 = 0.0
-        algo = rendered = h2d = d2h = 0
+        acc = dict(k1=0.0, k2=0.0, k3=0.0, algo=0, rendered=0, h2d=0, d2h=0)
         l0 = eng.stats()["kernel_launches"]
+
+        def account():
+            st = eng.stats()
+            acc["k1"] += st["last_params_kernel_ms"]; acc["k2"] += st["last_mix_kernel_ms"]; acc["k3"] += st["last_finish_kernel_ms"]
+            acc["algo"] += st["last_algorithmic_bytes"]; acc["rendered"] += st["last_rendered_sources"]
+            acc["h2d"] += st["last_h2d_bytes"]; acc["d2h"] += st["last_d2h_bytes"]
+
         e0.record(stream)
         for s in range(args.steps):
-            step_fn(s0 + args.warmup + s)
-            st = eng.stats()
-            k1 += st["last_params_kernel_ms"]; k2 += st["last_mix_kernel_ms"]; k3 += st["last_finish_kernel_ms"]
-            algo += st["last_algorithmic_bytes"]; rendered += st["last_rendered_sources"]
-            h2d += st["last_h2d_bytes"]; d2h += st["last_d2h_bytes"]
+            prep_fn(s0 + args.warmup + s)
+            if pipelined:
+                mixer.submit()
+                if s >= 1:
+                    mixer.collect(out_host); account()
+            else:
+                mixer.mix(out_host); account()
+            if voices:
+                ring_state["consumed"] += F
+        if pipelined:
+            mixer.collect(out_host); account()
         e1.record(stream)
         sync_all()
         ms = e0.elapsed_time(e1)
@@ -364,14 +378,14 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         K = args.steps
-        return dict(ms=ms / K, k1=k1 / K, k2=k2 / K, k3=k3 / K, algo=algo / K, rendered=rendered / K, h2d=h2d / K, d2h=d2h / K,
-                    launches=eng.stats()["kernel_launches"] - l0)
+        return dict(ms=ms / K, k1=acc["k1"] / K, k2=acc["k2"] / K, k3=acc["k3"] / K, algo=acc["algo"] / K, rendered=acc["rendered"] / K,
+                    h2d=acc["h2d"] / K, d2h=acc["d2h"] / K, launches=eng.stats()["kernel_launches"] - l0)
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    res = timed(step_resident, 0)
-    e2e = timed(step_e2e, args.warmup + args.steps)
+    res = timed(prep_resident, 0, True)
+    e2e = timed(prep_e2e, args.warmup + args.steps, False)
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
@@ -396,7 +410,8 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
                        "l2": "per-step PCM windows %.0f MB >> 126 MB L2: inputs larger than L2, no flush" % (res["algo"] / 1e6),
                        "parallelism": "sources sharded, 1 rank/GPU" + ((", 18x%d bus exchanged over NVLink peer memory inside K3 / the gather kernel" % F if args.exchange == "peer"
                                                                         else ", NCCL all-reduce of the 18x%d bus" % F) if world > 1 else ""),
-                       "realtime_budget_ms": 1e3 * F / 48000.0},
+                       "realtime_budget_ms": 1e3 * F / 48000.0,
+                       "buffers_in_flight": 2 if pipelined else 1},
             "e2e": {"value": total / (e2e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e2e["ms"], "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "what": ("%d source positions + listener pose from host arrays per step, stereo buffer back to host, through sbm_set_*/sbm_mix" % movers) +
                             ("; %d voice packets of 480 samples per 10 ms of audio through sbm_source_ring_push_batch" % voices if voices else "")},
@@ -429,6 +444,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
     ap.add_argument("--exchange", default="peer", choices=["peer", "allreduce"],
                     help="N > 1: bus exchange inside the kernels over NVLink peer memory (default) or an NCCL all-reduce between mix_begin and mix_finish")
+    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+                    help="buffers in flight: 2 = sbm_mix_submit / sbm_mix_collect (default), 1 = synchronous sbm_mix")
     ap.add_argument("--sources", type=int, default=0, help="override the workload's sources per GPU (profiling under ncu only; the line says so)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -137,6 +137,15 @@ SBM_API int sbm_mix(sbm_engine* e, float* out_interleaved, int* out_valid);
  * followed by 4 floats of flags {ambisonic bus used, stereo bus used, 0, 0} that sum across ranks like the audio. */
 SBM_API int sbm_mix_begin(sbm_engine* e);
 SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid);
+/* Pipelined form of sbm_mix: sbm_mix_submit enqueues one whole buffer (uploads, kernels, the copy of the result into
+ * pinned memory) and returns without waiting; sbm_mix_collect waits for the OLDEST submitted buffer and hands it out.
+ * At most two buffers may be in flight, so the host's launch latency hides behind the previous buffer's kernels --
+ * ResonanceThread::doRun likewise runs ahead of the device callback through its ring (AudioEngine.cpp:540-545).
+ * Setters called between two submits apply to the later buffer, like Resonance's task queue.  sbm_poll_finished and
+ * the ring capacity seen by sbm_source_ring_push* lag by the buffers not yet collected. */
+SBM_API int sbm_mix_submit(sbm_engine* e);
+SBM_API int sbm_mix_collect(sbm_engine* e, float* out_interleaved, int* out_valid);
+
 /* Multi-GPU (one engine per GPU, one process per GPU, sources sharded by the caller): the only exchange of
  * the path -- the sum of the ranks' [18][frames] buses -- runs over NVLink peer memory inside the kernels: K3 stores
  * its bus into every rank's gather area and signals, a gather kernel in front of K4 waits and sums in rank order.

@@ -223,6 +223,17 @@ class MixEngine:
         self._ck(self._l.sbm_mix(self.h, _p(out), C.byref(valid)), "sbm_mix")
         return valid.value, out
 
+    def mix_submit(self):
+        """Enqueue one whole buffer without waiting (at most two in flight); pair with mix_collect()."""
+        self._ck(self._l.sbm_mix_submit(self.h), "sbm_mix_submit")
+
+    def mix_collect(self, out=None):
+        if out is None:
+            out = np.zeros(2 * self.frames, dtype=np.float32)
+        valid = C.c_int()
+        self._ck(self._l.sbm_mix_collect(self.h, _p(out), C.byref(valid)), "sbm_mix_collect")
+        return valid.value, out
+
     def mix_begin(self):
         self._ck(self._l.sbm_mix_begin(self.h), "sbm_mix_begin")
 

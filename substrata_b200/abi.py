@@ -49,6 +49,8 @@ SIGNATURES = {
     "sbm_set_master_volume": (_i, [_vp, _f]),
     "sbm_enable_room_effects": (_i, [_vp, _i]),
     "sbm_mix": (_i, [_vp, _vp, _vp]),
+    "sbm_mix_submit": (_i, [_vp]),
+    "sbm_mix_collect": (_i, [_vp, _vp, _vp]),
     "sbm_mix_begin": (_i, [_vp]),
     "sbm_mix_finish": (_i, [_vp, _vp, _vp]),
     "sbm_peer_export": (_i, [_vp, _vp, _sz]),

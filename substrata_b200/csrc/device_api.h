@@ -122,6 +122,7 @@ int launch_peer_gather(const PeerArgs& pa, float* bus_sum, size_t bus_floats, ui
 void* event_create();
 void event_destroy(void* ev);
 void event_record(void* ev, void* stream);
+int event_sync(void* ev);                        // blocks the host until the event has happened
 float event_elapsed_ms(void* a, void* b);
 unsigned long long launches();                   // kernels launched so far by this library
 }  // namespace dev

@@ -91,7 +91,20 @@ struct sbm_engine {
 	unsigned long long peer_epoch = 0;       // buffer_index at which the peers were connected (arrival counters count from there)
 	size_t pending_ring_h2d_bytes = 0;       // ring pushes since the last sbm_mix_begin (reported with the next buffer's stats)
 	bool ring_stage_in_flight = false;       // an H2D from h_ring_stage may still be running (cleared by every stream sync in mix)
-	unsigned char* h_out = nullptr;          // pinned D2H staging: 2F floats + OutTail + ring read counters
+	// Up to two buffers in flight (sbm_mix_submit / sbm_mix_collect): everything a submitted buffer's completion needs.
+	struct InFlight {
+		bool pending = false;
+		unsigned long long seq = 0;          // buffer_index of the buffer
+		unsigned char* h_out = nullptr;      // pinned D2H staging: 2F floats + OutTail + ring read counters
+		void* done = nullptr;                // event after the D2H
+		void* ev[4] = {nullptr, nullptr, nullptr, nullptr};   // profiling: before K1 / after K1 / after K2 / after K4
+		int* dv_finished = nullptr;          // this parity's finished-id list on the device
+		std::vector<uint32_t> list_ring;     // ring-fed slots in the order their read counters were reported
+		size_t h2d_bytes = 0, d2h_bytes = 0;
+		uint32_t active = 0;
+	} fl[2];
+	unsigned long long collected = 0;        // buffers collected so far (== buffer_index when nothing is in flight)
+	unsigned long long ring_stage_seq = 0;   // the staged ring push precedes buffer `ring_stage_seq` in stream order
 	Globals g;
 	unsigned long long buffer_index = 0;
 	bool begun = false;
@@ -99,7 +112,6 @@ struct sbm_engine {
 
 	// stats
 	bool profiling = false;
-	void* ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	sbm_stats stats;
 };
 
@@ -215,7 +227,7 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	ok = ok && dalloc(e->dv_stat, cap) && dalloc(e->dv_posvol, cap) && dalloc(e->dv_occl, cap) && dalloc(e->dv_ring_write, cap) && dalloc(e->dv_mixz, mixcap);
 	A.stat = e->dv_stat; A.posvol = e->dv_posvol; A.occl = e->dv_occl; A.ring_write = e->dv_ring_write; A.mixz = e->dv_mixz;
 	ok = ok && dalloc(A.live, cap) && dalloc(A.read_i, cap) && dalloc(A.eof, cap) && dalloc(A.rs, cap) && dalloc(A.dgain, cap) &&
-	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.finished, cap) &&
+	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.finished, 2 * (size_t)cap) &&
 	     dalloc(A.mix_pos, mixcap) && dalloc(A.mix_pos0, mixcap);
 	A.cstride = kNumSh;
 	ok = ok && dalloc(A.cgain, (size_t)cap * kNumSh);
@@ -229,8 +241,12 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	ok = ok && dalloc(e->dv_partials, e->partials_floats);
 	e->out_bytes = sizeof(float) * 2 * F + sizeof(OutTail) + sizeof(unsigned long long) * (size_t)cap;
 	e->dv_out = (float*)dev::alloc(e->out_bytes);
-	e->h_out = (unsigned char*)dev::alloc_pinned(e->out_bytes);
-	ok = ok && e->dv_out && e->h_out;
+	for (int k = 0; k < 2; ++k) {
+		e->fl[k].h_out = (unsigned char*)dev::alloc_pinned(e->out_bytes);
+		e->fl[k].dv_finished = A.finished ? A.finished + (size_t)k * cap : nullptr;
+		ok = ok && e->fl[k].h_out;
+	}
+	ok = ok && e->dv_out;
 	if (ok && hrtf) {
 		const size_t T = (size_t)cfg->sh_hrir_taps;
 		ok = dalloc(e->dv_hrir, kNumSh * T) && dalloc(e->dv_hist, kNumSh * T) && dalloc(e->dv_dec, 2 * (size_t)F);
@@ -245,7 +261,10 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	if (!ok) { fprintf(stderr, "sbm_create: %s\n", dev::last_error()); sbm_destroy(e); return SBM_ERR_CUDA; }
 	memset(&e->g, 0, sizeof(e->g));
 	e->g.head_q[3] = 1.0f; e->g.master = 1.0f; e->g.frames = F; e->g.rate = cfg->sample_rate_hz;
-	for (int i = 0; i < 4; ++i) e->ev[i] = dev::event_create();
+	for (int k = 0; k < 2; ++k) {
+		e->fl[k].done = dev::event_create();
+		for (int i = 0; i < 4; ++i) e->fl[k].ev[i] = dev::event_create();
+	}
 	*out_engine = e;
 	return SBM_OK;
 }
@@ -256,19 +275,22 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	if (e->stream) dev::sync(e->stream);
 	SlotArrays& A = e->A;
 	void* ptrs[] = {e->dv_stat, e->dv_posvol, e->dv_occl, e->dv_ring_write, e->dv_mixz, A.live, A.read_i, A.eof, A.rs, A.dgain, A.occ_cur,
-	                A.lpf_prev, A.bits, A.rec, A.finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
+	                A.lpf_prev, A.bits, A.rec, e->fl[0].dv_finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
 	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
 	                e->dv_hist, e->dv_dec, e->dv_patches, e->dv_mix_patches};
 	for (void* p : ptrs) if (p) dev::release(p);
 	for (auto& b : e->buffers) if (b.owned && b.dptr) dev::release(b.dptr);
 	for (auto& r : e->rings) if (r.storage) dev::release(r.storage);
-	if (e->h_out) dev::release_pinned(e->h_out);
+	for (int k = 0; k < 2; ++k) {
+		if (e->fl[k].h_out) dev::release_pinned(e->fl[k].h_out);
+		if (e->fl[k].done) dev::event_destroy(e->fl[k].done);
+		for (int i = 0; i < 4; ++i) if (e->fl[k].ev[i]) dev::event_destroy(e->fl[k].ev[i]);
+	}
 	for (void* m : e->peer_mapped) dev::peer_close(m);
 	if (e->dv_gather) dev::release(e->dv_gather);
 	if (e->dv_bus_sum) dev::release(e->dv_bus_sum);
 	if (e->h_ring_stage) dev::release_pinned(e->h_ring_stage);
 	if (e->d_ring_stage) dev::release(e->d_ring_stage);
-	for (int i = 0; i < 4; ++i) if (e->ev[i]) dev::event_destroy(e->ev[i]);
 	dev::shutdown(e->stream);
 	delete e;
 }
@@ -450,6 +472,7 @@ SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, con
 	const size_t table_bytes = (sizeof(RingPush) * (size_t)n + 255) & ~(size_t)255;
 	const size_t bytes = table_bytes + sizeof(float) * total;
 	if (e->ring_stage_in_flight) { if (dev::sync(e->stream)) return fail_cuda(e, "sbm_source_ring_push_batch"); e->ring_stage_in_flight = false; }
+	e->ring_stage_seq = e->buffer_index;
 	if (bytes > e->ring_stage_bytes) {
 		dev::sync(e->stream);
 		dev::release_pinned(e->h_ring_stage); dev::release(e->d_ring_stage);
@@ -651,11 +674,15 @@ SBM_API int sbm_enable_room_effects(sbm_engine* e, int enable) {
 // ---------------------------------------------------------------------------------------------------------------
 // the per-buffer call
 // ---------------------------------------------------------------------------------------------------------------
-SBM_API int sbm_mix_begin(sbm_engine* e) {
-	if (!e) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
+// One buffer = sbm_mix_begin (uploads, K1, K2, K3) -> [the caller may sum buses across ranks here] -> the finish part
+// (gather, K4, D2H of the result into pinned memory, an event) -> collection (wait for the event, hand the samples out,
+// host bookkeeping).  sbm_mix / sbm_mix_finish do all of it synchronously; sbm_mix_submit + sbm_mix_collect split it so
+// that up to two buffers are in flight and the host's launch latency hides behind the previous buffer's kernels -- the
+// mixer thread of the reference also runs ahead of the device callback (AudioEngine.cpp:540-545).
+static int mix_begin_locked(sbm_engine* e) {
 	if (e->begun) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_begin called twice without sbm_mix_finish");
+	sbm_engine::InFlight& fl = e->fl[e->buffer_index & 1];
+	if (fl.pending) return fail(e, SBM_ERR_INVALID_ARG, "two buffers already in flight: call sbm_mix_collect first");
 	// bytes pushed into rings since the previous buffer belong to this buffer's host->device traffic
 	e->stats.last_h2d_bytes = e->pending_ring_h2d_bytes; e->stats.last_d2h_bytes = 0;
 	e->pending_ring_h2d_bytes = 0;
@@ -685,33 +712,34 @@ SBM_API int sbm_mix_begin(sbm_engine* e) {
 	e->g.parity = (uint32_t)(e->buffer_index & 1);
 	e->g.n_slots = e->n_slots;
 	e->g.n_pan = (uint32_t)e->list_pan.size(); e->g.n_sh = (uint32_t)e->list_sh.size();
+	e->A.finished = fl.dv_finished;      // per-parity list: the previous buffer's may not have been collected yet
 	// 2. kernels
-	if (e->profiling) dev::event_record(e->ev[0], st);
+	if (e->profiling) dev::event_record(fl.ev[0], st);
 	if (e->g.n_pan + e->g.n_sh && dev::launch_params(e->g, e->A, e->dv_flags, e->dv_table, e->dv_lists, e->n_slots, st)) return fail_cuda(e, "k1_params");
-	if (e->profiling) dev::event_record(e->ev[1], st);
+	if (e->profiling) dev::event_record(fl.ev[1], st);
 	MixArgs m;
 	m.rec = e->A.rec; m.shg = e->A.shg; m.shr = e->A.shr; m.mixz = e->dv_mixz; m.mix_pos0 = e->A.mix_pos0; m.rs = e->A.rs; m.lpf_prev = e->A.lpf_prev;
 	m.n_pan = (uint32_t)e->list_pan.size();
 	m.n_sh = (uint32_t)e->list_sh.size();
 	m.frames = e->g.frames; m.rate = e->g.rate; m.partials = e->dv_partials; m.partials_floats = e->partials_floats;
 	m.bus = e->dv_bus; m.flags = e->dv_flags; m.parity = e->g.parity;
-	m.ev_after_k2 = e->profiling ? e->ev[2] : nullptr;
+	m.ev_after_k2 = e->profiling ? fl.ev[2] : nullptr;
 	m.peer = e->peer; m.bus_floats = e->bus_floats;
 	if (dev::launch_mix(m, st)) return fail_cuda(e, "k2_mix");
 	e->begun = true;
-	e->stats.active_sources = (uint32_t)(e->list_pan.size() + e->list_sh.size());
+	fl.active = (uint32_t)(e->list_pan.size() + e->list_sh.size());
+	fl.h2d_bytes = e->stats.last_h2d_bytes;
 	return SBM_OK;
 }
 
-SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid) {
-	if (!e) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
+// Enqueues the finish part of the buffer begun last; no host synchronisation.
+static int mix_enqueue_finish_locked(sbm_engine* e) {
 	if (!e->begun) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_finish without sbm_mix_begin");
 	e->begun = false;
 	void* st = e->stream;
 	const uint32_t F = e->g.frames;
 	const uint32_t parity = (uint32_t)(e->buffer_index & 1);
+	sbm_engine::InFlight& fl = e->fl[parity];
 	if (e->peer.world) {
 		// wait for every rank's bus of this buffer (K3 stored them into our gather area) and sum them in rank order
 		const unsigned int target = (unsigned int)(e->peer.world * ((e->buffer_index >> 1) - (e->peer_epoch >> 1) + 1));
@@ -722,23 +750,43 @@ SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid
 	f.flags = e->dv_flags; f.parity = parity; f.frames = F; f.out = e->dv_out;
 	f.list_ring = e->dv_list_ring; f.n_ring = (uint32_t)e->list_ring.size(); f.read_i = e->A.read_i; f.finished_count_reset = nullptr;
 	if (dev::launch_finish(f, st)) return fail_cuda(e, "k4_finish");
-	if (e->profiling) dev::event_record(e->ev[3], st);
+	if (e->profiling) dev::event_record(fl.ev[3], st);
 	const size_t bytes = sizeof(float) * 2 * F + sizeof(OutTail) + sizeof(unsigned long long) * e->list_ring.size();
-	if (dev::d2h(e->h_out, e->dv_out, bytes, st) || dev::sync(st)) return fail_cuda(e, "sbm_mix_finish(d2h)");
-	e->ring_stage_in_flight = false;
-	e->stats.last_d2h_bytes += bytes;
+	if (dev::d2h(fl.h_out, e->dv_out, bytes, st)) return fail_cuda(e, "sbm_mix_finish(d2h)");
+	dev::event_record(fl.done, st);
+	fl.pending = true; fl.seq = e->buffer_index; fl.list_ring = e->list_ring; fl.d2h_bytes = bytes;
+	e->buffer_index++;
+	return SBM_OK;
+}
+
+// Waits for the oldest buffer in flight and hands it out.
+static int mix_collect_locked(sbm_engine* e, float* out_interleaved, int* out_valid) {
+	sbm_engine::InFlight& fl = e->fl[e->collected & 1];
+	if (!fl.pending || fl.seq != e->collected) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_collect: no buffer in flight");
+	void* st = e->stream;
+	const uint32_t F = e->g.frames;
+	if (dev::event_sync(fl.done)) return fail_cuda(e, "sbm_mix_collect");
+	fl.pending = false;
+	e->collected++;
+	if (e->ring_stage_in_flight && e->ring_stage_seq <= fl.seq) e->ring_stage_in_flight = false;
+	e->stats.last_h2d_bytes = fl.h2d_bytes;
+	e->stats.last_d2h_bytes = fl.d2h_bytes;
+	e->stats.active_sources = fl.active;
 	OutTail tail;
-	memcpy(&tail, e->h_out + sizeof(float) * 2 * F, sizeof(tail));
-	if (out_interleaved) memcpy(out_interleaved, e->h_out, sizeof(float) * 2 * F);
+	memcpy(&tail, fl.h_out + sizeof(float) * 2 * F, sizeof(tail));
+	if (out_interleaved) memcpy(out_interleaved, fl.h_out, sizeof(float) * 2 * F);
 	if (out_valid) *out_valid = tail.valid;
 	e->last_valid = tail.valid;
 	// ring read counters
-	const unsigned long long* reads = (const unsigned long long*)(e->h_out + sizeof(float) * 2 * F + sizeof(OutTail));
-	for (size_t k = 0; k < e->list_ring.size(); ++k) e->rings[e->list_ring[k]].read_known = reads[k];
+	const unsigned long long* reads = (const unsigned long long*)(fl.h_out + sizeof(float) * 2 * F + sizeof(OutTail));
+	for (size_t k = 0; k < fl.list_ring.size(); ++k) {
+		RingInfo& r = e->rings[fl.list_ring[k]];
+		if (r.storage && reads[k] <= r.written && reads[k] >= r.read_known) r.read_known = reads[k];     // (the slot may have been recycled since)
+	}
 	// sources stopped by the feeder (AudioEngine.cpp:499-515)
 	if (tail.n_finished > 0) {
 		std::vector<int> ids((size_t)tail.n_finished);
-		if (dev::d2h(ids.data(), e->A.finished, sizeof(int) * ids.size(), st) || dev::sync(st)) return fail_cuda(e, "sbm_mix_finish(finished)");
+		if (dev::d2h(ids.data(), fl.dv_finished, sizeof(int) * ids.size(), st) || dev::sync(st)) return fail_cuda(e, "sbm_mix_finish(finished)");
 		e->stats.last_d2h_bytes += sizeof(int) * ids.size();
 		std::sort(ids.begin(), ids.end());
 		for (int id : ids) {
@@ -752,12 +800,28 @@ SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid
 	e->stats.last_algorithmic_bytes = tail.algo_bytes;
 	e->stats.last_rendered_sources = tail.n_rendered;
 	if (e->profiling) {
-		e->stats.last_params_kernel_ms = dev::event_elapsed_ms(e->ev[0], e->ev[1]);
-		e->stats.last_mix_kernel_ms = dev::event_elapsed_ms(e->ev[1], e->ev[2]);
-		e->stats.last_finish_kernel_ms = dev::event_elapsed_ms(e->ev[2], e->ev[3]);
+		e->stats.last_params_kernel_ms = dev::event_elapsed_ms(fl.ev[0], fl.ev[1]);
+		e->stats.last_mix_kernel_ms = dev::event_elapsed_ms(fl.ev[1], fl.ev[2]);
+		e->stats.last_finish_kernel_ms = dev::event_elapsed_ms(fl.ev[2], fl.ev[3]);
 	}
-	e->buffer_index++;
 	return SBM_OK;
+}
+
+SBM_API int sbm_mix_begin(sbm_engine* e) {
+	if (!e) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	if (e->collected != e->buffer_index) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_begin with a submitted buffer outstanding: use sbm_mix_submit / sbm_mix_collect");
+	return mix_begin_locked(e);
+}
+
+SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid) {
+	if (!e) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	const int rc = mix_enqueue_finish_locked(e);
+	if (rc) return rc;
+	return mix_collect_locked(e, out_interleaved, out_valid);
 }
 
 SBM_API int sbm_mix(sbm_engine* e, float* out_interleaved, int* out_valid) {
@@ -765,6 +829,22 @@ SBM_API int sbm_mix(sbm_engine* e, float* out_interleaved, int* out_valid) {
 	const int rc = sbm_mix_begin(e);
 	if (rc) return rc;
 	return sbm_mix_finish(e, out_interleaved, out_valid);
+}
+
+SBM_API int sbm_mix_submit(sbm_engine* e) {
+	if (!e) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	const int rc = mix_begin_locked(e);
+	if (rc) return rc;
+	return mix_enqueue_finish_locked(e);
+}
+
+SBM_API int sbm_mix_collect(sbm_engine* e, float* out_interleaved, int* out_valid) {
+	if (!e) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	return mix_collect_locked(e, out_interleaved, out_valid);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -65,3 +65,11 @@ class ShardedMixer:
         else:
             self.dist.all_reduce(self.bus, group=self.group)
         return self.engine.mix_finish(out)
+
+    def submit(self):
+        """Pipelined form (peer exchange or single GPU only): enqueue one buffer, collect it later."""
+        assert self.exchange == "peer" or self.world == 1, "submit/collect needs the in-kernel exchange"
+        self.engine.mix_submit()
+
+    def collect(self, out=None):
+        return self.engine.mix_collect(out)

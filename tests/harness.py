@@ -371,6 +371,22 @@ class Scenario:
         return np.stack(outs), valids
 
 
+def run_pipelined(sc, be, n_buffers):
+    """Scenario.run through sbm_mix_submit / sbm_mix_collect with two buffers in flight: the events of buffer b are applied
+    while buffer b - 1 is still being mixed."""
+    sc.build(be)
+    outs, valids = [], []
+    for b in range(n_buffers):
+        sc.step(be, b)
+        be.mix_submit()
+        if b >= 1:
+            v, o = be.mix_collect()
+            outs.append(o); valids.append(v)
+    v, o = be.mix_collect()
+    outs.append(o); valids.append(v)
+    return np.stack(outs), valids
+
+
 def rel_rms(a, b):
     a = np.asarray(a, dtype=np.float64).ravel()
     b = np.asarray(b, dtype=np.float64).ravel()

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import substrata_b200 as sb
-from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, ROOT, OracleBackend, Scenario, load_sh_hrir, rel_rms)
+from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, ROOT, OracleBackend, Scenario, load_sh_hrir, rel_rms, run_pipelined)
 from golden.make_golden import GOLDEN_SCENARIOS
 
 EMU_DIR = os.path.join(ROOT, "tests", "native")
@@ -139,3 +139,41 @@ def test_batched_ring_push_is_all_or_nothing():
     assert e.source_ring_size(ids[1]) == 450
     with pytest.raises(sb.SbmError):
         e.sources_ring_push([12345], [np.ones(4, np.float32)])
+
+
+@pytest.mark.parametrize("kw,F", [
+    (dict(n_sources=40, mixed_kinds=True, feeder="resample", volume_toggle=True, occlusion_toggle=True, seed=61), 256),
+    (dict(n_sources=24, kind=KIND_HRTF, feeder="ring", rates=(48000, 24000), rate_probs=(0.5, 0.5), seed=62, batched_ring_push=True), 256),
+])
+def test_submit_collect_equals_synchronous_mix(kw, F):
+    """sbm_mix_submit / sbm_mix_collect (two buffers in flight) must produce exactly the buffers sbm_mix produces."""
+    hr = load_sh_hrir()
+    a, va = Scenario(frames=F, **kw).run(emu_engine(F, hr), 10)
+    b, vb = run_pipelined(Scenario(frames=F, **kw), emu_engine(F, hr), 10)
+    assert va == vb and np.array_equal(a, b)
+
+
+def test_submit_collect_reports_finished_sources_and_limits_depth():
+    F = 128
+    e = emu_engine(F)
+    rng = np.random.default_rng(4)
+    buf = e.buffer_create((0.3 * rng.uniform(-1, 1, 300)).astype(np.float32))
+    sid = e.source_create(KIND_PAN)
+    e.source_attach_buffer(sid, buf, 0, 48000, False, True)       # one-shot: stops after 300 samples
+    e.set_source_positions([sid], np.array([[1.0, 0.0, -2.0]], np.float32))
+    e.mix_submit(); e.mix_submit()
+    with pytest.raises(sb.SbmError):
+        e.mix_submit()                                               # at most two in flight
+    with pytest.raises(sb.SbmError):
+        e.mix_begin()                                                # the synchronous form needs an empty pipeline
+    fin = []
+    for _ in range(4):
+        e.mix_collect(); fin += e.poll_finished()
+        e.mix_submit()
+    e.mix_collect(); e.mix_collect()
+    fin += e.poll_finished()
+    assert fin == [sid]
+    with pytest.raises(sb.SbmError):
+        e.mix_collect()                                              # nothing in flight
+    v, o = e.mix()                                                   # and the synchronous call works again
+    assert v == 0
