@@ -833,7 +833,19 @@ __global__ void __launch_bounds__(256) k3_reduce_kernel(const float* __restrict_
 	const float* part = row < 16 ? part_sh : part_pan;
 	const uint32_t g = row < 16 ? g_sh : g_pan, rows = row < 16 ? 16u : 2u, r = row < 16 ? row : row - 16;
 	float s = 0.0f;
-	if (f < F) for (uint32_t b = w; b < g; b += 8) s += part[((size_t)b * rows + r) * F + f];
+	if (f < F) {
+		// four independent running sums (fixed assignment b -> sum, fixed combination order: still bit-stable) keep
+		// several loads in flight per lane instead of one dependent add chain
+		float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+		const float* pp = part + (size_t)r * F + f;
+		const size_t stride = (size_t)rows * F;
+		uint32_t b = w;
+		for (; b + 24 < g; b += 32) {
+			s0 += pp[(size_t)b * stride]; s1 += pp[(size_t)(b + 8) * stride]; s2 += pp[(size_t)(b + 16) * stride]; s3 += pp[(size_t)(b + 24) * stride];
+		}
+		for (; b < g; b += 8) s0 += pp[(size_t)b * stride];
+		s = (s0 + s1) + (s2 + s3);
+	}
 	warp_sum[w][lane] = s;
 	__syncthreads();
 	// multi-GPU: this rank's slot in rank p's gather area

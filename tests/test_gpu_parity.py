@@ -138,6 +138,59 @@ def test_linearity_at_full_size():
     assert rel_rms(a + b, whole) <= TOL
 
 
+def test_linearity_at_c3_size():
+    """C3's full size (65 536 ambisonic sources, 1024-frame buffers, 128-tap SH-HRIRs): mix(A u B) == mix(A) + mix(B) --
+    encode, bus sum and the SH-domain decode are linear, and the decode's tail carry must add up across buffers too."""
+    F, N, L, taps = 1024, 65536, 4096, 128
+    rng = np.random.default_rng(79)
+    n_buf = 128
+    pcm = (0.3 * rng.uniform(-1, 1, (n_buf, L))).astype(np.float32)
+    pos = rng.uniform([-40, -10, -40], [40, 10, 40], (N, 3)).astype(np.float32)
+    pos[np.linalg.norm(pos, axis=1) < 1.05] += 2.0
+    vol = rng.uniform(0.25, 1.0, N).astype(np.float32)
+    start = rng.integers(0, L, N)
+    hr = load_sh_hrir()[:, :taps]
+
+    def run(sel):
+        e = engine(F, hr, max_sources=len(sel))
+        bufs = np.array([e.buffer_create(p) for p in pcm], np.int32)
+        first = e.source_create(KIND_HRTF, len(sel))
+        ids = np.arange(first, first + len(sel), dtype=np.int32)
+        e.sources_attach_buffer(ids, bufs[sel % n_buf], start[sel], np.full(len(sel), 48000, np.int32))
+        e.set_source_positions(ids, pos[sel]); e.set_source_volumes(ids, vol[sel])
+        outs = []
+        for b in range(3):
+            e.set_head([0.02 * b, 0, 0], [0, np.sin(0.004 * b), 0, np.cos(0.004 * b)])
+            outs.append(e.mix()[1].astype(np.float64))
+        return np.stack(outs)
+
+    al = np.arange(N)
+    whole, a, b = run(al), run(al[0::2]), run(al[1::2])
+    assert rel_rms(a + b, whole) <= TOL
+
+
+def test_still_scene_is_time_invariant_at_c5_size():
+    """C5's source count (32 768 ambient loops, 256-frame buffers): with listener and sources at rest and loops whose length
+    is a multiple of the buffer, every loop period reproduces the same buffers bit for bit (no drift in read indices,
+    no stray gain ramps, deterministic reduction order)."""
+    F, N, L = 256, 32768, 1024
+    rng = np.random.default_rng(80)
+    n_buf = 64
+    pcm = (0.3 * rng.uniform(-1, 1, (n_buf, L))).astype(np.float32)
+    pos = rng.uniform([-40, -10, -40], [40, 10, 40], (N, 3)).astype(np.float32)
+    pos[np.linalg.norm(pos, axis=1) < 1.05] += 2.0
+    e = engine(F, load_sh_hrir(), max_sources=N)
+    bufs = np.array([e.buffer_create(p) for p in pcm], np.int32)
+    first = e.source_create(KIND_HRTF, N)
+    ids = np.arange(first, first + N, dtype=np.int32)
+    e.sources_attach_buffer(ids, bufs[np.arange(N) % n_buf], (rng.integers(0, L // F, N) * F), np.full(N, 48000, np.int32))
+    e.set_source_positions(ids, pos)
+    outs = [e.mix()[1].copy() for _ in range(3 * L // F)]
+    period = L // F
+    for k in range(period, 2 * period):          # second period == third period (the first one contains the decoder's start-up)
+        assert np.array_equal(outs[k], outs[k + period])
+
+
 def test_resampler_dropin_matches_reference_golden():
     """glare::AudioResampler drop-in against outputs of the reference class (tests/golden/resampler.npz: the reference's
     own test pattern, AudioResampler.cpp:213-287 -- ramp src[i] = i fed in 4-sample destination chunks, 13 rate pairs),
