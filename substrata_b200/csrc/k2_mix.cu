@@ -51,6 +51,9 @@ namespace {
 #ifndef SBM_PRODUCER_SLEEP_NS
 #define SBM_PRODUCER_SLEEP_NS 200
 #endif
+#ifndef SBM_SH_BIG_FUSE
+#define SBM_SH_BIG_FUSE 4
+#endif
 #ifndef SBM_SH_BIG_CTAS
 #define SBM_SH_BIG_CTAS 1             // resident CTAs per SM the 1024-frame ambisonic kernel's register budget is set for (2 -> 96 registers and spills)
 #endif
@@ -587,8 +590,11 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 //   buffer = iteration k = 0 of the first warps: those warps evaluate the 16 ramping gains in registers, the others
 //   never see the ramp.
 // =====================================================================================================================
-constexpr int K = 4;
-template <int TMAX, bool EXACT>     // TMAX = 128 (frames <= 512) or 256 (frames <= 1024): sets the register budget;
+#ifndef SBM_SH_BIG_K
+#define SBM_SH_BIG_K 4                // frames per thread of the > 512-frame ambisonic kernel (2 = 16 math warps per CTA measured 4 % slower: per-warp overhead scales with the warp count)
+#endif
+constexpr int kShK = 4, kShBigK = SBM_SH_BIG_K, kShBigT = 1024 / kShBigK;
+template <int TMAX, int K, bool EXACT>     // TMAX math threads x K frames each: <128, 4> (frames <= 512), <kShBigT, kShBigK> (frames <= 1024);
                                     // EXACT: frames == 4 * TMAX, no per-frame bounds checks
 __global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : SBM_SH_BIG_CTAS)
 k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
@@ -664,40 +670,48 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 				any |= (dh[b].x & ~(kMdInterp | kMdRamp | kMdShRamp)) | (dh[b].w > (uint32_t)TMAX ? kMdGeneric : 0u);
 			}
 			if (any == 0) {
-				float xs[kBatch][K];
+				// FUSE sources at a time: all their sample loads first, then the arithmetic (4 with the 128-register budget of the
+				// <= 512-frame kernel, 2 where two 288-thread CTAs must share the SM's register file)
+				constexpr int FUSE = TMAX == 128 ? 4 : SBM_SH_BIG_FUSE;
 #pragma unroll
-				for (int b = 0; b < kBatch; ++b) {
-					const float* wb = sm.wring + dh[b].y;
-					if (dh[b].x & kMdInterp) {
-						const MathDesc& d = sm.descs[qr * kBatch + b];
+				for (int b0f = 0; b0f < kBatch; b0f += FUSE) {
+					float xs[FUSE][K];
 #pragma unroll
-						for (int k = 0; k < K; ++k) {
-							const unsigned long long p = d.x0 + (unsigned long long)(t + (uint32_t)k * T) * d.step;
-							const uint32_t di = (uint32_t)(p >> 32);
-							const float v0 = wb[di], v1 = wb[di + 1];
-							xs[b][k] = fmaf(frac_of(p), v1 - v0, v0);
+					for (int bb = 0; bb < FUSE; ++bb) {
+						const int b = b0f + bb;
+						const float* wb = sm.wring + dh[b].y;
+						if (dh[b].x & kMdInterp) {
+							const MathDesc& d = sm.descs[qr * kBatch + b];
+#pragma unroll
+							for (int k = 0; k < K; ++k) {
+								const unsigned long long p = d.x0 + (unsigned long long)(t + (uint32_t)k * T) * d.step;
+								const uint32_t di = (uint32_t)(p >> 32);
+								const float v0 = wb[di], v1 = wb[di + 1];
+								xs[bb][k] = fmaf(frac_of(p), v1 - v0, v0);
+							}
+						} else {
+#pragma unroll
+							for (int k = 0; k < K; ++k) xs[bb][k] = wb[t + (uint32_t)k * T];
 						}
-					} else {
-#pragma unroll
-						for (int k = 0; k < K; ++k) xs[b][k] = wb[t + (uint32_t)k * T];
 					}
-				}
 #pragma unroll
-				for (int b = 0; b < kBatch; ++b) {
-					const float gdf = __uint_as_float(dh[b].z);
-					const float* gk = sm.shgs[qr * kBatch + b].konst;
-					const uint32_t nramp = dh[b].w;
+					for (int bb = 0; bb < FUSE; ++bb) {
+						const int b = b0f + bb;
+						const float gdf = __uint_as_float(dh[b].z);
+						const float* gk = sm.shgs[qr * kBatch + b].konst;
+						const uint32_t nramp = dh[b].w;
 #pragma unroll
-					for (int k = 1; k < K; ++k) accumulate_const(gk, xs[b][k] * gdf, k);
-					if (warp_i0 < nramp) {
-						// this warp's first frames lie inside a ramp of the direct gain and / or of channel gains
-						const MathDesc& d = sm.descs[qr * kBatch + b];
-						const WorkRec& r = sm.recs[qr * kBatch + b];
-						const float yv = (xs[b][0] * d.mfx) * gain_at(r.direct, t);
-						accumulate_ramped(gk, (dh[b].x & kMdShRamp) ? &sm.shrs[qw * kBatch + b] : nullptr, yv, t, ft, 0);
-					} else accumulate_const(gk, xs[b][0] * gdf, 0);
-					// frame F - 1 = t + (K - 1) T of thread T - 1: the bypassed occlusion filter's memory (mono_pole_filter.cc:40-44)
-					if (t == T - 1) a.lpf_prev[sm.descs[qr * kBatch + b].slot] = xs[b][K - 1] * gdf;
+						for (int k = 1; k < K; ++k) accumulate_const(gk, xs[bb][k] * gdf, k);
+						if (warp_i0 < nramp) {
+							// this warp's first frames lie inside a ramp of the direct gain and / or of channel gains
+							const MathDesc& d = sm.descs[qr * kBatch + b];
+							const WorkRec& r = sm.recs[qr * kBatch + b];
+							const float yv = (xs[bb][0] * d.mfx) * gain_at(r.direct, t);
+							accumulate_ramped(gk, (dh[b].x & kMdShRamp) ? &sm.shrs[qw * kBatch + b] : nullptr, yv, t, ft, 0);
+						} else accumulate_const(gk, xs[bb][0] * gdf, 0);
+						// frame F - 1 = t + (K - 1) T of thread T - 1: the bypassed occlusion filter's memory (mono_pole_filter.cc:40-44)
+						if (t == T - 1) a.lpf_prev[sm.descs[qr * kBatch + b].slot] = xs[bb][K - 1] * gdf;
+					}
 				}
 				batch_done = true;
 			}
@@ -920,7 +934,8 @@ int sm_count() {
 // Stage slot per source, in floats: room for a window of frames * 1.25 (sample-rate ratios <= 1, doppler / pitch up
 // to +25 %) plus alignment slack; larger windows take the generic path.
 uint32_t window_slot(uint32_t F) { return (F + F / 4 + 24u + 3u) & ~3u; }
-uint32_t sh_threads(uint32_t F) { return ((F + K - 1) / K + 31) / 32 * 32; }
+uint32_t sh_frames_per_thread(uint32_t F) { return F <= 512 ? (uint32_t)kShK : (uint32_t)kShBigK; }
+uint32_t sh_threads(uint32_t F) { const uint32_t K = sh_frames_per_thread(F); return ((F + K - 1) / K + 31) / 32 * 32; }
 int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig); }
 size_t mix_smem_bytes(uint32_t F, bool sh) {
 	const size_t st = (size_t)mix_stages(F, sh), rst = st + 2, kBatch = sh ? kBatchSh : kBatchPan;
@@ -1004,12 +1019,12 @@ int launch_mix(const MixArgs& a, void* stream) {
 		static KernelConfig conf_sh, conf_sh_big, conf_sh_x, conf_sh_big_x;
 		const uint32_t tm = sh_threads(F);
 		const uint32_t mg = (uint32_t)num_mix_ctas(F, 1);
-		const bool exact = (tm == 128 || tm == 256) && F == tm * K;     // the EXACT instantiations fix T = TMAX at compile time
+		const bool exact = (tm == 128 || tm == (uint32_t)kShBigT) && F == tm * sh_frames_per_thread(F);     // the EXACT instantiations fix T = TMAX at compile time
 		int rc;
-		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<128, true>, &conf_sh_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
-		                         : launch_one(k2_mix_ambisonic_kernel<128, false>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
-		else rc = exact ? launch_one(k2_mix_ambisonic_kernel<256, true>, &conf_sh_big_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
-		                : launch_one(k2_mix_ambisonic_kernel<256, false>, &conf_sh_big, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
+		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<128, kShK, true>, &conf_sh_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
+		                         : launch_one(k2_mix_ambisonic_kernel<128, kShK, false>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
+		else rc = exact ? launch_one(k2_mix_ambisonic_kernel<kShBigT, kShBigK, true>, &conf_sh_big_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
+		                : launch_one(k2_mix_ambisonic_kernel<kShBigT, kShBigK, false>, &conf_sh_big, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
