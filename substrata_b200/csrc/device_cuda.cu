@@ -104,9 +104,15 @@ __global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
 	if (i == 0) {
 		tail->valid = plan.valid;
 		tail->n_finished = a.flags->n_finished;
-		tail->n_rendered = a.flags->n_rendered;
+		unsigned long long bytes = a.flags->algo_bytes;
+		unsigned int rendered = a.flags->n_rendered;
+		for (uint32_t p = 0; p < kStatParts; ++p) {
+			bytes += a.flags->part_bytes[p][0]; rendered += a.flags->part_rendered[p][0];
+			a.flags->part_bytes[p][0] = 0; a.flags->part_rendered[p][0] = 0;
+		}
+		tail->n_rendered = rendered;
 		tail->pad = 0;
-		tail->algo_bytes = a.flags->algo_bytes;
+		tail->algo_bytes = bytes;
 		a.flags->n_finished = 0; a.flags->n_rendered = 0; a.flags->algo_bytes = 0;
 	}
 	unsigned long long* reads = reinterpret_cast<unsigned long long*>(tail + 1);

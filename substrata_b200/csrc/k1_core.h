@@ -83,6 +83,9 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	float occ = A.occ_cur[slot];
 	const float lpf_prev0 = A.lpf_prev[slot];
 	uint8_t bits = A.bits[slot];
+	// stereo-pan bus gains (the first two of the slot's cstride floats), loaded with the rest: left where they are used,
+	// the compiler must keep them behind the state stores above them (possible aliasing) = one more DRAM round trip
+	const float cg_pan0 = A.cgain[(size_t)slot * (size_t)A.cstride], cg_pan1 = A.cgain[(size_t)slot * (size_t)A.cstride + 1];
 	WorkRec rec;
 	rec.pcm = st.pcm; rec.len = st.len; rec.start = 0; rec.n_src = 0; rec.avail = 0; rec.flags = kRecSkip;
 	rec.slot = slot; rec.x0_fx = 0; rec.step_fx = 0; rec.prev0 = 0.0f; rec.prev1 = 0.0f; rec.lpf_coef = 0.0f; rec.lpf_prev = 0.0f;
@@ -259,7 +262,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		float g[2];
 		stereo_pan_gains(az, el, &g[0], &g[1]);
 		for (int c = 0; c < 2; ++c) {
-			float cur = cg[c];
+			float cur = c == 0 ? cg_pan0 : cg_pan1;
 			rec.ch[c] = plan_gain(&cur, chan_init, g[c], F, /*accumulate=*/true);
 			cg[c] = cur;
 			if (rec.ch[c].n) rec.ch_ramp_mask |= 1u << c;

@@ -18,10 +18,10 @@ __global__ void __launch_bounds__(256, SBM_K1_MINB) k1_params_kernel(Globals g, 
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;    // position in the render lists
 	uint32_t used = 0, n_src = 0;
 	if (k < g.n_pan + g.n_sh) used = update_source(g, A, flags, table, lists[k], k, &n_src);
-	// Block-level reduction of the "mixer used" bits and the accounting counters: warp shuffles, then one thread per block
-	// publishes.  The flags are the same few words for every block of the grid, and same-address atomics serialise in
-	// L2 (one per warp cost ~100 us per million sources): a flag is only OR-ed while it still reads 0, and the counters
-	// take one atomic each per block.
+	// Warp-level reduction of the "mixer used" bits and the accounting counters, then one lane publishes.  The flags are
+	// the same few words for the whole grid and same-address atomics serialise in L2 (one set per warp on ONE address cost
+	// ~100 us per million sources): a flag is only OR-ed while it still reads 0, and the counters go to one of kStatParts
+	// padded slots chosen by the block index (K4b sums them).  No block-wide barrier: a finished warp leaves the SM.
 	const unsigned full = 0xffffffffu;
 	uint32_t u = used;
 	unsigned long long bytes = n_src ? 4ull * n_src : 0ull;
@@ -31,17 +31,15 @@ __global__ void __launch_bounds__(256, SBM_K1_MINB) k1_params_kernel(Globals g, 
 		bytes += __shfl_xor_sync(full, bytes, o);
 		rendered += __shfl_xor_sync(full, rendered, o);
 	}
-	__shared__ unsigned long long s_bytes[8];
-	__shared__ uint32_t s_used[8], s_rendered[8];
-	const uint32_t w = threadIdx.x >> 5;
-	if ((threadIdx.x & 31) == 0) { s_bytes[w] = bytes; s_used[w] = u; s_rendered[w] = rendered; }
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		for (uint32_t q = 1; q < blockDim.x / 32; ++q) { bytes += s_bytes[q]; u |= s_used[q]; rendered += s_rendered[q]; }
+	if ((threadIdx.x & 31) == 0) {
 		if ((u & kUsedPan) && !*(volatile int*)&flags->pan_used[g.parity]) atomicOr(&flags->pan_used[g.parity], 1);
 		if ((u & kUsedSh) && !*(volatile int*)&flags->sh_used[g.parity]) atomicOr(&flags->sh_used[g.parity], 1);
 		if ((u & kUsedStereo) && !*(volatile int*)&flags->st_used[g.parity]) atomicOr(&flags->st_used[g.parity], 1);
-		if (rendered) { atomicAdd(&flags->algo_bytes, bytes); atomicAdd(&flags->n_rendered, rendered); }
+		if (rendered) {
+			const uint32_t part = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kStatParts;
+			atomicAdd(&flags->part_bytes[part][0], bytes);
+			atomicAdd(&flags->part_rendered[part][0], rendered);
+		}
 	}
 }
 

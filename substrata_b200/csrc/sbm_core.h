@@ -145,7 +145,12 @@ struct DevFlags {
 	unsigned long long algo_bytes;  // accounting: sum of 4*n_src over rendered sources
 	unsigned int n_rendered;
 	int pad;
+	// K1 spreads its per-warp accounting atomics over kStatParts padded slots (same-address atomics serialise in L2;
+	// a block-wide reduction would hold every warp of a block until its slowest one is done); K4b folds them into the tail.
+	unsigned long long part_bytes[32][4];      // [part][0] used, rest = 32-byte padding
+	unsigned int part_rendered[32][8];
 };
+constexpr uint32_t kStatParts = 32;
 
 // All per-slot arrays (device pointers), passed by value to K1.
 struct SlotArrays {
