@@ -32,6 +32,10 @@ GOLDEN_SCENARIOS = {
     "mixed_toggles": (dict(n_sources=64, mixed_kinds=True, volume_toggle=True, occlusion_toggle=True), 512, 14, 0),
     "f480_hq": (dict(n_sources=32, kind=KIND_HRTF), 480, 8, 0),
     "short_loops": (dict(n_sources=40, kind=KIND_PAN, loop_len=300, feeder="resample"), 256, 8, 0),
+    # loop lengths that are not a multiple of 4 samples with a pitch / doppler read head (re-aligned second TMA segment)
+    "doppler_odd_loop_pan": (dict(n_sources=48, kind=KIND_PAN, feeder="doppler", loop_len=4099, seed=101), 512, 8, 0),
+    "doppler_odd_loop_hq": (dict(n_sources=48, kind=KIND_HRTF, feeder="doppler", loop_len=4098, seed=102, volume_toggle=True), 256, 10, 0),
+    "hq_resample_1024": (dict(n_sources=40, kind=KIND_HRTF, feeder="resample", loop_len=3001, seed=103, occlusion_toggle=True), 1024, 8, 0),
 }
 
 RESAMPLER_PAIRS = [(8000, 48000), (12000, 48000), (16000, 48000), (24000, 48000), (44100, 48000), (48000, 48000),
