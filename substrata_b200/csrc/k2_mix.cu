@@ -7,19 +7,24 @@
 // Decomposition.  A CTA owns ALL frames of the buffer and every grid-th batch of the render list, and keeps its partial
 // sums in registers across the whole slice, so per-source contributions never leave the register file; each CTA then
 // stores one partial bus [NCH][frames] and K3 sums the partial buses in CTA order (deterministic; no atomics on audio).
-//   stereo bus (2 channels):  one WARP per source -- lane l owns frames l, l+32, ... (2 x frames/32 accumulators), the
-//                             four math warps of a CTA work on the four sources of a batch independently and combine
-//                             their tiles through shared memory once, at the end of the slice;
-//   ambisonic bus (16 ch):    one CTA per source -- thread t owns frames t, t+T, t+2T, t+3T (16 x 4 accumulators, FFMA2).
+//   stereo bus (2 channels):  one WARP per source -- lane l owns frames l, l+32, ... as (L, R) accumulator pairs (one FFMA2
+//                             per frame; the interpolations of two frames share packed f32x2 instructions); the four math
+//                             warps of a CTA take the eight sources of a batch in two rounds and combine their tiles
+//                             through shared memory once, at the end of the slice;
+//   ambisonic bus (16 ch):    one CTA per batch of four sources -- thread t owns frames t, t+T, t+2T, t+3T and all 16
+//                             channels (32 channel-pair accumulators, FFMA2 with the gain pair from an LDS.128 and the
+//                             sample broadcast); a batch of simple sources runs as one straight-line block.
 //
 // Data movement.  Source windows are not loaded by the math threads: a dedicated producer warp drives a multi-stage
 // shared-memory ring with the TMA unit -- one cp.async.bulk (UBLKCP) per window segment, completion signalled on an
-// mbarrier per stage, stages handed back through a second mbarrier by the math warps -- kStages batches of kBatch sources
-// ahead of the math, which keeps ~100 KB of reads in flight per SM regardless of how the math is scheduled.  The
-// per-source records (WorkRec, 128 B, render-list order, + 64 B of SH gains) stream through a second, deeper TMA ring
-// so that the producer never waits on a dependent global load; producer lane b condenses record b of a batch into a
-// 64-byte MathDesc (shared-memory window index, fixed-point read head, pre-multiplied gains, mode bits) so that the math
-// threads spend a handful of instructions per source on set-up.
+// mbarrier per stage, stages handed back through a second mbarrier by the math warps.  The per-source records (WorkRec,
+// 128 B, render-list order, + 64 B of SH gains) stream through a second TMA ring two batches deeper, so that the producer
+// never waits on a dependent global load; producer lane b condenses record b of a batch into a 64-byte MathDesc
+// (shared-memory window index, fixed-point read head, pre-multiplied gains, mode bits; what the fast paths need sits in
+// its first 16 bytes) so that the math threads spend a handful of instructions per source on set-up.  The producer is a
+// serial, latency-bound warp: it plans a batch BEFORE it waits for the stage, and the stereo kernel uses batches of 8
+// sources because the producer's cost per batch does not depend on how many of its lanes are busy.  (Handing a stage
+// back in two halves, one per round of the math warps, was measured 4 % slower: more barrier traffic, no more overlap.)
 // Windows start at arbitrary sample offsets; the copy fetches the enclosing 16-byte-aligned span and the math indexes
 // from the sub-offset.  A looping window that crosses the end of its buffer is fetched as two segments.
 // Sources the fast path cannot express (zero-padded ends, ring underflow, multi-source pitch mixes, windows larger
@@ -73,7 +78,6 @@ constexpr int kBatchSh = 4, kBatchPan = SBM_BATCH_PAN, kPanWarps = 4;
 #endif
 constexpr int kStagesPan = SBM_STAGES, kStagesSh = SBM_STAGES_SH, kStagesShBig = SBM_STAGES_SH_BIG;
 constexpr int kMaxStages = 10;
-constexpr int kPanThreads = 128;
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + TMA bulk copy (global -> shared), sm_90+ / sm_100a.
