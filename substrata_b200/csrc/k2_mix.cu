@@ -388,6 +388,47 @@ __device__ __forceinline__ void init_barriers(MixSmemHdr* hdr, uint32_t n_consum
 	fence_mbar_init();
 }
 
+// Stereo kernel, every case the lean forms cannot express (zero-padded ends, ring underflow, multi-source pitch mixes, oversize
+// windows, unaligned buffers, re-aligned loop wraps, occlusion low-pass): OUT OF LINE, one warp per source, straightforward
+// arithmetic.  Leaves the source's engine-rate samples in its own stage slot -- slot[i], i < frames, mix_factor applied; the
+// direct gain and the low-pass too when it returns true -- and does the feeder / filter bookkeeping; the caller then reads the
+// slot like a native-rate window.  Keeping this (large, rarely executed) code out of the kernel body shrinks the hot path's
+// instruction footprint; its staging array lives in local memory, which only this path touches.
+__device__ __noinline__ bool careful_source_to_slot(const MixArgs& a, const WorkRec& r, float* slot, uint32_t wslot, uint32_t lane) {
+	const uint32_t F = a.frames;
+	const WinPlan wp = plan_window(r, wslot);
+	const float* w = slot + 4 + wp.off0;
+	float x[kMaxFrames / 32];     // held until every lane has read the staged window: the result overwrites it
+#pragma unroll 1
+	for (uint32_t k = 0; k * 32u < F; ++k) {
+		const uint32_t i = lane + 32u * k;
+		x[k] = 0.0f;
+		if (i < F) x[k] = wp.fast ? staged_sample(r, w, wp, i) : source_sample(r, a.mixz, a.mix_pos0, i);
+	}
+	if ((r.flags & kRecResample) && lane == 0) {
+		float p0, p1;
+		if (wp.fast) { p0 = staged_tmp(r, w, wp, (int)r.n_src); p1 = staged_tmp(r, w, wp, (int)r.n_src + 1); }
+		else resampler_tail(r, &p0, &p1);
+		a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
+	}
+	__syncwarp();
+	const bool lpf = (r.flags & kRecLpf) != 0;
+#pragma unroll 1
+	for (uint32_t k = 0; k * 32u < F; ++k) {
+		const uint32_t i = lane + 32u * k;
+		if (i < F) slot[i] = lpf ? x[k] * gain_at(r.direct, i) : x[k];
+	}
+	__syncwarp();
+	if (lpf) {
+		// direct gain applied above; the recurrence runs in place in the stage slot
+		const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane);
+		__syncwarp();
+		if (lane == 0) a.lpf_prev[r.slot] = carry;
+	}
+	fence_proxy_async();     // generic-proxy writes to the slot precede the TMA refill
+	return lpf;
+}
+
 template <int V> struct IntTag { static constexpr int value = V; };
 
 __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_as_float(0x3f800000u | ((uint32_t)p >> 9)) - 1.0f; }
@@ -443,36 +484,11 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 				float mf = 1.0f;       // MixSource::mix_factor where it is not already inside x
 				bool filtered = false; // x already carries the direct gain and the occlusion low-pass
 				if (mode & (kMdGeneric | kMdLpf | kMdAdjust)) {
-					// ---------------- careful fetch (rare): every case, straightforward arithmetic ----------------
-					const WinPlan wp = plan_window(r, wslot);
-					float* slot = sm.wring + (size_t)(qw * kBatch + src) * wslot;     // this source's stage slot
-					const float* w = slot + 4 + wp.off0;
+					// ---------------- careful fetch (rare, out of line): leaves the samples in this source's stage slot ----------------
+					float* slot = sm.wring + (size_t)(qw * kBatch + src) * wslot;
+					filtered = careful_source_to_slot(a, r, slot, wslot, lane);
 #pragma unroll
-					for (int k = 0; k < KF; ++k) {
-						const uint32_t i = lane + 32u * k;
-						x[k] = 0.0f;
-						if (EXACT || i < F) x[k] = wp.fast ? staged_sample(r, w, wp, i) : source_sample(r, a.mixz, a.mix_pos0, i);
-					}
-					if ((r.flags & kRecResample) && lane == 0) {
-						float p0, p1;
-						if (wp.fast) { p0 = staged_tmp(r, w, wp, (int)r.n_src); p1 = staged_tmp(r, w, wp, (int)r.n_src + 1); }
-						else resampler_tail(r, &p0, &p1);
-						a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
-					}
-					if (mode & kMdLpf) {
-						// the window is in registers now: reuse this warp's stage slot as scratch for the recurrence
-						__syncwarp();
-#pragma unroll
-						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; if (EXACT || i < F) slot[i] = x[k] * gain_at(r.direct, i); }
-						__syncwarp();
-						const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane);
-						__syncwarp();
-#pragma unroll
-						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; if (EXACT || i < F) x[k] = slot[i]; }
-						if (lane == 0) a.lpf_prev[r.slot] = carry;
-						fence_proxy_async();     // generic-proxy writes to the slot precede the TMA refill
-						filtered = true;
-					}
+					for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; x[k] = (EXACT || i < F) ? slot[i] : 0.0f; }
 				} else {
 					// ---------------- lean fetch: window staged in shared memory by the TMA ring ----------------
 					const float* wb = sm.wring + d.w_idx;
