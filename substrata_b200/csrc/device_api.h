@@ -82,6 +82,7 @@ struct FinishArgs {
 	uint32_t n_ring;
 	const unsigned long long* read_i;
 	int* finished_count_reset;  // unused
+	int hist_smem_all;          // set by launch_finish: K4b updates the FIR history of all 16 channels in one pass
 };
 
 struct OutTail {                // follows the 2*frames output floats in the D2H staging buffer

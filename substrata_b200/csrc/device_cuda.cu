@@ -8,6 +8,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <type_traits>
 
 #include "device_internal.h"
 #include "k2_core.h"
@@ -29,8 +30,13 @@ thread_local std::string t_err_copy;
 // Whether this buffer decodes at all is the read-only half of plan_finish (K4b makes the same decision and records it).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kDecFrames = 32;
+// DBL: taps and inputs are converted to double ONCE while they are staged (f32 -> f64 conversions run on the 16-lane XU
+// pipe: two per tap and thread made this kernel 16 us long); the float staging is the fall-back when 8-byte copies of
+// [16][taps] + [16][taps + 31] do not fit in shared memory (taps > ~430).
+template <bool DBL>
 __global__ void __launch_bounds__(kNumSh * 32) k4a_decode_kernel(FinishArgs a) {
-	extern __shared__ float smem[];   // [16][taps] HRIRs | [16][taps - 1 + 32] inputs | [16][32] channel results
+	typedef typename std::conditional<DBL, double, float>::type stage_t;
+	extern __shared__ __align__(16) unsigned char smem_raw[];   // [16][taps] HRIRs | [16][taps - 1 + 32] inputs | [16][32] channel results (float)
 	const uint32_t F = a.frames, taps = a.taps;
 	const int H = (int)taps - 1;
 	const float* bf = a.bus + (size_t)kBusRows * F;
@@ -38,21 +44,31 @@ __global__ void __launch_bounds__(kNumSh * 32) k4a_decode_kernel(FinishArgs a) {
 	const uint32_t c = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 	const uint32_t i0 = blockIdx.x * kDecFrames;
 	const uint32_t span = (uint32_t)H + kDecFrames;
-	float* h = smem + (size_t)c * taps;
-	float* x = smem + (size_t)kNumSh * taps + (size_t)c * span;
-	float* ys = smem + (size_t)kNumSh * taps + (size_t)kNumSh * span;
+	stage_t* sm = reinterpret_cast<stage_t*>(smem_raw);
+	stage_t* h = sm + (size_t)c * taps;
+	stage_t* x = sm + (size_t)kNumSh * taps + (size_t)c * span;
+	float* ys = reinterpret_cast<float*>(sm + (size_t)kNumSh * taps + (size_t)kNumSh * span);
 	const float* bus_c = a.bus + (size_t)c * F;
 	const float* hist_c = a.hist + (size_t)c * (size_t)(H > 0 ? H : 1);
-	for (uint32_t q = lane; q < taps; q += 32) h[q] = a.hrir[(size_t)c * taps + q];
+	for (uint32_t q = lane; q < taps; q += 32) h[q] = (stage_t)a.hrir[(size_t)c * taps + q];
 	for (uint32_t q = lane; q < span; q += 32) {
 		const int j = (int)i0 - H + (int)q;                        // input sample index; negative = history
-		x[q] = j < (int)F ? decode_input(bus_c, hist_c, H, j) : 0.0f;
+		x[q] = (stage_t)(j < (int)F ? decode_input(bus_c, hist_c, H, j) : 0.0f);
 	}
 	__syncwarp();
-	double acc = 0.0;
-	const float* xi = x + H + lane;
-	for (uint32_t t = 0; t < taps; ++t) acc = fma((double)h[t], (double)xi[-(int)t], acc);
-	ys[c * kDecFrames + lane] = (float)acc;
+	// four interleaved partial sums break the taps' dependent DFMA chain; everything is accumulated in double, so the
+	// summation order does not show in the float result
+	double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+	const stage_t* xi = x + H + lane;
+	uint32_t t = 0;
+	for (; t + 4 <= taps; t += 4) {
+		acc0 = fma((double)h[t], (double)xi[-(int)t], acc0);
+		acc1 = fma((double)h[t + 1], (double)xi[-(int)t - 1], acc1);
+		acc2 = fma((double)h[t + 2], (double)xi[-(int)t - 2], acc2);
+		acc3 = fma((double)h[t + 3], (double)xi[-(int)t - 3], acc3);
+	}
+	for (; t < taps; ++t) acc0 = fma((double)h[t], (double)xi[-(int)t], acc0);
+	ys[c * kDecFrames + lane] = (float)((acc0 + acc1) + (acc2 + acc3));
 	__syncthreads();
 	if (c == 0 && i0 + lane < F) {
 		float l = 0.0f, r = 0.0f;
@@ -84,7 +100,16 @@ __global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
 	float l = 0.0f, r = 0.0f;
 	if (plan.decode) {
 		if (i < F) { l = a.dec[i]; r = a.dec[F + i]; }
-		if (H > 0) {
+		if (H > 0 && a.hist_smem_all) {
+			// all 16 channels at once: the new history goes through shared memory (it may overlap the old one when frames < taps)
+			const uint32_t n = (uint32_t)kNumSh * (uint32_t)H;
+			for (uint32_t q = i; q < n; q += T) {
+				const uint32_t c = q / (uint32_t)H, k = q - c * (uint32_t)H;
+				smem[q] = decode_input(a.bus + (size_t)c * F, a.hist + (size_t)c * (size_t)H, H, (int)F - H + (int)k);
+			}
+			__syncthreads();
+			for (uint32_t q = i; q < n; q += T) a.hist[q] = smem[q];
+		} else if (H > 0) {
 			for (int c = 0; c < kNumSh; ++c) {
 				const float* bus_c = a.bus + (size_t)c * F;
 				float* hist_c = a.hist + (size_t)c * (size_t)H;
@@ -101,18 +126,19 @@ __global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
 		a.out[2 * i] = l; a.out[2 * i + 1] = r;
 	}
 	OutTail* tail = reinterpret_cast<OutTail*>(a.out + 2 * F);
+	// K1's accounting slots: one lane each (kStatParts == 32), summed by shuffles
+	unsigned long long part_bytes = 0; unsigned int part_rendered = 0;
+	if (i < 32) {
+		part_bytes = a.flags->part_bytes[i][0]; part_rendered = a.flags->part_rendered[i][0];
+		a.flags->part_bytes[i][0] = 0; a.flags->part_rendered[i][0] = 0;
+		for (int o = 16; o > 0; o >>= 1) { part_bytes += __shfl_xor_sync(0xffffffffu, part_bytes, o); part_rendered += __shfl_xor_sync(0xffffffffu, part_rendered, o); }
+	}
 	if (i == 0) {
 		tail->valid = plan.valid;
 		tail->n_finished = a.flags->n_finished;
-		unsigned long long bytes = a.flags->algo_bytes;
-		unsigned int rendered = a.flags->n_rendered;
-		for (uint32_t p = 0; p < kStatParts; ++p) {
-			bytes += a.flags->part_bytes[p][0]; rendered += a.flags->part_rendered[p][0];
-			a.flags->part_bytes[p][0] = 0; a.flags->part_rendered[p][0] = 0;
-		}
-		tail->n_rendered = rendered;
+		tail->n_rendered = a.flags->n_rendered + part_rendered;
 		tail->pad = 0;
-		tail->algo_bytes = bytes;
+		tail->algo_bytes = a.flags->algo_bytes + part_bytes;
 		a.flags->n_finished = 0; a.flags->n_rendered = 0; a.flags->algo_bytes = 0;
 	}
 	unsigned long long* reads = reinterpret_cast<unsigned long long*>(tail + 1);
@@ -228,19 +254,26 @@ int launch_finish(const FinishArgs& a, void* stream) {
 	const uint32_t F = a.frames;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (a.hrir) {
-		const size_t smem = sizeof(float) * ((size_t)kNumSh * a.taps + (size_t)kNumSh * (a.taps - 1 + kDecFrames) + (size_t)kNumSh * kDecFrames);
-		static size_t configured = 48 * 1024;
-		if (smem > configured) {
-			if (check(cudaFuncSetAttribute(k4a_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k4a)")) return -1;
-			configured = smem;
+		const size_t elems = (size_t)kNumSh * a.taps + (size_t)kNumSh * (a.taps - 1 + kDecFrames);
+		const bool dbl = sizeof(double) * elems + sizeof(float) * kNumSh * kDecFrames <= 200 * 1024;
+		const size_t smem = (dbl ? sizeof(double) : sizeof(float)) * elems + sizeof(float) * (size_t)kNumSh * kDecFrames;
+		static size_t configured[2] = {48 * 1024, 48 * 1024};
+		if (smem > configured[dbl]) {
+			if (check(dbl ? cudaFuncSetAttribute(k4a_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+			              : cudaFuncSetAttribute(k4a_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k4a)")) return -1;
+			configured[dbl] = smem;
 		}
-		k4a_decode_kernel<<<(F + kDecFrames - 1) / kDecFrames, kNumSh * 32, smem, st>>>(a);
+		if (dbl) k4a_decode_kernel<true><<<(F + kDecFrames - 1) / kDecFrames, kNumSh * 32, smem, st>>>(a);
+		else k4a_decode_kernel<false><<<(F + kDecFrames - 1) / kDecFrames, kNumSh * 32, smem, st>>>(a);
 		note_launch();
 		if (check_launch("k4a_decode")) return -1;
 	}
 	const uint32_t threads = ((F + 31) / 32) * 32;
-	const size_t smem = sizeof(float) * (size_t)(a.hrir && a.taps > 1 ? a.taps - 1 : 1);
-	k4b_finish_kernel<<<1, threads, smem, st>>>(a);
+	const size_t h1 = a.hrir && a.taps > 1 ? a.taps - 1 : 1;
+	FinishArgs b = a;
+	b.hist_smem_all = sizeof(float) * h1 * kNumSh <= 48 * 1024 ? 1 : 0;      // 16 channels' history in one pass when it fits the default limit
+	const size_t smem = sizeof(float) * h1 * (b.hist_smem_all ? (size_t)kNumSh : 1);
+	k4b_finish_kernel<<<1, threads, smem, st>>>(b);
 	note_launch();
 	return check_launch("k4b_finish");
 }

@@ -748,7 +748,7 @@ static int mix_enqueue_finish_locked(sbm_engine* e) {
 	FinishArgs f;
 	f.bus = e->peer.world ? e->dv_bus_sum : e->dv_bus; f.hrir = e->dv_hrir; f.taps = (uint32_t)e->cfg.sh_hrir_taps; f.hist = e->dv_hist; f.dec = e->dv_dec;
 	f.flags = e->dv_flags; f.parity = parity; f.frames = F; f.out = e->dv_out;
-	f.list_ring = e->dv_list_ring; f.n_ring = (uint32_t)e->list_ring.size(); f.read_i = e->A.read_i; f.finished_count_reset = nullptr;
+	f.list_ring = e->dv_list_ring; f.n_ring = (uint32_t)e->list_ring.size(); f.read_i = e->A.read_i; f.finished_count_reset = nullptr; f.hist_smem_all = 0;
 	if (dev::launch_finish(f, st)) return fail_cuda(e, "k4_finish");
 	if (e->profiling) dev::event_record(fl.ev[3], st);
 	const size_t bytes = sizeof(float) * 2 * F + sizeof(OutTail) + sizeof(unsigned long long) * e->list_ring.size();
