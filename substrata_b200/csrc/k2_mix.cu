@@ -855,13 +855,14 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 }
 
 // K3: bus[row][f] = sum over CTAs of the partial buses; rows 0-15 from the ambisonic kernel's partials, rows 16-17 from
-// the stereo kernel's.  One CTA per (row, 32 frames): warp w sums the partials of CTAs w, w+8, w+16, ... and the eight
+// the stereo kernel's.  One CTA per (row, 32 frames): warp w sums the partials of CTAs w, w+32, w+64, ... and the 32
 // warp sums are added in warp order -- a fixed tree, so the result is bit-stable from run to run (no atomics on audio).
 // Also publishes this rank's "mixer used" flags as floats behind the audio so that they sum across ranks with it.
-__global__ void __launch_bounds__(256) k3_reduce_kernel(const float* __restrict__ part_pan, uint32_t g_pan, const float* __restrict__ part_sh,
+constexpr uint32_t kK3Warps = 32;
+__global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* __restrict__ part_pan, uint32_t g_pan, const float* __restrict__ part_sh,
                                                        uint32_t g_sh, float* __restrict__ bus, const DevFlags* __restrict__ flags,
                                                        uint32_t parity, uint32_t F, PeerArgs pa, size_t bus_floats) {
-	__shared__ float warp_sum[8][32];
+	__shared__ float warp_sum[kK3Warps][32];
 	const uint32_t row = blockIdx.y, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	const uint32_t f = blockIdx.x * 32 + lane;
 	const float* part = row < 16 ? part_sh : part_pan;
@@ -874,10 +875,10 @@ __global__ void __launch_bounds__(256) k3_reduce_kernel(const float* __restrict_
 		const float* pp = part + (size_t)r * F + f;
 		const size_t stride = (size_t)rows * F;
 		uint32_t b = w;
-		for (; b + 24 < g; b += 32) {
-			s0 += pp[(size_t)b * stride]; s1 += pp[(size_t)(b + 8) * stride]; s2 += pp[(size_t)(b + 16) * stride]; s3 += pp[(size_t)(b + 24) * stride];
+		for (; b + 3 * kK3Warps < g; b += 4 * kK3Warps) {
+			s0 += pp[(size_t)b * stride]; s1 += pp[(size_t)(b + kK3Warps) * stride]; s2 += pp[(size_t)(b + 2 * kK3Warps) * stride]; s3 += pp[(size_t)(b + 3 * kK3Warps) * stride];
 		}
-		for (; b < g; b += 8) s0 += pp[(size_t)b * stride];
+		for (; b < g; b += kK3Warps) s0 += pp[(size_t)b * stride];
 		s = (s0 + s1) + (s2 + s3);
 	}
 	warp_sum[w][lane] = s;
@@ -887,7 +888,7 @@ __global__ void __launch_bounds__(256) k3_reduce_kernel(const float* __restrict_
 	if (w == 0 && f < F) {
 		float t = warp_sum[0][lane];
 #pragma unroll
-		for (int q = 1; q < 8; ++q) t += warp_sum[q][lane];
+		for (int q = 1; q < (int)kK3Warps; ++q) t += warp_sum[q][lane];
 		bus[(size_t)row * F + f] = t;
 		for (uint32_t p = 0; p < pa.world; ++p) pa.gather[p][slot_off + (size_t)row * F + f] = t;     // NVLink peer stores (local for p == rank)
 	}
@@ -1048,7 +1049,7 @@ int launch_mix(const MixArgs& a, void* stream) {
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
-	k3_reduce_kernel<<<dim3((F + 31) / 32, kBusRows), 256, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F, a.peer, a.bus_floats);
+	k3_reduce_kernel<<<dim3((F + 31) / 32, kBusRows), kK3Warps * 32, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F, a.peer, a.bus_floats);
 	note_launch();
 	return check_launch("k3_reduce");
 }
