@@ -282,6 +282,29 @@ def parity_sample(wl):
     return {"rel_rms": harness.rel_rms(go, oo), "sample": "%d sources x 4 buffers vs oracle (CPU port pinned to the compiled reference)" % n}
 
 
+ALSO = [("c2_4096_resample_pan", 200), ("c3_65536_hq_128tap", 100), ("c5_voice_ambient", 100)]
+
+
+def also_workloads(args):
+    """The other single-GPU configurations of BASELINE.json (C2, C3, C5), each measured by a fresh `bench.py --workload ...
+    --no-cpu` process on the same GPU right after the headline run; only the figures, the full lines come from running those
+    commands directly."""
+    out = {}
+    for name, steps in ALSO:
+        if name == args.workload:
+            continue
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(steps), "--warmup", "5", "--no-cpu",
+                                "--pipeline", str(args.pipeline)], capture_output=True, text=True, timeout=300)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out[name] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "e2e_value": d["e2e"]["value"],
+                         "e2e_ms_per_step": d["e2e"]["ms_per_step"], "k2_roofline_frac": d["roofline"]["frac"], "k2_ms": d["roofline"]["kernel_ms"],
+                         "realtime_budget_ms": d["config"]["realtime_budget_ms"], "description": d["config"]["description"]}
+        except Exception as ex:
+            out[name] = {"error": str(ex)[:200]}
+    return out
+
+
 def run_gpu_arm(args, wl, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -430,6 +453,8 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
                 line["parity"] = {"error": str(ex)}
             threads = min(host_threads(), 64)
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_run(wl, threads, min(1024, max(1, wl["n"] // threads)), 0, 2, target_seconds=12.0).items() if k != "ms_per_step"}
+            if not args.no_also:
+                line["also"] = also_workloads(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -443,7 +468,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4_1m_doppler_pan", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs (and the secondary workloads)")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (C2 / C3 / C5 figures under \"also\")")
     ap.add_argument("--exchange", default="peer", choices=["peer", "allreduce"],
                     help="N > 1: bus exchange inside the kernels over NVLink peer memory (default) or an NCCL all-reduce between mix_begin and mix_finish")
     ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
