@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kNumSh * 32) k4a_decode_kernel(FinishArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];   // [16][taps] HRIRs | [16][taps - 1 + 32] inputs | [16][32] channel results (float)
 	const uint32_t F = a.frames, taps = a.taps;
 	const int H = (int)taps - 1;
+	grid_dep_wait();
 	const float* bf = a.bus + (size_t)kBusRows * F;
 	if (!(bf[0] > 0.0f) && !(a.flags->sh_flush_frames < (int)F)) return;      // nothing to decode, no tail to flush
 	const uint32_t c = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
 	const uint32_t F = a.frames, i = threadIdx.x, T = blockDim.x;
 	const uint32_t taps = a.hrir ? a.taps : 0;
 	const int H = (int)taps - 1;
+	grid_dep_wait();
 	if (i == 0) plan = plan_finish(a.bus + (size_t)kBusRows * F, a.hrir != nullptr, a.flags, a.parity, F);
 	__syncthreads();
 	float l = 0.0f, r = 0.0f;
@@ -263,8 +265,8 @@ int launch_finish(const FinishArgs& a, void* stream) {
 			              : cudaFuncSetAttribute(k4a_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k4a)")) return -1;
 			configured[dbl] = smem;
 		}
-		if (dbl) k4a_decode_kernel<true><<<(F + kDecFrames - 1) / kDecFrames, kNumSh * 32, smem, st>>>(a);
-		else k4a_decode_kernel<false><<<(F + kDecFrames - 1) / kDecFrames, kNumSh * 32, smem, st>>>(a);
+		if (dbl) launch_pdl(k4a_decode_kernel<true>, dim3((F + kDecFrames - 1) / kDecFrames), dim3(kNumSh * 32), smem, st, a);
+		else launch_pdl(k4a_decode_kernel<false>, dim3((F + kDecFrames - 1) / kDecFrames), dim3(kNumSh * 32), smem, st, a);
 		note_launch();
 		if (check_launch("k4a_decode")) return -1;
 	}
@@ -273,7 +275,7 @@ int launch_finish(const FinishArgs& a, void* stream) {
 	FinishArgs b = a;
 	b.hist_smem_all = sizeof(float) * h1 * kNumSh <= 48 * 1024 ? 1 : 0;      // 16 channels' history in one pass when it fits the default limit
 	const size_t smem = sizeof(float) * h1 * (b.hist_smem_all ? (size_t)kNumSh : 1);
-	k4b_finish_kernel<<<1, threads, smem, st>>>(b);
+	launch_pdl(k4b_finish_kernel, dim3(1), dim3(threads), smem, st, b);
 	note_launch();
 	return check_launch("k4b_finish");
 }

@@ -456,6 +456,7 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 #endif
 	if (t == 0) init_barriers<kStages>(hdr, kPanWarps);
 	__syncthreads();
+	grid_dep_wait();     // everything above overlaps the tail of K1; its records are read from here on
 	if (warp == (uint32_t)kPanWarps) { producer_warp<2, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[KF];     // (L, R) of frame lane + 32 k: one FFMA2 (gain pair x broadcast sample) per frame on the constant-gain path
@@ -637,6 +638,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 #endif
 	if (t == 0) init_barriers<kStages>(hdr, T / 32);
 	__syncthreads();
+	grid_dep_wait();     // everything above overlaps the tail of the previous kernel; K1's records are read from here on
 	if (t >= T) { producer_warp<16, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1) x frames t + k T
@@ -863,6 +865,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* _
                                                        uint32_t g_sh, float* __restrict__ bus, const DevFlags* __restrict__ flags,
                                                        uint32_t parity, uint32_t F, PeerArgs pa, size_t bus_floats) {
 	__shared__ float warp_sum[kK3Warps][32];
+	grid_dep_wait();
 	const uint32_t row = blockIdx.y, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	const uint32_t f = blockIdx.x * 32 + lane;
 	const float* part = row < 16 ? part_sh : part_pan;
@@ -923,6 +926,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* _
 // local gather area, then sums the slots in rank order -- every rank computes the identical sum.  A peer that never
 // arrives (crashed rank) trips the trap after ~2 s instead of hanging the device.
 __global__ void __launch_bounds__(256) k_peer_gather_kernel(PeerArgs pa, float* __restrict__ bus_sum, size_t bus_floats, uint32_t parity, unsigned int target) {
+	grid_dep_wait();
 	if (threadIdx.x == 0) {
 		const volatile unsigned int* cnt = pa.arrive[pa.rank] + parity;
 		unsigned int spins = 0;
@@ -991,7 +995,7 @@ int launch_one(Kernel kernel, KernelConfig* cfg, const char* name, const MixArgs
 	uint32_t wave = (uint32_t)(sm_count() * cfg->ctas_per_sm);
 	if (wave > max_grid) wave = max_grid;
 	const uint32_t g = pick_grid(n, wave);
-	kernel<<<g, threads, smem, st>>>(a, first, n, window_slot(F), partials);
+	launch_pdl(kernel, dim3(g), dim3(threads), smem, st, a, first, n, window_slot(F), partials);
 	dev::note_launch();
 	*grid_out = g;
 	return dev::check_launch(name);
@@ -1049,14 +1053,14 @@ int launch_mix(const MixArgs& a, void* stream) {
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
-	k3_reduce_kernel<<<dim3((F + 31) / 32, kBusRows), kK3Warps * 32, 0, st>>>(part_pan, g_pan, part_sh, g_sh, a.bus, a.flags, a.parity, F, a.peer, a.bus_floats);
+	launch_pdl(k3_reduce_kernel, dim3((F + 31) / 32, kBusRows), dim3(kK3Warps * 32), 0, st, (const float*)part_pan, g_pan, (const float*)part_sh, g_sh, a.bus, a.flags, a.parity, F, a.peer, a.bus_floats);
 	note_launch();
 	return check_launch("k3_reduce");
 }
 
 int launch_peer_gather(const PeerArgs& pa, float* bus_sum, size_t bus_floats, uint32_t parity, unsigned int target, void* stream) {
 	const uint32_t grid = (uint32_t)((bus_floats + 255) / 256);
-	k_peer_gather_kernel<<<grid < 148u ? grid : 148u, 256, 0, (cudaStream_t)stream>>>(pa, bus_sum, bus_floats, parity, target);
+	launch_pdl(k_peer_gather_kernel, dim3(grid < 148u ? grid : 148u), dim3(256), 0, (cudaStream_t)stream, pa, bus_sum, bus_floats, parity, target);
 	note_launch();
 	return check_launch("k_peer_gather");
 }
