@@ -442,12 +442,22 @@ SBM_HD RampDesc plan_gain(float* cur, bool initialised, float target, uint32_t F
 	const uint32_t ramp = (uint32_t)(fmul(fabsf(fsub(target, c)), kUnitRampLength));
 	d.start = c; d.inc = 0.0f; d.n = 0;
 	if (ramp > 0) {
-		d.inc = fdiv(fsub(target, c), (float)ramp);
 		d.n = ramp < F ? ramp : F;
+#if defined(__CUDA_ARCH__)
+		// On the device: increment and end value in closed form.  Both are continuous in their inputs (the end value feeds
+		// the next buffer's ramp length only through |target - c| * 2048, which is 0 for a finished ramp either way), and
+		// they differ from the reference's n running additions by < n ulp -- while K1's duration is the length of its
+		// dependent instruction chain, of which a bit-exact division and up to 48 chained additions (or the closed-form
+		// binade walk) per ramping gain, 17 gains per ambisonic source, were the largest part.
+		d.inc = __fdividef(fsub(target, c), (float)ramp);
+		c = fmaf((float)d.n, d.inc, c);
+#else
+		d.inc = fdiv(fsub(target, c), (float)ramp);
 		// the value after d.n running additions, bit for bit: literally for short ramps (the usual few frames while the
 		// listener moves), through the closed form for long ones
 		if (d.n <= 48u) { for (uint32_t j = 0; j < d.n; ++j) c = fadd(c, d.inc); }
 		else c = ramp_advance(c, d.inc, d.n);
+#endif
 	} else {
 		c = target;
 	}
