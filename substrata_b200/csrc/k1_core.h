@@ -97,6 +97,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	float occ = A.occ_cur[slot];
 	const float lpf_prev0 = A.lpf_prev[slot];
 	uint8_t bits = A.bits[slot];
+	const int prev_used_sh = flags->sh_used[G.parity ^ 1], prev_used_pan = flags->pan_used[G.parity ^ 1];   // previous buffer's mixers (GainMixer sweep)
 	// stereo-pan bus gains (the first two of the slot's cstride floats), loaded with the rest: left where they are used,
 	// the compiler must keep them behind the state stores above them (possible aliasing) = one more DRAM round trip
 	const float cg_pan0 = A.cgain[(size_t)slot * (size_t)A.cstride], cg_pan1 = A.cgain[(size_t)slot * (size_t)A.cstride + 1];
@@ -222,7 +223,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	if (kind != kKindStereo) {
 		// GainMixer::Reset sweep (gain_mixer.cc:80-96): it runs once between two non-empty buffers of that mixer and
 		// touches every source that owns processors, whether or not the source reaches the mixer this buffer.
-		const int prev_used = hrtf ? flags->sh_used[G.parity ^ 1] : flags->pan_used[G.parity ^ 1];
+		const int prev_used = hrtf ? prev_used_sh : prev_used_pan;
 		if (prev_used) {
 			if (bits & kBitMixActive) bits &= (uint8_t)~kBitMixActive;
 			else bits &= (uint8_t)~kBitMixExists;

@@ -16,11 +16,14 @@ namespace sbm {
 __global__ void __launch_bounds__(256, SBM_K1_MINB) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table,
                                                        const uint32_t* __restrict__ lists) {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;    // position in the render lists
+	// whether this buffer's "mixer used" flags are already set: read NOW, so that the loads overlap the work below instead
+	// of being a dependent round trip at the end of every warp (a stale 0 only costs a redundant atomicOr)
+	const int set_pan = flags->pan_used[g.parity], set_sh = flags->sh_used[g.parity], set_st = flags->st_used[g.parity];
 	uint32_t used = 0, n_src = 0;
 	if (k < g.n_pan + g.n_sh) used = update_source(g, A, flags, table, lists[k], k, &n_src);
 	// Warp-level reduction of the "mixer used" bits and the accounting counters, then one lane publishes.  The flags are
 	// the same few words for the whole grid and same-address atomics serialise in L2 (one set per warp on ONE address cost
-	// ~100 us per million sources): a flag is only OR-ed while it still reads 0, and the counters go to one of kStatParts
+	// ~100 us per million sources): a flag is only OR-ed by the warps that started while it still read 0, and the counters go to one of kStatParts
 	// padded slots chosen by the block index (K4b sums them).  No block-wide barrier: a finished warp leaves the SM.
 	const unsigned full = 0xffffffffu;
 	uint32_t u = used;
@@ -32,9 +35,9 @@ __global__ void __launch_bounds__(256, SBM_K1_MINB) k1_params_kernel(Globals g, 
 		rendered += __shfl_xor_sync(full, rendered, o);
 	}
 	if ((threadIdx.x & 31) == 0) {
-		if ((u & kUsedPan) && !*(volatile int*)&flags->pan_used[g.parity]) atomicOr(&flags->pan_used[g.parity], 1);
-		if ((u & kUsedSh) && !*(volatile int*)&flags->sh_used[g.parity]) atomicOr(&flags->sh_used[g.parity], 1);
-		if ((u & kUsedStereo) && !*(volatile int*)&flags->st_used[g.parity]) atomicOr(&flags->st_used[g.parity], 1);
+		if ((u & kUsedPan) && !set_pan) atomicOr(&flags->pan_used[g.parity], 1);
+		if ((u & kUsedSh) && !set_sh) atomicOr(&flags->sh_used[g.parity], 1);
+		if ((u & kUsedStereo) && !set_st) atomicOr(&flags->st_used[g.parity], 1);
 		if (rendered) {
 			const uint32_t part = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kStatParts;
 			atomicAdd(&flags->part_bytes[part][0], bytes);
