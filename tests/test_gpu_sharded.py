@@ -88,7 +88,7 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_peer_memory_sharded_mix_matches_oracle(tmp_path, world):
     if _gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
