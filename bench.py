@@ -307,6 +307,7 @@ def also_workloads(args):
 
 def run_gpu_arm(args, wl, rank, world, local_rank):
     import torch
+    import substrata_b200 as sb
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -333,7 +334,11 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
     if voices:
         v_ids = np.ascontiguousarray(ids[:voices])
         v_offs = (np.arange(voices + 1, dtype=np.uint64) * np.uint64(480))
-        v_payload = [(0.3 * rng.uniform(-1, 1, voices * 480)).astype(np.float32) for _ in range(4)]
+        v_payload = []
+        for _ in range(4):      # packet payloads assembled in page-locked host memory, as a network thread feeding the engine would
+            buf = sb.pinned_array(voices * 480)
+            buf[:] = (0.3 * rng.uniform(-1, 1, voices * 480)).astype(np.float32)
+            v_payload.append(buf)
         ring_state = {"pushed": 0, "consumed": 0}
 
         def feed_voices(upto_samples):

@@ -100,6 +100,11 @@ SBM_API int sbm_source_ring_push(sbm_engine* e, int id, const float* samples, si
  * CircularBuffer::pushBackNItems per source (ClientUDPHandlerThread.cpp:239-242, StreamerThread.cpp:33-60).
  * All-or-nothing: SBM_ERR_CAPACITY (some ring full) or SBM_ERR_UNKNOWN_ID leave every ring untouched. */
 SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, const float* samples, const size_t* offsets /* n + 1 */);
+/* Page-locked host memory (cudaHostAlloc) for callers that do not link CUDA: a sbm_source_ring_push_batch payload that
+ * lives in it (or in any memory registered with the CUDA driver) goes to the device without the staging copy -- it must
+ * then stay unmodified until the next sbm_mix / sbm_mix_collect returns. */
+SBM_API void* sbm_host_alloc_pinned(size_t bytes);
+SBM_API void sbm_host_free_pinned(void* p);
 SBM_API int sbm_source_ring_size(sbm_engine* e, int id, uint64_t* out_size);
 /* SourceType_Streaming with mix_sources: pitch/doppler mixer (AudioEngine.cpp:435-458). */
 SBM_API int sbm_source_attach_mix(sbm_engine* e, int id, int sampling_rate, int nz, const int* buffers, const double* sound_file_i,

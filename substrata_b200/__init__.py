@@ -68,6 +68,17 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def pinned_array(n, dtype=np.float32, _lib_path=None):
+    """A numpy array over page-locked host memory (sbm_host_alloc_pinned); kept alive for the life of the process."""
+    l = lib(_lib_path) if _lib_path else lib()
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    ptr = l.sbm_host_alloc_pinned(nbytes)
+    if not ptr:
+        raise MemoryError("sbm_host_alloc_pinned(%d)" % nbytes)
+    buf = (C.c_ubyte * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
 class MixEngine:
     """ctypes wrapper of sbm_engine with the method names of the test harness backends (tests/harness.py)."""
 

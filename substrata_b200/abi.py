@@ -36,6 +36,8 @@ SIGNATURES = {
     "sbm_source_attach_ring": (_i, [_vp, _i, _i, _i]),
     "sbm_source_ring_push": (_i, [_vp, _i, _vp, _sz]),
     "sbm_source_ring_push_batch": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "sbm_host_alloc_pinned": (_vp, [_sz]),
+    "sbm_host_free_pinned": (None, [_vp]),
     "sbm_source_ring_size": (_i, [_vp, _i, _vp]),
     "sbm_source_attach_mix": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sbm_source_attach_mix1": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -102,6 +102,7 @@ void* alloc(size_t bytes);                       // zero-initialised device memo
 void release(void* p);
 void* alloc_pinned(size_t bytes);
 void release_pinned(void* p);
+bool is_pinned(const void* p);                   // page-locked host memory known to the CUDA driver (a copy from it needs no staging)
 int h2d(void* dst, const void* src, size_t bytes, void* stream);
 int d2h(void* dst, const void* src, size_t bytes, void* stream);
 int zero(void* dst, size_t bytes, void* stream);

@@ -220,6 +220,11 @@ void* alloc_pinned(size_t bytes) {
 	return p;
 }
 void release_pinned(void* p) { if (p) cudaFreeHost(p); }
+bool is_pinned(const void* p) {
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return at.type == cudaMemoryTypeHost;
+}
 int h2d(void* dst, const void* src, size_t bytes, void* stream) {
 	return bytes ? check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "cudaMemcpyAsync(H2D)") : 0;
 }

@@ -482,8 +482,19 @@ SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, con
 		if (!e->h_ring_stage || !e->d_ring_stage) { e->ring_stage_bytes = 0; return fail_cuda(e, "sbm_source_ring_push_batch(alloc)"); }
 	}
 	memcpy(e->h_ring_stage, pk.data(), sizeof(RingPush) * (size_t)n);
-	memcpy(e->h_ring_stage + table_bytes, samples + offsets[0], sizeof(float) * total);
-	if (dev::h2d(e->d_ring_stage, e->h_ring_stage, bytes, e->stream) ||
+	// A payload that already lives in page-locked memory (sbm_host_alloc_pinned, cudaHostRegister ...) is copied to the
+	// device straight from the caller's buffer -- it must then stay unmodified until the next sbm_mix / sbm_mix_collect
+	// returns; anything else is first copied into the engine's own pinned staging buffer.
+	const bool direct = dev::is_pinned(samples + offsets[0]);
+	int rc;
+	if (direct) {
+		rc = dev::h2d(e->d_ring_stage, e->h_ring_stage, table_bytes, e->stream) ||
+		     dev::h2d(e->d_ring_stage + table_bytes, samples + offsets[0], sizeof(float) * total, e->stream);
+	} else {
+		memcpy(e->h_ring_stage + table_bytes, samples + offsets[0], sizeof(float) * total);
+		rc = dev::h2d(e->d_ring_stage, e->h_ring_stage, bytes, e->stream);
+	}
+	if (rc ||
 	    dev::launch_ring_scatter((const RingPush*)e->d_ring_stage, (uint32_t)n, (const float*)(e->d_ring_stage + table_bytes), e->stream))
 		return fail_cuda(e, "sbm_source_ring_push_batch");
 	e->ring_stage_in_flight = true;      // the pinned staging buffer is reused: the next push waits for this copy
@@ -496,6 +507,11 @@ SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, con
 	}
 	return SBM_OK;
 }
+
+// Page-locked host memory for callers that do not link CUDA themselves (packet payloads for sbm_source_ring_push_batch,
+// PCM for sbm_buffer_create): copies from it need no staging.
+SBM_API void* sbm_host_alloc_pinned(size_t bytes) { return dev::alloc_pinned(bytes); }
+SBM_API void sbm_host_free_pinned(void* p) { dev::release_pinned(p); }
 
 SBM_API int sbm_source_ring_size(sbm_engine* e, int id, uint64_t* out_size) {
 	if (!e || !out_size) return SBM_ERR_INVALID_ARG;

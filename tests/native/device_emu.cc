@@ -27,6 +27,7 @@ void* alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
 void release(void* p) { free(p); }
 void* alloc_pinned(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
 void release_pinned(void* p) { free(p); }
+bool is_pinned(const void*) { return false; }
 int h2d(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
 int d2h(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
 int zero(void* dst, size_t bytes, void*) { memset(dst, 0, bytes); return 0; }

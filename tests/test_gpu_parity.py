@@ -76,6 +76,36 @@ def test_cuda_submit_collect_equals_synchronous_mix(kw, F):
     assert rel_rms(b, o) <= TOL
 
 
+def test_ring_push_from_pinned_memory_equals_staged_push():
+    """A packet payload in page-locked memory (sbm_host_alloc_pinned) skips the staging copy; the rings must end up the same."""
+    F, nv = 256, 96
+    rng = np.random.default_rng(11)
+    pos = rng.uniform([-20, -5, -20], [20, 5, 20], (nv, 3)).astype(np.float32) + np.float32(1.5)
+    outs = []
+    for pinned in (False, True):
+        e = engine(F, load_sh_hrir(), max_sources=nv)
+        first = e.source_create(KIND_HRTF, nv)
+        ids = np.arange(first, first + nv, dtype=np.int32)
+        for sid in ids:
+            e.source_attach_ring(int(sid), 48000)
+        e.set_source_positions(ids, pos)
+        offs = np.arange(nv + 1, dtype=np.uint64) * np.uint64(480)
+        prng = np.random.default_rng(12)
+        res = []
+        for b in range(8):
+            payload = (0.3 * prng.uniform(-1, 1, nv * 480)).astype(np.float32)
+            if b % 2 == 0:          # 480-sample packets every other 256-frame buffer
+                if pinned:
+                    buf = sb.pinned_array(nv * 480)
+                    buf[:] = payload
+                    e.sources_ring_push_flat(ids, buf, offs)
+                else:
+                    e.sources_ring_push_flat(ids, payload, offs)
+            res.append(e.mix()[1].copy())
+        outs.append(np.stack(res))
+    assert outs[0].any() and np.array_equal(outs[0], outs[1])
+
+
 def test_cuda_feeder_bookkeeping():
     F = 256
     rng = np.random.default_rng(3)
