@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 	constexpr int kStages = kStagesPan, kRecStages = kStages + 2, kBatch = kBatchPan;
 	const SmemView<2, kStages, kBatch> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
-	const uint32_t F = a.frames, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+	// EXACT: the frame count is a compile-time constant (every "is this frame F - 1 / inside the buffer" test folds away)
+	const uint32_t F = EXACT ? 32u * (uint32_t)KF : a.frames, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
 	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
 	// run of expensive sources (long ramps, occlusion, generic fetches) is spread over the whole grid.
 	const uint32_t s0 = first, s1 = first + n;
@@ -626,6 +627,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 	MixSmemHdr* hdr = sm.hdr;
 	// blockDim.x = T math threads + one producer warp (the last warp)
 	const uint32_t F = a.frames, T = EXACT ? (uint32_t)TMAX : blockDim.x - 32, t = threadIdx.x, lane = t & 31u;   // EXACT: T is a compile-time constant
+	// (making F a compile-time constant too was measured 5 % slower here: it tips the register allocation into spills)
 	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
 	// run of expensive sources (long ramps, occlusion, generic fetches) is spread over the whole grid.
 	const uint32_t s0 = first, s1 = first + n;
