@@ -56,6 +56,9 @@ namespace {
 #ifndef SBM_PRODUCER_SLEEP_NS
 #define SBM_PRODUCER_SLEEP_NS 200
 #endif
+#ifndef SBM_SH_FUSE
+#define SBM_SH_FUSE 4
+#endif
 #ifndef SBM_SH_BIG_FUSE
 #define SBM_SH_BIG_FUSE 4
 #endif
@@ -696,7 +699,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 			if (any == 0) {
 				// FUSE sources at a time: all their sample loads first, then the arithmetic (4 with the 128-register budget of the
 				// <= 512-frame kernel, 2 where two 288-thread CTAs must share the SM's register file)
-				constexpr int FUSE = TMAX == 128 ? 4 : SBM_SH_BIG_FUSE;
+				constexpr int FUSE = TMAX == 128 ? SBM_SH_FUSE : SBM_SH_BIG_FUSE;
 #pragma unroll
 				for (int b0f = 0; b0f < kBatch; b0f += FUSE) {
 					float xs[FUSE][K];
