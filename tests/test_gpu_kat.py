@@ -104,6 +104,27 @@ def test_log_distance_attenuation_at_substrata_defaults(d):
     np.testing.assert_allclose(out[1::2], 0.5 * att, rtol=2e-6, atol=1e-7)
 
 
+def test_occlusion_mono_pole_impulse_response():
+    """MonoPoleFilter (mono_pole_filter_test.cc:33-57): impulse response (1 - a) a^n; the coefficient comes from the smoothed
+    occlusion, occ <- o + 0.75 (occ - o) per buffer and a = 1 - 1 / (occ + 1)^4 (occlusion_node.cc:53-99,
+    occlusion_calculator.cc:43-50): intensity 4 on the first buffer gives occ = 1, a = 0.9375."""
+    e = sb.MixEngine(F, max_sources=4)
+    pcm = np.zeros(4 * F, np.float32)
+    pcm[0] = 1.0
+    buf = e.buffer_create(pcm)
+    sid = e.source_create(KIND_PAN)
+    e.source_attach_buffer(sid, buf, 0, 48000, True, False)
+    e.set_source_positions([sid], position(0, 0, 0.9).reshape(1, 3))
+    e.set_source_occlusions([sid], np.array([4.0], np.float32))
+    _, out = e.mix()
+    a = 0.9375
+    exp = 0.5 * (1.0 - a) * a ** np.arange(F)          # front: both pan gains are 0.5
+    np.testing.assert_allclose(out[0::2], exp, atol=EPS)
+    np.testing.assert_allclose(out[1::2], exp, atol=EPS)
+    _, out2 = e.mix()                                   # the filter state carries into the next buffer (and the coefficient moves on)
+    assert abs(out2[0]) > 0 and np.all(np.diff(np.abs(out2[0::2])) < 0)
+
+
 def test_mix_is_not_clamped_but_the_callback_is():
     e, _ = one_source(KIND_STEREO, [0, 0, 0], volume=1.0, pcm_value=3.0)
     _, out = e.mix()
