@@ -488,7 +488,28 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 				float x[KF];           // engine-rate input samples of this lane's frames, before the direct gain
 				float mf = 1.0f;       // MixSource::mix_factor where it is not already inside x
 				bool filtered = false; // x already carries the direct gain and the occlusion low-pass
-				if (mode & (kMdGeneric | kMdLpf | kMdAdjust)) {
+				if (EXACT && SBM_PACKED_LERP && (mode & ~kMdRamp) == kMdInterp) {
+					// ---------------- single read head (pitch / doppler), window staged by TMA, nothing else: the C4 case.  All
+					// frames in pairs, the two interpolations of a pair share packed f32x2 instructions. ----------------
+					const float* wb = sm.wring + d.w_idx;
+					mf = d.mfx;
+					unsigned long long p = d.x0 + (unsigned long long)lane * d.step;
+					const unsigned long long step32 = d.step << 5;
+#pragma unroll
+					for (int k = 0; k < KF; k += 2) {
+						const unsigned long long pa = p, pb = p + step32;
+						const uint32_t da = (uint32_t)(pa >> 32), db = (uint32_t)(pb >> 32);
+						const float2 v0 = make_float2(wb[da], wb[db]), v1 = make_float2(wb[da + 1], wb[db + 1]);
+						const float2 fb = make_float2(__uint_as_float(0x3f800000u | ((uint32_t)pa >> 9)), __uint_as_float(0x3f800000u | ((uint32_t)pb >> 9)));
+						const float2 fr = fadd2(fb, make_float2(-1.0f, -1.0f));
+						float2 dv = v1;
+						ffma2(dv, v0, make_float2(-1.0f, -1.0f));     // v1 - v0
+						float2 v = v0;
+						ffma2(v, fr, dv);                              // v0 + fr (v1 - v0)
+						x[k] = v.x; x[k + 1] = v.y;
+						p += step32 << 1;
+					}
+				} else if (mode & (kMdGeneric | kMdLpf | kMdAdjust)) {
 					// ---------------- careful fetch (rare, out of line): leaves the samples in this source's stage slot ----------------
 					float* slot = sm.wring + (size_t)(qw * kBatch + src) * wslot;
 					filtered = careful_source_to_slot(a, r, slot, wslot, lane);
