@@ -210,6 +210,7 @@ constexpr uint32_t kMdSkip = 1, kMdGeneric = 2, kMdInterp = 4, kMdAdjust = 8, kM
 
 // Barrier among the math warps only (the producer warp never joins): named barrier 1.
 __device__ __forceinline__ void math_sync(uint32_t n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+__device__ __forceinline__ void math_sync_id(uint32_t id, uint32_t n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
 
 __device__ __forceinline__ MathDesc make_desc(const WorkRec& r, const WinPlan& p, uint32_t slot_float0, bool sh) {
 	MathDesc d;
@@ -639,18 +640,31 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 #ifndef SBM_SH_BIG_K
 #define SBM_SH_BIG_K 4                // frames per thread of the > 512-frame ambisonic kernel (2 = 16 math warps per CTA measured 4 % slower: per-warp overhead scales with the warp count)
 #endif
-constexpr int kShK = 4, kShBigK = SBM_SH_BIG_K, kShBigT = 1024 / kShBigK;
-template <int TMAX, int K, bool EXACT>     // TMAX math threads x K frames each: <128, 4> (frames <= 512), <kShBigT, kShBigK> (frames <= 1024);
-                                    // EXACT: frames == 4 * TMAX, no per-frame bounds checks
-__global__ void __launch_bounds__(TMAX + 32, TMAX == 128 ? 3 : SBM_SH_BIG_CTAS)
-k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+#ifndef SBM_SH_BIG_MAXNREG
+#define SBM_SH_BIG_MAXNREG 96         // register cap of the two-group shape (see SBM_SH_BIG_G)
+#endif
+#ifndef SBM_SH_BIG_G
+#define SBM_SH_BIG_G 1                // math groups per CTA of the > 512-frame ambisonic kernel.  2 (two groups sharing the producer, each taking every
+                                      // other batch) needs 17 warps x >= 112 registers, which the SM's allocation granularity (CTAs rounded up to
+                                      // 20 warps) refuses: "too many resources requested for launch"; at the 96 registers that do fit it spills
+#endif
+constexpr int kShK = 4, kShBigK = SBM_SH_BIG_K, kShBigT = 1024 / kShBigK, kShBigG = SBM_SH_BIG_G;
+// G: independent groups of TMAX math threads in one CTA.  Each group has its own accumulators and takes every G-th batch of
+// the CTA's slice; the groups share the producer warp and its rings.  Where the register file leaves room for only one CTA
+// per SM (frames > 512: 256 math threads x ~120 registers), two groups overlap each other's barrier waits and dependent
+// chains the way two resident CTAs would.
+template <int TMAX, int K, int G, bool EXACT>     // TMAX math threads x K frames each: <128, 4, 1> (frames <= 512), <kShBigT, kShBigK, kShBigG> (frames <= 1024);
+                                           // EXACT: frames == K * TMAX, no per-frame bounds checks
+__device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	constexpr int kStages = TMAX == 128 ? kStagesSh : kStagesShBig, kRecStages = kStages + 2, kBatch = kBatchSh;
 	const SmemView<16, kStages, kBatch> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
 	// blockDim.x = T math threads + one producer warp (the last warp)
-	const uint32_t F = a.frames, T = EXACT ? (uint32_t)TMAX : blockDim.x - 32, t = threadIdx.x, lane = t & 31u;   // EXACT: T is a compile-time constant
+	const uint32_t F = a.frames, T = EXACT ? (uint32_t)TMAX : (blockDim.x - 32) / G;   // EXACT: T is a compile-time constant
+	const uint32_t grp = G == 1 ? 0u : (threadIdx.x / T < (uint32_t)G ? threadIdx.x / T : 0u);      // math group of this thread
+	const uint32_t t = threadIdx.x - grp * T, lane = threadIdx.x & 31u;                          // index inside the group
 	// (making F a compile-time constant too was measured 5 % slower here: it tips the register allocation into spills)
 	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
 	// run of expensive sources (long ramps, occlusion, generic fetches) is spread over the whole grid.
@@ -662,10 +676,10 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 #else
 	const uint32_t nbatch = blockIdx.x < total_batches ? (total_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 #endif
-	if (t == 0) init_barriers<kStages>(hdr, T / 32);
+	if (threadIdx.x == 0) init_barriers<kStages>(hdr, T / 32);     // a batch is consumed by the T / 32 warps of ONE group
 	__syncthreads();
 	grid_dep_wait();     // everything above overlaps the tail of the previous kernel; K1's records are read from here on
-	if (t >= T) { producer_warp<16, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+	if (threadIdx.x >= (uint32_t)G * T) { producer_warp<16, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1) x frames t + k T
 #pragma unroll
@@ -702,8 +716,8 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 		}
 	};
 
-	uint32_t qr = 0, qw = 0, ph_w = 0;     // record slot / window stage of batch jb, parity of its full_w
-	for (uint32_t jb = 0; jb < nbatch; ++jb, qr = qr + 1 == (uint32_t)kRecStages ? 0u : qr + 1, ph_w ^= (qw + 1 == (uint32_t)kStages), qw = qw + 1 == (uint32_t)kStages ? 0u : qw + 1) {
+	for (uint32_t jb = grp; jb < nbatch; jb += G) {     // this group's batches
+		const uint32_t qr = jb % kRecStages, qw = jb % kStages, ph_w = (jb / kStages) & 1u;     // record slot / window stage of batch jb, parity of its full_w
 		mbar_wait(&hdr->full_w[qw], ph_w);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
@@ -799,12 +813,12 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 				}
 				if (mode & kMdLpf) {
 					// direct gain, then the recurrence in the (now free) stage slot; x becomes the filtered, gained signal
-					math_sync(T);
+					math_sync_id(1u + grp, T);
 #pragma unroll
 					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) slot[i] = x[k] * gain_at(r.direct, i); }
-					math_sync(T);
+					math_sync_id(1u + grp, T);
 					if (t < 32) { const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane); if (lane == 0) a.lpf_prev[r.slot] = carry; }
-					math_sync(T);
+					math_sync_id(1u + grp, T);
 #pragma unroll
 					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) x[k] = slot[i]; }
 					fence_proxy_async();     // generic-proxy writes to the slot precede the TMA refill
@@ -872,7 +886,7 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 		__syncwarp();
 		if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }
 	}
-	float* out = partials + (size_t)blockIdx.x * NCH * F;
+	float* out = partials + ((size_t)blockIdx.x * G + grp) * NCH * F;     // one partial bus per group
 #pragma unroll
 	for (int c = 0; c < NCH / 2; ++c)
 #pragma unroll
@@ -880,6 +894,23 @@ k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, f
 			const uint32_t i = t + (uint32_t)k * T;
 			if (EXACT || i < F) { out[(size_t)(2 * c) * F + i] = acc[c][k].x; out[(size_t)(2 * c + 1) * F + i] = acc[c][k].y; }
 		}
+}
+
+// The two entry points of the ambisonic kernel: the register budget is set per shape (launch bounds for three 5-warp CTAs
+// per SM; an explicit cap for the one 17-warp CTA of the two-group shape, where the launch-bounds heuristic rounds the
+// CTA up to 20 warps and would allow only 96 registers).
+template <bool EXACT>
+__global__ void __launch_bounds__(128 + 32, 3) k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+	ambisonic_body<128, kShK, 1, EXACT>(a, first, n, wslot, partials);
+}
+template <bool EXACT>
+#if SBM_SH_BIG_G == 1
+__global__ void __launch_bounds__(kShBigT + 32, 1)
+#else
+__global__ void __maxnreg__(SBM_SH_BIG_MAXNREG)
+#endif
+k2_mix_ambisonic_big_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+	ambisonic_body<kShBigT, kShBigK, kShBigG, EXACT>(a, first, n, wslot, partials);
 }
 
 // K3: bus[row][f] = sum over CTAs of the partial buses; rows 0-15 from the ambisonic kernel's partials, rows 16-17 from
@@ -1049,7 +1080,8 @@ int num_mix_ctas(uint32_t frames, int sh) {
 }
 
 size_t partials_floats(uint32_t frames) {
-	return ((size_t)num_mix_ctas(frames, 0) * 2 + (size_t)num_mix_ctas(frames, 1) * 16) * frames;
+	const size_t groups = sh_threads(frames) <= 128 ? 1 : (size_t)kShBigG;
+	return ((size_t)num_mix_ctas(frames, 0) * 2 + (size_t)num_mix_ctas(frames, 1) * groups * 16) * frames;
 }
 
 int launch_mix(const MixArgs& a, void* stream) {
@@ -1072,10 +1104,13 @@ int launch_mix(const MixArgs& a, void* stream) {
 		const uint32_t mg = (uint32_t)num_mix_ctas(F, 1);
 		const bool exact = (tm == 128 || tm == (uint32_t)kShBigT) && F == tm * sh_frames_per_thread(F);     // the EXACT instantiations fix T = TMAX at compile time
 		int rc;
-		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<128, kShK, true>, &conf_sh_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
-		                         : launch_one(k2_mix_ambisonic_kernel<128, kShK, false>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
-		else rc = exact ? launch_one(k2_mix_ambisonic_kernel<kShBigT, kShBigK, true>, &conf_sh_big_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
-		                : launch_one(k2_mix_ambisonic_kernel<kShBigT, kShBigK, false>, &conf_sh_big, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
+		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<true>, &conf_sh_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
+		                         : launch_one(k2_mix_ambisonic_kernel<false>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
+		else {
+			rc = exact ? launch_one(k2_mix_ambisonic_big_kernel<true>, &conf_sh_big_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm * kShBigG + 32, true, mg, part_sh, st, &g_sh)
+			           : launch_one(k2_mix_ambisonic_big_kernel<false>, &conf_sh_big, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm * kShBigG + 32, true, mg, part_sh, st, &g_sh);
+			g_sh *= (uint32_t)kShBigG;     // one partial bus per math group
+		}
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
