@@ -887,7 +887,7 @@ SBM_API int sbm_peer_connect(sbm_engine* e, int rank, int world, const void* han
 	std::lock_guard<std::mutex> lk(e->mu);
 	dev::use(e->cfg.device);
 	if (!e->dv_gather) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect before sbm_peer_export");
-	if (e->begun) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect between sbm_mix_begin and sbm_mix_finish");
+	if (e->begun || e->collected != e->buffer_index) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect with a buffer in flight");
 	if (e->peer.world) return fail(e, SBM_ERR_INVALID_ARG, "already connected");
 	// the arrival counters count buffers per parity from now on: all ranks must connect at the same, even, buffer index
 	if (e->buffer_index & 1) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect needs an even number of buffers mixed so far (all ranks alike)");
