@@ -295,19 +295,28 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	} else {
 		float g[kNumSh];
 		encoding_coeffs(table, az, el, g);
-		ShGains sg;
-		for (int c = 0; c < kNumSh; ++c) {
-			float cur = cg[c];
-			const RampDesc d = plan_gain(&cur, chan_init, g[c], F, /*accumulate=*/true);
-			cg[c] = cur;
-			sg.konst[c] = d.konst;
-			if (d.n) {
-				rec.ch_ramp_mask |= 1u << c;
-				A.shr[out].start[c] = d.start; A.shr[out].inc[c] = d.inc; A.shr[out].n[c] = d.n;
-				if (d.n > rec.ch[0].n) rec.ch[0].n = d.n;       // ambisonic sources: ch[0].n = longest channel ramp (K2's fix-up region)
+		// Four channels at a time: the slot's 16 bus gains are read and written back as four 16-byte accesses, and the
+		// effective constant gains leave as four 16-byte stores (read and written one float at a time, the 16 loads were
+		// 16 dependent round trips -- each sits behind the previous iteration's stores, which may alias as far as the compiler
+		// knows -- and the 4-byte stores of a warp scatter over 32 sectors each).
+		F4* cg4 = reinterpret_cast<F4*>(cg);                        // cstride == 16 floats: 64-byte aligned rows
+		F4* sg4 = reinterpret_cast<F4*>(A.shg[out].konst);
+		for (int q = 0; q < kNumSh / 4; ++q) {
+			const F4 v = cg4[q];
+			float cur[4] = {v.x, v.y, v.z, v.w}, kon[4];
+			for (int j = 0; j < 4; ++j) {
+				const int c = 4 * q + j;
+				const RampDesc d = plan_gain(&cur[j], chan_init, g[c], F, /*accumulate=*/true);
+				kon[j] = d.konst;
+				if (d.n) {
+					rec.ch_ramp_mask |= 1u << c;
+					A.shr[out].start[c] = d.start; A.shr[out].inc[c] = d.inc; A.shr[out].n[c] = d.n;
+					if (d.n > rec.ch[0].n) rec.ch[0].n = d.n;       // ambisonic sources: ch[0].n = longest channel ramp (K2's ramp region)
+				}
 			}
+			cg4[q] = F4{cur[0], cur[1], cur[2], cur[3]};
+			sg4[q] = F4{kon[0], kon[1], kon[2], kon[3]};
 		}
-		A.shg[out] = sg;
 		// K2 reads n[] of all 16 channels of a source that has any channel ramp: the non-ramping ones must say 0
 		if (rec.ch_ramp_mask)
 			for (int c = 0; c < kNumSh; ++c)
