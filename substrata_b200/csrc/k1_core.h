@@ -303,24 +303,32 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		F4* sg4 = reinterpret_cast<F4*>(A.shg[out].konst);
 		for (int q = 0; q < kNumSh / 4; ++q) {
 			const F4 v = cg4[q];
-			float cur[4] = {v.x, v.y, v.z, v.w}, kon[4];
+			float cur[4] = {v.x, v.y, v.z, v.w}, kon[4], rst[4], rin[4];
+			uint32_t rn[4], gm = 0;
 			for (int j = 0; j < 4; ++j) {
 				const int c = 4 * q + j;
 				const RampDesc d = plan_gain(&cur[j], chan_init, g[c], F, /*accumulate=*/true);
-				kon[j] = d.konst;
+				kon[j] = d.konst; rst[j] = d.start; rin[j] = d.inc; rn[j] = d.n;
 				if (d.n) {
-					rec.ch_ramp_mask |= 1u << c;
-					A.shr[out].start[c] = d.start; A.shr[out].inc[c] = d.inc; A.shr[out].n[c] = d.n;
+					gm |= 1u << j;
 					if (d.n > rec.ch[0].n) rec.ch[0].n = d.n;       // ambisonic sources: ch[0].n = longest channel ramp (K2's ramp region)
 				}
 			}
 			cg4[q] = F4{cur[0], cur[1], cur[2], cur[3]};
 			sg4[q] = F4{kon[0], kon[1], kon[2], kon[3]};
+			if (gm) {
+				// ramp parameters of the group, 16 bytes each (n = 0 for the channels of the group that do not ramp)
+				reinterpret_cast<F4*>(A.shr[out].start)[q] = F4{rst[0], rst[1], rst[2], rst[3]};
+				reinterpret_cast<F4*>(A.shr[out].inc)[q] = F4{rin[0], rin[1], rin[2], rin[3]};
+				U4 nn; nn.x = rn[0]; nn.y = rn[1]; nn.z = rn[2]; nn.w = rn[3];
+				reinterpret_cast<U4*>(A.shr[out].n)[q] = nn;
+				rec.ch_ramp_mask |= gm << (4 * q);
+			}
 		}
-		// K2 reads n[] of all 16 channels of a source that has any channel ramp: the non-ramping ones must say 0
+		// K2 reads n[] of all 16 channels of a source that has any channel ramp: the groups without one must say 0
 		if (rec.ch_ramp_mask)
-			for (int c = 0; c < kNumSh; ++c)
-				if (!((rec.ch_ramp_mask >> c) & 1u)) A.shr[out].n[c] = 0;
+			for (int q = 0; q < kNumSh / 4; ++q)
+				if (!((rec.ch_ramp_mask >> (4 * q)) & 0xfu)) { U4 z; z.x = z.y = z.z = z.w = 0; reinterpret_cast<U4*>(A.shr[out].n)[q] = z; }
 		rflags |= kRecHrtf;
 	}
 	rec.flags = rflags;

@@ -64,6 +64,7 @@ constexpr uint32_t kRecMix1 = 1u << 7;              // exactly one mix source, e
 // by the kernels (state).  Per buffer K1 condenses a slot into one 128-byte WorkRec that K2 consumes.
 // ------------------------------------------------------------------------------------------------
 struct __attribute__((aligned(16))) F4 { float x, y, z, w; };   // position xyz + volume
+struct __attribute__((aligned(16))) U4 { uint32_t x, y, z, w; };
 
 struct SrcStatic {              // 32 B, host-written on attach
 	const float* pcm;           // device pointer to the source's PCM (shared buffer, or ring storage)
