@@ -36,6 +36,9 @@ GOLDEN_SCENARIOS = {
     "doppler_odd_loop_pan": (dict(n_sources=48, kind=KIND_PAN, feeder="doppler", loop_len=4099, seed=101), 512, 8, 0),
     "doppler_odd_loop_hq": (dict(n_sources=48, kind=KIND_HRTF, feeder="doppler", loop_len=4098, seed=102, volume_toggle=True), 256, 10, 0),
     "hq_resample_1024": (dict(n_sources=40, kind=KIND_HRTF, feeder="resample", loop_len=3001, seed=103, occlusion_toggle=True), 1024, 8, 0),
+    # the bike: three pitch-shifted mix sources per AudioSource, retuned every buffer (AudioEngine.cpp:435-458, BikePhysics.cpp:712-740)
+    "bike_mix3_pan": (dict(n_sources=24, kind=KIND_PAN, feeder="mix3", loop_len=4099, seed=111, n_shared_buffers=9), 512, 8, 0),
+    "bike_mix3_hq": (dict(n_sources=24, kind=KIND_HRTF, feeder="mix3", loop_len=4096, seed=112, n_shared_buffers=9, volume_toggle=True), 256, 10, 0),
 }
 
 RESAMPLER_PAIRS = [(8000, 48000), (12000, 48000), (16000, 48000), (24000, 48000), (44100, 48000), (48000, 48000),

@@ -316,6 +316,14 @@ class Scenario:
                 be.source_attach_buffer(sid, b, int(self.start[s]), int(self.rates[s]), True, False)
             elif self.feeder == "doppler":
                 be.source_attach_mix(sid, 48000, [b], [float(self.start[s])], [float(self.delta[s])], [float(self.mixf[s])])
+            elif self.feeder == "mix3":
+                # the bike: three mix sources per AudioSource, each with its own sound file, read head, pitch and level
+                # (BikePhysics.cpp:712-740; AudioEngine.cpp:435-458)
+                nb_ = len(bufs)
+                zb = [bufs[(self.buf_of[s] + z) % nb_] for z in range(3)]
+                be.source_attach_mix(sid, 48000, zb, [float(self.start[s]) * (0.5 + 0.25 * z) for z in range(3)],
+                                     [float(self.delta[s]) * self.MIX3_PITCH[z] for z in range(3)],
+                                     [float(self.mixf[s]) * self.MIX3_LEVEL[z] for z in range(3)])
             elif self.feeder == "ring":
                 be.source_attach_ring(sid, int(self.rates[s]))
             else:
@@ -325,8 +333,19 @@ class Scenario:
         be.set_source_volumes(self.ids, self.vol)
         return self.ids
 
+    MIX3_PITCH = (1.0, 0.5, 1.87)
+    MIX3_LEVEL = (0.6, 0.3, 0.45)
+
     def step(self, be, b):
         """Events before buffer `b`."""
+        if self.feeder == "mix3" and b > 0:
+            # the game thread retunes the engine sound every frame: new source_delta / mix_factor for one of the three
+            # mix sources of every other AudioSource
+            z = b % 3
+            for s in range(0, self.n, 2):
+                k = 1.0 + 0.03 * np.sin(0.7 * b + s)
+                be.source_set_mix_params(int(self.ids[s]), z, float(self.delta[s]) * self.MIX3_PITCH[z] * k,
+                                         float(self.mixf[s]) * self.MIX3_LEVEL[z] * (2.0 - k))
         if self.moving:
             t = b * self.F / 48000.0
             be.set_head([1.0 * t, 0.0, 0.0], quat_yaw(np.deg2rad(30.0) * t))

@@ -49,6 +49,9 @@ def test_cuda_matches_reference_golden(name):
     (dict(n_sources=512, kind=KIND_HRTF, feeder="doppler", loop_len=4096, seed=34, volume_toggle=True), 256, 8, 0),
     (dict(n_sources=300, mixed_kinds=True, occlusion_toggle=True, volume_toggle=True, seed=35, feeder="resample", loop_len=3001), 1024, 8, 0),
     (dict(n_sources=300, mixed_kinds=True, occlusion_toggle=True, seed=36, feeder="doppler", loop_len=2049), 480, 8, 0),
+    # three mix sources per AudioSource (the bike), retuned every buffer: the generic multi-read-head path
+    (dict(n_sources=600, mixed_kinds=True, feeder="mix3", loop_len=4099, seed=38, n_shared_buffers=31, occlusion_toggle=True), 512, 8, 0),
+    (dict(n_sources=200, kind=KIND_HRTF, feeder="mix3", loop_len=2048, seed=39, n_shared_buffers=17), 1024, 6, 0),
 ])
 def test_cuda_matches_oracle(kw, F, nb, taps):
     hr = load_sh_hrir()
