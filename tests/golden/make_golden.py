@@ -38,6 +38,9 @@ GOLDEN_SCENARIOS = {
     "hq_resample_1024": (dict(n_sources=40, kind=KIND_HRTF, feeder="resample", loop_len=3001, seed=103, occlusion_toggle=True), 1024, 8, 0),
     # the bike: three pitch-shifted mix sources per AudioSource, retuned every buffer (AudioEngine.cpp:435-458, BikePhysics.cpp:712-740)
     "bike_mix3_pan": (dict(n_sources=24, kind=KIND_PAN, feeder="mix3", loop_len=4099, seed=111, n_shared_buffers=9), 512, 8, 0),
+    # master volume moves, including to silence and back (every source crosses the -60 dB rules at once; `valid` goes false
+    # once the decoder tail is flushed)
+    "master_moves": (dict(n_sources=48, mixed_kinds=True, feeder="resample", seed=113, master_script={1: 0.5, 3: 0.0, 15: 0.8}), 256, 20, 0),
     "bike_mix3_hq": (dict(n_sources=24, kind=KIND_HRTF, feeder="mix3", loop_len=4096, seed=112, n_shared_buffers=9, volume_toggle=True), 256, 10, 0),
 }
 

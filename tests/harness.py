@@ -282,7 +282,8 @@ class Scenario:
 
     def __init__(self, n_sources, frames, seed=12345, kind=KIND_PAN, feeder="native", loop_len=16384, moving=True,
                  rates=(44100, 24000, 16000, 48000), rate_probs=(0.5, 0.2, 0.15, 0.15), boundary_safe=False,
-                 volume_toggle=False, occlusion_toggle=False, mixed_kinds=False, n_shared_buffers=0, batched_ring_push=False):
+                 volume_toggle=False, occlusion_toggle=False, mixed_kinds=False, n_shared_buffers=0, batched_ring_push=False,
+                 master_script=None):
         self.n, self.F, self.seed = n_sources, frames, seed
         rng = np.random.default_rng(seed)
         self.moving = moving
@@ -304,6 +305,7 @@ class Scenario:
         self.mixf = rng.uniform(0.5, 1.0, n_sources).astype(np.float32)
         self.ring_rng_seed = seed + 1
         self.batched_ring_push = batched_ring_push
+        self.master_script = master_script or {}      # buffer index -> master volume (AudioEngine::setMasterVolume, AudioEngine.cpp:805-811)
 
     def build(self, be):
         bufs = [be.buffer_create(p) for p in self.pcm]
@@ -349,6 +351,8 @@ class Scenario:
         if self.moving:
             t = b * self.F / 48000.0
             be.set_head([1.0 * t, 0.0, 0.0], quat_yaw(np.deg2rad(30.0) * t))
+        if b in self.master_script:
+            be.set_master_volume(self.master_script[b])
         if self.volume_toggle:
             sel = self.ids[::4]
             if b % 6 == 2:
