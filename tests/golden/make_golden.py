@@ -21,6 +21,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from harness import ROOT, KIND_HRTF, KIND_PAN, RefBackend, Scenario, ref_lib  # noqa: E402
 
+SPECIAL_POSITIONS = [(0, 0, 0), (0, 5, 0), (0, -5, 0), (3, 0, 0), (-3, 0, 0), (0, 0, 3), (0, 0, -3), (600, 0, 0), (0.5, 0, 0),
+                     (2, 2, -2), (-1, 0, -1), (0, 1e-3, -1), (499.5, 0, 0), (1, 0, 0), (0, 0, -1)]
+
 GOLDEN_SCENARIOS = {
     # name: (Scenario kwargs, frames, n_buffers, hrir_taps)
     "c1_pan16": (dict(n_sources=16, kind=KIND_PAN, loop_len=48000), 512, 8, 0),
@@ -41,6 +44,10 @@ GOLDEN_SCENARIOS = {
     # master volume moves, including to silence and back (every source crosses the -60 dB rules at once; `valid` goes false
     # once the decoder tail is flushed)
     "master_moves": (dict(n_sources=48, mixed_kinds=True, feeder="resample", seed=113, master_script={1: 0.5, 3: 0.0, 15: 0.8}), 256, 20, 0),
+    # sources on the axes, at the poles, at the listener's own position, on one-degree cell edges, at the near-field threshold and
+    # out of range; the listener at rest for three buffers (exact cell edges), then moving
+    "special_positions_hq": (dict(n_sources=30, kind=KIND_HRTF, seed=114, positions_override=SPECIAL_POSITIONS, moving=False), 256, 6, 0),
+    "special_positions_mixed": (dict(n_sources=45, mixed_kinds=True, seed=115, positions_override=SPECIAL_POSITIONS, feeder="resample"), 512, 8, 0),
     "bike_mix3_hq": (dict(n_sources=24, kind=KIND_HRTF, feeder="mix3", loop_len=4096, seed=112, n_shared_buffers=9, volume_toggle=True), 256, 10, 0),
 }
 

@@ -283,12 +283,15 @@ class Scenario:
     def __init__(self, n_sources, frames, seed=12345, kind=KIND_PAN, feeder="native", loop_len=16384, moving=True,
                  rates=(44100, 24000, 16000, 48000), rate_probs=(0.5, 0.2, 0.15, 0.15), boundary_safe=False,
                  volume_toggle=False, occlusion_toggle=False, mixed_kinds=False, n_shared_buffers=0, batched_ring_push=False,
-                 master_script=None):
+                 master_script=None, positions_override=None):
         self.n, self.F, self.seed = n_sources, frames, seed
         rng = np.random.default_rng(seed)
         self.moving = moving
         self.volume_toggle, self.occlusion_toggle = volume_toggle, occlusion_toggle
         self.pos = positions(rng, n_sources, boundary_safe)
+        if positions_override is not None:      # hand-picked positions (cycled over the sources): axes, poles, the listener's own position, out of range
+            po = np.asarray(positions_override, np.float32)
+            self.pos = po[np.arange(n_sources) % len(po)].copy()
         self.vol = rng.uniform(0.25, 1.0, n_sources).astype(np.float32)
         if mixed_kinds:
             self.kinds = rng.choice([KIND_PAN, KIND_HRTF, KIND_STEREO], n_sources, p=[0.45, 0.45, 0.1])
