@@ -19,7 +19,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from harness import ROOT, KIND_HRTF, KIND_PAN, RefBackend, Scenario, ref_lib  # noqa: E402
+from harness import ROOT, KIND_HRTF, KIND_PAN, RefBackend, Scenario, ref_lib, run_churn  # noqa: E402
 
 SPECIAL_POSITIONS = [(0, 0, 0), (0, 5, 0), (0, -5, 0), (3, 0, 0), (-3, 0, 0), (0, 0, 3), (0, 0, -3), (600, 0, 0), (0.5, 0, 0),
                      (2, 2, -2), (-1, 0, -1), (0, 1e-3, -1), (499.5, 0, 0), (1, 0, 0), (0, 0, -1)]
@@ -90,6 +90,12 @@ def main():
         o, v = sc.run(RefBackend(F, hrir_taps=taps), nb)
         out[name] = o
         out[name + "__valid"] = np.array(v, np.int32)
+    # create / destroy churn with one-shots finishing on their own (tests/harness.py run_churn): outputs, valid flags, finished ids
+    co, cv, cf = run_churn(RefBackend(256), 256)
+    out["churn"] = co
+    out["churn__valid"] = np.array(cv, np.int32)
+    out["churn__fin_flat"] = np.array([i for f in cf for i in f], np.int32)
+    out["churn__fin_off"] = np.cumsum([0] + [len(f) for f in cf]).astype(np.int32)
     np.savez_compressed(os.path.join(HERE, "scenarios.npz"), **out)
     # 4. resampler (the reference's own test pattern: ramp src[i] = i, 4-sample chunks; AudioResampler.cpp:213-287)
     L.ref_resampler_create.restype = C.c_void_p

@@ -397,6 +397,55 @@ class Scenario:
         return np.stack(outs), valids
 
 
+def run_churn(be, frames, n_buffers=10, n_start=400, per_buffer=60, seed=5, kinds=(KIND_PAN, KIND_HRTF)):
+    """playOneShotSound / removeSource churn (AudioEngine.cpp:900-943,1022-1052): every buffer a batch of sources is destroyed
+    and a batch of new ones (one-shots with remove_on_finish among them) is created; ids keep increasing, slots are recycled.
+    Returns (outputs, valid flags, finished ids per buffer)."""
+    rng = np.random.default_rng(seed)
+    pcm = [synth_pcm(rng, L) for L in (700, 1500, 4096, 3001)]
+    bufs = [be.buffer_create(p) for p in pcm]
+    alive = []
+
+    def add(n):
+        for _ in range(n):
+            kind = int(rng.choice(kinds))
+            sid = be.source_create(kind)
+            b = int(rng.integers(0, len(bufs)))
+            one_shot = rng.uniform() < 0.3
+            rate = int(rng.choice([48000, 44100, 24000]))
+            be.source_attach_buffer(sid, bufs[b], int(rng.integers(0, len(pcm[b]))), rate, not one_shot, bool(one_shot))
+            pos = rng.uniform([-20, -5, -20], [20, 5, 20], (1, 3)).astype(np.float32) + np.float32(1.5)
+            be.set_source_positions([sid], pos)
+            be.set_source_volumes([sid], np.array([rng.uniform(0.3, 1.0)], np.float32))
+            alive.append(sid)
+
+    add(n_start)
+    outs, valids, fins = [], [], []
+    for b in range(n_buffers):
+        t = b * frames / 48000.0
+        be.set_head([t, 0.0, 0.0], quat_yaw(0.4 * t))
+        v, o = be.mix()
+        outs.append(o); valids.append(v)
+        fin = sorted(be.poll_finished())
+        fins.append(fin)
+        for f in fin:
+            if f in alive:
+                alive.remove(f)
+        kill = [alive[i] for i in sorted(rng.choice(len(alive), size=min(per_buffer, len(alive)), replace=False))]
+        for sid in kill:
+            be.source_destroy(sid)
+            alive.remove(sid)
+        add(per_buffer)
+    return np.stack(outs), valids, fins
+
+
+def churn_golden():
+    g = np.load(os.path.join(GOLDEN_DIR, "scenarios.npz"))
+    off = g["churn__fin_off"]
+    fins = [g["churn__fin_flat"][off[k]:off[k + 1]].tolist() for k in range(len(off) - 1)]
+    return g["churn"], g["churn__valid"].tolist(), fins
+
+
 def run_pipelined(sc, be, n_buffers):
     """Scenario.run through sbm_mix_submit / sbm_mix_collect with two buffers in flight: the events of buffer b are applied
     while buffer b - 1 is still being mixed."""

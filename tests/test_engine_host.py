@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import substrata_b200 as sb
-from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, ROOT, OracleBackend, Scenario, load_sh_hrir, rel_rms, run_pipelined)
+from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, ROOT, OracleBackend, Scenario, load_sh_hrir, rel_rms, churn_golden, run_churn, run_pipelined)
 from golden.make_golden import GOLDEN_SCENARIOS
 
 EMU_DIR = os.path.join(ROOT, "tests", "native")
@@ -177,3 +177,20 @@ def test_submit_collect_reports_finished_sources_and_limits_depth():
         e.mix_collect()                                              # nothing in flight
     v, o = e.mix()                                                   # and the synchronous call works again
     assert v == 0
+
+
+def test_source_churn_matches_oracle():
+    """Sources created and destroyed between every pair of buffers, one-shots finishing on their own: outputs, valid flags
+    and the finished-id lists must follow the oracle (ids keep increasing; slots, list positions and DSP state are recycled)."""
+    hr = load_sh_hrir()
+    oo, ov, of = run_churn(OracleBackend(256, sh_hrir=hr), 256)
+    eo, ev, ef = run_churn(emu_engine(256, hr, max_sources=1024), 256)
+    assert ov == ev and of == ef
+    assert rel_rms(eo, oo) <= TOL
+
+
+def test_source_churn_matches_reference_golden():
+    ro, rv, rf = churn_golden()
+    eo, ev, ef = run_churn(emu_engine(256, load_sh_hrir(), max_sources=1024), 256)
+    assert ev == rv and ef == rf
+    assert rel_rms(eo, ro) <= TOL

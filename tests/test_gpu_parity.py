@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import substrata_b200 as sb
-from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, KIND_STEREO, OracleBackend, Scenario, load_sh_hrir, rel_rms, run_pipelined)
+from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, KIND_STEREO, OracleBackend, Scenario, load_sh_hrir, rel_rms, churn_golden, run_churn, run_pipelined)
 from golden.make_golden import GOLDEN_SCENARIOS
 
 pytestmark = pytest.mark.gpu
@@ -107,6 +107,23 @@ def test_ring_push_from_pinned_memory_equals_staged_push():
             res.append(e.mix()[1].copy())
         outs.append(np.stack(res))
     assert outs[0].any() and np.array_equal(outs[0], outs[1])
+
+
+def test_cuda_source_churn_matches_oracle():
+    """Sources created and destroyed between every pair of buffers, one-shots finishing on their own (AudioEngine.cpp:900-943,
+    1022-1052): outputs, valid flags and finished-id lists follow the oracle while slots and list positions are recycled."""
+    hr = load_sh_hrir()
+    oo, ov, of = run_churn(OracleBackend(512, sh_hrir=hr), 512, n_buffers=12, n_start=1500, per_buffer=200)
+    go, gv, gf = run_churn(engine(512, hr, max_sources=4096), 512, n_buffers=12, n_start=1500, per_buffer=200)
+    assert ov == gv and of == gf
+    assert rel_rms(go, oo) <= TOL
+
+
+def test_cuda_source_churn_matches_reference_golden():
+    ro, rv, rf = churn_golden()
+    go, gv, gf = run_churn(engine(256, load_sh_hrir(), max_sources=1024), 256)
+    assert gv == rv and gf == rf
+    assert rel_rms(go, ro) <= TOL
 
 
 def test_cuda_feeder_bookkeeping():

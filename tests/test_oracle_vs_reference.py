@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, OracleBackend, RefBackend, Scenario, load_sh_hrir, ref_library_path,
+from harness import (GOLDEN_DIR, KIND_HRTF, KIND_PAN, OracleBackend, RefBackend, Scenario, load_sh_hrir, ref_library_path, run_churn,
                      rel_rms)
 from golden.make_golden import GOLDEN_SCENARIOS
 
@@ -69,4 +69,15 @@ def test_feeder_state_and_eof_bookkeeping():
     oo, of, oq = res["oracle"]
     assert rf == of
     assert [x["cur_read_i"] for x in rq] == [x["cur_read_i"] for x in oq]
+    assert rel_rms(oo, ro) <= TOL
+
+
+@needs_ref
+def test_source_churn_oracle_vs_reference():
+    """Create / destroy churn between buffers and one-shots finishing on their own: the oracle follows the compiled reference
+    (outputs, valid flags, finished ids) -- the reference's GainMixer processor bookkeeping and DestroySource ordering."""
+    hr = load_sh_hrir()
+    oo, ov, of = run_churn(OracleBackend(256, sh_hrir=hr), 256)
+    ro, rv, rf = run_churn(RefBackend(256), 256)
+    assert ov == rv and of == rf
     assert rel_rms(oo, ro) <= TOL
