@@ -93,7 +93,6 @@ SBM_API int sbm_source_attach_buffer(sbm_engine* e, int n, const int* ids, const
 SBM_API int sbm_source_attach_ring(sbm_engine* e, int id, int sampling_rate, int capacity_samples);
 /* CircularBuffer::pushBackNItems by StreamerThread / ClientUDPHandlerThread (StreamerThread.cpp:53-80, ClientUDPHandlerThread.cpp:239). */
 SBM_API int sbm_source_ring_push(sbm_engine* e, int id, const float* samples, size_t n);
-/* CircularBuffer::size() as of the last sbm_mix() plus pushes since (StreamerThread.cpp:53 polls it). */
 /* Batched push for many ring-fed sources at once: packet k = samples[offsets[k] .. offsets[k+1]) goes to source ids[k]
  * (the same id may appear more than once; packets are appended in order).  One pinned staging copy + one H2D + one
  * scatter kernel for the whole call -- what glare::AudioEngine's voice / streaming feeders use instead of one
@@ -105,6 +104,7 @@ SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, con
  * then stay unmodified until the next sbm_mix / sbm_mix_collect returns. */
 SBM_API void* sbm_host_alloc_pinned(size_t bytes);
 SBM_API void sbm_host_free_pinned(void* p);
+/* CircularBuffer::size() as of the last collected buffer plus pushes since (StreamerThread.cpp:53 polls it). */
 SBM_API int sbm_source_ring_size(sbm_engine* e, int id, uint64_t* out_size);
 /* SourceType_Streaming with mix_sources: pitch/doppler mixer (AudioEngine.cpp:435-458). */
 SBM_API int sbm_source_attach_mix(sbm_engine* e, int id, int sampling_rate, int nz, const int* buffers, const double* sound_file_i,
