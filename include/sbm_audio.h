@@ -9,9 +9,15 @@
  * unavailable.
  *
  * Conventions: plain C, opaque handle, int status codes (0 = OK, < 0 = error), no exceptions cross the boundary;
- * pointers are HOST pointers unless the name says `device`.  Setters may be called from any thread and take effect
- * at the next sbm_mix() (like Resonance's task queue, resonance_audio_api_impl.cc:462,538); sbm_mix() itself must be
- * called from one thread at a time (the reference holds AudioEngine::mutex around it, AudioEngine.cpp:367).
+ * pointers are HOST pointers unless the name says `device`.
+ *
+ * Threading (RA/graph/resonance_audio_api_impl.cc:136-316, RA/utils/lockless_task_queue.cc:43-51): the per-frame
+ * setters (sbm_set_source_positions / _volumes / _occlusions, sbm_set_head, sbm_set_master_volume, sbm_source_set_mix_params)
+ * may be called from any thread, take no lock and never wait for the mixer or the GPU: each call is queued (lock-free MPSC
+ * queue) and takes effect at the next sbm_mix / sbm_mix_begin / sbm_mix_submit, in the order queued.  The structural calls
+ * (buffers, source create / attach / destroy, ring pushes) take the engine lock, which is never held while waiting for the
+ * GPU.  sbm_mix* itself must be called from one thread at a time (the reference holds AudioEngine::mutex around its
+ * per-buffer body, AudioEngine.cpp:367).
  *
  * "file:line" notes name the reference interface each entry point stands in for.
  */
@@ -38,9 +44,11 @@ enum {
 	SBM_ERR_INVALID_ARG = -1,
 	SBM_ERR_CUDA = -2,         /* CUDA runtime / kernel failure; sbm_last_error() has the message */
 	SBM_ERR_NO_MEMORY = -3,
-	SBM_ERR_UNKNOWN_ID = -4,   /* Resonance ignores unknown ids silently (resonance_audio_api_impl.cc:551-554); we report it */
+	SBM_ERR_UNKNOWN_ID = -4,   /* create / attach / destroy / query calls report unknown ids; the queued setters ignore them silently like
+	                              Resonance does (resonance_audio_api_impl.cc:551-554) and count them in sbm_stats.ignored_setter_items */
 	SBM_ERR_CAPACITY = -5,     /* more sources / buffers / ring samples than configured */
-	SBM_ERR_UNSUPPORTED = -6   /* room effects etc.: rows marked "next" in SURVEY.md 8(f) */
+	SBM_ERR_UNSUPPORTED = -6,  /* rows marked "next" in SURVEY.md 8(f) that are not built */
+	SBM_ERR_PEER_TIMEOUT = -7  /* multi-GPU: a peer rank's bus did not arrive in time; the buffer holds this rank's sources only */
 };
 
 /* Source kinds.  Values match vraudio::RenderingMode (resonance_audio_api.h:35-45) for sound objects. */
@@ -76,6 +84,10 @@ SBM_API int sbm_buffer_create(sbm_engine* e, const float* samples, size_t n, int
  * sample (i.e. stride_samples >= n rounded up to 4, stride_samples % 4 == 0); other layouts are rendered identically
  * through the generic fetch path. */
 SBM_API int sbm_buffer_adopt_device(sbm_engine* e, const float* device_base, size_t n, size_t stride_samples, int count, int* out_first_buffer);
+/* Drops the registry's reference to a buffer (`AudioBufferRef` going out of scope, AudioEngine.h:39-45,122): its device memory
+ * is freed once the last source that was attached to it is gone and no buffer in flight can still read it.  New attachments
+ * to a destroyed buffer are rejected. */
+SBM_API int sbm_buffer_destroy(sbm_engine* e, int buffer);
 
 /* ---- sources ---- */
 /* CreateSoundObjectSource / CreateStereoSource (AudioEngine.cpp:857,867).  Ids increase monotonically like
@@ -101,7 +113,9 @@ SBM_API int sbm_source_ring_push(sbm_engine* e, int id, const float* samples, si
 SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, const float* samples, const size_t* offsets /* n + 1 */);
 /* Page-locked host memory (cudaHostAlloc) for callers that do not link CUDA: a sbm_source_ring_push_batch payload that
  * lives in it (or in any memory registered with the CUDA driver) goes to the device without the staging copy -- it must
- * then stay unmodified until the next sbm_mix / sbm_mix_collect returns. */
+ * then stay unmodified until the buffer SUBMITTED AFTER the push has been collected (synchronous sbm_mix: until the next
+ * sbm_mix returns; pipelined: the collect that returns the first buffer submitted after the push -- NOT merely the next
+ * collect, which may hand out an older buffer). */
 SBM_API void* sbm_host_alloc_pinned(size_t bytes);
 SBM_API void sbm_host_free_pinned(void* p);
 /* CircularBuffer::size() as of the last collected buffer plus pushes since (StreamerThread.cpp:53 polls it). */
@@ -162,6 +176,13 @@ SBM_API int sbm_mix_collect(sbm_engine* e, float* out_interleaved, int* out_vali
  * sbm_mix_finish (sbm_bus_device), which is what the CPU-only tests do over gloo. */
 SBM_API int sbm_peer_export(sbm_engine* e, void* handle_out, size_t handle_bytes /* >= 64 */);
 SBM_API int sbm_peer_connect(sbm_engine* e, int rank, int world, const void* handles, size_t handle_stride);
+/* A rank that stalls (debugger, long upload, a failed sbm_mix that skipped a buffer) must not take the others down: the gather
+ * kernel gives up after the timeout (default 2000 ms), the buffer is rendered from this rank's sources alone and
+ * sbm_mix / sbm_mix_collect return SBM_ERR_PEER_TIMEOUT; the engine stays usable.  After a timeout (or after any rank skipped
+ * a buffer) the ranks' exchange counts disagree: quiesce all ranks (nothing in flight), synchronise them on the host, and
+ * call sbm_peer_resync on every rank before mixing again. */
+SBM_API int sbm_set_peer_timeout_ms(sbm_engine* e, int timeout_ms);
+SBM_API int sbm_peer_resync(sbm_engine* e);
 SBM_API int sbm_bus_device(sbm_engine* e, float** out_device_ptr, size_t* out_num_floats);
 SBM_API int sbm_out_device(sbm_engine* e, float** out_device_ptr);
 SBM_API void* sbm_stream(sbm_engine* e);   /* cudaStream_t */
@@ -193,7 +214,7 @@ typedef struct sbm_stats {
 	uint64_t last_algorithmic_bytes; /* PCM bytes the rendered sources had to read: sum of 4 * source samples */
 	uint64_t last_h2d_bytes, last_d2h_bytes;
 	uint32_t last_rendered_sources;  /* sources that reached a bus in the last buffer */
-	uint32_t reserved;
+	uint32_t ignored_setter_items;   /* queued setter items dropped so far because their id was unknown when they were applied */
 } sbm_stats;
 SBM_API int sbm_get_stats(sbm_engine* e, sbm_stats* out);
 /* Enables CUDA-event timing of the kernels inside mix_begin/finish (off by default). */

@@ -23,6 +23,10 @@ void orc_set_bus_precision(orc_engine* e, int use_double);
 
 int  orc_buffer_create(orc_engine* e, const float* samples, size_t n);
 int  orc_source_create(orc_engine* e, int kind);  /* 0 stereo-pan object, 3 HQ binaural object, 100 stereo */
+int  orc_sources_create(orc_engine* e, int kind, int count);   /* batched orc_source_create: returns the first id */
+void orc_sources_attach_buffer(orc_engine* e, int n, const int* ids, const int* bufs, const uint64_t* cur_read_i, const int* rates,
+                               const uint8_t* looping, const uint8_t* remove_on_finish);
+void orc_sources_attach_mix1(orc_engine* e, int n, const int* ids, const int* bufs, const double* sound_file_i, const double* source_delta, const float* mix_factor);
 void orc_source_attach_buffer(orc_engine* e, int id, int buf, uint64_t cur_read_i, int sampling_rate, int looping, int remove_on_finish);
 void orc_source_attach_ring(orc_engine* e, int id, int sampling_rate);
 void orc_source_ring_push(orc_engine* e, int id, const float* samples, size_t n);

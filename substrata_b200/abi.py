@@ -4,7 +4,7 @@ import ctypes as C
 _vp, _i, _f, _sz, _u64, _i64, _d = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_uint64, C.c_int64, C.c_double
 
 ERROR_NAMES = {0: "SBM_OK", -1: "SBM_ERR_INVALID_ARG", -2: "SBM_ERR_CUDA", -3: "SBM_ERR_NO_MEMORY", -4: "SBM_ERR_UNKNOWN_ID",
-               -5: "SBM_ERR_CAPACITY", -6: "SBM_ERR_UNSUPPORTED"}
+               -5: "SBM_ERR_CAPACITY", -6: "SBM_ERR_UNSUPPORTED", -7: "SBM_ERR_PEER_TIMEOUT"}
 
 
 class SbmConfig(C.Structure):
@@ -20,7 +20,7 @@ class SbmSourceState(C.Structure):
 class SbmStats(C.Structure):
     _fields_ = [("buffers_mixed", _u64), ("kernel_launches", _u64), ("active_sources", C.c_uint32), ("last_params_kernel_ms", _f),
                 ("last_mix_kernel_ms", _f), ("last_finish_kernel_ms", _f), ("last_algorithmic_bytes", _u64), ("last_h2d_bytes", _u64),
-                ("last_d2h_bytes", _u64), ("last_rendered_sources", C.c_uint32), ("reserved", C.c_uint32)]
+                ("last_d2h_bytes", _u64), ("last_rendered_sources", C.c_uint32), ("ignored_setter_items", C.c_uint32)]
 
 
 # name -> (restype, argtypes); every SBM_API symbol of the header.
@@ -30,6 +30,7 @@ SIGNATURES = {
     "sbm_last_error": (C.c_char_p, [_vp]),
     "sbm_buffer_create": (_i, [_vp, _vp, _sz, _vp]),
     "sbm_buffer_adopt_device": (_i, [_vp, _vp, _sz, _sz, _i, _vp]),
+    "sbm_buffer_destroy": (_i, [_vp, _i]),
     "sbm_source_create": (_i, [_vp, _i, _i, _vp]),
     "sbm_source_destroy": (_i, [_vp, _i, _vp]),
     "sbm_source_attach_buffer": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -56,6 +57,8 @@ SIGNATURES = {
     "sbm_mix_begin": (_i, [_vp]),
     "sbm_mix_finish": (_i, [_vp, _vp, _vp]),
     "sbm_peer_export": (_i, [_vp, _vp, _sz]),
+    "sbm_set_peer_timeout_ms": (_i, [_vp, _i]),
+    "sbm_peer_resync": (_i, [_vp]),
     "sbm_peer_connect": (_i, [_vp, _i, _i, _vp, _sz]),
     "sbm_bus_device": (_i, [_vp, _vp, _vp]),
     "sbm_out_device": (_i, [_vp, _vp]),

@@ -34,6 +34,18 @@ struct RingPush {               // one packet of a batched ring push: stage[src_
 	uint32_t n;
 };
 
+// One segment of the per-buffer upload block (engine.cc: upload_block_locked): `count` elements of `elem_words` 4-byte words,
+// values at word `src_word` of the block, copied to dst[0 .. count) (idx_word == 0xffffffff) or scattered to dst[idx[j]].
+struct UpSeg {
+	void* dst;
+	uint32_t elem_words, count;
+	uint32_t src_word, idx_word;
+	uint32_t pad, pad2;
+};
+static_assert(sizeof(UpSeg) == 32, "UpSeg is 32 bytes");
+constexpr int kMaxUpSegs = 16;
+constexpr int kInlineFinished = 1024;   // finished-source ids that ride in the result block (more: fetched separately)
+
 constexpr int kMaxPeers = 8;
 // Cross-GPU exchange of the bus over NVLink peer memory (world == 0: single GPU, nothing is exchanged).
 // Every rank owns one gather area [2 buffer parities][world][bus_floats] plus two arrival counters; K3 of rank r stores
@@ -44,6 +56,9 @@ struct PeerArgs {
 	float* gather[kMaxPeers];           // gather[p]: rank p's area (own memory for p == rank, peer-mapped otherwise)
 	unsigned int* arrive[kMaxPeers];    // arrive[p]: rank p's two monotonic arrival counters
 	unsigned int* done;                 // local: K3 CTAs finished (last-CTA election)
+	uint32_t parity;                    // which half of the gather areas / which arrival counter this buffer uses (exchange count & 1)
+	uint32_t pad;
+	unsigned long long timeout_ns;      // gather kernel: give up waiting for the peers after this long (the buffer then holds the local bus only)
 };
 
 struct MixArgs {
@@ -81,7 +96,7 @@ struct FinishArgs {
 	const uint32_t* list_ring;  // ring-fed slots whose read counters are reported back
 	uint32_t n_ring;
 	const unsigned long long* read_i;
-	int* finished_count_reset;  // unused
+	const int* finished;        // this buffer's finished-id list (device); the first kInlineFinished ids are copied behind the ring counters
 	int hist_smem_all;          // set by launch_finish: K4b updates the FIR history of all 16 channels in one pass
 };
 
@@ -89,12 +104,14 @@ struct OutTail {                // follows the 2*frames output floats in the D2H
 	int valid;
 	int n_finished;
 	unsigned int n_rendered;
-	int pad;
+	int status;                 // kTail*
 	unsigned long long algo_bytes;
 };
+constexpr int kTailOk = 0, kTailPeerTimeout = 1;
 
 namespace dev {
 int init(int device, void** stream_out);
+void* stream_create();                           // another non-blocking stream on the current device
 int use(int device);                             // make `device` current on the calling thread
 void shutdown(void* stream);
 const char* last_error();
@@ -110,6 +127,7 @@ int sync(void* stream);
 int num_mix_ctas(uint32_t frames, int sh);       // largest grid K2 will use (sizes the partials buffer)
 size_t partials_floats(uint32_t frames);         // floats needed for MixArgs::partials
 // kernels
+int launch_apply_uploads(const UpSeg* segs, uint32_t n_segs, const uint32_t* block, uint32_t max_words, void* stream);   // copies / scatters every segment of an upload block
 int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, const MixPatch* mp, uint32_t nmp, void* stream);
 int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, const uint32_t* lists, uint32_t n_slots, void* stream);   // lists: [n_pan + n_sh] slots in render order
 int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void* stream);   // batched ring push: one CTA per packet
@@ -119,7 +137,7 @@ int launch_finish(const FinishArgs& a, void* stream);
 int peer_export(void* device_ptr, void* handle_out64);             // cudaIpcGetMemHandle
 void* peer_open(const void* handle64);                             // cudaIpcOpenMemHandle (other process, any GPU of the node)
 void peer_close(void* mapped);
-int launch_peer_gather(const PeerArgs& pa, float* bus_sum, size_t bus_floats, uint32_t parity, unsigned int target, void* stream);
+int launch_peer_gather(const PeerArgs& pa, const float* own_bus, float* bus_sum, size_t bus_floats, unsigned int target, DevFlags* flags, void* stream);
 // timing
 void* event_create();
 void event_destroy(void* ev);

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -135,16 +136,21 @@ __global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
 		a.flags->part_bytes[i][0] = 0; a.flags->part_rendered[i][0] = 0;
 		for (int o = 16; o > 0; o >>= 1) { part_bytes += __shfl_xor_sync(0xffffffffu, part_bytes, o); part_rendered += __shfl_xor_sync(0xffffffffu, part_rendered, o); }
 	}
+	const int n_fin = a.flags->n_finished;     // (read by every thread before thread 0 clears it below: barrier first)
+	__syncthreads();
 	if (i == 0) {
 		tail->valid = plan.valid;
-		tail->n_finished = a.flags->n_finished;
+		tail->n_finished = n_fin;
 		tail->n_rendered = a.flags->n_rendered + part_rendered;
-		tail->pad = 0;
+		tail->status = a.flags->peer_timeout ? kTailPeerTimeout : kTailOk;
 		tail->algo_bytes = a.flags->algo_bytes + part_bytes;
-		a.flags->n_finished = 0; a.flags->n_rendered = 0; a.flags->algo_bytes = 0;
+		a.flags->n_finished = 0; a.flags->n_rendered = 0; a.flags->algo_bytes = 0; a.flags->peer_timeout = 0;
 	}
 	unsigned long long* reads = reinterpret_cast<unsigned long long*>(tail + 1);
 	for (uint32_t q = i; q < a.n_ring; q += T) reads[q] = a.read_i[a.list_ring[q]];
+	// the ids of sources the feeder stopped this buffer ride along (engine.cc fetches the list separately only when it is longer)
+	int* fin = reinterpret_cast<int*>(reads + a.n_ring);
+	for (int q = (int)i; q < n_fin && q < kInlineFinished; q += (int)T) fin[q] = a.finished[q];
 }
 
 // Batched ring push (the streaming feed, AE.cpp:540-545 / ClientUDPHandlerThread.cpp:239-242 for many sources at once):
@@ -160,9 +166,34 @@ __global__ void __launch_bounds__(128) k_ring_scatter_kernel(const RingPush* __r
 	}
 }
 
+// Applies one upload block (engine.cc): blockIdx.y = segment; the segment's words are copied to its device array, element j
+// to dst[j] (contiguous) or dst[idx[j]] (scattered setters).  Word-granular so that one kernel serves 4- to 32-byte elements.
+__global__ void __launch_bounds__(256) k_apply_uploads_kernel(const UpSeg* __restrict__ segs, const uint32_t* __restrict__ block) {
+	const UpSeg sg = segs[blockIdx.y];
+	uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(sg.dst);
+	const uint32_t* __restrict__ val = block + sg.src_word;
+	const uint32_t ew = sg.elem_words;
+	const size_t total = (size_t)sg.count * ew;
+	for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t j = (uint32_t)(w / ew), k = (uint32_t)(w - (size_t)j * ew);
+		const uint32_t at = sg.idx_word == 0xffffffffu ? j : block[sg.idx_word + j];
+		dst[(size_t)at * ew + k] = val[w];
+	}
+}
+
 namespace dev {
 
 void note_launch(unsigned n) { g_launches += n; }
+
+int launch_apply_uploads(const UpSeg* segs, uint32_t n_segs, const uint32_t* block, uint32_t max_words, void* stream) {
+	if (!n_segs) return 0;
+	uint32_t gx = (max_words + 1023) / 1024;      // <= 4 words per thread
+	if (gx < 1) gx = 1;
+	if (gx > 592) gx = 592;
+	k_apply_uploads_kernel<<<dim3(gx, n_segs), 256, 0, (cudaStream_t)stream>>>(segs, block);
+	note_launch();
+	return check_launch("k_apply_uploads");
+}
 
 int check(cudaError_t e, const char* what) {
 	if (e == cudaSuccess) return 0;
@@ -200,6 +231,11 @@ int init(int device, void** stream_out) {
 	if (check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return -1;
 	*stream_out = (void*)s;
 	return 0;
+}
+
+void* stream_create() {
+	cudaStream_t s;
+	return check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate") ? nullptr : (void*)s;
 }
 
 void shutdown(void* stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }

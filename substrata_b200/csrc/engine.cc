@@ -5,11 +5,15 @@
 // the per-buffer launch sequence  patch -> K1 (params) -> K2 (mix) -> K3 (reduce) -> [all-reduce by the caller] ->
 // K4 (decode + stereo mix + interleave) -> D2H.  All arithmetic on audio happens in the kernels (device_api.h);
 // nothing here touches a sample except to copy pushed ring packets to the device.
+#include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <limits>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -25,24 +29,72 @@ using namespace sbm;
 
 namespace {
 
-struct DirtyRange {
-	uint32_t lo = 0xffffffffu, hi = 0;
-	void mark(uint32_t i) { if (i < lo) lo = i; if (i + 1 > hi) hi = i + 1; }
+// Which elements of a host-written per-slot array changed since the last buffer: an index list (deduplicated by an epoch
+// stamp per element) for the usual few-thousand scattered setters per frame, or a dense range once a batched setter has
+// touched a whole run of slots.
+struct DirtySet {
+	std::vector<uint32_t> idx, stamp;
+	uint32_t epoch = 1, lo = 0xffffffffu, hi = 0;
+	bool dense = false;
+	void init(size_t cap) { stamp.assign(cap, 0u); }
+	void mark(uint32_t i) {
+		if (i < lo) lo = i;
+		if (i + 1 > hi) hi = i + 1;
+		if (!dense && stamp[i] != epoch) { stamp[i] = epoch; idx.push_back(i); }
+	}
+	void mark_range(uint32_t a, uint32_t b) { if (b <= a) return; if (a < lo) lo = a; if (b > hi) hi = b; dense = true; }
 	bool any() const { return hi > lo; }
-	void clear() { lo = 0xffffffffu; hi = 0; }
+	void clear() {
+		idx.clear(); lo = 0xffffffffu; hi = 0; dense = false;
+		if (++epoch == 0) { std::fill(stamp.begin(), stamp.end(), 0u); epoch = 1; }
+	}
 };
 
-struct BufferInfo { float* dptr; size_t n; bool owned; };
+struct BufferInfo { float* dptr; size_t n; bool owned; uint32_t refs; bool doomed; };
 
 struct RingInfo { float* storage; uint32_t capacity; unsigned long long written; unsigned long long read_known; };
+
+// One setter call, queued by any thread without taking a lock (Resonance posts its setters to a lock-free task queue the
+// same way: RA/utils/lockless_task_queue.cc:43-51, RA/graph/resonance_audio_api_impl.cc:305-317) and applied by the mixer
+// thread at the next sbm_mix_begin / sbm_mix_submit.  Payload follows the header.
+struct SetterRec {
+	SetterRec* next;
+	uint32_t kind, n;
+};
+enum : uint32_t { kSetPositions, kSetVolumes, kSetOcclusions, kSetHead, kSetMaster, kSetMixParams };
+
+// Page-locked staging for everything the host sends per buffer (parameter upload blocks, ring packets), with a device
+// mirror of the same size: a FIFO ring -- regions are allocated in stream order and released when the buffer that follows
+// them has been collected.  Every H2D the engine issues per buffer reads from here (or from memory the caller pinned), so
+// no copy ever synchronises the stream behind the caller's back.
+struct StageRing {
+	unsigned char *h = nullptr, *d = nullptr;
+	size_t cap = 0;
+	unsigned long long head = 0, tail = 0;      // monotonic byte counters
+	uint32_t gen = 0;
+	size_t alloc(size_t bytes) {                  // offset of a 256-byte aligned region, or (size_t)-1
+		bytes = (bytes + 255) & ~(size_t)255;
+		if (!cap || bytes > cap) return (size_t)-1;
+		unsigned long long at = head;
+		const size_t pos = (size_t)(at % cap);
+		if (pos + bytes > cap) at += cap - pos;
+		if (at + bytes - tail > cap) return (size_t)-1;
+		head = at + bytes;
+		return (size_t)(at % cap);
+	}
+};
+struct Retired { void* pinned; void* device; unsigned long long after_seq; };   // freed once buffer `after_seq` has been collected
 
 }  // namespace
 
 struct sbm_engine {
 	sbm_config cfg;
 	void* stream = nullptr;
+	void* upload_stream = nullptr;   // sbm_buffer_create: PCM uploads do not queue behind (or hold up) the mixer's stream
 	std::string error;
-	std::mutex mu;               // guards everything the setters touch
+	std::mutex mu;               // guards the engine state below; setters never take it, and it is never held across a wait on the GPU
+	std::atomic<SetterRec*> setq{nullptr};
+	std::atomic<unsigned long long> setters_queued{0};
 
 	uint32_t cap = 0;            // slot capacity
 	uint32_t n_slots = 0;        // high-water mark
@@ -56,8 +108,11 @@ struct sbm_engine {
 	std::vector<float> h_occl;
 	std::vector<unsigned long long> h_ring_write;
 	std::vector<MixZ> h_mixz;
-	DirtyRange d_stat, d_posvol, d_occl, d_ring, d_mixz;
-	uint32_t mix_used = 0;       // MixZ entries handed out (bump allocation; freed entries are not recycled in this round)
+	DirtySet d_stat, d_posvol, d_occl, d_ring, d_mixz;
+	uint32_t mix_used = 0;       // MixZ entries handed out so far (high-water mark; freed ranges are recycled through mix_free)
+	std::map<uint32_t, std::vector<uint32_t>> mix_free;   // nz -> first entries of free MixZ ranges of that length
+	std::vector<int> slot_buf;   // slot -> PCM buffer its feeder references (-1 = none)
+	std::vector<int> mixz_buf;   // MixZ entry -> PCM buffer
 	std::vector<SlotPatch> patches;          // at most one (merged) pending patch per slot
 	std::vector<int> patch_of_slot;          // slot -> index into patches, -1 = none pending
 	std::vector<MixPatch> mix_patches;
@@ -66,6 +121,7 @@ struct sbm_engine {
 	bool lists_dirty = true;
 	std::vector<BufferInfo> buffers;
 	std::vector<int> finished_queue;
+	std::vector<Retired> retired;
 
 	// device
 	SlotArrays A;                // device pointers
@@ -74,41 +130,38 @@ struct sbm_engine {
 	DevFlags* dv_flags = nullptr;
 	float* dv_table = nullptr;
 	uint32_t *dv_lists = nullptr, *dv_list_ring = nullptr;   // dv_lists: pan list followed by the ambisonic list
-	SlotPatch* dv_patches = nullptr; uint32_t dv_patches_cap = 0;
-	MixPatch* dv_mix_patches = nullptr; uint32_t dv_mix_patches_cap = 0;
 	float* dv_partials = nullptr; size_t partials_floats = 0;
 	float* dv_bus = nullptr; size_t bus_floats = 0;
 	float* dv_hrir = nullptr; float* dv_hist = nullptr; float* dv_dec = nullptr;
 	float* dv_out = nullptr; size_t out_bytes = 0;
+	StageRing stage;
 	// multi-GPU bus exchange over peer memory (sbm_peer_export / sbm_peer_connect)
 	PeerArgs peer{};                         // world == 0 until connected
 	float* dv_gather = nullptr;              // own gather area [2][kMaxPeers][bus_floats] followed by the counters
 	float* dv_bus_sum = nullptr;             // bus summed over ranks (what K4 reads when connected)
 	void* peer_mapped[kMaxPeers] = {};       // IPC mappings of the other ranks' areas
-	unsigned char* h_ring_stage = nullptr;   // pinned staging of sbm_source_ring_push_batch: packet table + payload
-	unsigned char* d_ring_stage = nullptr;
-	size_t ring_stage_bytes = 0;
-	unsigned long long peer_epoch = 0;       // buffer_index at which the peers were connected (arrival counters count from there)
+	unsigned long long peer_buffers = 0;     // collective buffers since sbm_peer_connect / sbm_peer_resync
+	unsigned long long peer_timeout_ns = 2000000000ull;
 	size_t pending_ring_h2d_bytes = 0;       // ring pushes since the last sbm_mix_begin (reported with the next buffer's stats)
-	bool ring_stage_in_flight = false;       // an H2D from h_ring_stage may still be running (cleared by every stream sync in mix)
 	// Up to two buffers in flight (sbm_mix_submit / sbm_mix_collect): everything a submitted buffer's completion needs.
 	struct InFlight {
 		bool pending = false;
 		unsigned long long seq = 0;          // buffer_index of the buffer
-		unsigned char* h_out = nullptr;      // pinned D2H staging: 2F floats + OutTail + ring read counters
+		unsigned char* h_out = nullptr;      // pinned D2H staging: 2F floats + OutTail + ring read counters + inline finished ids
 		void* done = nullptr;                // event after the D2H
 		void* ev[4] = {nullptr, nullptr, nullptr, nullptr};   // profiling: before K1 / after K1 / after K2 / after K4
 		int* dv_finished = nullptr;          // this parity's finished-id list on the device
 		std::vector<uint32_t> list_ring;     // ring-fed slots in the order their read counters were reported
 		size_t h2d_bytes = 0, d2h_bytes = 0;
 		uint32_t active = 0;
+		unsigned long long stage_mark = 0; uint32_t stage_gen = 0;   // staging consumed up to here once this buffer is done
 	} fl[2];
 	unsigned long long collected = 0;        // buffers collected so far (== buffer_index when nothing is in flight)
-	unsigned long long ring_stage_seq = 0;   // the staged ring push precedes buffer `ring_stage_seq` in stream order
 	Globals g;
 	unsigned long long buffer_index = 0;
 	bool begun = false;
 	int last_valid = 0;
+	int room_effects = 0;
 
 	// stats
 	bool profiling = false;
@@ -163,36 +216,174 @@ void rebuild_lists(sbm_engine* e) {
 	e->lists_dirty = false;
 }
 
+// Device (and pinned) memory that kernels already enqueued may still touch is not freed on the spot: it is parked until
+// the next buffer to be submitted has been collected (stream order: everything enqueued before it is done by then).
+void retire(sbm_engine* e, void* pinned, void* device) {
+	if (pinned || device) e->retired.push_back(Retired{pinned, device, e->buffer_index});
+}
+void free_retired(sbm_engine* e, bool all) {
+	size_t k = 0;
+	for (size_t i = 0; i < e->retired.size(); ++i) {
+		const Retired& r = e->retired[i];
+		if (all || e->collected > r.after_seq) { if (r.pinned) dev::release_pinned(r.pinned); if (r.device) dev::release(r.device); }
+		else e->retired[k++] = r;
+	}
+	e->retired.resize(k);
+}
+
+void buffer_unref(sbm_engine* e, int buf) {
+	if (buf < 0 || (size_t)buf >= e->buffers.size()) return;
+	BufferInfo& b = e->buffers[(size_t)buf];
+	if (b.refs) --b.refs;
+	if (!b.refs && b.doomed && b.dptr) { if (b.owned) retire(e, nullptr, b.dptr); b.dptr = nullptr; b.n = 0; }
+}
+
+// Drops what a slot's feeder references: its PCM buffer, its MixZ range (back to the free list of that length) and the buffers
+// of its mix sources.  The reference frees an AudioSource's mix_sources and shared_buffer reference with the source.
+void detach_slot_refs(sbm_engine* e, uint32_t slot) {
+	if (e->slot_buf[slot] >= 0) { buffer_unref(e, e->slot_buf[slot]); e->slot_buf[slot] = -1; }
+	SrcStatic& st = e->h_stat[slot];
+	if (st.nz) {
+		for (uint32_t z = 0; z < st.nz; ++z) { buffer_unref(e, e->mixz_buf[st.mix_first + z]); e->mixz_buf[st.mix_first + z] = -1; }
+		e->mix_free[st.nz].push_back(st.mix_first);
+		st.nz = 0; st.mix_first = 0;
+	}
+}
+
 void kill_slot(sbm_engine* e, uint32_t slot) {
 	SrcStatic& st = e->h_stat[slot];
 	if (!(st.flags & kFlagAlive)) return;
 	if (st.id < e->slot_of_id.size()) e->slot_of_id[st.id] = -1;
 	st.flags &= ~kFlagAlive;
+	detach_slot_refs(e, slot);
 	e->d_stat.mark(slot);
-	if (e->rings[slot].storage) { dev::release(e->rings[slot].storage); e->rings[slot] = RingInfo{nullptr, 0, 0, 0}; }
+	if (e->rings[slot].storage) { retire(e, nullptr, e->rings[slot].storage); e->rings[slot] = RingInfo{nullptr, 0, 0, 0}; }
 	e->free_slots.push_back(slot);
 	e->lists_dirty = true;
 }
 
-template <class T> int upload_range(sbm_engine* e, T* dv, const std::vector<T>& h, DirtyRange& d) {
-	if (!d.any()) return 0;
-	const size_t bytes = sizeof(T) * (size_t)(d.hi - d.lo);
-	if (dev::h2d(dv + d.lo, h.data() + d.lo, bytes, e->stream)) return -1;
-	e->stats.last_h2d_bytes += bytes;
-	d.clear();
+// ---- staging ----
+// A region of `bytes` in the staging ring; grows the ring (the old one is retired, never waited for) when it is full.
+int stage_alloc(sbm_engine* e, size_t bytes, size_t* off) {
+	size_t at = e->stage.alloc(bytes);
+	if (at == (size_t)-1) {
+		const size_t want = std::max<size_t>(std::max<size_t>(e->stage.cap * 2, 4 * bytes + 4096), (size_t)1 << 20);
+		unsigned char* h = (unsigned char*)dev::alloc_pinned(want);
+		unsigned char* d = (unsigned char*)dev::alloc(want);
+		if (!h || !d) { dev::release_pinned(h); dev::release(d); return -1; }
+		retire(e, e->stage.h, e->stage.d);
+		e->stage.h = h; e->stage.d = d; e->stage.cap = want; e->stage.head = e->stage.tail = 0; e->stage.gen++;
+		at = e->stage.alloc(bytes);
+		if (at == (size_t)-1) return -1;
+	}
+	*off = at;
 	return 0;
 }
 
-template <class T> int upload_list(sbm_engine* e, T*& dv, uint32_t& cap, const std::vector<T>& h) {
-	if (h.empty()) return 0;
-	if (h.size() > cap) {
-		if (dv) { dev::sync(e->stream); dev::release(dv); }
-		cap = (uint32_t)std::max<size_t>(h.size() * 2, 1024);
-		if (!dalloc(dv, cap)) return -1;
+// ---- setter queue ----
+SetterRec* setter_new(uint32_t kind, uint32_t n, size_t payload_bytes) {
+	SetterRec* r = (SetterRec*)malloc(sizeof(SetterRec) + payload_bytes);
+	if (r) { r->next = nullptr; r->kind = kind; r->n = n; }
+	return r;
+}
+inline unsigned char* setter_payload(SetterRec* r) { return (unsigned char*)(r + 1); }
+void setter_push(sbm_engine* e, SetterRec* r) {
+	r->next = e->setq.load(std::memory_order_relaxed);
+	while (!e->setq.compare_exchange_weak(r->next, r, std::memory_order_release, std::memory_order_relaxed)) {}
+	e->setters_queued.fetch_add(1, std::memory_order_relaxed);
+}
+
+// ids[0..n) ascending by one AND their slots ascending by one (sources created in one batch): the batched setters then
+// touch one contiguous run of the mirrors.
+int contiguous_run(sbm_engine* e, uint32_t n, const int* ids) {
+	if (n < 1024) return -1;
+	const int s0 = slot_for(e, ids[0]);
+	if (s0 < 0 || (size_t)ids[0] + n > e->slot_of_id.size()) return -1;
+	for (uint32_t i = 1; i < n; ++i) if (ids[i] != ids[0] + (int)i) return -1;
+	const int* so = e->slot_of_id.data() + ids[0];
+	for (uint32_t i = 1; i < n; ++i) if (so[i] != s0 + (int)i) return -1;
+	return s0;
+}
+
+void apply_setter(sbm_engine* e, SetterRec* r) {
+	unsigned char* p = setter_payload(r);
+	const uint32_t n = r->n;
+	switch (r->kind) {
+	case kSetPositions: {
+		const int* ids = (const int*)p; const float* xyz = (const float*)(ids + n);
+		const int s0 = contiguous_run(e, n, ids);
+		for (uint32_t i = 0; i < n; ++i) {
+			const int slot = s0 >= 0 ? s0 + (int)i : slot_for(e, ids[i]);
+			if (slot < 0) { e->stats.ignored_setter_items++; continue; }
+			const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+			// AudioEngine drops non-finite poses before they reach Resonance (AudioEngine.cpp:951).
+			if (!(std::isfinite(x) && std::isfinite(y) && std::isfinite(z))) continue;
+			F4& q = e->h_posvol[(uint32_t)slot];
+			q.x = x; q.y = y; q.z = z;
+			if (s0 < 0) e->d_posvol.mark((uint32_t)slot);
+		}
+		if (s0 >= 0) e->d_posvol.mark_range((uint32_t)s0, (uint32_t)s0 + n);
+		break;
 	}
-	if (dev::h2d(dv, h.data(), sizeof(T) * h.size(), e->stream)) return -1;
-	e->stats.last_h2d_bytes += sizeof(T) * h.size();
-	return 0;
+	case kSetVolumes: case kSetOcclusions: {
+		const int* ids = (const int*)p; const float* v = (const float*)(ids + n);
+		const bool vol = r->kind == kSetVolumes;
+		DirtySet& ds = vol ? e->d_posvol : e->d_occl;
+		const int s0 = contiguous_run(e, n, ids);
+		for (uint32_t i = 0; i < n; ++i) {
+			const int slot = s0 >= 0 ? s0 + (int)i : slot_for(e, ids[i]);
+			if (slot < 0) { e->stats.ignored_setter_items++; continue; }
+			if (vol) e->h_posvol[(uint32_t)slot].w = v[i]; else e->h_occl[(uint32_t)slot] = v[i];
+			if (s0 < 0) ds.mark((uint32_t)slot);
+		}
+		if (s0 >= 0) ds.mark_range((uint32_t)s0, (uint32_t)s0 + n);
+		break;
+	}
+	case kSetHead: {
+		const float* f = (const float*)p;
+		memcpy(e->g.head_pos, f, 12); memcpy(e->g.head_q, f + 3, 16);
+		break;
+	}
+	case kSetMaster: e->g.master = *(const float*)p; break;
+	case kSetMixParams: {
+		const double* delta = (const double*)p; const int* ids = (const int*)(delta + n); const int* z = ids + n; const float* mixf = (const float*)(z + n);
+		for (uint32_t i = 0; i < n; ++i) {
+			const int slot = slot_for(e, ids[i]);
+			if (slot < 0) { e->stats.ignored_setter_items++; continue; }
+			const SrcStatic& st = e->h_stat[(uint32_t)slot];
+			if ((uint32_t)z[i] >= st.nz) { e->stats.ignored_setter_items++; continue; }
+			MixZ& m = e->h_mixz[st.mix_first + (uint32_t)z[i]];
+			m.delta = delta[i]; m.mix_factor = mixf[i];
+			e->d_mixz.mark(st.mix_first + (uint32_t)z[i]);
+		}
+		break;
+	}
+	default: break;
+	}
+}
+
+// Applies every queued setter call in the order it was queued (mixer thread, under e->mu).
+void drain_setters(sbm_engine* e) {
+	SetterRec* l = e->setq.exchange(nullptr, std::memory_order_acquire);
+	SetterRec* fifo = nullptr;
+	while (l) { SetterRec* nx = l->next; l->next = fifo; fifo = l; l = nx; }     // the stack holds the newest call first
+	while (fifo) { SetterRec* nx = fifo->next; apply_setter(e, fifo); free(fifo); fifo = nx; }
+}
+
+// ---- the per-buffer upload block ----
+// One pinned block = [kMaxUpSegs segment descriptors][values / element indices of every segment][patch lists], one H2D,
+// one kernel (k_apply_uploads) that copies or scatters every segment into its device array.
+struct SegPlan { void* dst; const unsigned char* src; DirtySet* ds; uint32_t elem_bytes; bool scatter; uint32_t count, lo; };
+
+template <class T> void plan_dirty(std::vector<SegPlan>& plans, T* dv, const std::vector<T>& mirror, DirtySet& ds) {
+	if (!ds.any()) return;
+	SegPlan p;
+	p.dst = dv; p.src = (const unsigned char*)mirror.data(); p.ds = &ds; p.elem_bytes = (uint32_t)sizeof(T);
+	const size_t span = (size_t)(ds.hi - ds.lo);
+	p.scatter = !ds.dense && ds.idx.size() * (sizeof(T) + 4) < span * sizeof(T);
+	p.count = p.scatter ? (uint32_t)ds.idx.size() : (uint32_t)span;
+	p.lo = ds.lo;
+	plans.push_back(p);
 }
 
 }  // namespace
@@ -211,6 +402,7 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	e->cfg.sh_hrir = nullptr;   // caller's pointer is not retained
 	memset(&e->stats, 0, sizeof(e->stats));
 	if (dev::init(cfg->device, &e->stream)) { const int rc = SBM_ERR_CUDA; fprintf(stderr, "sbm_create: %s\n", dev::last_error()); delete e; return rc; }
+	e->upload_stream = dev::stream_create();
 	const uint32_t cap = (uint32_t)cfg->max_sources;
 	const uint32_t mixcap = (uint32_t)std::max(cfg->max_mix_sources, 1);
 	const uint32_t F = (uint32_t)cfg->frames_per_buffer;
@@ -222,6 +414,9 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	e->h_mixz.assign(mixcap, MixZ{nullptr, 0, 0.0f, 0.0, 0.0});
 	e->rings.assign(cap, RingInfo{nullptr, 0, 0, 0});
 	e->patch_of_slot.assign(cap, -1);
+	e->slot_buf.assign(cap, -1);
+	e->mixz_buf.assign(mixcap, -1);
+	e->d_stat.init(cap); e->d_posvol.init(cap); e->d_occl.init(cap); e->d_ring.init(cap); e->d_mixz.init(mixcap);
 	bool ok = true;
 	SlotArrays& A = e->A;
 	ok = ok && dalloc(e->dv_stat, cap) && dalloc(e->dv_posvol, cap) && dalloc(e->dv_occl, cap) && dalloc(e->dv_ring_write, cap) && dalloc(e->dv_mixz, mixcap);
@@ -239,14 +434,14 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	ok = ok && dalloc(e->dv_bus, e->bus_floats);
 	e->partials_floats = dev::partials_floats(F);
 	ok = ok && dalloc(e->dv_partials, e->partials_floats);
-	e->out_bytes = sizeof(float) * 2 * F + sizeof(OutTail) + sizeof(unsigned long long) * (size_t)cap;
+	e->out_bytes = sizeof(float) * 2 * F + sizeof(OutTail) + sizeof(unsigned long long) * (size_t)cap + sizeof(int) * kInlineFinished;
 	e->dv_out = (float*)dev::alloc(e->out_bytes);
 	for (int k = 0; k < 2; ++k) {
 		e->fl[k].h_out = (unsigned char*)dev::alloc_pinned(e->out_bytes);
 		e->fl[k].dv_finished = A.finished ? A.finished + (size_t)k * cap : nullptr;
 		ok = ok && e->fl[k].h_out;
 	}
-	ok = ok && e->dv_out;
+	ok = ok && e->dv_out && e->upload_stream;
 	if (ok && hrtf) {
 		const size_t T = (size_t)cfg->sh_hrir_taps;
 		ok = dalloc(e->dv_hrir, kNumSh * T) && dalloc(e->dv_hist, kNumSh * T) && dalloc(e->dv_dec, 2 * (size_t)F);
@@ -273,11 +468,13 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	if (!e) return;
 	dev::use(e->cfg.device);
 	if (e->stream) dev::sync(e->stream);
+	if (e->upload_stream) dev::sync(e->upload_stream);
+	for (SetterRec* l = e->setq.exchange(nullptr); l;) { SetterRec* nx = l->next; free(l); l = nx; }
 	SlotArrays& A = e->A;
 	void* ptrs[] = {e->dv_stat, e->dv_posvol, e->dv_occl, e->dv_ring_write, e->dv_mixz, A.live, A.read_i, A.eof, A.rs, A.dgain, A.occ_cur,
 	                A.lpf_prev, A.bits, A.rec, e->fl[0].dv_finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
 	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
-	                e->dv_hist, e->dv_dec, e->dv_patches, e->dv_mix_patches};
+	                e->dv_hist, e->dv_dec};
 	for (void* p : ptrs) if (p) dev::release(p);
 	for (auto& b : e->buffers) if (b.owned && b.dptr) dev::release(b.dptr);
 	for (auto& r : e->rings) if (r.storage) dev::release(r.storage);
@@ -289,8 +486,10 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	for (void* m : e->peer_mapped) dev::peer_close(m);
 	if (e->dv_gather) dev::release(e->dv_gather);
 	if (e->dv_bus_sum) dev::release(e->dv_bus_sum);
-	if (e->h_ring_stage) dev::release_pinned(e->h_ring_stage);
-	if (e->d_ring_stage) dev::release(e->d_ring_stage);
+	free_retired(e, true);
+	if (e->stage.h) dev::release_pinned(e->stage.h);
+	if (e->stage.d) dev::release(e->stage.d);
+	if (e->upload_stream) dev::shutdown(e->upload_stream);
 	dev::shutdown(e->stream);
 	delete e;
 }
@@ -302,12 +501,14 @@ SBM_API const char* sbm_last_error(const sbm_engine* e) { return e ? e->error.c_
 // ---------------------------------------------------------------------------------------------------------------
 SBM_API int sbm_buffer_create(sbm_engine* e, const float* samples, size_t n, int* out_buffer) {
 	if (!e || !samples || n == 0 || !out_buffer || n > 0xfffffff0ull) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
 	dev::use(e->cfg.device);
+	// allocation + upload happen outside the engine lock, on their own stream: a long sound file neither waits for the
+	// buffers in flight nor keeps the mixer thread out of the engine
 	float* d = (float*)dev::alloc(sizeof(float) * (n + 8));   // slack: the mix kernel may read whole 32-byte sectors
 	if (!d) return fail_cuda(e, "sbm_buffer_create");
-	if (dev::h2d(d, samples, sizeof(float) * n, e->stream) || dev::sync(e->stream)) { dev::release(d); return fail_cuda(e, "sbm_buffer_create"); }
-	e->buffers.push_back(BufferInfo{d, n, true});
+	if (dev::h2d(d, samples, sizeof(float) * n, e->upload_stream) || dev::sync(e->upload_stream)) { dev::release(d); return fail_cuda(e, "sbm_buffer_create"); }
+	std::lock_guard<std::mutex> lk(e->mu);
+	e->buffers.push_back(BufferInfo{d, n, true, 0, false});
 	*out_buffer = (int)e->buffers.size() - 1;
 	return SBM_OK;
 }
@@ -318,7 +519,18 @@ SBM_API int sbm_buffer_adopt_device(sbm_engine* e, const float* device_base, siz
 	dev::use(e->cfg.device);
 	*out_first_buffer = (int)e->buffers.size();
 	e->buffers.reserve(e->buffers.size() + (size_t)count);
-	for (int k = 0; k < count; ++k) e->buffers.push_back(BufferInfo{const_cast<float*>(device_base) + (size_t)k * stride_samples, n, false});
+	for (int k = 0; k < count; ++k) e->buffers.push_back(BufferInfo{const_cast<float*>(device_base) + (size_t)k * stride_samples, n, false, 0, false});
+	return SBM_OK;
+}
+
+SBM_API int sbm_buffer_destroy(sbm_engine* e, int buffer) {
+	if (!e) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	if (buffer < 0 || (size_t)buffer >= e->buffers.size() || !e->buffers[(size_t)buffer].dptr) return SBM_ERR_UNKNOWN_ID;
+	BufferInfo& b = e->buffers[(size_t)buffer];
+	b.doomed = true;
+	if (!b.refs) { if (b.owned) retire(e, nullptr, b.dptr); b.dptr = nullptr; b.n = 0; }
 	return SBM_OK;
 }
 
@@ -376,11 +588,13 @@ SBM_API int sbm_source_attach_buffer(sbm_engine* e, int n, const int* ids, const
 	for (int i = 0; i < n; ++i) {
 		const int slot = slot_for(e, ids[i]);
 		if (slot < 0) { rc = SBM_ERR_UNKNOWN_ID; continue; }
-		if (buffers[i] < 0 || (size_t)buffers[i] >= e->buffers.size()) { rc = SBM_ERR_INVALID_ARG; continue; }
+		if (buffers[i] < 0 || (size_t)buffers[i] >= e->buffers.size() || !e->buffers[(size_t)buffers[i]].dptr || e->buffers[(size_t)buffers[i]].doomed) { rc = SBM_ERR_INVALID_ARG; continue; }
 		const int rate = sampling_rate ? sampling_rate[i] : e->cfg.sample_rate_hz;
 		// AudioEngine::addSource rejects rates outside 8000..48000 (AudioEngine.cpp:884-885).
 		if (rate < 8000 || rate > 48000) { rc = fail(e, SBM_ERR_INVALID_ARG, "Unsupported sampling rate for audio source"); continue; }
-		const BufferInfo& b = e->buffers[(size_t)buffers[i]];
+		detach_slot_refs(e, (uint32_t)slot);
+		BufferInfo& b = e->buffers[(size_t)buffers[i]];
+		b.refs++; e->slot_buf[(uint32_t)slot] = buffers[i];
 		SrcStatic& st = e->h_stat[(uint32_t)slot];
 		st.pcm = b.dptr; st.len = (uint32_t)b.n; st.rate = rate;
 		st.flags &= ~(kFlagLooping | kFlagRemoveOnFinish | (3u << kFlagFeedShift));
@@ -397,14 +611,16 @@ SBM_API int sbm_source_attach_buffer(sbm_engine* e, int n, const int* ids, const
 SBM_API int sbm_source_attach_ring(sbm_engine* e, int id, int sampling_rate, int capacity_samples) {
 	if (!e || capacity_samples < 64) return SBM_ERR_INVALID_ARG;
 	if (sampling_rate < 8000 || sampling_rate > 48000) return fail(e, SBM_ERR_INVALID_ARG, "Unsupported sampling rate for audio source");
-	std::lock_guard<std::mutex> lk(e->mu);
 	dev::use(e->cfg.device);
+	float* storage = (float*)dev::alloc(sizeof(float) * ((size_t)capacity_samples + 8));
+	if (!storage) return fail_cuda(e, "sbm_source_attach_ring");
+	std::lock_guard<std::mutex> lk(e->mu);
 	const int slot = slot_for(e, id);
-	if (slot < 0) return SBM_ERR_UNKNOWN_ID;
+	if (slot < 0) { dev::release(storage); return SBM_ERR_UNKNOWN_ID; }
+	detach_slot_refs(e, (uint32_t)slot);
 	RingInfo& r = e->rings[(uint32_t)slot];
-	if (r.storage) { dev::sync(e->stream); dev::release(r.storage); }
-	r = RingInfo{(float*)dev::alloc(sizeof(float) * ((size_t)capacity_samples + 8)), (uint32_t)capacity_samples, 0, 0};
-	if (!r.storage) return fail_cuda(e, "sbm_source_attach_ring");
+	if (r.storage) retire(e, nullptr, r.storage);
+	r = RingInfo{storage, (uint32_t)capacity_samples, 0, 0};
 	SrcStatic& st = e->h_stat[(uint32_t)slot];
 	st.pcm = r.storage; st.len = (uint32_t)capacity_samples; st.rate = sampling_rate;
 	st.flags &= ~(3u << kFlagFeedShift);
@@ -416,45 +632,15 @@ SBM_API int sbm_source_attach_ring(sbm_engine* e, int id, int sampling_rate, int
 	return SBM_OK;
 }
 
-SBM_API int sbm_source_ring_push(sbm_engine* e, int id, const float* samples, size_t n) {
-	if (!e || (!samples && n)) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
-	const int slot = slot_for(e, id);
-	if (slot < 0) return SBM_ERR_UNKNOWN_ID;
-	RingInfo& r = e->rings[(uint32_t)slot];
-	if (!r.storage) return fail(e, SBM_ERR_INVALID_ARG, "source is not ring-fed");
-	if (r.written - r.read_known + n > r.capacity) return fail(e, SBM_ERR_CAPACITY, "ring full");
-	size_t done = 0;
-	while (done < n) {
-		const uint32_t at = (uint32_t)((r.written + done) % r.capacity);
-		const size_t chunk = std::min<size_t>(n - done, r.capacity - at);
-		if (dev::h2d(r.storage + at, samples + done, sizeof(float) * chunk, e->stream)) return fail_cuda(e, "sbm_source_ring_push");
-		done += chunk;
-	}
-	// The packet is copied from the caller's memory asynchronously only if it is pinned; make the call safe for any memory.
-	if (dev::sync(e->stream)) return fail_cuda(e, "sbm_source_ring_push");
-	e->pending_ring_h2d_bytes += sizeof(float) * n;
-	r.written += n;
-	e->h_ring_write[(uint32_t)slot] = r.written;
-	e->d_ring.mark((uint32_t)slot);
-	return SBM_OK;
-}
-
-// Batched form of sbm_source_ring_push: the packets of MANY ring-fed sources in one call (what the voice / streaming threads
-// deliver between two buffers).  All payloads and the packet table are staged in one pinned buffer, cross PCIe as ONE
-// copy, and a scatter kernel writes each packet into its source's ring -- instead of one copy + one stream
-// synchronisation per source.  offsets[k] .. offsets[k + 1] is packet k inside `samples`.  Either every packet is
-// accepted or none (ring full / unknown id -> nothing is written).
-SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, const float* samples, const size_t* offsets) {
-	if (!e || n < 0 || (n && (!ids || !samples || !offsets))) return SBM_ERR_INVALID_ARG;
-	if (!n) return SBM_OK;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
+// Batched ring push: the packets of MANY ring-fed sources in one call (what the voice / streaming threads deliver between
+// two buffers).  Packet table and payloads are staged in the engine's pinned staging ring, cross PCIe as ONE copy, and a
+// scatter kernel writes each packet into its source's ring -- no stream synchronisation.  offsets[k] .. offsets[k + 1] is
+// packet k inside `samples`.  Either every packet is accepted or none (ring full / unknown id -> nothing is written).
+static int ring_push_locked(sbm_engine* e, int n, const int* ids, const float* samples, const size_t* offsets) {
 	const size_t total = offsets[n] - offsets[0];
 	std::vector<RingPush> pk((size_t)n);
 	std::vector<uint32_t> slots((size_t)n);
-	std::vector<unsigned long long> pending(e->rings.size(), 0);     // samples accepted earlier in this call, per slot
+	std::map<uint32_t, unsigned long long> pending;     // samples accepted earlier in this call, per slot
 	for (int k = 0; k < n; ++k) {
 		const int slot = slot_for(e, ids[k]);
 		if (slot < 0) return SBM_ERR_UNKNOWN_ID;
@@ -471,33 +657,24 @@ SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, con
 	// staging layout: [packet table, padded to 256 B][payload]
 	const size_t table_bytes = (sizeof(RingPush) * (size_t)n + 255) & ~(size_t)255;
 	const size_t bytes = table_bytes + sizeof(float) * total;
-	if (e->ring_stage_in_flight) { if (dev::sync(e->stream)) return fail_cuda(e, "sbm_source_ring_push_batch"); e->ring_stage_in_flight = false; }
-	e->ring_stage_seq = e->buffer_index;
-	if (bytes > e->ring_stage_bytes) {
-		dev::sync(e->stream);
-		dev::release_pinned(e->h_ring_stage); dev::release(e->d_ring_stage);
-		e->ring_stage_bytes = std::max<size_t>(bytes * 2, 1 << 20);
-		e->h_ring_stage = (unsigned char*)dev::alloc_pinned(e->ring_stage_bytes);
-		e->d_ring_stage = (unsigned char*)dev::alloc(e->ring_stage_bytes);
-		if (!e->h_ring_stage || !e->d_ring_stage) { e->ring_stage_bytes = 0; return fail_cuda(e, "sbm_source_ring_push_batch(alloc)"); }
-	}
-	memcpy(e->h_ring_stage, pk.data(), sizeof(RingPush) * (size_t)n);
+	size_t off;
+	if (stage_alloc(e, bytes, &off)) return fail_cuda(e, "sbm_source_ring_push(staging)");
+	unsigned char* hs = e->stage.h + off;
+	unsigned char* ds = e->stage.d + off;
+	memcpy(hs, pk.data(), sizeof(RingPush) * (size_t)n);
 	// A payload that already lives in page-locked memory (sbm_host_alloc_pinned, cudaHostRegister ...) is copied to the
-	// device straight from the caller's buffer -- it must then stay unmodified until the next sbm_mix / sbm_mix_collect
-	// returns; anything else is first copied into the engine's own pinned staging buffer.
-	const bool direct = dev::is_pinned(samples + offsets[0]);
+	// device straight from the caller's buffer (see the header for how long it must stay unmodified); anything else is
+	// first copied into the staging ring.
+	const bool direct = total && dev::is_pinned(samples + offsets[0]);
 	int rc;
 	if (direct) {
-		rc = dev::h2d(e->d_ring_stage, e->h_ring_stage, table_bytes, e->stream) ||
-		     dev::h2d(e->d_ring_stage + table_bytes, samples + offsets[0], sizeof(float) * total, e->stream);
+		rc = dev::h2d(ds, hs, table_bytes, e->stream) || dev::h2d(ds + table_bytes, samples + offsets[0], sizeof(float) * total, e->stream);
 	} else {
-		memcpy(e->h_ring_stage + table_bytes, samples + offsets[0], sizeof(float) * total);
-		rc = dev::h2d(e->d_ring_stage, e->h_ring_stage, bytes, e->stream);
+		memcpy(hs + table_bytes, samples + offsets[0], sizeof(float) * total);
+		rc = dev::h2d(ds, hs, bytes, e->stream);
 	}
-	if (rc ||
-	    dev::launch_ring_scatter((const RingPush*)e->d_ring_stage, (uint32_t)n, (const float*)(e->d_ring_stage + table_bytes), e->stream))
-		return fail_cuda(e, "sbm_source_ring_push_batch");
-	e->ring_stage_in_flight = true;      // the pinned staging buffer is reused: the next push waits for this copy
+	if (rc || dev::launch_ring_scatter((const RingPush*)ds, (uint32_t)n, (const float*)(ds + table_bytes), e->stream))
+		return fail_cuda(e, "sbm_source_ring_push");
 	e->pending_ring_h2d_bytes += bytes;
 	for (int k = 0; k < n; ++k) {
 		RingInfo& r = e->rings[slots[(size_t)k]];
@@ -508,6 +685,23 @@ SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, con
 	return SBM_OK;
 }
 
+SBM_API int sbm_source_ring_push_batch(sbm_engine* e, int n, const int* ids, const float* samples, const size_t* offsets) {
+	if (!e || n < 0 || (n && (!ids || !samples || !offsets))) return SBM_ERR_INVALID_ARG;
+	if (!n) return SBM_OK;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	return ring_push_locked(e, n, ids, samples, offsets);
+}
+
+SBM_API int sbm_source_ring_push(sbm_engine* e, int id, const float* samples, size_t n) {
+	if (!e || (!samples && n)) return SBM_ERR_INVALID_ARG;
+	if (!n) return SBM_OK;
+	const size_t offsets[2] = {0, n};
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	return ring_push_locked(e, 1, &id, samples, offsets);
+}
+
 // Page-locked host memory for callers that do not link CUDA themselves (packet payloads for sbm_source_ring_push_batch,
 // PCM for sbm_buffer_create): copies from it need no staging.
 SBM_API void* sbm_host_alloc_pinned(size_t bytes) { return dev::alloc_pinned(bytes); }
@@ -516,7 +710,6 @@ SBM_API void sbm_host_free_pinned(void* p) { dev::release_pinned(p); }
 SBM_API int sbm_source_ring_size(sbm_engine* e, int id, uint64_t* out_size) {
 	if (!e || !out_size) return SBM_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
 	const int slot = slot_for(e, id);
 	if (slot < 0) return SBM_ERR_UNKNOWN_ID;
 	const RingInfo& r = e->rings[(uint32_t)slot];
@@ -532,17 +725,30 @@ static int attach_mix_locked(sbm_engine* e, int id, int sampling_rate, int nz, c
 	// through AudioResampler in the reference (AudioEngine.cpp:485-494).  Not needed by Substrata's callers (BikePhysics
 	// uses the engine rate); rejected rather than rendered differently.
 	if (sampling_rate != e->cfg.sample_rate_hz) return fail(e, SBM_ERR_UNSUPPORTED, "mix_sources at a rate other than the engine rate");
-	if (e->mix_used + (uint32_t)nz > e->h_mixz.size()) return fail(e, SBM_ERR_CAPACITY, "max_mix_sources exceeded");
-	for (int z = 0; z < nz; ++z) if (buffers[z] < 0 || (size_t)buffers[z] >= e->buffers.size()) return SBM_ERR_INVALID_ARG;
-	const uint32_t first = e->mix_used;
-	e->mix_used += (uint32_t)nz;
+	for (int z = 0; z < nz; ++z)
+		if (buffers[z] < 0 || (size_t)buffers[z] >= e->buffers.size() || !e->buffers[(size_t)buffers[z]].dptr || e->buffers[(size_t)buffers[z]].doomed) return SBM_ERR_INVALID_ARG;
+	SrcStatic& st = e->h_stat[(uint32_t)slot];
+	// a range of nz MixZ entries: the slot's own when it already has one of that length, else a recycled one, else fresh
+	uint32_t first;
+	std::vector<uint32_t>* fr = nullptr;
+	if (st.nz != (uint32_t)nz) { auto it = e->mix_free.find((uint32_t)nz); if (it != e->mix_free.end() && !it->second.empty()) fr = &it->second; }
+	if (st.nz != (uint32_t)nz && !fr && e->mix_used + (uint32_t)nz > e->h_mixz.size()) return fail(e, SBM_ERR_CAPACITY, "max_mix_sources exceeded");
+	if (st.nz == (uint32_t)nz) {
+		first = st.mix_first;
+		for (int z = 0; z < nz; ++z) { buffer_unref(e, e->mixz_buf[first + (uint32_t)z]); e->mixz_buf[first + (uint32_t)z] = -1; }
+		if (e->slot_buf[(uint32_t)slot] >= 0) { buffer_unref(e, e->slot_buf[(uint32_t)slot]); e->slot_buf[(uint32_t)slot] = -1; }
+	} else {
+		detach_slot_refs(e, (uint32_t)slot);
+		if (fr) { first = fr->back(); fr->pop_back(); }
+		else { first = e->mix_used; e->mix_used += (uint32_t)nz; }
+	}
 	for (int z = 0; z < nz; ++z) {
-		const BufferInfo& b = e->buffers[(size_t)buffers[z]];
+		BufferInfo& b = e->buffers[(size_t)buffers[z]];
+		b.refs++; e->mixz_buf[first + (uint32_t)z] = buffers[z];
 		e->h_mixz[first + (uint32_t)z] = MixZ{b.dptr, (uint32_t)b.n, mixf[z], delta[z], 0.0};
 		e->d_mixz.mark(first + (uint32_t)z);
 		e->mix_patches.push_back(MixPatch{first + (uint32_t)z, 0, pos[z]});
 	}
-	SrcStatic& st = e->h_stat[(uint32_t)slot];
 	st.rate = sampling_rate; st.mix_first = first; st.nz = (uint32_t)nz;
 	st.flags &= ~(3u << kFlagFeedShift);
 	st.flags |= (kFeedMix << kFlagFeedShift);
@@ -574,28 +780,9 @@ SBM_API int sbm_source_attach_mix1(sbm_engine* e, int n, const int* ids, const i
 	return SBM_OK;
 }
 
-SBM_API int sbm_source_set_mix_params(sbm_engine* e, int n, const int* ids, const int* z, const double* source_delta, const float* mix_factor) {
-	if (!e || n < 0 || !ids || !source_delta || !mix_factor) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
-	int rc = SBM_OK;
-	for (int i = 0; i < n; ++i) {
-		const int slot = slot_for(e, ids[i]);
-		if (slot < 0) { rc = SBM_ERR_UNKNOWN_ID; continue; }
-		const SrcStatic& st = e->h_stat[(uint32_t)slot];
-		const uint32_t zz = z ? (uint32_t)z[i] : 0u;
-		if (zz >= st.nz) { rc = SBM_ERR_INVALID_ARG; continue; }
-		MixZ& m = e->h_mixz[st.mix_first + zz];
-		m.delta = source_delta[i]; m.mix_factor = mix_factor[i];
-		e->d_mixz.mark(st.mix_first + zz);
-	}
-	return rc;
-}
-
 SBM_API int sbm_source_set_eof_marker(sbm_engine* e, int id, int64_t samples_to_eof) {
 	if (!e) return SBM_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
 	const int slot = slot_for(e, id);
 	if (slot < 0) return SBM_ERR_UNKNOWN_ID;
 	add_patch(e, SlotPatch{(uint32_t)slot, kPatchEof, 0ull, (long long)samples_to_eof, 0, 0});
@@ -605,7 +792,6 @@ SBM_API int sbm_source_set_eof_marker(sbm_engine* e, int id, int64_t samples_to_
 SBM_API int sbm_source_set_looping(sbm_engine* e, int id, int looping) {
 	if (!e) return SBM_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
 	const int slot = slot_for(e, id);
 	if (slot < 0) return SBM_ERR_UNKNOWN_ID;
 	SrcStatic& st = e->h_stat[(uint32_t)slot];
@@ -615,70 +801,55 @@ SBM_API int sbm_source_set_looping(sbm_engine* e, int id, int looping) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// setters
+// setters: lock-free, any thread, never wait for the mixer or the GPU.  Each call is one record in an MPSC queue, applied by
+// the mixer thread at the start of the next buffer in the order queued.  Ids that are unknown (or already destroyed) by
+// then are ignored like Resonance ignores them (resonance_audio_api_impl.cc:551-554) and counted in sbm_stats.
 // ---------------------------------------------------------------------------------------------------------------
-SBM_API int sbm_set_source_positions(sbm_engine* e, int n, const int* ids, const float* xyz) {
-	if (!e || n < 0 || (n && (!ids || !xyz))) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
-	int rc = SBM_OK;
-	for (int i = 0; i < n; ++i) {
-		const int slot = slot_for(e, ids[i]);
-		if (slot < 0) { rc = SBM_ERR_UNKNOWN_ID; continue; }
-		const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-		// AudioEngine drops non-finite poses before they reach Resonance (AudioEngine.cpp:951).
-		if (!(std::isfinite(x) && std::isfinite(y) && std::isfinite(z))) continue;
-		F4& p = e->h_posvol[(uint32_t)slot];
-		p.x = x; p.y = y; p.z = z;
-		e->d_posvol.mark((uint32_t)slot);
-	}
-	return rc;
+static int queue_ids_floats(sbm_engine* e, uint32_t kind, int n, const int* ids, const float* v, int per) {
+	if (!e || n < 0 || (n && (!ids || !v))) return SBM_ERR_INVALID_ARG;
+	if (!n) return SBM_OK;
+	SetterRec* r = setter_new(kind, (uint32_t)n, (size_t)n * (4 + 4 * (size_t)per));
+	if (!r) return SBM_ERR_NO_MEMORY;
+	unsigned char* p = setter_payload(r);
+	memcpy(p, ids, 4 * (size_t)n);
+	memcpy(p + 4 * (size_t)n, v, 4 * (size_t)per * (size_t)n);
+	setter_push(e, r);
+	return SBM_OK;
 }
+SBM_API int sbm_set_source_positions(sbm_engine* e, int n, const int* ids, const float* xyz) { return queue_ids_floats(e, kSetPositions, n, ids, xyz, 3); }
+SBM_API int sbm_set_source_volumes(sbm_engine* e, int n, const int* ids, const float* volume) { return queue_ids_floats(e, kSetVolumes, n, ids, volume, 1); }
+SBM_API int sbm_set_source_occlusions(sbm_engine* e, int n, const int* ids, const float* occ) { return queue_ids_floats(e, kSetOcclusions, n, ids, occ, 1); }
 
-SBM_API int sbm_set_source_volumes(sbm_engine* e, int n, const int* ids, const float* volume) {
-	if (!e || n < 0 || (n && (!ids || !volume))) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
-	int rc = SBM_OK;
-	for (int i = 0; i < n; ++i) {
-		const int slot = slot_for(e, ids[i]);
-		if (slot < 0) { rc = SBM_ERR_UNKNOWN_ID; continue; }
-		e->h_posvol[(uint32_t)slot].w = volume[i];
-		e->d_posvol.mark((uint32_t)slot);
-	}
-	return rc;
-}
-
-SBM_API int sbm_set_source_occlusions(sbm_engine* e, int n, const int* ids, const float* occ) {
-	if (!e || n < 0 || (n && (!ids || !occ))) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
-	int rc = SBM_OK;
-	for (int i = 0; i < n; ++i) {
-		const int slot = slot_for(e, ids[i]);
-		if (slot < 0) { rc = SBM_ERR_UNKNOWN_ID; continue; }
-		e->h_occl[(uint32_t)slot] = occ[i];
-		e->d_occl.mark((uint32_t)slot);
-	}
-	return rc;
+SBM_API int sbm_source_set_mix_params(sbm_engine* e, int n, const int* ids, const int* z, const double* source_delta, const float* mix_factor) {
+	if (!e || n < 0 || !ids || !source_delta || !mix_factor) return SBM_ERR_INVALID_ARG;
+	if (!n) return SBM_OK;
+	SetterRec* r = setter_new(kSetMixParams, (uint32_t)n, (size_t)n * 20);
+	if (!r) return SBM_ERR_NO_MEMORY;
+	double* d = (double*)setter_payload(r); int* pi = (int*)(d + n); int* pz = pi + n; float* pm = (float*)(pz + n);
+	memcpy(d, source_delta, 8 * (size_t)n); memcpy(pi, ids, 4 * (size_t)n);
+	if (z) memcpy(pz, z, 4 * (size_t)n); else memset(pz, 0, 4 * (size_t)n);
+	memcpy(pm, mix_factor, 4 * (size_t)n);
+	setter_push(e, r);
+	return SBM_OK;
 }
 
 SBM_API int sbm_set_head(sbm_engine* e, const float* pos, const float* q) {
 	if (!e || !pos || !q) return SBM_ERR_INVALID_ARG;
 	for (int i = 0; i < 3; ++i) if (!std::isfinite(pos[i])) return SBM_OK;   // AudioEngine.cpp:985
 	for (int i = 0; i < 4; ++i) if (!std::isfinite(q[i])) return SBM_OK;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
-	memcpy(e->g.head_pos, pos, 12);
-	memcpy(e->g.head_q, q, 16);
+	SetterRec* r = setter_new(kSetHead, 0, 28);
+	if (!r) return SBM_ERR_NO_MEMORY;
+	memcpy(setter_payload(r), pos, 12); memcpy(setter_payload(r) + 12, q, 16);
+	setter_push(e, r);
 	return SBM_OK;
 }
 
 SBM_API int sbm_set_master_volume(sbm_engine* e, float volume) {
 	if (!e) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
-	e->g.master = volume;
+	SetterRec* r = setter_new(kSetMaster, 0, 4);
+	if (!r) return SBM_ERR_NO_MEMORY;
+	memcpy(setter_payload(r), &volume, 4);
+	setter_push(e, r);
 	return SBM_OK;
 }
 
@@ -690,11 +861,71 @@ SBM_API int sbm_enable_room_effects(sbm_engine* e, int enable) {
 // ---------------------------------------------------------------------------------------------------------------
 // the per-buffer call
 // ---------------------------------------------------------------------------------------------------------------
-// One buffer = sbm_mix_begin (uploads, K1, K2, K3) -> [the caller may sum buses across ranks here] -> the finish part
-// (gather, K4, D2H of the result into pinned memory, an event) -> collection (wait for the event, hand the samples out,
-// host bookkeeping).  sbm_mix / sbm_mix_finish do all of it synchronously; sbm_mix_submit + sbm_mix_collect split it so
-// that up to two buffers are in flight and the host's launch latency hides behind the previous buffer's kernels -- the
-// mixer thread of the reference also runs ahead of the device callback (AudioEngine.cpp:540-545).
+// One buffer = sbm_mix_begin (queued setters applied, ONE upload block, K1, K2, K3) -> [the caller may sum buses across
+// ranks here] -> the finish part (gather, K4, D2H of the result into pinned memory, an event) -> collection (wait for the
+// event WITHOUT the engine lock, hand the samples out, host bookkeeping).  sbm_mix / sbm_mix_finish do all of it
+// synchronously; sbm_mix_submit + sbm_mix_collect split it so that up to two buffers are in flight and the host's launch
+// latency hides behind the previous buffer's kernels -- the mixer thread of the reference also runs ahead of the device
+// callback (AudioEngine.cpp:540-545).
+static int upload_block_locked(sbm_engine* e, const SlotPatch** d_patches, const MixPatch** d_mix_patches) {
+	std::vector<SegPlan> plans;
+	plan_dirty(plans, e->dv_stat, e->h_stat, e->d_stat);
+	plan_dirty(plans, e->dv_posvol, e->h_posvol, e->d_posvol);
+	plan_dirty(plans, e->dv_occl, e->h_occl, e->d_occl);
+	plan_dirty(plans, e->dv_ring_write, e->h_ring_write, e->d_ring);
+	plan_dirty(plans, e->dv_mixz, e->h_mixz, e->d_mixz);
+	if (e->lists_dirty) {
+		rebuild_lists(e);
+		// the render lists travel as plain contiguous segments
+		if (!e->list_pan.empty()) plans.push_back(SegPlan{e->dv_lists, (const unsigned char*)e->list_pan.data(), nullptr, 4, false, (uint32_t)e->list_pan.size(), 0});
+		if (!e->list_sh.empty()) plans.push_back(SegPlan{e->dv_lists + e->list_pan.size(), (const unsigned char*)e->list_sh.data(), nullptr, 4, false, (uint32_t)e->list_sh.size(), 0});
+		if (!e->list_ring.empty()) plans.push_back(SegPlan{e->dv_list_ring, (const unsigned char*)e->list_ring.data(), nullptr, 4, false, (uint32_t)e->list_ring.size(), 0});
+	}
+	*d_patches = nullptr; *d_mix_patches = nullptr;
+	if (plans.empty() && e->patches.empty() && e->mix_patches.empty()) return 0;
+	if (plans.size() > (size_t)kMaxUpSegs) return -1;
+	// layout
+	size_t bytes = sizeof(UpSeg) * kMaxUpSegs;
+	std::vector<size_t> val_off(plans.size()), idx_off(plans.size());
+	for (size_t k = 0; k < plans.size(); ++k) {
+		const SegPlan& p = plans[k];
+		val_off[k] = bytes; bytes += ((size_t)p.count * p.elem_bytes + 15) & ~(size_t)15;
+		idx_off[k] = bytes; if (p.scatter) bytes += ((size_t)p.count * 4 + 15) & ~(size_t)15;
+	}
+	const size_t patch_off = bytes; bytes += (sizeof(SlotPatch) * e->patches.size() + 15) & ~(size_t)15;
+	const size_t mpatch_off = bytes; bytes += (sizeof(MixPatch) * e->mix_patches.size() + 15) & ~(size_t)15;
+	size_t off;
+	if (stage_alloc(e, bytes, &off)) return -1;
+	unsigned char* hs = e->stage.h + off;
+	unsigned char* ds = e->stage.d + off;
+	UpSeg* segs = (UpSeg*)hs;
+	uint32_t max_words = 0;
+	for (size_t k = 0; k < plans.size(); ++k) {
+		const SegPlan& p = plans[k];
+		UpSeg& sg = segs[k];
+		sg.elem_words = p.elem_bytes / 4; sg.count = p.count; sg.src_word = (uint32_t)(val_off[k] / 4); sg.pad = 0;
+		unsigned char* vals = hs + val_off[k];
+		if (p.scatter) {
+			uint32_t* ix = (uint32_t*)(hs + idx_off[k]);
+			for (uint32_t j = 0; j < p.count; ++j) { const uint32_t i = p.ds->idx[j]; ix[j] = i; memcpy(vals + (size_t)j * p.elem_bytes, p.src + (size_t)i * p.elem_bytes, p.elem_bytes); }
+			sg.dst = p.dst; sg.idx_word = (uint32_t)(idx_off[k] / 4);
+		} else {
+			memcpy(vals, p.src + (size_t)p.lo * p.elem_bytes, (size_t)p.count * p.elem_bytes);
+			sg.dst = (unsigned char*)p.dst + (size_t)p.lo * p.elem_bytes; sg.idx_word = 0xffffffffu;
+		}
+		max_words = std::max(max_words, sg.elem_words * sg.count);
+		if (p.ds) p.ds->clear();
+	}
+	if (!e->patches.empty()) memcpy(hs + patch_off, e->patches.data(), sizeof(SlotPatch) * e->patches.size());
+	if (!e->mix_patches.empty()) memcpy(hs + mpatch_off, e->mix_patches.data(), sizeof(MixPatch) * e->mix_patches.size());
+	if (dev::h2d(ds, hs, bytes, e->stream)) return -1;
+	e->stats.last_h2d_bytes += bytes;
+	if (!plans.empty() && dev::launch_apply_uploads((const UpSeg*)ds, (uint32_t)plans.size(), (const uint32_t*)ds, max_words, e->stream)) return -1;
+	*d_patches = (const SlotPatch*)(ds + patch_off);
+	*d_mix_patches = (const MixPatch*)(ds + mpatch_off);
+	return 0;
+}
+
 static int mix_begin_locked(sbm_engine* e) {
 	if (e->begun) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_begin called twice without sbm_mix_finish");
 	sbm_engine::InFlight& fl = e->fl[e->buffer_index & 1];
@@ -703,25 +934,13 @@ static int mix_begin_locked(sbm_engine* e) {
 	e->stats.last_h2d_bytes = e->pending_ring_h2d_bytes; e->stats.last_d2h_bytes = 0;
 	e->pending_ring_h2d_bytes = 0;
 	void* st = e->stream;
-	// 1. pending parameter uploads
-	if (upload_range(e, e->dv_stat, e->h_stat, e->d_stat) || upload_range(e, e->dv_posvol, e->h_posvol, e->d_posvol) ||
-	    upload_range(e, e->dv_occl, e->h_occl, e->d_occl) || upload_range(e, e->dv_ring_write, e->h_ring_write, e->d_ring) ||
-	    upload_range(e, e->dv_mixz, e->h_mixz, e->d_mixz))
-		return fail_cuda(e, "sbm_mix_begin(upload)");
-	if (e->lists_dirty) {
-		rebuild_lists(e);
-		if ((!e->list_pan.empty() && dev::h2d(e->dv_lists, e->list_pan.data(), 4 * e->list_pan.size(), st)) ||
-		    (!e->list_sh.empty() && dev::h2d(e->dv_lists + e->list_pan.size(), e->list_sh.data(), 4 * e->list_sh.size(), st)) ||
-		    (!e->list_ring.empty() && dev::h2d(e->dv_list_ring, e->list_ring.data(), 4 * e->list_ring.size(), st)))
-			return fail_cuda(e, "sbm_mix_begin(lists)");
-		e->stats.last_h2d_bytes += 4 * (e->list_pan.size() + e->list_sh.size() + e->list_ring.size());
-	}
+	// 1. queued setters -> mirrors; everything the host changed since the last buffer -> ONE block, one copy, one kernel
+	drain_setters(e);
+	const SlotPatch* d_patches; const MixPatch* d_mix_patches;
+	if (upload_block_locked(e, &d_patches, &d_mix_patches)) return fail_cuda(e, "sbm_mix_begin(upload)");
 	if (!e->patches.empty() || !e->mix_patches.empty()) {
-		if (upload_list(e, e->dv_patches, e->dv_patches_cap, e->patches) || upload_list(e, e->dv_mix_patches, e->dv_mix_patches_cap, e->mix_patches))
-			return fail_cuda(e, "sbm_mix_begin(patches)");
-		if (dev::launch_patch(e->A, e->dv_patches, (uint32_t)e->patches.size(), e->dv_mix_patches, (uint32_t)e->mix_patches.size(), st))
+		if (dev::launch_patch(e->A, d_patches, (uint32_t)e->patches.size(), d_mix_patches, (uint32_t)e->mix_patches.size(), st))
 			return fail_cuda(e, "k_patch");
-		// the host vectors must stay valid until the copy has been consumed (pageable source => staged synchronously)
 		for (const SlotPatch& p : e->patches) e->patch_of_slot[p.slot] = -1;
 		e->patches.clear(); e->mix_patches.clear();
 	}
@@ -740,7 +959,7 @@ static int mix_begin_locked(sbm_engine* e) {
 	m.frames = e->g.frames; m.rate = e->g.rate; m.partials = e->dv_partials; m.partials_floats = e->partials_floats;
 	m.bus = e->dv_bus; m.flags = e->dv_flags; m.parity = e->g.parity;
 	m.ev_after_k2 = e->profiling ? fl.ev[2] : nullptr;
-	m.peer = e->peer; m.bus_floats = e->bus_floats;
+	m.peer = e->peer; m.peer.parity = (uint32_t)(e->peer_buffers & 1); m.bus_floats = e->bus_floats;
 	if (dev::launch_mix(m, st)) return fail_cuda(e, "k2_mix");
 	e->begun = true;
 	fl.active = (uint32_t)(e->list_pan.size() + e->list_sh.size());
@@ -758,33 +977,42 @@ static int mix_enqueue_finish_locked(sbm_engine* e) {
 	sbm_engine::InFlight& fl = e->fl[parity];
 	if (e->peer.world) {
 		// wait for every rank's bus of this buffer (K3 stored them into our gather area) and sum them in rank order
-		const unsigned int target = (unsigned int)(e->peer.world * ((e->buffer_index >> 1) - (e->peer_epoch >> 1) + 1));
-		if (dev::launch_peer_gather(e->peer, e->dv_bus_sum, e->bus_floats, parity, target, st)) return fail_cuda(e, "k_peer_gather");
+		PeerArgs pa = e->peer; pa.parity = (uint32_t)(e->peer_buffers & 1); pa.timeout_ns = e->peer_timeout_ns;
+		const unsigned int target = (unsigned int)(e->peer.world * ((e->peer_buffers >> 1) + 1));
+		if (dev::launch_peer_gather(pa, e->dv_bus, e->dv_bus_sum, e->bus_floats, target, e->dv_flags, st)) return fail_cuda(e, "k_peer_gather");
+		e->peer_buffers++;
 	}
 	FinishArgs f;
 	f.bus = e->peer.world ? e->dv_bus_sum : e->dv_bus; f.hrir = e->dv_hrir; f.taps = (uint32_t)e->cfg.sh_hrir_taps; f.hist = e->dv_hist; f.dec = e->dv_dec;
 	f.flags = e->dv_flags; f.parity = parity; f.frames = F; f.out = e->dv_out;
-	f.list_ring = e->dv_list_ring; f.n_ring = (uint32_t)e->list_ring.size(); f.read_i = e->A.read_i; f.finished_count_reset = nullptr; f.hist_smem_all = 0;
+	f.list_ring = e->dv_list_ring; f.n_ring = (uint32_t)e->list_ring.size(); f.read_i = e->A.read_i; f.finished = fl.dv_finished; f.hist_smem_all = 0;
 	if (dev::launch_finish(f, st)) return fail_cuda(e, "k4_finish");
 	if (e->profiling) dev::event_record(fl.ev[3], st);
-	const size_t bytes = sizeof(float) * 2 * F + sizeof(OutTail) + sizeof(unsigned long long) * e->list_ring.size();
+	const size_t bytes = sizeof(float) * 2 * F + sizeof(OutTail) + sizeof(unsigned long long) * e->list_ring.size() + sizeof(int) * kInlineFinished;
 	if (dev::d2h(fl.h_out, e->dv_out, bytes, st)) return fail_cuda(e, "sbm_mix_finish(d2h)");
 	dev::event_record(fl.done, st);
 	fl.pending = true; fl.seq = e->buffer_index; fl.list_ring = e->list_ring; fl.d2h_bytes = bytes;
+	fl.stage_mark = e->stage.head; fl.stage_gen = e->stage.gen;
 	e->buffer_index++;
 	return SBM_OK;
 }
 
-// Waits for the oldest buffer in flight and hands it out.
-static int mix_collect_locked(sbm_engine* e, float* out_interleaved, int* out_valid) {
+// Waits for the oldest buffer in flight -- with the engine lock RELEASED: source creation / destruction and ring pushes by
+// other threads go on meanwhile -- and hands it out.  `lk` holds e->mu on entry and on return.
+static int mix_collect_locked(sbm_engine* e, std::unique_lock<std::mutex>& lk, float* out_interleaved, int* out_valid) {
 	sbm_engine::InFlight& fl = e->fl[e->collected & 1];
 	if (!fl.pending || fl.seq != e->collected) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_collect: no buffer in flight");
 	void* st = e->stream;
 	const uint32_t F = e->g.frames;
-	if (dev::event_sync(fl.done)) return fail_cuda(e, "sbm_mix_collect");
+	void* done = fl.done;
+	lk.unlock();
+	const int wait_rc = dev::event_sync(done);     // only the mixer thread submits / collects: `fl` cannot change under us
+	lk.lock();
+	if (wait_rc) return fail_cuda(e, "sbm_mix_collect");
 	fl.pending = false;
 	e->collected++;
-	if (e->ring_stage_in_flight && e->ring_stage_seq <= fl.seq) e->ring_stage_in_flight = false;
+	if (fl.stage_gen == e->stage.gen) e->stage.tail = fl.stage_mark;
+	free_retired(e, false);
 	e->stats.last_h2d_bytes = fl.h2d_bytes;
 	e->stats.last_d2h_bytes = fl.d2h_bytes;
 	e->stats.active_sources = fl.active;
@@ -799,11 +1027,16 @@ static int mix_collect_locked(sbm_engine* e, float* out_interleaved, int* out_va
 		RingInfo& r = e->rings[fl.list_ring[k]];
 		if (r.storage && reads[k] <= r.written && reads[k] >= r.read_known) r.read_known = reads[k];     // (the slot may have been recycled since)
 	}
-	// sources stopped by the feeder (AudioEngine.cpp:499-515)
+	// sources stopped by the feeder (AudioEngine.cpp:499-515): the first kInlineFinished ids ride in the result block
 	if (tail.n_finished > 0) {
 		std::vector<int> ids((size_t)tail.n_finished);
-		if (dev::d2h(ids.data(), fl.dv_finished, sizeof(int) * ids.size(), st) || dev::sync(st)) return fail_cuda(e, "sbm_mix_finish(finished)");
-		e->stats.last_d2h_bytes += sizeof(int) * ids.size();
+		const int* inl = (const int*)(reads + fl.list_ring.size());
+		if (tail.n_finished <= kInlineFinished) memcpy(ids.data(), inl, sizeof(int) * ids.size());
+		else {
+			// more than fit inline (a mass expiry): fetch the whole list; the only path that waits for the stream here
+			if (dev::d2h(ids.data(), fl.dv_finished, sizeof(int) * ids.size(), st) || dev::sync(st)) return fail_cuda(e, "sbm_mix_finish(finished)");
+			e->stats.last_d2h_bytes += sizeof(int) * ids.size();
+		}
 		std::sort(ids.begin(), ids.end());
 		for (int id : ids) {
 			const int slot = slot_for(e, id);
@@ -820,6 +1053,7 @@ static int mix_collect_locked(sbm_engine* e, float* out_interleaved, int* out_va
 		e->stats.last_mix_kernel_ms = dev::event_elapsed_ms(fl.ev[1], fl.ev[2]);
 		e->stats.last_finish_kernel_ms = dev::event_elapsed_ms(fl.ev[2], fl.ev[3]);
 	}
+	if (tail.status == kTailPeerTimeout) return fail(e, SBM_ERR_PEER_TIMEOUT, "a peer rank did not deliver its bus in time: this buffer holds the local sources only (see sbm_peer_resync)");
 	return SBM_OK;
 }
 
@@ -833,11 +1067,11 @@ SBM_API int sbm_mix_begin(sbm_engine* e) {
 
 SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid) {
 	if (!e) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
+	std::unique_lock<std::mutex> lk(e->mu);
 	dev::use(e->cfg.device);
 	const int rc = mix_enqueue_finish_locked(e);
 	if (rc) return rc;
-	return mix_collect_locked(e, out_interleaved, out_valid);
+	return mix_collect_locked(e, lk, out_interleaved, out_valid);
 }
 
 SBM_API int sbm_mix(sbm_engine* e, float* out_interleaved, int* out_valid) {
@@ -858,9 +1092,9 @@ SBM_API int sbm_mix_submit(sbm_engine* e) {
 
 SBM_API int sbm_mix_collect(sbm_engine* e, float* out_interleaved, int* out_valid) {
 	if (!e) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
+	std::unique_lock<std::mutex> lk(e->mu);
 	dev::use(e->cfg.device);
-	return mix_collect_locked(e, out_interleaved, out_valid);
+	return mix_collect_locked(e, lk, out_interleaved, out_valid);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -889,8 +1123,6 @@ SBM_API int sbm_peer_connect(sbm_engine* e, int rank, int world, const void* han
 	if (!e->dv_gather) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect before sbm_peer_export");
 	if (e->begun || e->collected != e->buffer_index) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect with a buffer in flight");
 	if (e->peer.world) return fail(e, SBM_ERR_INVALID_ARG, "already connected");
-	// the arrival counters count buffers per parity from now on: all ranks must connect at the same, even, buffer index
-	if (e->buffer_index & 1) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_connect needs an even number of buffers mixed so far (all ranks alike)");
 	PeerArgs pa{};
 	pa.rank = (uint32_t)rank; pa.world = (uint32_t)world;
 	for (int p = 0; p < world; ++p) {
@@ -905,7 +1137,26 @@ SBM_API int sbm_peer_connect(sbm_engine* e, int rank, int world, const void* han
 	}
 	pa.done = (unsigned int*)(e->dv_gather + gather_area_floats(e)) + 4;
 	e->peer = pa;
-	e->peer_epoch = e->buffer_index;
+	e->peer_buffers = 0;     // the exchange keeps its own buffer count (parity of the gather area, arrival targets): ranks need not agree on buffer_index
+	return SBM_OK;
+}
+
+SBM_API int sbm_set_peer_timeout_ms(sbm_engine* e, int timeout_ms) {
+	if (!e || timeout_ms <= 0) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	e->peer_timeout_ns = (unsigned long long)timeout_ms * 1000000ull;
+	return SBM_OK;
+}
+
+SBM_API int sbm_peer_resync(sbm_engine* e) {
+	if (!e) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	if (!e->peer.world) return fail(e, SBM_ERR_INVALID_ARG, "not connected");
+	if (e->begun || e->collected != e->buffer_index) return fail(e, SBM_ERR_INVALID_ARG, "sbm_peer_resync with a buffer in flight");
+	// own arrival counters + the K3 election counter back to zero; the exchange count restarts
+	if (dev::zero(e->dv_gather + gather_area_floats(e), sizeof(float) * 16, e->stream) || dev::sync(e->stream)) return fail_cuda(e, "sbm_peer_resync");
+	e->peer_buffers = 0;
 	return SBM_OK;
 }
 
@@ -924,7 +1175,6 @@ SBM_API void* sbm_stream(sbm_engine* e) { return e ? e->stream : nullptr; }
 SBM_API int sbm_poll_finished(sbm_engine* e, int* ids, int cap, int* out_n) {
 	if (!e || !ids || cap < 0 || !out_n) return SBM_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
 	const int n = std::min<int>(cap, (int)e->finished_queue.size());
 	for (int i = 0; i < n; ++i) ids[i] = e->finished_queue[(size_t)i];
 	e->finished_queue.erase(e->finished_queue.begin(), e->finished_queue.begin() + n);
@@ -934,21 +1184,26 @@ SBM_API int sbm_poll_finished(sbm_engine* e, int* ids, int cap, int* out_n) {
 
 SBM_API int sbm_source_query(sbm_engine* e, int id, sbm_source_state* out) {
 	if (!e || !out) return SBM_ERR_INVALID_ARG;
-	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
 	memset(out, 0, sizeof(*out));
-	const int slot = slot_for(e, id);
-	if (slot < 0) return SBM_ERR_UNKNOWN_ID;
-	const SrcStatic& st = e->h_stat[(uint32_t)slot];
-	unsigned long long rd = 0; long long eof = 0; float dg = 0, occ = 0; double pos = 0; uint32_t live = 0;
-	int rc = dev::d2h(&rd, e->A.read_i + slot, 8, e->stream) | dev::d2h(&eof, e->A.eof + slot, 8, e->stream) |
-	         dev::d2h(&dg, e->A.dgain + slot, 4, e->stream) | dev::d2h(&occ, e->A.occ_cur + slot, 4, e->stream) |
-	         dev::d2h(&live, e->A.live + slot, 4, e->stream);
-	if (st.nz) rc |= dev::d2h(&pos, e->A.mix_pos + st.mix_first, 8, e->stream);
-	if (rc || dev::sync(e->stream)) return fail_cuda(e, "sbm_source_query");
-	const bool ring = ((st.flags >> kFlagFeedShift) & 3) == kFeedRing;
+	unsigned long long rd = 0, written = 0; long long eof = 0; float dg = 0, occ = 0; double pos = 0; uint32_t live = 0;
+	bool ring = false;
+	{
+		std::lock_guard<std::mutex> lk(e->mu);
+		dev::use(e->cfg.device);
+		const int slot = slot_for(e, id);
+		if (slot < 0) return SBM_ERR_UNKNOWN_ID;
+		const SrcStatic& st = e->h_stat[(uint32_t)slot];
+		int rc = dev::d2h(&rd, e->A.read_i + slot, 8, e->stream) | dev::d2h(&eof, e->A.eof + slot, 8, e->stream) |
+		         dev::d2h(&dg, e->A.dgain + slot, 4, e->stream) | dev::d2h(&occ, e->A.occ_cur + slot, 4, e->stream) |
+		         dev::d2h(&live, e->A.live + slot, 4, e->stream);
+		if (st.nz) rc |= dev::d2h(&pos, e->A.mix_pos + st.mix_first, 8, e->stream);
+		if (rc) return fail_cuda(e, "sbm_source_query");
+		ring = ((st.flags >> kFlagFeedShift) & 3) == kFeedRing;
+		written = e->rings[(uint32_t)slot].written;
+	}
+	if (dev::sync(e->stream)) return fail_cuda(e, "sbm_source_query");     // waits for the buffers in flight, without the engine lock
 	out->cur_read_i = ring ? 0 : rd;
-	out->ring_size = ring ? e->rings[(uint32_t)slot].written - rd : 0;
+	out->ring_size = ring ? written - rd : 0;
 	out->eof_marker = eof; out->mix_pos0 = pos; out->direct_gain = dg; out->occlusion = occ; out->alive = (int)live;
 	return SBM_OK;
 }
@@ -956,7 +1211,6 @@ SBM_API int sbm_source_query(sbm_engine* e, int id, sbm_source_state* out) {
 SBM_API int sbm_get_stats(sbm_engine* e, sbm_stats* out) {
 	if (!e || !out) return SBM_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(e->mu);
-	dev::use(e->cfg.device);
 	e->stats.kernel_launches = dev::launches();
 	*out = e->stats;
 	return SBM_OK;

@@ -32,6 +32,9 @@
 //
 // HBM traffic: 4 B per source sample (PCM, + <= 24 B alignment over-fetch per segment) + 128 B WorkRec (+64 B SH gains)
 // per source; writes are O(grid * frames).  Roofline: HBM read.  No tensor cores: 2..16 FMA per 4 B loaded.
+#include <map>
+#include <mutex>
+
 #include "device_internal.h"
 #include "k2_core.h"
 
@@ -944,7 +947,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* _
 	warp_sum[w][lane] = s;
 	__syncthreads();
 	// multi-GPU: this rank's slot in rank p's gather area
-	const size_t slot_off = ((size_t)parity * pa.world + pa.rank) * bus_floats;
+	const size_t slot_off = ((size_t)pa.parity * pa.world + pa.rank) * bus_floats;
 	if (w == 0 && f < F) {
 		float t = warp_sum[0][lane];
 #pragma unroll
@@ -973,44 +976,68 @@ __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* _
 			if (atomicAdd(pa.done, 1u) == total - 1u) {
 				*pa.done = 0u;
 				__threadfence_system();
-				for (uint32_t p = 0; p < pa.world; ++p) atomicAdd_system(pa.arrive[p] + parity, 1u);
+				for (uint32_t p = 0; p < pa.world; ++p) atomicAdd_system(pa.arrive[p] + pa.parity, 1u);
 			}
 		}
 	}
 }
 
 // Gather kernel in front of K4 (multi-GPU): waits until all `world` ranks have delivered this buffer's bus into the
-// local gather area, then sums the slots in rank order -- every rank computes the identical sum.  A peer that never
-// arrives (crashed rank) trips the trap after ~2 s instead of hanging the device.
-__global__ void __launch_bounds__(256) k_peer_gather_kernel(PeerArgs pa, float* __restrict__ bus_sum, size_t bus_floats, uint32_t parity, unsigned int target) {
+// local gather area, then sums the slots in rank order -- every rank computes the identical sum.  A peer that does not
+// arrive within pa.timeout_ns (stalled or crashed rank) does not take this rank down: the kernel flags the buffer
+// (DevFlags::peer_timeout -> OutTail::status -> SBM_ERR_PEER_TIMEOUT) and renders this rank's own bus alone.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+__global__ void __launch_bounds__(256) k_peer_gather_kernel(PeerArgs pa, const float* __restrict__ own_bus, float* __restrict__ bus_sum, size_t bus_floats,
+                                                            unsigned int target, DevFlags* flags) {
+	__shared__ int timed_out;
 	grid_dep_wait();
 	if (threadIdx.x == 0) {
-		const volatile unsigned int* cnt = pa.arrive[pa.rank] + parity;
-		unsigned int spins = 0;
+		const volatile unsigned int* cnt = pa.arrive[pa.rank] + pa.parity;
+		const unsigned long long t0 = global_timer_ns();
+		int late = 0;
 		while ((int)(*cnt - target) < 0) {
-			__nanosleep(256);
-			if (++spins > (1u << 23)) __trap();
+			__nanosleep(128);
+			if (global_timer_ns() - t0 > pa.timeout_ns) { late = 1; break; }
 		}
 		__threadfence_system();
+		timed_out = late;
+		if (late && blockIdx.x == 0) flags->peer_timeout = 1;
 	}
 	__syncthreads();
-	const float* area = pa.gather[pa.rank] + (size_t)parity * pa.world * bus_floats;
+	const float* area = pa.gather[pa.rank] + (size_t)pa.parity * pa.world * bus_floats;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bus_floats; i += (size_t)gridDim.x * blockDim.x) {
 		float s = 0.0f;
-		for (uint32_t p = 0; p < pa.world; ++p) s += __ldcg(area + (size_t)p * bus_floats + i);
+		if (timed_out) s = own_bus[i];
+		else for (uint32_t p = 0; p < pa.world; ++p) s += __ldcg(area + (size_t)p * bus_floats + i);
 		bus_sum[i] = s;
 	}
 }
 
-int sm_count() {
-	static int n = 0;
-	if (!n) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-		if (n <= 0) n = 148;
+// Everything a launch needs to know about the CURRENT device, cached per device ordinal (engines on different devices and
+// threads share this library): SM count, and per kernel the dynamic shared memory it was configured for and its occupancy.
+struct KernelConfig { size_t smem = 0; int ctas_per_sm = 0; };
+struct DeviceCache { int sms = 0; std::map<const void*, KernelConfig> kernels; };
+std::mutex g_cfg_mu;
+std::map<int, DeviceCache> g_devices;
+
+DeviceCache& device_cache_locked() {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	DeviceCache& c = g_devices[dev];
+	if (!c.sms) {
+		cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
+		if (c.sms <= 0) c.sms = 148;
 	}
-	return n;
+	return c;
+}
+
+int sm_count() {
+	std::lock_guard<std::mutex> lk(g_cfg_mu);
+	return device_cache_locked().sms;
 }
 
 // Stage slot per source, in floats: room for a window of frames * 1.25 (sample-rate ratios <= 1, doppler / pitch up
@@ -1034,22 +1061,28 @@ uint32_t pick_grid(uint32_t n, uint32_t max_grid) {
 }
 
 // Launches one K2 kernel as a single wave: grid = SM count x resident CTAs per SM (never more than the sources warrant).
-struct KernelConfig { size_t smem = 0; int ctas_per_sm = 0; };
 template <class Kernel>
-int launch_one(Kernel kernel, KernelConfig* cfg, const char* name, const MixArgs& a, uint32_t first, uint32_t n, uint32_t threads, bool sh,
+int launch_one(Kernel kernel, const char* name, const MixArgs& a, uint32_t first, uint32_t n, uint32_t threads, bool sh,
                uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
 	const uint32_t F = a.frames;
 	const size_t smem = mix_smem_bytes(F, sh);
-	if (smem != cfg->smem) {
-		if (dev::check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)") ||
-		    dev::check(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
-			return -1;
-		int per_sm = 0;
-		if (dev::check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor")) return -1;
-		cfg->smem = smem;
-		cfg->ctas_per_sm = per_sm > 0 ? per_sm : 1;
+	uint32_t wave;
+	{
+		// cudaFuncSetAttribute and the occupancy query apply to the current device only: configured once per (device, kernel, size)
+		std::lock_guard<std::mutex> lk(g_cfg_mu);
+		DeviceCache& dc = device_cache_locked();
+		KernelConfig* cfg = &dc.kernels[(const void*)kernel];
+		if (smem != cfg->smem) {
+			if (dev::check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)") ||
+			    dev::check(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(carveout)"))
+				return -1;
+			int per_sm = 0;
+			if (dev::check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor")) return -1;
+			cfg->smem = smem;
+			cfg->ctas_per_sm = per_sm > 0 ? per_sm : 1;
+		}
+		wave = (uint32_t)(dc.sms * cfg->ctas_per_sm);
 	}
-	uint32_t wave = (uint32_t)(sm_count() * cfg->ctas_per_sm);
 	if (wave > max_grid) wave = max_grid;
 	const uint32_t g = pick_grid(n, wave);
 	launch_pdl(kernel, dim3(g), dim3(threads), smem, st, a, first, n, window_slot(F), partials);
@@ -1060,10 +1093,9 @@ int launch_one(Kernel kernel, KernelConfig* cfg, const char* name, const MixArgs
 
 template <int KF>
 int launch_stereo(const MixArgs& a, uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
-	static KernelConfig conf_exact, conf_any;
 	const uint32_t threads = kPanWarps * 32 + 32;
-	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true>, &conf_exact, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
-	return launch_one(k2_mix_stereo_kernel<KF, false>, &conf_any, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+	return launch_one(k2_mix_stereo_kernel<KF, false>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
 }
 
 }  // namespace
@@ -1099,16 +1131,15 @@ int launch_mix(const MixArgs& a, void* stream) {
 		if (rc) return -1;
 	}
 	if (a.n_sh) {
-		static KernelConfig conf_sh, conf_sh_big, conf_sh_x, conf_sh_big_x;
 		const uint32_t tm = sh_threads(F);
 		const uint32_t mg = (uint32_t)num_mix_ctas(F, 1);
 		const bool exact = (tm == 128 || tm == (uint32_t)kShBigT) && F == tm * sh_frames_per_thread(F);     // the EXACT instantiations fix T = TMAX at compile time
 		int rc;
-		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<true>, &conf_sh_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
-		                         : launch_one(k2_mix_ambisonic_kernel<false>, &conf_sh, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
+		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<true>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
+		                         : launch_one(k2_mix_ambisonic_kernel<false>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
 		else {
-			rc = exact ? launch_one(k2_mix_ambisonic_big_kernel<true>, &conf_sh_big_x, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm * kShBigG + 32, true, mg, part_sh, st, &g_sh)
-			           : launch_one(k2_mix_ambisonic_big_kernel<false>, &conf_sh_big, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm * kShBigG + 32, true, mg, part_sh, st, &g_sh);
+			rc = exact ? launch_one(k2_mix_ambisonic_big_kernel<true>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm * kShBigG + 32, true, mg, part_sh, st, &g_sh)
+			           : launch_one(k2_mix_ambisonic_big_kernel<false>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm * kShBigG + 32, true, mg, part_sh, st, &g_sh);
 			g_sh *= (uint32_t)kShBigG;     // one partial bus per math group
 		}
 		if (rc) return -1;
@@ -1119,9 +1150,9 @@ int launch_mix(const MixArgs& a, void* stream) {
 	return check_launch("k3_reduce");
 }
 
-int launch_peer_gather(const PeerArgs& pa, float* bus_sum, size_t bus_floats, uint32_t parity, unsigned int target, void* stream) {
+int launch_peer_gather(const PeerArgs& pa, const float* own_bus, float* bus_sum, size_t bus_floats, unsigned int target, DevFlags* flags, void* stream) {
 	const uint32_t grid = (uint32_t)((bus_floats + 255) / 256);
-	launch_pdl(k_peer_gather_kernel, dim3(grid < 148u ? grid : 148u), dim3(256), 0, (cudaStream_t)stream, pa, bus_sum, bus_floats, parity, target);
+	launch_pdl(k_peer_gather_kernel, dim3(grid < 148u ? grid : 148u), dim3(256), 0, (cudaStream_t)stream, pa, own_bus, bus_sum, bus_floats, target, flags);
 	note_launch();
 	return check_launch("k_peer_gather");
 }

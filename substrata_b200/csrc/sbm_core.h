@@ -145,7 +145,7 @@ struct DevFlags {
 	int n_finished;             // entries in the finished list
 	unsigned long long algo_bytes;  // accounting: sum of 4*n_src over rendered sources
 	unsigned int n_rendered;
-	int pad;
+	int peer_timeout;               // set by the gather kernel when a peer rank's bus did not arrive in time (reported and cleared by K4b)
 	// K1 spreads its per-warp accounting atomics over kStatParts padded slots (same-address atomics serialise in L2;
 	// a block-wide reduction would hold every warp of a block until its slowest one is done); K4b folds them into the tail.
 	unsigned long long part_bytes[32][4];      // [part][0] used, rest = 32-byte padding

@@ -375,7 +375,10 @@ bool AudioEngine::mixOneBuffer() {
 	}
 	frames_mixed += (int64)F;
 	if (!valid) return false;                                           // AE.cpp:535-536
-	if (frames_mixed <= (int64)options.initial_mute_frames) return true;   // AE.cpp:532-533: the first second is discarded
+	// AE.cpp:527-536: `if(buffers_processed * frames_per_buffer < 48000) filled_valid_buffer = false;` -- a buffer of the first
+	// second is treated exactly like an invalid one: nothing is pushed and the fill loop breaks (and sleeps 1 ms), so streamed
+	// sources are not drained faster than real time during the mute.
+	if (frames_mixed < (int64)options.initial_mute_frames) return false;
 	{
 		Lock lock(callback_data.buffer_mutex);
 		callback_data.buffer.pushBackNItems(out.data(), 2 * F);         // AE.cpp:540-545

@@ -218,6 +218,30 @@ class OracleBackend(_CBackend):
         if double_bus:
             lib.orc_set_bus_precision.argtypes = [_vp, _i]
             lib.orc_set_bus_precision(self.h, 1)
+        lib.orc_sources_create.restype, lib.orc_sources_create.argtypes = _i, [_vp, _i, _i]
+        lib.orc_sources_attach_buffer.restype, lib.orc_sources_attach_buffer.argtypes = None, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+        lib.orc_sources_attach_mix1.restype, lib.orc_sources_attach_mix1.argtypes = None, [_vp, _i, _vp, _vp, _vp, _vp, _vp]
+        self._lib = lib
+
+    # batched forms (same names and argument meaning as substrata_b200.MixEngine's): the full-size parity runs
+    def sources_create(self, kind, count):
+        return self._lib.orc_sources_create(self.h, int(kind), int(count))
+
+    def sources_attach_buffer(self, ids, bufs, cur_read_i=None, sampling_rate=None, looping=None, remove_on_finish=None):
+        i, b = np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(bufs, np.int32)
+        n = i.size
+        cur = np.ascontiguousarray(cur_read_i if cur_read_i is not None else np.zeros(n), dtype=np.uint64)
+        sr = np.ascontiguousarray(sampling_rate if sampling_rate is not None else np.full(n, 48000), dtype=np.int32)
+        lo = np.ascontiguousarray(looping if looping is not None else np.ones(n), dtype=np.uint8)
+        rm = np.ascontiguousarray(remove_on_finish if remove_on_finish is not None else np.zeros(n), dtype=np.uint8)
+        self._lib.orc_sources_attach_buffer(self.h, n, _ptr(i), _ptr(b), _ptr(cur), _ptr(sr), _ptr(lo), _ptr(rm))
+
+    def sources_attach_mix1(self, ids, bufs, sound_file_i, source_delta, mix_factor):
+        i, b = np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(bufs, np.int32)
+        p = np.ascontiguousarray(sound_file_i, dtype=np.float64)
+        d = np.ascontiguousarray(source_delta, dtype=np.float64)
+        m = _f32(mix_factor)
+        self._lib.orc_sources_attach_mix1(self.h, i.size, _ptr(i), _ptr(b), _ptr(p), _ptr(d), _ptr(m))
 
 
 class RefBackend(_CBackend):
@@ -467,3 +491,143 @@ def rel_rms(a, b):
     b = np.asarray(b, dtype=np.float64).ravel()
     den = np.sqrt(np.sum(b * b))
     return float(np.sqrt(np.sum((a - b) ** 2)) / den) if den > 0 else float(np.sqrt(np.sum(a * a)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Full-size scenes: BASELINE.json's own source counts against the oracle (tests/test_gpu_fullsize.py, bench.py's parity leg).
+# The per-source arrays are drawn once for the WHOLE scene; any backend can build any subset of it (`sel`), so the oracle
+# runs as P engines on disjoint subsets in P host threads (ctypes releases the GIL) whose outputs add up -- the mix is
+# linear in the source set (one bus sum; the SH decode is a linear filter).  PCM comes from a pool of shared loops (what
+# AudioBuffer sharing looks like, AudioEngine.h:122): 10^6 private loops would be 64 GB on the host.
+# ---------------------------------------------------------------------------------------------------
+FULL_SCENES = {
+    # name: BASELINE config it is the full-size form of
+    "c2": dict(n=4096, frames=512, kind=KIND_PAN, feeder="resample", taps=0, pool=256, loop=16384, buffers=4, seed=901),
+    "c3": dict(n=65536, frames=1024, kind=KIND_HRTF, feeder="native", taps=128, pool=1024, loop=16384, buffers=4, seed=902),
+    "c4_rank": dict(n=131072, frames=512, kind=KIND_PAN, feeder="doppler", taps=0, pool=2048, loop=16384, buffers=4, seed=903),
+    "c4_1m": dict(n=1048576, frames=512, kind=KIND_PAN, feeder="doppler", taps=0, pool=4096, loop=16384, buffers=4, seed=904),
+    "c5": dict(n=33792, frames=256, kind=KIND_HRTF, feeder="c5", taps=256, pool=512, loop=16384, buffers=6, seed=905, voices=1024),
+}
+
+
+class BigScene:
+    """One of FULL_SCENES (or an override of it): seeded arrays for every source, replayable on a subset."""
+
+    def __init__(self, n, frames, kind, feeder, taps, pool, loop, buffers, seed, voices=0, volume_toggle=True):
+        rng = np.random.default_rng(seed)
+        self.n, self.F, self.kind, self.feeder, self.taps, self.nb, self.voices = n, frames, kind, feeder, taps, buffers, voices
+        self.volume_toggle = volume_toggle
+        t = np.arange(loop, dtype=np.float64) / 48000.0
+        f = rng.uniform(100.0, 4000.0, (pool, 1))
+        self.pcm = (0.5 * np.sin(2 * np.pi * f * t) + 0.1 * rng.uniform(-1, 1, (pool, loop))).astype(np.float32)
+        self.pos = positions(rng, n)
+        self.vol = rng.uniform(0.25, 1.0, n).astype(np.float32)
+        self.buf_of = rng.integers(0, pool, n).astype(np.int32)
+        self.start = rng.integers(0, loop, n)
+        v = rng.uniform(-30, 30, (n, 2))
+        self.delta = (343.0 - v[:, 0]) / (343.0 - v[:, 1])
+        self.mixf = rng.uniform(0.5, 1.0, n).astype(np.float32)
+        self.rates = (rng.choice([44100, 24000, 16000, 48000], n, p=[0.5, 0.2, 0.15, 0.15]) if feeder == "resample" else np.full(n, 48000)).astype(np.int32)
+        self.seed = seed
+        self.hrir = (load_sh_hrir()[:, :taps] if taps else load_sh_hrir()) if kind == KIND_HRTF else None
+
+    def oracle(self, double_bus=False):
+        return OracleBackend(self.F, sh_hrir=self.hrir, double_bus=double_bus)
+
+    def build(self, be, sel):
+        sel = np.asarray(sel)
+        bufs = np.array([be.buffer_create(p) for p in self.pcm], np.int32)
+        create = be.sources_create if hasattr(be, "sources_create") else be.source_create
+        first = create(int(self.kind), len(sel))
+        ids = np.arange(first, first + len(sel), dtype=np.int32)
+        if self.feeder == "doppler":
+            be.sources_attach_mix1(ids, bufs[self.buf_of[sel]], self.start[sel].astype(np.float64), self.delta[sel], self.mixf[sel])
+        elif self.feeder == "c5":
+            ring = sel < self.voices
+            for sid in ids[ring]:
+                be.source_attach_ring(int(sid), 48000)
+            be.sources_attach_buffer(ids[~ring], bufs[self.buf_of[sel[~ring]]], self.start[sel[~ring]], self.rates[sel[~ring]])
+        else:
+            be.sources_attach_buffer(ids, bufs[self.buf_of[sel]], self.start[sel], self.rates[sel])
+        be.set_source_positions(ids, self.pos[sel])
+        be.set_source_volumes(ids, self.vol[sel])
+        return ids
+
+    def step(self, be, ids, sel, b):
+        """Events before buffer b: the listener moves and turns (gain ramps on every source), every 8th source of the scene is
+        switched off for buffers 1-2 and back on (the -60 dB rules and the mixer-processor sweep), voices receive their packets."""
+        t = b * self.F / 48000.0
+        be.set_head([1.0 * t, 0.0, 0.0], quat_yaw(np.deg2rad(30.0) * t))
+        if self.volume_toggle and b in (1, 3):
+            m = (np.asarray(sel) % 8) == 3
+            if m.any():
+                be.set_source_volumes(ids[m], np.zeros(int(m.sum()), np.float32) if b == 1 else self.vol[np.asarray(sel)[m]])
+        if self.feeder == "c5":
+            ring = np.asarray(sel) < self.voices
+            if ring.any():
+                n_pk = int(np.ceil(self.F / 480.0)) + (1 if b == 0 else 0)
+                vids, packets = [], []
+                for sid, s in zip(ids[ring], np.asarray(sel)[ring]):
+                    if b == 3 and s % 5 == 0:
+                        continue                       # a dropped packet: ring underflow, zero-padded (AudioEngine.cpp:466-473)
+                    prng = np.random.default_rng(self.seed * 7919 + int(s) * 64 + b)
+                    vids.append(int(sid)); packets.append((0.3 * prng.uniform(-1, 1, n_pk * 480)).astype(np.float32))
+                if hasattr(be, "sources_ring_push"):
+                    be.sources_ring_push(vids, packets)
+                else:
+                    for sid, pk in zip(vids, packets):
+                        be.source_ring_push(sid, pk)
+
+    def run(self, be, sel=None, n_buffers=None):
+        sel = np.arange(self.n) if sel is None else np.asarray(sel)
+        ids = self.build(be, sel)
+        outs, valids = [], []
+        for b in range(n_buffers or self.nb):
+            self.step(be, ids, sel, b)
+            v, o = be.mix()
+            outs.append(o.copy()); valids.append(v)
+        return np.stack(outs), valids
+
+    def run_oracle_partitioned(self, parts, double_bus=False, n_buffers=None):
+        """The oracle on `parts` disjoint interleaved subsets of the scene in as many threads; returns the f64 sum of the
+        partitions' outputs (and the per-buffer valid flag = any partition valid)."""
+        import threading
+        res = [None] * parts
+
+        def work(p):
+            res[p] = self.run(self.oracle(double_bus), np.arange(p, self.n, parts), n_buffers)
+
+        th = [threading.Thread(target=work, args=(p,)) for p in range(parts)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        out = np.sum([r[0].astype(np.float64) for r in res], axis=0)
+        valid = [int(any(r[1][b] for r in res)) for b in range(len(res[0][1]))]
+        return out, valid
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def full_scene_parity(name, make_engine, parts=None, double_bus=None, **override):
+    """rel RMS of an engine (make_engine(scene) -> backend with the MixEngine interface) against the oracle on one of
+    FULL_SCENES.  Scenes up to ~1.3e5 sources are also compared with the single f32-bus oracle summing in id order (the
+    reference's arithmetic); larger ones only with the partitioned fp64-bus oracle (SURVEY.md 8d: at 10^6 sources the f32 sum's
+    own order noise exceeds the 1e-5 bar)."""
+    kw = dict(FULL_SCENES[name]); kw.update(override)
+    sc = BigScene(**kw)
+    parts = parts or min(host_cores(), 16)
+    go, gv = sc.run(make_engine(sc))
+    res = {"scene": name, "sources": sc.n, "frames": sc.F, "buffers": sc.nb}
+    if double_bus is None:
+        double_bus = sc.n > 200000
+    oo, ov = sc.run_oracle_partitioned(parts, double_bus=double_bus)
+    res["oracle"] = "%d partitions x %s bus, outputs summed in f64" % (parts, "fp64" if double_bus else "f32")
+    res["rel_rms"] = rel_rms(go, oo)
+    res["valid_equal"] = bool(gv == ov)
+    return res

@@ -20,6 +20,7 @@ namespace dev {
 static unsigned long long g_launches = 0;
 
 int init(int, void** stream_out) { *stream_out = (void*)1; return 0; }
+void* stream_create() { return (void*)2; }
 int use(int) { return 0; }
 void shutdown(void*) {}
 const char* last_error() { return "emulator"; }
@@ -34,6 +35,20 @@ int zero(void* dst, size_t bytes, void*) { memset(dst, 0, bytes); return 0; }
 int sync(void*) { return 0; }
 int num_mix_ctas(uint32_t, int) { return 1; }
 size_t partials_floats(uint32_t) { return 1; }
+
+int launch_apply_uploads(const UpSeg* segs, uint32_t n_segs, const uint32_t* block, uint32_t, void*) {
+	++g_launches;
+	for (uint32_t k = 0; k < n_segs; ++k) {
+		const UpSeg& sg = segs[k];
+		uint32_t* dst = (uint32_t*)sg.dst;
+		const uint32_t* val = block + sg.src_word;
+		for (uint32_t j = 0; j < sg.count; ++j) {
+			const uint32_t at = sg.idx_word == 0xffffffffu ? j : block[sg.idx_word + j];
+			memcpy(dst + (size_t)at * sg.elem_words, val + (size_t)j * sg.elem_words, 4 * (size_t)sg.elem_words);
+		}
+	}
+	return 0;
+}
 
 int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, const MixPatch* mp, uint32_t nmp, void*) {
 	++g_launches;
@@ -125,7 +140,7 @@ int launch_mix(const MixArgs& a, void*) {
 int peer_export(void*, void*) { return -1; }
 void* peer_open(const void*) { return nullptr; }
 void peer_close(void*) {}
-int launch_peer_gather(const PeerArgs&, float*, size_t, uint32_t, unsigned int, void*) { return -1; }
+int launch_peer_gather(const PeerArgs&, const float*, float*, size_t, unsigned int, DevFlags*, void*) { return -1; }
 
 int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void*) {
 	if (!n) return 0;
@@ -161,11 +176,13 @@ int launch_finish(const FinishArgs& a, void*) {
 		a.out[2 * i] = lo; a.out[2 * i + 1] = ro;
 	}
 	OutTail* tail = reinterpret_cast<OutTail*>(a.out + 2 * F);
-	tail->valid = plan.valid; tail->n_finished = a.flags->n_finished; tail->n_rendered = a.flags->n_rendered; tail->pad = 0;
+	tail->valid = plan.valid; tail->n_finished = a.flags->n_finished; tail->n_rendered = a.flags->n_rendered; tail->status = kTailOk;
 	tail->algo_bytes = a.flags->algo_bytes;
 	a.flags->n_finished = 0; a.flags->n_rendered = 0; a.flags->algo_bytes = 0;
 	unsigned long long* reads = reinterpret_cast<unsigned long long*>(tail + 1);
 	for (uint32_t q = 0; q < a.n_ring; ++q) reads[q] = a.read_i[a.list_ring[q]];
+	int* fin = reinterpret_cast<int*>(reads + a.n_ring);
+	for (int q = 0; q < tail->n_finished && q < kInlineFinished; ++q) fin[q] = a.finished[q];
 	return 0;
 }
 

@@ -42,7 +42,7 @@ def test_reference_arm_other_ranks_print_nothing():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = run_bench("--workload", "c2_4096_resample_pan", "--steps", "20", "--warmup", "3", "--no-also")
+    d = run_bench("--workload", "c2_4096_resample_pan", "--steps", "20", "--warmup", "3", "--no-also", "--no-full-parity", "--blocks", "3")
     for k in REQUIRED + ["e2e", "gpu_launches", "roofline", "clocks", "cpu_baseline", "parity"]:
         assert k in d, k
     assert d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["value"] > 0
@@ -51,3 +51,6 @@ def test_gpu_arm_line():
     assert set(["value", "unit", "cores", "kind", "sample"]) <= set(d["cpu_baseline"])
     assert set(["sm_mhz", "sm_max_mhz", "reasons"]) <= set(d["clocks"])
     assert d["parity"]["rel_rms"] <= 1e-5
+    assert d["timing"]["blocks"] == 3 and len(d["timing"]["value_block_ms_per_step"]) == 3
+    assert d["e2e"]["all_move"]["h2d_bytes_per_step"] >= 4096 * 16 and d["roofline"]["l2_resident"] is True and d["roofline"]["frac"] is None
+    assert d["latency_us"]["p50"] > 0

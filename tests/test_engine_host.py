@@ -96,8 +96,10 @@ def test_capacity_and_argument_errors():
     assert ei.value.code == -5
     with pytest.raises(sb.SbmError):
         e.source_create(KIND_HRTF)            # engine created without SH-HRIRs
-    with pytest.raises(sb.SbmError):
-        e.set_source_positions([99], np.zeros((1, 3), np.float32))
+    # queued setters ignore unknown ids like Resonance (resonance_audio_api_impl.cc:551-554) and count them
+    e.set_source_positions([99], np.zeros((1, 3), np.float32))
+    e.mix()
+    assert e.stats()["ignored_setter_items"] == 1
     buf = e.buffer_create(np.zeros(100, np.float32))
     with pytest.raises(sb.SbmError):          # AudioEngine::addSource rejects rates outside 8000..48000 (AudioEngine.cpp:884-885)
         e.source_attach_buffer(0, buf, 0, 96000)
@@ -194,3 +196,89 @@ def test_source_churn_matches_reference_golden():
     eo, ev, ef = run_churn(emu_engine(256, load_sh_hrir(), max_sources=1024), 256)
     assert ev == rv and ef == rf
     assert rel_rms(eo, ro) <= TOL
+
+
+@pytest.mark.parametrize("name,override", [
+    ("c2", dict(n=300, pool=8)), ("c3", dict(n=200, pool=8, frames=256)), ("c4_rank", dict(n=400, pool=8)),
+    ("c5", dict(n=260, voices=40, pool=8)),
+])
+def test_full_scene_harness_on_host_engine(name, override):
+    """The full-size scene harness (tests/test_gpu_fullsize.py runs it at BASELINE's sizes on the GPU) at toy sizes: the host
+    engine on the emulated device against the partitioned oracle, f32 and fp64 bus."""
+    from harness import full_scene_parity
+    for dbl in (False, True):
+        r = full_scene_parity(name, lambda sc: emu_engine(sc.F, sc.hrir, max_sources=sc.n), parts=3, double_bus=dbl, **override)
+        assert r["valid_equal"] and r["rel_rms"] <= TOL, r
+
+
+def test_setters_never_block_and_are_race_free_under_tsan():
+    """Four threads hammer every queued setter while the mixer thread runs sbm_mix_submit / sbm_mix_collect and churns sources:
+    ThreadSanitizer build of the real host engine on the emulated device (tests/native/test_setters_tsan.cc).  No TSAN report,
+    and the setters' latency stays in microseconds -- they never wait for the mixer, which here spends milliseconds per
+    buffer inside the engine lock (Resonance: lock-free task queue, RA/utils/lockless_task_queue.cc:43-51)."""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR, "test_setters_tsan"])
+    r = subprocess.run([os.path.join(EMU_DIR, "test_setters_tsan")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[-4000:]
+    f = dict(zip(r.stdout.split()[0::2], r.stdout.split()[1::2]))
+    assert int(f["buffers"]) >= 4 and int(f["setter_calls"]) > 1000
+    assert float(f["median_us"]) < 100.0 and float(f["p999_us"]) < 2000.0, r.stdout      # (worst_us is OS scheduling noise under TSAN)
+
+
+def test_mix_source_entries_and_buffers_are_recycled():
+    """MixZ ranges return to a free list when their source dies (1365 bike creations used to exhaust the table), and
+    sbm_buffer_destroy frees a PCM buffer once its last source is gone while rejecting new attachments."""
+    F = 256
+    e = sb.MixEngine(F, max_sources=8, max_mix_sources=6, _lib_path=EMU)
+    rng = np.random.default_rng(5)
+    bufs = [e.buffer_create((0.3 * rng.uniform(-1, 1, 1000)).astype(np.float32)) for _ in range(3)]
+    for k in range(40):      # 40 x 3 mix sources through a 6-entry table
+        sid = e.source_create(KIND_PAN)
+        e.source_attach_mix(sid, 48000, bufs, [0.0, 10.0, 20.0], [1.0, 0.5, 1.87], [0.6, 0.3, 0.45])
+        e.set_source_positions([sid], np.array([[2.0, 0.0, -3.0]], np.float32))
+        v, o = e.mix()
+        assert v == 1 and o.any()
+        if k % 2:
+            e.source_attach_mix(sid, 48000, bufs[:1], [0.0], [1.0], [1.0])      # re-attach with another length: old range recycled too
+            e.mix()
+        e.source_destroy(sid)
+    # buffer life time
+    sid = e.source_create(KIND_PAN)
+    e.source_attach_buffer(sid, bufs[0], 0, 48000)
+    assert e._l.sbm_buffer_destroy(e.h, bufs[0]) == 0           # still referenced: stays alive for its source ...
+    v, o = e.mix()
+    assert v == 1
+    s2 = e.source_create(KIND_PAN)
+    with pytest.raises(sb.SbmError):                              # ... but takes no new attachments
+        e.source_attach_buffer(s2, bufs[0], 0, 48000)
+    e.source_destroy(sid)
+    e.mix()
+    assert e._l.sbm_buffer_destroy(e.h, bufs[0]) == -4          # gone
+    assert e._l.sbm_buffer_destroy(e.h, bufs[1]) == 0 and e._l.sbm_buffer_destroy(e.h, 99) == -4
+
+
+def test_scattered_and_contiguous_setters_reach_the_device():
+    """The per-buffer upload block: a few scattered ids (index list + scatter) and a whole batch of consecutive ids (dense
+    range fast path) must leave the same state as the oracle sees."""
+    F, N = 256, 3000
+    rng = np.random.default_rng(8)
+    pcm = (0.3 * rng.uniform(-1, 1, 2048)).astype(np.float32)
+    outs = {}
+    for be in (OracleBackend(F), sb.MixEngine(F, max_sources=N, _lib_path=EMU)):
+        r = np.random.default_rng(9)
+        b = be.buffer_create(pcm)
+        first = be.sources_create(KIND_PAN, N) if hasattr(be, "sources_create") else be.source_create(KIND_PAN, N)
+        ids = np.arange(first, first + N, dtype=np.int32)
+        be.sources_attach_buffer(ids, np.full(N, b, np.int32), r.integers(0, 2048, N), np.full(N, 48000, np.int32))
+        res = []
+        for k in range(6):
+            if k % 2 == 0:
+                be.set_source_positions(ids, r.uniform(-20, 20, (N, 3)).astype(np.float32) + np.float32(1.5))      # all: dense
+                be.set_source_volumes(ids[100:2900], r.uniform(0.2, 1, 2800).astype(np.float32))
+            else:
+                sel = np.sort(r.choice(N, 37, replace=False))
+                be.set_source_positions(ids[sel], r.uniform(-20, 20, (37, 3)).astype(np.float32) + np.float32(1.5))  # few: scattered
+                be.set_source_occlusions(ids[sel[:5]], np.ones(5, np.float32))
+            res.append(be.mix()[1].copy())
+        outs[be.name] = np.stack(res)
+    assert rel_rms(outs["b200"], outs["oracle"]) <= TOL
