@@ -674,7 +674,7 @@ def main():
     if args.sources:
         wl["n"] = args.sources
         wl["desc"] += " [--sources override: %d sources/GPU, NOT the named configuration]" % args.sources
-    wl["ring_capacity"] = max(96000, (args.warmup + args.steps + 8) * wl["frames"] + 960)
+    wl["ring_capacity"] = max(96000, (args.warmup + args.steps * args.blocks + 8) * wl["frames"] + 960)     # the resident leg pre-fills every timed buffer's packets
     if args.impl == "reference":
         run_reference_arm(args, wl, rank, world)
         return

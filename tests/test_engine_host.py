@@ -282,3 +282,16 @@ def test_scattered_and_contiguous_setters_reach_the_device():
             res.append(be.mix()[1].copy())
         outs[be.name] = np.stack(res)
     assert rel_rms(outs["b200"], outs["oracle"]) <= TOL
+
+
+def test_partitioned_oracle_equals_single_oracle():
+    """The threaded oracle of the full-size runs (block partitions summed in f64) renders what ONE oracle engine renders,
+    including the buffers in which every 8th source is switched off and on again (the GainMixer sweep is shared state)."""
+    from harness import BigScene, FULL_SCENES
+    kw = dict(FULL_SCENES["c3"]); kw.update(n=2048, pool=16)
+    sc = BigScene(**kw)
+    a, va = sc.run(sc.oracle())
+    b, vb = sc.run_oracle_partitioned(16)
+    assert va == vb
+    for k in range(sc.nb):
+        assert rel_rms(b[k], a[k]) <= 3e-6
