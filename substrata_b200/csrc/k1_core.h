@@ -303,32 +303,36 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		F4* sg4 = reinterpret_cast<F4*>(A.shg[out].konst);
 		for (int q = 0; q < kNumSh / 4; ++q) {
 			const F4 v = cg4[q];
-			float cur[4] = {v.x, v.y, v.z, v.w}, kon[4], rst[4], rin[4];
-			uint32_t rn[4], gm = 0;
+			float cur[4] = {v.x, v.y, v.z, v.w}, kon[4], stm[4], rin[4], rnf[4];
+			uint32_t gm = 0;
 			for (int j = 0; j < 4; ++j) {
 				const int c = 4 * q + j;
 				const RampDesc d = plan_gain(&cur[j], chan_init, g[c], F, /*accumulate=*/true);
-				kon[j] = d.konst; rst[j] = d.start; rin[j] = d.inc; rn[j] = d.n;
+				kon[j] = d.konst; stm[j] = 0.0f; rin[j] = 0.0f; rnf[j] = 0.0f;
 				if (d.n) {
+					stm[j] = fsub(d.start, d.konst); rin[j] = d.inc; rnf[j] = (float)d.n;
 					gm |= 1u << j;
 					if (d.n > rec.ch[0].n) rec.ch[0].n = d.n;       // ambisonic sources: ch[0].n = longest channel ramp (K2's ramp region)
+					if (d.n < F && d.konst != cur[j]) rflags |= kRecRampCareful;     // ended on a near-zero value: konst is 0, not the end value
 				}
 			}
 			cg4[q] = F4{cur[0], cur[1], cur[2], cur[3]};
 			sg4[q] = F4{kon[0], kon[1], kon[2], kon[3]};
 			if (gm) {
-				// ramp parameters of the group, 16 bytes each (n = 0 for the channels of the group that do not ramp)
-				reinterpret_cast<F4*>(A.shr[out].start)[q] = F4{rst[0], rst[1], rst[2], rst[3]};
+				// ramp parameters of the group, 16 bytes each (zeros for the channels of the group that do not ramp)
+				reinterpret_cast<F4*>(A.shr[out].stm)[q] = F4{stm[0], stm[1], stm[2], stm[3]};
 				reinterpret_cast<F4*>(A.shr[out].inc)[q] = F4{rin[0], rin[1], rin[2], rin[3]};
-				U4 nn; nn.x = rn[0]; nn.y = rn[1]; nn.z = rn[2]; nn.w = rn[3];
-				reinterpret_cast<U4*>(A.shr[out].n)[q] = nn;
+				reinterpret_cast<F4*>(A.shr[out].nf)[q] = F4{rnf[0], rnf[1], rnf[2], rnf[3]};
 				rec.ch_ramp_mask |= gm << (4 * q);
 			}
 		}
-		// K2 reads n[] of all 16 channels of a source that has any channel ramp: the groups without one must say 0
+		// K2 reads all 48 ramp parameters of a source that has any channel ramp: the groups without one must say 0
 		if (rec.ch_ramp_mask)
 			for (int q = 0; q < kNumSh / 4; ++q)
-				if (!((rec.ch_ramp_mask >> (4 * q)) & 0xfu)) { U4 z; z.x = z.y = z.z = z.w = 0; reinterpret_cast<U4*>(A.shr[out].n)[q] = z; }
+				if (!((rec.ch_ramp_mask >> (4 * q)) & 0xfu)) {
+					const F4 z = F4{0.0f, 0.0f, 0.0f, 0.0f};
+					reinterpret_cast<F4*>(A.shr[out].stm)[q] = z; reinterpret_cast<F4*>(A.shr[out].inc)[q] = z; reinterpret_cast<F4*>(A.shr[out].nf)[q] = z;
+				}
 		rflags |= kRecHrtf;
 	}
 	rec.flags = rflags;

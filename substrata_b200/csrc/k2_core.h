@@ -98,6 +98,13 @@ SBM_HD float gain_at(const RampDesc& d, uint32_t i) {
 	return i < d.n ? fmaf((float)i, d.inc, d.start) : d.konst;
 }
 
+// Gain of ambisonic bus channel c at frame i (ShRamps, sbm_core.h): constant part + the ramp's offset from it while it lasts.
+SBM_HD float sh_gain_at(float konst, const ShRamps* rp, int c, uint32_t i) {
+	if (!rp) return konst;
+	const float fi = (float)i;
+	return fi < rp->nf[c] ? fadd(konst, fmaf(fi, rp->inc[c], rp->stm[c])) : konst;
+}
+
 // New AudioResampler::prev_samples after this buffer (AR.cpp:108-110): the last two of {prev0, prev1, window}.
 SBM_HD void resampler_tail(const WorkRec& r, float* p0, float* p1) {
 	const int n_tmp = (int)r.n_src + 2;

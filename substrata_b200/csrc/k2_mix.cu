@@ -60,13 +60,13 @@ namespace {
 #define SBM_PRODUCER_SLEEP_NS 200
 #endif
 #ifndef SBM_SH_FUSE
-#define SBM_SH_FUSE 4
+#define SBM_SH_FUSE 2
 #endif
 #ifndef SBM_SH_BIG_FUSE
-#define SBM_SH_BIG_FUSE 4
+#define SBM_SH_BIG_FUSE 2
 #endif
 #ifndef SBM_SH_BIG_CTAS
-#define SBM_SH_BIG_CTAS 1             // resident CTAs per SM the 1024-frame ambisonic kernel's register budget is set for (2 -> 96 registers and spills)
+#define SBM_SH_BIG_CTAS 2             // resident CTAs per SM the 1024-frame ambisonic kernel's register budget is set for (2 -> 96 registers and spills)
 #endif
 #ifndef SBM_BATCH_PAN
 #define SBM_BATCH_PAN 8
@@ -80,7 +80,7 @@ constexpr int kBatchSh = 4, kBatchPan = SBM_BATCH_PAN, kPanWarps = 4;
 #define SBM_STAGES_SH 4
 #endif
 #ifndef SBM_STAGES_SH_BIG
-#define SBM_STAGES_SH_BIG 6
+#define SBM_STAGES_SH_BIG 4
 #endif
 constexpr int kStagesPan = SBM_STAGES, kStagesSh = SBM_STAGES_SH, kStagesShBig = SBM_STAGES_SH_BIG;
 constexpr int kMaxStages = 10;
@@ -195,10 +195,10 @@ static_assert(sizeof(MixSmemHdr) <= 512, "header must fit its 512-byte slot");
 struct __attribute__((aligned(16))) MathDesc {
 	// first 16 bytes: everything the fused fast paths need, one LDS.128
 	uint32_t mode;              // kMd*
+	uint32_t nramp;             // frames from the start of the buffer in which some gain of this source still ramps
 	uint32_t w_idx;             // float index into the window ring of element 0 of the array the read head indexes:
 	                            // window sample 0, or two before it for the resampler's {prev0, prev1, window...}
 	float gd;                   // direct gain * mix factor (constant part)
-	uint32_t nramp;             // frames from the start of the buffer in which some gain of this source still ramps
 	unsigned long long x0, step;   // 32.32 read head
 	float g0, g1;               // stereo kernel: direct gain * mix factor * bus gain (constant parts)
 	uint32_t n1b;               // index (same coordinates as w_idx) from which `wadj` applies (loop wrap), 0xffffffff = never
@@ -221,7 +221,8 @@ __device__ __forceinline__ MathDesc make_desc(const WorkRec& r, const WinPlan& p
 	const bool rs = (f & kRecResample) != 0;
 	d.mode = 0;
 	if (f & kRecSkip) d.mode |= kMdSkip;
-	if (!p.fast) d.mode |= kMdGeneric;
+	const bool careful = !p.fast || (f & kRecRampCareful) != 0;     // (the careful path evaluates every channel ramp with its own end test)
+	if (careful) d.mode |= kMdGeneric;
 	if (f & (kRecResample | kRecMix1)) d.mode |= kMdInterp;
 	if (rs) d.mode |= kMdResample;
 	if (p.wadj) d.mode |= kMdAdjust;
@@ -232,7 +233,7 @@ __device__ __forceinline__ MathDesc make_desc(const WorkRec& r, const WinPlan& p
 	d.wadj = p.wadj;
 	d.x0 = r.x0_fx; d.step = r.step_fx;
 	// mix_factor: folded into the constant gains on the lean path; the careful paths (staged_sample / source_sample) apply it to the samples
-	const float mf = (p.fast && (f & kRecMix1) && !p.wadj && !(f & kRecLpf)) ? r.mix_factor : 1.0f;
+	const float mf = (!careful && (f & kRecMix1) && !p.wadj && !(f & kRecLpf)) ? r.mix_factor : 1.0f;
 	d.gd = mf * r.direct.konst;
 	d.g0 = d.gd * r.ch[0].konst; d.g1 = d.gd * r.ch[1].konst;
 	uint32_t nr = r.direct.n;
@@ -702,17 +703,18 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 			ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(yv, yv));
 		}
 	};
-	// same for a frame inside a ramp: channel c ramps while i < n[c] (GainProcessor in accumulate mode, gain.cc:25-92)
-	auto accumulate_ramped = [&](const float* gk, const ShRamps* rp, float yv, uint32_t i, float fi, int k) {
+	// same for a frame inside a ramp: channel c's gain is konst + (i < nf ? stm + i inc : 0)  (ShRamps, sbm_core.h; GainProcessor in
+	// accumulate mode, gain.cc:25-92)
+	auto accumulate_ramped = [&](const float* gk, const ShRamps* rp, float yv, uint32_t, float fi, int k) {
 		const float4* gk4 = reinterpret_cast<const float4*>(gk);
 #pragma unroll
 		for (int q = 0; q < NCH / 4; ++q) {
 			float4 g = gk4[q];
 			if (rp) {     // null: no channel ramps this buffer (only the direct gain ramps), ShRamps was not staged
-				const uint4 nn = reinterpret_cast<const uint4*>(rp->n)[q];
-				const float4 st = reinterpret_cast<const float4*>(rp->start)[q], in = reinterpret_cast<const float4*>(rp->inc)[q];
-				g.x = i < nn.x ? fmaf(fi, in.x, st.x) : g.x; g.y = i < nn.y ? fmaf(fi, in.y, st.y) : g.y;
-				g.z = i < nn.z ? fmaf(fi, in.z, st.z) : g.z; g.w = i < nn.w ? fmaf(fi, in.w, st.w) : g.w;
+				const float4 nn = reinterpret_cast<const float4*>(rp->nf)[q];
+				const float4 st = reinterpret_cast<const float4*>(rp->stm)[q], in = reinterpret_cast<const float4*>(rp->inc)[q];
+				g.x = fi < nn.x ? g.x + fmaf(fi, in.x, st.x) : g.x; g.y = fi < nn.y ? g.y + fmaf(fi, in.y, st.y) : g.y;
+				g.z = fi < nn.z ? g.z + fmaf(fi, in.z, st.z) : g.z; g.w = fi < nn.w ? g.w + fmaf(fi, in.w, st.w) : g.w;
 			}
 			ffma2(acc[2 * q][k], make_float2(g.x, g.y), make_float2(yv, yv));
 			ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(yv, yv));
@@ -725,57 +727,109 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
 		// ---------------- whole-batch fast path ----------------
+		// A batch whose sources are all "simple" (window staged by TMA, native rate or one read head, no filter, every gain ramp
+		// over within the first T frames) runs in two straight-line passes:
+		//   1. constant pass -- all K frames of all sources with the constant gains: per source and thread 4 sample loads, the 16
+		//      gains as four LDS.128, 32 FFMA2; no branch depends on whether anything ramps;
+		//   2. fix-up pass -- only the warps whose k = 0 frames lie inside a ramp, only for the sources that ramp: adds
+		//      (gain(i) - konst) * y for the channel ramps, branch-free as konst + stm + inc * min(i, nf) (ShRamps), and
+		//      konst * (y(i) - y_const) for a ramping direct gain.
 		bool batch_done = false;
 		if (EXACT && nb == (uint32_t)kBatch) {
-			uint4 dh[kBatch];     // {mode, w_idx, gd, nramp} of the four sources
-			uint32_t any = 0;
+			const MathDesc* dsc = sm.descs + qr * kBatch;
+			uint32_t any = 0, ramps = 0;
 #pragma unroll
 			for (int b = 0; b < kBatch; ++b) {
-				dh[b] = *reinterpret_cast<const uint4*>(&sm.descs[qr * kBatch + b]);
-				any |= (dh[b].x & ~(kMdInterp | kMdRamp | kMdShRamp)) | (dh[b].w > (uint32_t)TMAX ? kMdGeneric : 0u);
+				const uint2 mn = *reinterpret_cast<const uint2*>(&dsc[b]);     // {mode, nramp}
+				any |= (mn.x & ~(kMdInterp | kMdRamp | kMdShRamp)) | (mn.y > (uint32_t)TMAX ? kMdGeneric : 0u);
+				ramps |= mn.x;
 			}
 			if (any == 0) {
-				// FUSE sources at a time: all their sample loads first, then the arithmetic (4 with the 128-register budget of the
-				// <= 512-frame kernel, 2 where two 288-thread CTAs must share the SM's register file)
-				constexpr int FUSE = TMAX == 128 ? SBM_SH_FUSE : SBM_SH_BIG_FUSE;
+				// this thread's K samples of source b, before any gain
+				auto fetch = [&](int b, uint32_t w_idx, float* x) {
+					const float* wb = sm.wring + w_idx;
+					if (ramps & kMdInterp) {     // (batch-uniform test first: native-rate batches never look at the per-source mode)
+						const MathDesc& d = dsc[b];
+						if (d.mode & kMdInterp) {
+							unsigned long long p = d.x0 + (unsigned long long)t * d.step;
+							const unsigned long long stepT = d.step * (unsigned long long)T;
+#pragma unroll
+							for (int k = 0; k < K; ++k) {
+								const uint32_t di = (uint32_t)(p >> 32);
+								const float v0 = wb[di], v1 = wb[di + 1];
+								x[k] = fmaf(frac_of(p), v1 - v0, v0);
+								p += stepT;
+							}
+							return;
+						}
+					}
+#pragma unroll
+					for (int k = 0; k < K; ++k) x[k] = wb[t + (uint32_t)k * T];
+				};
+				constexpr int FUSE = TMAX == 128 ? SBM_SH_FUSE : SBM_SH_BIG_FUSE;     // sources whose sample loads are issued together
 #pragma unroll
 				for (int b0f = 0; b0f < kBatch; b0f += FUSE) {
 					float xs[FUSE][K];
+					float gds[FUSE];
 #pragma unroll
 					for (int bb = 0; bb < FUSE; ++bb) {
-						const int b = b0f + bb;
-						const float* wb = sm.wring + dh[b].y;
-						if (dh[b].x & kMdInterp) {
-							const MathDesc& d = sm.descs[qr * kBatch + b];
-#pragma unroll
-							for (int k = 0; k < K; ++k) {
-								const unsigned long long p = d.x0 + (unsigned long long)(t + (uint32_t)k * T) * d.step;
-								const uint32_t di = (uint32_t)(p >> 32);
-								const float v0 = wb[di], v1 = wb[di + 1];
-								xs[bb][k] = fmaf(frac_of(p), v1 - v0, v0);
-							}
-						} else {
-#pragma unroll
-							for (int k = 0; k < K; ++k) xs[bb][k] = wb[t + (uint32_t)k * T];
-						}
+						const uint2 wg = reinterpret_cast<const uint2*>(&dsc[b0f + bb])[1];     // {w_idx, gd}
+						gds[bb] = __uint_as_float(wg.y);
+						fetch(b0f + bb, wg.x, xs[bb]);
 					}
 #pragma unroll
 					for (int bb = 0; bb < FUSE; ++bb) {
 						const int b = b0f + bb;
-						const float gdf = __uint_as_float(dh[b].z);
-						const float* gk = sm.shgs[qr * kBatch + b].konst;
-						const uint32_t nramp = dh[b].w;
+						const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
+						float2 yy[K];
 #pragma unroll
-						for (int k = 1; k < K; ++k) accumulate_const(gk, xs[bb][k] * gdf, k);
-						if (warp_i0 < nramp) {
-							// this warp's first frames lie inside a ramp of the direct gain and / or of channel gains
-							const MathDesc& d = sm.descs[qr * kBatch + b];
-							const WorkRec& r = sm.recs[qr * kBatch + b];
-							const float yv = (xs[bb][0] * d.mfx) * gain_at(r.direct, t);
-							accumulate_ramped(gk, (dh[b].x & kMdShRamp) ? &sm.shrs[qw * kBatch + b] : nullptr, yv, t, ft, 0);
-						} else accumulate_const(gk, xs[bb][0] * gdf, 0);
+						for (int k = 0; k < K; ++k) { const float y = xs[bb][k] * gds[bb]; yy[k] = make_float2(y, y); }
+#pragma unroll
+						for (int q = 0; q < NCH / 4; ++q) {
+							const float4 g = gk4[q];
+#pragma unroll
+							for (int k = 0; k < K; ++k) {
+								ffma2(acc[2 * q][k], make_float2(g.x, g.y), yy[k]);
+								ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), yy[k]);
+							}
+						}
 						// frame F - 1 = t + (K - 1) T of thread T - 1: the bypassed occlusion filter's memory (mono_pole_filter.cc:40-44)
-						if (t == T - 1) a.lpf_prev[sm.descs[qr * kBatch + b].slot] = xs[bb][K - 1] * gdf;
+						if (t == T - 1) a.lpf_prev[dsc[b].slot] = yy[K - 1].x;
+					}
+				}
+				if (ramps & kMdRamp) {
+#pragma unroll 1
+					for (int b = 0; b < kBatch; ++b) {
+						const MathDesc& d = dsc[b];
+						if (!(d.mode & kMdRamp) || warp_i0 >= d.nramp) continue;     // warp-uniform
+						const WorkRec& r = sm.recs[qr * kBatch + b];
+						const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
+						float x[K];
+						fetch(b, d.w_idx, x);     // (the window is still staged: re-reading frame t costs less than keeping it in a register)
+						const float y0 = x[0] * d.gd;
+						const float Y = (x[0] * d.mfx) * gain_at(r.direct, t);
+						if (r.direct.n) {
+							const float dl = Y - y0;
+#pragma unroll
+							for (int q = 0; q < NCH / 4; ++q) {
+								const float4 g = gk4[q];
+								ffma2(acc[2 * q][0], make_float2(g.x, g.y), make_float2(dl, dl));
+								ffma2(acc[2 * q + 1][0], make_float2(g.z, g.w), make_float2(dl, dl));
+							}
+						}
+						if (d.mode & kMdShRamp) {
+							const ShRamps* rp = &sm.shrs[qw * kBatch + b];
+#pragma unroll
+							for (int q = 0; q < NCH / 4; ++q) {
+								const float4 nn = reinterpret_cast<const float4*>(rp->nf)[q];
+								const float4 st = reinterpret_cast<const float4*>(rp->stm)[q], in = reinterpret_cast<const float4*>(rp->inc)[q];
+								float2 e0 = make_float2(st.x, st.y), e1 = make_float2(st.z, st.w);
+								ffma2(e0, make_float2(fminf(ft, nn.x), fminf(ft, nn.y)), make_float2(in.x, in.y));
+								ffma2(e1, make_float2(fminf(ft, nn.z), fminf(ft, nn.w)), make_float2(in.z, in.w));
+								ffma2(acc[2 * q][0], e0, make_float2(Y, Y));
+								ffma2(acc[2 * q + 1][0], e1, make_float2(Y, Y));
+							}
+						}
 					}
 				}
 				batch_done = true;
@@ -907,8 +961,11 @@ __global__ void __launch_bounds__(128 + 32, 3) k2_mix_ambisonic_kernel(MixArgs a
 	ambisonic_body<128, kShK, 1, EXACT>(a, first, n, wslot, partials);
 }
 template <bool EXACT>
-#if SBM_SH_BIG_G == 1
+#if SBM_SH_BIG_G == 1 && SBM_SH_BIG_CTAS == 1
 __global__ void __launch_bounds__(kShBigT + 32, 1)
+#elif SBM_SH_BIG_G == 1
+// two 288-thread CTAs per SM: 65536 / 576 = 113 registers per thread; the launch-bounds heuristic would settle on 96 and spill
+__global__ void __maxnreg__(112)
 #else
 __global__ void __maxnreg__(SBM_SH_BIG_MAXNREG)
 #endif

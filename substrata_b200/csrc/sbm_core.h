@@ -58,6 +58,7 @@ constexpr uint32_t kRecStereo = 1u << 4;            // non-spatial: L = R = y
 constexpr uint32_t kRecHrtf = 1u << 5;              // ambisonic encode (16 channels) instead of pan (2)
 constexpr uint32_t kRecWrap = 1u << 6;              // window index wraps modulo len (looping buffer / ring)
 constexpr uint32_t kRecMix1 = 1u << 7;              // exactly one mix source, expressed as a window + fixed-point read head
+constexpr uint32_t kRecRampCareful = 1u << 8;       // ambisonic: a channel ramp ends inside the buffer on a value the -60 dB rule then zeroes (konst != end value)
 
 // ------------------------------------------------------------------------------------------------
 // HBM layout.  One slot per live source; SoA arrays indexed by slot, written by the host (params) or
@@ -121,7 +122,11 @@ struct __attribute__((aligned(128))) WorkRec {   // 128 B, K1 -> K2, one per ent
 };
 
 struct ShGains { float konst[kNumSh]; };                       // 64 B per HRTF source: effective constant gains
-struct ShRamps { float start[kNumSh]; float inc[kNumSh]; uint32_t n[kNumSh]; };   // read only when ch_ramp_mask != 0
+// Channel ramps of an ambisonic source (read only when ch_ramp_mask != 0; all 48 entries are written then): the gain of bus
+// channel c at frame i is  konst[c] + (i < nf[c] ? stm[c] + i * inc[c] : 0)  with stm = ramp start - konst, nf = ramp frames in
+// this buffer as a float (0 for a channel that does not ramp).  Where the ramp ends inside the buffer on konst itself (every case
+// except the -60 dB rule zeroing the end value, kRecRampCareful) that is also  konst + stm + inc * min(i, nf)  -- branch-free.
+struct ShRamps { float stm[kNumSh]; float inc[kNumSh]; float nf[kNumSh]; };
 
 // Per-engine scalars that change every buffer (passed by value to K1).
 struct Globals {

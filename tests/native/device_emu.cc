@@ -113,10 +113,10 @@ static void mix_list(const MixArgs& a, uint32_t first, uint32_t n, bool sh) {
 			}
 		} else {
 			for (int c = 0; c < kNumSh; ++c) {
-				RampDesc d; d.konst = a.shg[k].konst[c]; d.n = 0; d.start = 0.0f; d.inc = 0.0f;
-				if (r.ch_ramp_mask & (1u << c)) { d.start = a.shr[k].start[c]; d.inc = a.shr[k].inc[c]; d.n = a.shr[k].n[c]; }
+				const float konst = a.shg[k].konst[c];
+				const bool ramps = (r.ch_ramp_mask & (1u << c)) != 0;
 				float* row = a.bus + (size_t)c * F;
-				for (uint32_t i = 0; i < F; ++i) row[i] = fmaf(gain_at(d, i), y[i], row[i]);
+				for (uint32_t i = 0; i < F; ++i) row[i] = fmaf(sh_gain_at(konst, ramps ? &a.shr[k] : nullptr, c, i), y[i], row[i]);
 			}
 		}
 	}
