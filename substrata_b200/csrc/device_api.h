@@ -62,7 +62,8 @@ struct PeerArgs {
 };
 
 struct MixArgs {
-	const WorkRec* rec;         // [n_pan + n_sh] render-list order: stereo-bus sources first, then ambisonic sources
+	const MixRec* mrec;         // [n_pan + n_sh] render-list order: stereo-bus sources first, then ambisonic sources (CUDA build)
+	const WorkRec* rec;         // indexed like mrec: the full records (the CUDA kernels read them on their careful paths only)
 	const ShGains* shg;         // indexed like rec
 	const ShRamps* shr;         // indexed like rec
 	const MixZ* mixz;
@@ -81,6 +82,7 @@ struct MixArgs {
 	void* ev_after_k2;          // optional event recorded between K2 and K3 (profiling)
 	PeerArgs peer;
 	size_t bus_floats;
+	uint32_t rot_div;           // set by the launcher: SM count (CTA index / rot_div = which resident CTA of its SM a CTA is, first wave)
 };
 
 struct FinishArgs {

@@ -422,7 +422,7 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	ok = ok && dalloc(e->dv_stat, cap) && dalloc(e->dv_posvol, cap) && dalloc(e->dv_occl, cap) && dalloc(e->dv_ring_write, cap) && dalloc(e->dv_mixz, mixcap);
 	A.stat = e->dv_stat; A.posvol = e->dv_posvol; A.occl = e->dv_occl; A.ring_write = e->dv_ring_write; A.mixz = e->dv_mixz;
 	ok = ok && dalloc(A.live, cap) && dalloc(A.read_i, cap) && dalloc(A.eof, cap) && dalloc(A.rs, cap) && dalloc(A.dgain, cap) &&
-	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.finished, 2 * (size_t)cap) &&
+	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.mrec, cap) && dalloc(A.finished, 2 * (size_t)cap) &&
 	     dalloc(A.mix_pos, mixcap) && dalloc(A.mix_pos0, mixcap);
 	A.cstride = kNumSh;
 	ok = ok && dalloc(A.cgain, (size_t)cap * kNumSh);
@@ -472,7 +472,7 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	for (SetterRec* l = e->setq.exchange(nullptr); l;) { SetterRec* nx = l->next; free(l); l = nx; }
 	SlotArrays& A = e->A;
 	void* ptrs[] = {e->dv_stat, e->dv_posvol, e->dv_occl, e->dv_ring_write, e->dv_mixz, A.live, A.read_i, A.eof, A.rs, A.dgain, A.occ_cur,
-	                A.lpf_prev, A.bits, A.rec, e->fl[0].dv_finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
+	                A.lpf_prev, A.bits, A.rec, A.mrec, e->fl[0].dv_finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
 	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
 	                e->dv_hist, e->dv_dec};
 	for (void* p : ptrs) if (p) dev::release(p);
@@ -953,13 +953,13 @@ static int mix_begin_locked(sbm_engine* e) {
 	if (e->g.n_pan + e->g.n_sh && dev::launch_params(e->g, e->A, e->dv_flags, e->dv_table, e->dv_lists, e->n_slots, st)) return fail_cuda(e, "k1_params");
 	if (e->profiling) dev::event_record(fl.ev[1], st);
 	MixArgs m;
-	m.rec = e->A.rec; m.shg = e->A.shg; m.shr = e->A.shr; m.mixz = e->dv_mixz; m.mix_pos0 = e->A.mix_pos0; m.rs = e->A.rs; m.lpf_prev = e->A.lpf_prev;
+	m.mrec = e->A.mrec; m.rec = e->A.rec; m.shg = e->A.shg; m.shr = e->A.shr; m.mixz = e->dv_mixz; m.mix_pos0 = e->A.mix_pos0; m.rs = e->A.rs; m.lpf_prev = e->A.lpf_prev;
 	m.n_pan = (uint32_t)e->list_pan.size();
 	m.n_sh = (uint32_t)e->list_sh.size();
 	m.frames = e->g.frames; m.rate = e->g.rate; m.partials = e->dv_partials; m.partials_floats = e->partials_floats;
 	m.bus = e->dv_bus; m.flags = e->dv_flags; m.parity = e->g.parity;
 	m.ev_after_k2 = e->profiling ? fl.ev[2] : nullptr;
-	m.peer = e->peer; m.peer.parity = (uint32_t)(e->peer_buffers & 1); m.bus_floats = e->bus_floats;
+	m.peer = e->peer; m.peer.parity = (uint32_t)(e->peer_buffers & 1); m.bus_floats = e->bus_floats; m.rot_div = 1;
 	if (dev::launch_mix(m, st)) return fail_cuda(e, "k2_mix");
 	e->begun = true;
 	fl.active = (uint32_t)(e->list_pan.size() + e->list_sh.size());

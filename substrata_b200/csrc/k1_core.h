@@ -80,9 +80,10 @@ SBM_HD unsigned long long to_fx(double x) { return (unsigned long long)(x * kFx)
 constexpr uint32_t kMaxMix1Window = 4096;
 
 // Returns kUsed* bits; *rendered_src = PCM samples a rendered source reads this buffer (0 when skipped / stopped).
-// `out` = position in the render lists: where this source's WorkRec / ShGains / ShRamps go.
-SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot, uint32_t out,
-                              uint32_t* rendered_src) {
+// `rec_out`, `shg_out`, `shr_out`: where this source's WorkRec / ShGains / ShRamps go (the arrays in HBM indexed by render-list
+// position, or -- fused kernel -- registers and the CTA's shared-memory rings).
+SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot, WorkRec* rec_out,
+                              ShGains* shg_out, ShRamps* shr_out, uint32_t* rendered_src) {
 	*rendered_src = 0;
 	// All per-slot state is loaded up front, unconditionally: the loads are independent of each other, so the memory
 	// system sees them as one batch instead of a chain of dependent round trips behind the branches below.
@@ -107,7 +108,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	rec.ch_ramp_mask = 0; rec.mix_factor = 1.0f; rec.mix_first = st.mix_first; rec.nz = st.nz;
 	rec.direct.konst = 0.0f; rec.direct.start = 0.0f; rec.direct.inc = 0.0f; rec.direct.n = 0;
 	rec.ch[0] = rec.direct; rec.ch[1] = rec.direct;
-	if (!(st.flags & kFlagAlive) || !live) { A.rec[out] = rec; return 0; }
+	if (!(st.flags & kFlagAlive) || !live) { *rec_out = rec; return 0; }
 
 	const uint32_t F = G.frames;
 	const uint32_t kind = (st.flags >> kFlagKindShift) & 0xff;
@@ -212,7 +213,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		// DestroySource runs from the task queue before the graph is processed: the last buffer is not rendered.
 		A.live[slot] = 0;
 		A.finished[finished_push(flags)] = (int)st.id;
-		A.rec[out] = rec;
+		*rec_out = rec;
 		return 0;
 	}
 
@@ -237,7 +238,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		// skip: nothing downstream runs, but the feeder still resampled this buffer (AE.cpp:485-494 precede the graph), so
 		// K2 must still carry AudioResampler::prev_samples forward.
 		rec.flags = kRecSkip | (rflags & (kRecResample | kRecWrap));
-		A.rec[out] = rec;
+		*rec_out = rec;
 		return 0;
 	}
 	if (near_unity(target) && near_unity(dg)) {
@@ -255,7 +256,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		rec.ch[0].konst = 1.0f; rec.ch[1].konst = 1.0f;
 		A.bits[slot] = bits;
 		rec.flags = rflags;
-		A.rec[out] = rec;
+		*rec_out = rec;
 		return kUsedStereo;
 	}
 
@@ -300,7 +301,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		// 16 dependent round trips -- each sits behind the previous iteration's stores, which may alias as far as the compiler
 		// knows -- and the 4-byte stores of a warp scatter over 32 sectors each).
 		F4* cg4 = reinterpret_cast<F4*>(cg);                        // cstride == 16 floats: 64-byte aligned rows
-		F4* sg4 = reinterpret_cast<F4*>(A.shg[out].konst);
+		F4* sg4 = reinterpret_cast<F4*>(shg_out->konst);
 		for (int q = 0; q < kNumSh / 4; ++q) {
 			const F4 v = cg4[q];
 			float cur[4] = {v.x, v.y, v.z, v.w}, kon[4], stm[4], rin[4], rnf[4];
@@ -313,16 +314,18 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 					stm[j] = fsub(d.start, d.konst); rin[j] = d.inc; rnf[j] = (float)d.n;
 					gm |= 1u << j;
 					if (d.n > rec.ch[0].n) rec.ch[0].n = d.n;       // ambisonic sources: ch[0].n = longest channel ramp (K2's ramp region)
-					if (d.n < F && d.konst != cur[j]) rflags |= kRecRampCareful;     // ended on a near-zero value: konst is 0, not the end value
+					// ended on a near-zero value that the -60 dB rule zeroes: konst is 0, not the ramp's end value.  (An end value
+					// below 1e-6 -- a coefficient whose target is exactly 0, reached to within rounding -- is as good as 0.)
+					if (d.n < F && d.konst != cur[j] && fabsf(cur[j]) > 1e-6f) rflags |= kRecRampCareful;
 				}
 			}
 			cg4[q] = F4{cur[0], cur[1], cur[2], cur[3]};
 			sg4[q] = F4{kon[0], kon[1], kon[2], kon[3]};
 			if (gm) {
 				// ramp parameters of the group, 16 bytes each (zeros for the channels of the group that do not ramp)
-				reinterpret_cast<F4*>(A.shr[out].stm)[q] = F4{stm[0], stm[1], stm[2], stm[3]};
-				reinterpret_cast<F4*>(A.shr[out].inc)[q] = F4{rin[0], rin[1], rin[2], rin[3]};
-				reinterpret_cast<F4*>(A.shr[out].nf)[q] = F4{rnf[0], rnf[1], rnf[2], rnf[3]};
+				reinterpret_cast<F4*>(shr_out->stm)[q] = F4{stm[0], stm[1], stm[2], stm[3]};
+				reinterpret_cast<F4*>(shr_out->inc)[q] = F4{rin[0], rin[1], rin[2], rin[3]};
+				reinterpret_cast<F4*>(shr_out->nf)[q] = F4{rnf[0], rnf[1], rnf[2], rnf[3]};
 				rec.ch_ramp_mask |= gm << (4 * q);
 			}
 		}
@@ -331,12 +334,12 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 			for (int q = 0; q < kNumSh / 4; ++q)
 				if (!((rec.ch_ramp_mask >> (4 * q)) & 0xfu)) {
 					const F4 z = F4{0.0f, 0.0f, 0.0f, 0.0f};
-					reinterpret_cast<F4*>(A.shr[out].stm)[q] = z; reinterpret_cast<F4*>(A.shr[out].inc)[q] = z; reinterpret_cast<F4*>(A.shr[out].nf)[q] = z;
+					reinterpret_cast<F4*>(shr_out->stm)[q] = z; reinterpret_cast<F4*>(shr_out->inc)[q] = z; reinterpret_cast<F4*>(shr_out->nf)[q] = z;
 				}
 		rflags |= kRecHrtf;
 	}
 	rec.flags = rflags;
-	A.rec[out] = rec;
+	*rec_out = rec;
 	return hrtf ? kUsedSh : kUsedPan;
 }
 

@@ -4,9 +4,11 @@
 //
 // Compiled with -fmad=false: results of this unit feed integer truncations and thresholds (lookup-table cell,
 // -60 dB rules, ramp lengths), so every float operation must round exactly like the reference's SSE build.
-// HBM traffic per slot: SrcStatic 32 B + pos/volume 16 B + ~60 B of state read-modify-write + 128 B WorkRec write.
+// HBM traffic per slot: SrcStatic 32 B + pos/volume 16 B + ~60 B of state read-modify-write + 128 B MixRec write (k2_rec.h;
+// + the 128 B WorkRec only for sources a careful path of the mix kernel will read back).
 #include "device_internal.h"
 #include "k1_core.h"
+#include "k2_rec.h"
 
 namespace sbm {
 
@@ -17,13 +19,20 @@ namespace sbm {
 #define SBM_K1_MINB (1024 / SBM_K1_THREADS)
 #endif
 __global__ void __launch_bounds__(SBM_K1_THREADS, SBM_K1_MINB) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table,
-                                                       const uint32_t* __restrict__ lists) {
+                                                       const uint32_t* __restrict__ lists, uint32_t wslot) {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;    // position in the render lists
 	// whether this buffer's "mixer used" flags are already set: read NOW, so that the loads overlap the work below instead
 	// of being a dependent round trip at the end of every warp (a stale 0 only costs a redundant atomicOr)
 	const int set_pan = flags->pan_used[g.parity], set_sh = flags->sh_used[g.parity], set_st = flags->st_used[g.parity];
 	uint32_t used = 0, n_src = 0;
-	if (k < g.n_pan + g.n_sh) used = update_source(g, A, flags, table, lists[k], k, &n_src);
+	if (k < g.n_pan + g.n_sh) {
+		WorkRec rec;
+		used = update_source(g, A, flags, table, lists[k], &rec, A.shg + k, A.shr + k, &n_src);
+		// the record the mix kernel consumes, in final form (k2_rec.h); the full WorkRec only where a careful path will read it back
+		const MixRec m = make_mixrec(rec, wslot, k >= g.n_pan);
+		A.mrec[k] = m;
+		if (mixrec_needs_workrec(m.mode)) A.rec[k] = rec;
+	}
 	// Warp-level reduction of the "mixer used" bits and the accounting counters, then one lane publishes.  The flags are
 	// the same few words for the whole grid and same-address atomics serialise in L2 (one set per warp on ONE address cost
 	// ~100 us per million sources): a flag is only OR-ed by the warps that started while it still read 0, and the counters go to one of kStatParts
@@ -85,7 +94,7 @@ int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const 
 	(void)n_slots;
 	const uint32_t n = g.n_pan + g.n_sh;
 	if (!n) return 0;
-	k1_params_kernel<<<(n + SBM_K1_THREADS - 1) / SBM_K1_THREADS, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists);
+	k1_params_kernel<<<(n + SBM_K1_THREADS - 1) / SBM_K1_THREADS, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
 	note_launch();
 	return check_launch("k1_params");
 }

@@ -15,28 +15,26 @@
 //                             channels (32 channel-pair accumulators, FFMA2 with the gain pair from an LDS.128 and the
 //                             sample broadcast); a batch of simple sources runs as one straight-line block.
 //
-// Data movement.  Source windows are not loaded by the math threads: a dedicated producer warp drives a multi-stage
+// Data movement.  Source windows are not loaded by the math threads: a dedicated ISSUE warp drives a multi-stage
 // shared-memory ring with the TMA unit -- one cp.async.bulk (UBLKCP) per window segment, completion signalled on an
-// mbarrier per stage, stages handed back through a second mbarrier by the math warps.  The per-source records (WorkRec,
-// 128 B, render-list order, + 64 B of SH gains) stream through a second TMA ring two batches deeper, so that the producer
-// never waits on a dependent global load; producer lane b condenses record b of a batch into a 64-byte MathDesc
-// (shared-memory window index, fixed-point read head, pre-multiplied gains, mode bits; what the fast paths need sits in
-// its first 16 bytes) so that the math threads spend a handful of instructions per source on set-up.  The producer is a
-// serial, latency-bound warp: it plans a batch BEFORE it waits for the stage, and the stereo kernel uses batches of 8
-// sources because the producer's cost per batch does not depend on how many of its lanes are busy.  (Handing a stage
-// back in two halves, one per round of the math warps, was measured 4 % slower: more barrier traffic, no more overlap.)
+// mbarrier per stage, stages handed back through a second mbarrier by the math warps.  The per-source records arrive in
+// FINAL form (MixRec, 128 B, sbm_core.h / k2_rec.h: render path, read head, pre-multiplied gains, ramps, and the 16-byte
+// fetch plan -- pointer, first sample, segment lengths) through a second TMA ring two batches deeper; the issue warp's lane
+// b reads the plan of source b and issues its copies, nothing else.  (Round 1 planned the windows and condensed the records
+// in that warp; ncu showed the math warps waiting on its serial ~300-instruction chain per batch, not on HBM.)
 // Windows start at arbitrary sample offsets; the copy fetches the enclosing 16-byte-aligned span and the math indexes
 // from the sub-offset.  A looping window that crosses the end of its buffer is fetched as two segments.
-// Sources the fast path cannot express (zero-padded ends, ring underflow, multi-source pitch mixes, windows larger
-// than a stage slot, unaligned buffers, occlusion low-pass) take a generic per-sample path that reads global memory.
+// Sources the lean paths cannot express (zero-padded ends, ring underflow, multi-source pitch mixes, windows larger
+// than a stage slot, unaligned buffers, occlusion low-pass) take a careful per-sample path that reads the full WorkRec and,
+// where the window is not staged, global memory.
 //
-// HBM traffic: 4 B per source sample (PCM, + <= 24 B alignment over-fetch per segment) + 128 B WorkRec (+64 B SH gains)
+// HBM traffic: 4 B per source sample (PCM, + <= 24 B alignment over-fetch per segment) + 128 B MixRec (+64 B SH gains)
 // per source; writes are O(grid * frames).  Roofline: HBM read.  No tensor cores: 2..16 FMA per 4 B loaded.
 #include <map>
 #include <mutex>
 
 #include "device_internal.h"
-#include "k2_core.h"
+#include "k2_rec.h"
 
 namespace sbm {
 
@@ -66,7 +64,7 @@ namespace {
 #define SBM_SH_BIG_FUSE 2
 #endif
 #ifndef SBM_SH_BIG_CTAS
-#define SBM_SH_BIG_CTAS 2             // resident CTAs per SM the 1024-frame ambisonic kernel's register budget is set for (2 -> 96 registers and spills)
+#define SBM_SH_BIG_CTAS 1             // resident CTAs per SM the 1024-frame ambisonic kernel's register budget is set for (2 -> 96 registers and spills)
 #endif
 #ifndef SBM_BATCH_PAN
 #define SBM_BATCH_PAN 8
@@ -80,7 +78,7 @@ constexpr int kBatchSh = 4, kBatchPan = SBM_BATCH_PAN, kPanWarps = 4;
 #define SBM_STAGES_SH 4
 #endif
 #ifndef SBM_STAGES_SH_BIG
-#define SBM_STAGES_SH_BIG 4
+#define SBM_STAGES_SH_BIG 6
 #endif
 constexpr int kStagesPan = SBM_STAGES, kStagesSh = SBM_STAGES_SH, kStagesShBig = SBM_STAGES_SH_BIG;
 constexpr int kMaxStages = 10;
@@ -146,111 +144,17 @@ __device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
 	return *reinterpret_cast<float2*>(&r);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// How a source's window is laid out in its stage slot.  Pure function of the record, evaluated identically by the
-// issuing thread and by the math threads.
-//   slot: [4 floats unused][TMA span ...]; span = pcm[a0 .. a1) with a0 = start & ~3.  Window sample j sits at
-//   w[j] for j < n1 and at w[j + wadj] after a loop wrap (second segment placed at the next 16-byte boundary).
-// ---------------------------------------------------------------------------------------------------------------
-struct WinPlan {
-	bool fast;           // window comes through the TMA ring
-	uint32_t off0;       // start & 3
-	uint32_t seg1_floats, seg2_floats;   // 16-byte multiples; seg2 = 0 without wrap
-	uint32_t a0;         // first fetched sample of segment 1
-	uint32_t n1;         // window samples before the wrap (0xffffffff: no wrap)
-	uint32_t wadj;       // index adjustment after the wrap
-};
-
-__device__ __forceinline__ WinPlan plan_window(const WorkRec& r, uint32_t wslot) {
-	WinPlan p;
-	p.fast = false; p.off0 = r.start & 3u; p.a0 = r.start & ~3u; p.seg1_floats = 0; p.seg2_floats = 0; p.n1 = 0xffffffffu; p.wadj = 0;
-	const uint32_t flags = r.flags;
-	if (flags & (kRecSkip | kRecMix)) return p;
-	if (r.avail != r.n_src || r.n_src == 0 || r.n_src > r.len) return p;
-	if ((reinterpret_cast<unsigned long long>(r.pcm) & 15ull) != 0) return p;
-	const uint32_t end = r.start + r.n_src;
-	if (end <= r.len) {
-		p.seg1_floats = ((end + 3u) & ~3u) - p.a0;
-	} else {
-		if (!(flags & kRecWrap)) return p;
-		const uint32_t len4 = (r.len + 3u) & ~3u;
-		p.n1 = r.len - r.start;
-		p.wadj = len4 - r.len;
-		p.seg1_floats = len4 - p.a0;
-		p.seg2_floats = (r.n_src - p.n1 + 3u) & ~3u;
-	}
-	if (p.seg1_floats + p.seg2_floats + 4u > wslot) return p;
-	p.fast = true;
-	return p;
-}
-
 struct MixSmemHdr {
 	unsigned long long full_w[kMaxStages], empty_w[kMaxStages];          // window ring: TMA landed / math warps done
 	unsigned long long full_r[kMaxStages + 2], empty_r[kMaxStages + 2];  // record ring
 	float lpf_carry[8];                                          // per math warp (stereo kernel) / [0] (ambisonic kernel)
+	unsigned int done[kMaxStages + 2];                           // self-service rings: warps that have finished the batch in record slot q
 };
 static_assert(sizeof(MixSmemHdr) <= 512, "header must fit its 512-byte slot");
-
-// What the math threads need to know about a source, condensed from its WorkRec by the producer (64 B).
-struct __attribute__((aligned(16))) MathDesc {
-	// first 16 bytes: everything the fused fast paths need, one LDS.128
-	uint32_t mode;              // kMd*
-	uint32_t nramp;             // frames from the start of the buffer in which some gain of this source still ramps
-	uint32_t w_idx;             // float index into the window ring of element 0 of the array the read head indexes:
-	                            // window sample 0, or two before it for the resampler's {prev0, prev1, window...}
-	float gd;                   // direct gain * mix factor (constant part)
-	unsigned long long x0, step;   // 32.32 read head
-	float g0, g1;               // stereo kernel: direct gain * mix factor * bus gain (constant parts)
-	uint32_t n1b;               // index (same coordinates as w_idx) from which `wadj` applies (loop wrap), 0xffffffff = never
-	uint32_t wadj;
-	uint32_t slot;
-	float mfx;                  // MixSource::mix_factor where the lean paths must apply it to the samples themselves (ramping direct gain), else 1
-	uint32_t pad[2];
-};
-static_assert(sizeof(MathDesc) == 64, "MathDesc is 64 bytes");
-constexpr uint32_t kMdSkip = 1, kMdGeneric = 2, kMdInterp = 4, kMdAdjust = 8, kMdResample = 16, kMdLpf = 32, kMdStereo = 64,
-                   kMdRamp = 128, kMdShRamp = 256;
 
 // Barrier among the math warps only (the producer warp never joins): named barrier 1.
 __device__ __forceinline__ void math_sync(uint32_t n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
 __device__ __forceinline__ void math_sync_id(uint32_t id, uint32_t n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
-
-__device__ __forceinline__ MathDesc make_desc(const WorkRec& r, const WinPlan& p, uint32_t slot_float0, bool sh) {
-	MathDesc d;
-	const uint32_t f = r.flags;
-	const bool rs = (f & kRecResample) != 0;
-	d.mode = 0;
-	if (f & kRecSkip) d.mode |= kMdSkip;
-	const bool careful = !p.fast || (f & kRecRampCareful) != 0;     // (the careful path evaluates every channel ramp with its own end test)
-	if (careful) d.mode |= kMdGeneric;
-	if (f & (kRecResample | kRecMix1)) d.mode |= kMdInterp;
-	if (rs) d.mode |= kMdResample;
-	if (p.wadj) d.mode |= kMdAdjust;
-	if (f & kRecLpf) d.mode |= kMdLpf;
-	if (f & kRecStereo) d.mode |= kMdStereo;
-	d.w_idx = slot_float0 + 4u + p.off0 - (rs ? 2u : 0u);
-	d.n1b = p.n1 == 0xffffffffu ? 0xffffffffu : p.n1 + (rs ? 2u : 0u);
-	d.wadj = p.wadj;
-	d.x0 = r.x0_fx; d.step = r.step_fx;
-	// mix_factor: folded into the constant gains on the lean path; the careful paths (staged_sample / source_sample) apply it to the samples
-	const float mf = (!careful && (f & kRecMix1) && !p.wadj && !(f & kRecLpf)) ? r.mix_factor : 1.0f;
-	d.gd = mf * r.direct.konst;
-	d.g0 = d.gd * r.ch[0].konst; d.g1 = d.gd * r.ch[1].konst;
-	uint32_t nr = r.direct.n;
-	if (!sh) {
-		if ((r.ch_ramp_mask & 1u) && r.ch[0].n > nr) nr = r.ch[0].n;
-		if ((r.ch_ramp_mask & 2u) && r.ch[1].n > nr) nr = r.ch[1].n;
-	} else if (r.ch_ramp_mask) {
-		d.mode |= kMdShRamp;
-		if (r.ch[0].n > nr) nr = r.ch[0].n;      // ambisonic sources: K1 leaves the longest channel ramp in ch[0].n
-	}
-	d.nramp = nr;
-	if (nr) d.mode |= kMdRamp;
-	d.slot = r.slot;
-	d.mfx = (f & kRecMix1) ? r.mix_factor : 1.0f;
-	d.pad[0] = d.pad[1] = 0;
-	return d;
-}
 
 // Element d of {prev0, prev1, window...} from the staged window, with the reference's index clamp (AR.cpp:68-71).
 __device__ __forceinline__ float staged_tmp(const WorkRec& r, const float* w, const WinPlan& p, int d) {
@@ -277,6 +181,16 @@ __device__ __forceinline__ float staged_sample(const WorkRec& r, const float* w,
 	return fmaf(fr, v1 - v0, v0);
 }
 
+// Same from a MixRec on the lean resample path: wb = element 0 of {prev0, prev1, window...} in the stage slot (wb[0], wb[1]
+// themselves are not staged: they come from the record).
+__device__ __forceinline__ float staged_tmp_m(const MixRec& m, const float* wb, int d) {
+	const int max_i = (int)(m.dn_nsrc >> 16) + 1;
+	d = d > max_i ? max_i : d;
+	if (d == 0) return m.prev0;
+	if (d == 1) return m.prev1;
+	return wb[(uint32_t)d + ((uint32_t)d >= m.n1b ? m.wadj : 0u)];
+}
+
 // Occlusion low-pass over `F` samples staged in shared memory, by ONE warp.  y[n] = c (y[n-1] - x[n]) + x[n] is linear
 // in y[n-1]: the warp splits the buffer into 32 contiguous chunks, runs each chunk from a zero state while accumulating
 // c^len, chains the 32 chunk states in order, and re-runs each chunk from its true initial state.  Returns the final state.
@@ -297,45 +211,41 @@ __device__ float lpf_warp(float* buf, uint32_t F, float coef, float prev, uint32
 	return carry;
 }
 
-// Shared-memory carve-up (both kernels): header | WorkRec ring | ShGains ring, ShRamps ring (ambisonic only) | MathDesc ring | window ring.
+// Shared-memory carve-up (both kernels): header | MixRec ring | ShGains ring, ShRamps ring (ambisonic only) | window ring.
 template <int NCH, int kStages, int kBatch>
 struct SmemView {
 	static constexpr int kRecStages = kStages + 2;
-	MixSmemHdr* hdr; WorkRec* recs; ShGains* shgs; ShRamps* shrs; MathDesc* descs; float* wring;
+	MixSmemHdr* hdr; MixRec* recs; ShGains* shgs; ShRamps* shrs; float* wring;
 	__device__ explicit SmemView(unsigned char* raw) {
 		hdr = reinterpret_cast<MixSmemHdr*>(raw);
-		recs = reinterpret_cast<WorkRec*>(raw + 512);
-		unsigned char* p = reinterpret_cast<unsigned char*>(recs) + sizeof(WorkRec) * kRecStages * kBatch;
+		recs = reinterpret_cast<MixRec*>(raw + 512);
+		unsigned char* p = reinterpret_cast<unsigned char*>(recs) + sizeof(MixRec) * kRecStages * kBatch;
 		shgs = reinterpret_cast<ShGains*>(p);
 		if (NCH == 16) p += sizeof(ShGains) * kRecStages * kBatch;
 		shrs = reinterpret_cast<ShRamps*>(p);       // channel ramps of the sources that have any, staged with the windows
 		if (NCH == 16) p += sizeof(ShRamps) * kStages * kBatch;
-		descs = reinterpret_cast<MathDesc*>(p);
-		p += sizeof(MathDesc) * kRecStages * kBatch;
 		wring = reinterpret_cast<float*>(p);
 	}
 };
 
-// ================= producer warp (both kernels): lane b looks after source b of each batch =================
+// ================= issue warp (both kernels): lane b looks after source b of each batch =================
 template <int NCH, int kStages, int kBatch>
-__device__ void producer_warp(const SmemView<NCH, kStages, kBatch>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane) {
+__device__ void issue_warp(const SmemView<NCH, kStages, kBatch>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane) {
 	constexpr int kRecStages = kStages + 2;
 	MixSmemHdr* hdr = sm.hdr;
-	const WorkRec* __restrict__ grec = a.rec;
+	const MixRec* __restrict__ grec = a.mrec;
 	const ShGains* __restrict__ gshg = a.shg;
-	// Records run two batches ahead of the windows.  Per batch: (1) wait for its records, plan the windows and write the
-	// MathDescs (desc ring indexed like the record ring, so this needs no free window stage), (2) refill the record slot
-	// two batches ahead, (3) wait for the window stage to be handed back, (4) arm the barrier and issue the copies --
-	// so that between "stage handed back" and "copies issued" there are only a few instructions.
+	// Records run two batches ahead of the windows.  Per batch: (1) wait for its records and read the fetch plans, (2) refill the
+	// record slot two batches ahead, (3) wait for the window stage to be handed back, (4) arm the barrier and issue the copies.
 	auto issue_recs = [&](uint32_t jb, uint32_t q, uint32_t parity_prev) {
 		if (jb >= nbatch) return;
 		if (jb >= (uint32_t)kRecStages) mbar_wait_relaxed(&hdr->empty_r[q], parity_prev);
 		if (lane == 0) {
 			const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 			const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
-			const uint32_t bytes = nb * (uint32_t)sizeof(WorkRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u);
+			const uint32_t bytes = nb * (uint32_t)sizeof(MixRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u);
 			mbar_expect_tx(&hdr->full_r[q], bytes);
-			bulk_g2s(sm.recs + q * kBatch, grec + b0, nb * (uint32_t)sizeof(WorkRec), &hdr->full_r[q]);
+			bulk_g2s(sm.recs + q * kBatch, grec + b0, nb * (uint32_t)sizeof(MixRec), &hdr->full_r[q]);
 			if (NCH == 16) bulk_g2s(sm.shgs + q * kBatch, gshg + b0, nb * (uint32_t)sizeof(ShGains), &hdr->full_r[q]);
 		}
 		__syncwarp();
@@ -349,36 +259,28 @@ __device__ void producer_warp(const SmemView<NCH, kStages, kBatch>& sm, const Mi
 		mbar_wait(&hdr->full_r[qr], ph_r);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
-		WinPlan p;
-		p.fast = false; p.seg1_floats = 0; p.seg2_floats = 0; p.a0 = 0;
-		const uint32_t slot_float0 = (qw * kBatch + lane) * wslot;
-		const float* pcm = nullptr;
+		uint4 pl = make_uint4(0u, 0u, 0u, 0u);     // {pcm lo, pcm hi, a0, segs}
 		bool want_ramps = false;
-		uint32_t bytes = 0;
 		if (lane < nb) {
-			const WorkRec& r = sm.recs[qr * kBatch + lane];
-			p = plan_window(r, wslot);
-			sm.descs[qr * kBatch + lane] = make_desc(r, p, slot_float0, NCH == 16);
-			pcm = r.pcm;
-			if (p.fast) bytes = 4u * (p.seg1_floats + p.seg2_floats);
-			if (NCH == 16) {
-				want_ramps = r.ch_ramp_mask != 0 && !(r.flags & kRecSkip);
-				if (want_ramps) bytes += (uint32_t)sizeof(ShRamps);
-			}
+			const MixRec& m = sm.recs[qr * kBatch + lane];
+			pl = *reinterpret_cast<const uint4*>(&m.pcm);
+			if (NCH == 16) want_ramps = (m.mode & (kMdShRamp | kMdSkip)) == kMdShRamp;
 		}
+		const uint32_t seg1 = pl.w & 0xffffu, seg2 = pl.w >> 16;
+		uint32_t bytes = 4u * (seg1 + seg2) + (want_ramps ? (uint32_t)sizeof(ShRamps) : 0u);
 		for (int o = kBatch / 2; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
 		issue_recs(jb + 2, q2, ph_2 ^ 1u);
 		if (jb >= (uint32_t)kStages) mbar_wait_relaxed(&hdr->empty_w[qw], ph_w ^ 1u);
 		__syncwarp();
-		// the arrive below releases the descriptors written above (and, transitively, the records) to the math warps
 		if (lane == 0) {
 			if (bytes) mbar_expect_tx(&hdr->full_w[qw], bytes); else mbar_arrive(&hdr->full_w[qw]);
 		}
 		__syncwarp();
-		if (p.fast) {
-			float* dst = sm.wring + slot_float0 + 4;
-			bulk_g2s(dst, pcm + p.a0, 4u * p.seg1_floats, &hdr->full_w[qw]);
-			if (p.seg2_floats) bulk_g2s(dst + p.seg1_floats, pcm, 4u * p.seg2_floats, &hdr->full_w[qw]);
+		if (seg1) {
+			const float* pcm = reinterpret_cast<const float*>((unsigned long long)pl.x | ((unsigned long long)pl.y << 32));
+			float* dst = sm.wring + (size_t)(qw * kBatch + lane) * wslot + 4;
+			bulk_g2s(dst, pcm + pl.z, 4u * seg1, &hdr->full_w[qw]);
+			if (seg2) bulk_g2s(dst + seg1, pcm, 4u * seg2, &hdr->full_w[qw]);
 		}
 		if (NCH == 16 && want_ramps) bulk_g2s(sm.shrs + qw * kBatch + lane, a.shr + (b0 + lane), (uint32_t)sizeof(ShRamps), &hdr->full_w[qw]);
 		__syncwarp();
@@ -388,11 +290,64 @@ __device__ void producer_warp(const SmemView<NCH, kStages, kBatch>& sm, const Mi
 	}
 }
 
+// ================= self-service rings (ambisonic kernel, frames 256 / 512 / 1024): no dedicated issue warp =================
+// With the records in final form, refilling a stage is ~40 instructions -- too little to justify a warp that holds registers
+// the math warps need (the register file is per scheduler: 4 x 16 K; a 5th or 9th warp per CTA costs a whole resident CTA at
+// 128 registers).  Every warp is a math warp; the warp that finishes a batch LAST (elected through a shared-memory counter)
+// refills the window stage and the record slot that batch just vacated.  Nobody ever waits for a stage to be handed back.
+template <int NCH, int kStages, int kBatch>
+__device__ __forceinline__ void fill_record_slot(const SmemView<NCH, kStages, kBatch>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t lane, uint32_t j) {
+	constexpr int kRecStages = kStages + 2;
+	if (j >= nbatch) return;
+	if (lane == 0) {
+		const uint32_t q = j % kRecStages;
+		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(j) * kBatch;
+		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
+		const uint32_t bytes = nb * (uint32_t)sizeof(MixRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u);
+		mbar_expect_tx(&sm.hdr->full_r[q], bytes);
+		bulk_g2s(sm.recs + q * kBatch, a.mrec + b0, nb * (uint32_t)sizeof(MixRec), &sm.hdr->full_r[q]);
+		if (NCH == 16) bulk_g2s(sm.shgs + q * kBatch, a.shg + b0, nb * (uint32_t)sizeof(ShGains), &sm.hdr->full_r[q]);
+	}
+	__syncwarp();
+}
+template <int NCH, int kStages, int kBatch>
+__device__ __forceinline__ void fill_window_stage(const SmemView<NCH, kStages, kBatch>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane, uint32_t j) {
+	constexpr int kRecStages = kStages + 2;
+	if (j >= nbatch) return;
+	MixSmemHdr* hdr = sm.hdr;
+	const uint32_t qr = j % kRecStages, qw = j % kStages;
+	mbar_wait(&hdr->full_r[qr], (j / kRecStages) & 1u);     // the batch's records (requested RS - S batches ago)
+	const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(j) * kBatch;
+	const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
+	uint4 pl = make_uint4(0u, 0u, 0u, 0u);     // {pcm lo, pcm hi, a0, segs}
+	bool want_ramps = false;
+	if (lane < nb) {
+		const MixRec& m = sm.recs[qr * kBatch + lane];
+		pl = *reinterpret_cast<const uint4*>(&m.pcm);
+		if (NCH == 16) want_ramps = (m.mode & (kMdShRamp | kMdSkip)) == kMdShRamp;
+	}
+	const uint32_t seg1 = pl.w & 0xffffu, seg2 = pl.w >> 16;
+	uint32_t bytes = 4u * (seg1 + seg2) + (want_ramps ? (uint32_t)sizeof(ShRamps) : 0u);
+	for (int o = kBatch / 2; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+	if (lane == 0) {
+		if (bytes) mbar_expect_tx(&hdr->full_w[qw], bytes); else mbar_arrive(&hdr->full_w[qw]);
+	}
+	__syncwarp();
+	if (seg1) {
+		const float* pcm = reinterpret_cast<const float*>((unsigned long long)pl.x | ((unsigned long long)pl.y << 32));
+		float* dst = sm.wring + (size_t)(qw * kBatch + lane) * wslot + 4;
+		bulk_g2s(dst, pcm + pl.z, 4u * seg1, &hdr->full_w[qw]);
+		if (seg2) bulk_g2s(dst + seg1, pcm, 4u * seg2, &hdr->full_w[qw]);
+	}
+	if (NCH == 16 && want_ramps) bulk_g2s(sm.shrs + qw * kBatch + lane, a.shr + (b0 + lane), (uint32_t)sizeof(ShRamps), &hdr->full_w[qw]);
+	__syncwarp();
+}
+
 template <int kStages>
 __device__ __forceinline__ void init_barriers(MixSmemHdr* hdr, uint32_t n_consumers) {
 	constexpr int kRecStages = kStages + 2;
 	for (int q = 0; q < kStages; ++q) { mbar_init(&hdr->full_w[q], 1); mbar_init(&hdr->empty_w[q], n_consumers); }
-	for (int q = 0; q < kRecStages; ++q) { mbar_init(&hdr->full_r[q], 1); mbar_init(&hdr->empty_r[q], n_consumers); }
+	for (int q = 0; q < kRecStages; ++q) { mbar_init(&hdr->full_r[q], 1); mbar_init(&hdr->empty_r[q], n_consumers); hdr->done[q] = 0u; }
 	fence_mbar_init();
 }
 
@@ -466,7 +421,7 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 	if (t == 0) init_barriers<kStages>(hdr, kPanWarps);
 	__syncthreads();
 	grid_dep_wait();     // everything above overlaps the tail of K1; its records are read from here on
-	if (warp == (uint32_t)kPanWarps) { producer_warp<2, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+	if (warp == (uint32_t)kPanWarps) { issue_warp<2, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[KF];     // (L, R) of frame lane + 32 k: one FFMA2 (gain pair x broadcast sample) per frame on the constant-gain path
 #pragma unroll
@@ -479,12 +434,13 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 #pragma unroll 1
 		for (uint32_t src = warp; src < (uint32_t)kBatch; src += kPanWarps)     // this warp's sources of the batch
 		if (b0 + src < s1) {
-			const MathDesc& d = sm.descs[qr * kBatch + src];
-			const WorkRec& r = sm.recs[qr * kBatch + src];
-			const uint32_t mode = d.mode;
+			const MixRec& m = sm.recs[qr * kBatch + src];
+			const uint32_t mode = m.mode;
+			float* slot = sm.wring + (size_t)(qw * kBatch + src) * wslot;      // this source's stage slot
 			if (mode & kMdSkip) {
 				// gain-skipped source: the feeder still consumed this buffer; carry the resampler history forward
-				if ((r.flags & kRecResample) && lane == 0) {
+				if ((mode & kMdResample) && lane == 0) {
+					const WorkRec& r = a.rec[b0 + src];
 					float p0, p1;
 					resampler_tail(r, &p0, &p1);
 					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
@@ -496,10 +452,11 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 				if (EXACT && SBM_PACKED_LERP && (mode & ~kMdRamp) == kMdInterp) {
 					// ---------------- single read head (pitch / doppler), window staged by TMA, nothing else: the C4 case.  All
 					// frames in pairs, the two interpolations of a pair share packed f32x2 instructions. ----------------
-					const float* wb = sm.wring + d.w_idx;
-					mf = d.mfx;
-					unsigned long long p = d.x0 + (unsigned long long)lane * d.step;
-					const unsigned long long step32 = d.step << 5;
+					const float* wb = slot + m.w_off;
+					mf = m.mfx;
+					const unsigned long long step = m.step;
+					unsigned long long p = m.x0 + (unsigned long long)lane * step;
+					const unsigned long long step32 = step << 5;
 #pragma unroll
 					for (int k = 0; k < KF; k += 2) {
 						const unsigned long long pa = p, pb = p + step32;
@@ -516,18 +473,18 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 					}
 				} else if (mode & (kMdGeneric | kMdLpf | kMdAdjust)) {
 					// ---------------- careful fetch (rare, out of line): leaves the samples in this source's stage slot ----------------
-					float* slot = sm.wring + (size_t)(qw * kBatch + src) * wslot;
-					filtered = careful_source_to_slot(a, r, slot, wslot, lane);
+					filtered = careful_source_to_slot(a, a.rec[b0 + src], slot, wslot, lane);
 #pragma unroll
 					for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; x[k] = (EXACT || i < F) ? slot[i] : 0.0f; }
 				} else {
 					// ---------------- lean fetch: window staged in shared memory by the TMA ring ----------------
-					const float* wb = sm.wring + d.w_idx;
-					if (r.flags & kRecMix1) mf = r.mix_factor;
+					const float* wb = slot + m.w_off;
+					mf = m.mfx;
 					if (mode & kMdInterp) {
 						const bool rsmp = (mode & kMdResample) != 0;
-						unsigned long long p = d.x0 + (unsigned long long)lane * d.step;
-						const unsigned long long step32 = d.step << 5;
+						const unsigned long long step = m.step;
+						unsigned long long p = m.x0 + (unsigned long long)lane * step;
+						const unsigned long long step32 = step << 5;
 						auto lerp1 = [&](int k) {
 							const uint32_t i = lane + 32u * k;
 							float v = 0.0f;
@@ -536,10 +493,8 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 								const float fr = frac_of(p);
 								float v0, v1;
 								// only the first frames (resampler history) and the last ones (index clamp) need the careful form
-								if ((k == 0 || k == KF - 1 || !EXACT) && rsmp) {
-									const WinPlan wp = plan_window(r, wslot);
-									v0 = staged_tmp(r, wb + 2, wp, (int)di); v1 = staged_tmp(r, wb + 2, wp, (int)di + 1);
-								} else { v0 = wb[di]; v1 = wb[di + 1]; }
+								if ((k == 0 || k == KF - 1 || !EXACT) && rsmp) { v0 = staged_tmp_m(m, wb, (int)di); v1 = staged_tmp_m(m, wb, (int)di + 1); }
+								else { v0 = wb[di]; v1 = wb[di + 1]; }
 								v = fmaf(fr, v1 - v0, v0);
 							}
 							x[k] = v;
@@ -568,9 +523,9 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 							for (int k = 0; k < KF; ++k) lerp1(k);
 						}
 						if (rsmp && lane == 0) {
-							const WinPlan wp = plan_window(r, wslot);
-							a.rs[d.slot].prev_samples[0] = staged_tmp(r, wb + 2, wp, (int)r.n_src);
-							a.rs[d.slot].prev_samples[1] = staged_tmp(r, wb + 2, wp, (int)r.n_src + 1);
+							const int ns = (int)(m.dn_nsrc >> 16);
+							a.rs[m.slot].prev_samples[0] = staged_tmp_m(m, wb, ns);
+							a.rs[m.slot].prev_samples[1] = staged_tmp_m(m, wb, ns + 1);
 						}
 					} else {
 #pragma unroll
@@ -581,8 +536,8 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 					}
 				}
 				// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
-				const float2 g01 = make_float2(d.g0, d.g1);
-				const uint32_t nramp = filtered ? F : d.nramp;     // frames that need per-frame gain evaluation
+				const float2 g01 = make_float2(m.g0, m.g1);
+				const uint32_t nramp = filtered ? F : m.nramp;     // frames that need per-frame gain evaluation
 				// RAMPS: 0 = no gain ramps in this buffer, 1 = ramps end within the first 32 frames (the usual case while the
 				// listener moves), 2 = anything (long ramps, filtered signal): per-iteration warp-uniform test.
 				auto gains = [&](auto ramps_tag) {
@@ -592,14 +547,14 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 						const uint32_t i = lane + 32u * k;
 						const bool per_frame = RAMPS == 2 ? (32u * k < nramp) : (RAMPS == 1 && k == 0);
 						if (per_frame) {
-							const float yv = filtered ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
-							acc[k].x = fmaf(gain_at(r.ch[0], i), yv, acc[k].x);
-							acc[k].y = fmaf(gain_at(r.ch[1], i), yv, acc[k].y);
-							if (!filtered && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[d.slot] = yv;
+							const float yv = filtered ? x[k] : (x[k] * mf) * direct_gain_at(m, i);
+							acc[k].x = fmaf(ch0_gain_at(m, i), yv, acc[k].x);
+							acc[k].y = fmaf(ch1_gain_at(m, i), yv, acc[k].y);
+							if (!filtered && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[m.slot] = yv;
 						} else {
 							ffma2(acc[k], g01, make_float2(x[k], x[k]));
 							// bypassed occlusion filter remembers the last input sample (mono_pole_filter.cc:40-44)
-							if ((k == KF - 1 || !EXACT) && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[d.slot] = x[k] * d.gd;
+							if ((k == KF - 1 || !EXACT) && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[m.slot] = x[k] * m.gd;
 						}
 					}
 				};
@@ -657,18 +612,24 @@ constexpr int kShK = 4, kShBigK = SBM_SH_BIG_K, kShBigT = 1024 / kShBigK, kShBig
 // the CTA's slice; the groups share the producer warp and its rings.  Where the register file leaves room for only one CTA
 // per SM (frames > 512: 256 math threads x ~120 registers), two groups overlap each other's barrier waits and dependent
 // chains the way two resident CTAs would.
-template <int TMAX, int K, int G, bool EXACT>     // TMAX math threads x K frames each: <128, 4, 1> (frames <= 512), <kShBigT, kShBigK, kShBigG> (frames <= 1024);
-                                           // EXACT: frames == K * TMAX, no per-frame bounds checks
+template <int TMAX, int K, int G, bool EXACT, bool SELF, int kStages>     // TMAX math threads x K frames each; EXACT: frames == K * TMAX, no per-frame
+                                                                          // bounds checks; SELF: self-service rings (no issue warp; implies EXACT, G == 1)
 __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	constexpr int kStages = TMAX == 128 ? kStagesSh : kStagesShBig, kRecStages = kStages + 2, kBatch = kBatchSh;
+	constexpr int kRecStages = kStages + 2, kBatch = kBatchSh;
 	const SmemView<16, kStages, kBatch> sm(smem_raw);
 	MixSmemHdr* hdr = sm.hdr;
-	// blockDim.x = T math threads + one producer warp (the last warp)
+	// blockDim.x = T math threads (+ one issue warp, the last warp, unless SELF)
 	const uint32_t F = a.frames, T = EXACT ? (uint32_t)TMAX : (blockDim.x - 32) / G;   // EXACT: T is a compile-time constant
 	const uint32_t grp = G == 1 ? 0u : (threadIdx.x / T < (uint32_t)G ? threadIdx.x / T : 0u);      // math group of this thread
-	const uint32_t t = threadIdx.x - grp * T, lane = threadIdx.x & 31u;                          // index inside the group
+	const uint32_t lane = threadIdx.x & 31u;
+	// Which 32-frame chunk a warp owns is rotated from CTA to CTA (SELF): gain ramps live in the first frames of a buffer, so
+	// the warp that owns chunk 0 does the fix-up work of every ramping source and is the slowest of its CTA; warp w of every
+	// CTA sits on scheduler w % 4, and without the rotation the slow warps of all resident CTAs would share one scheduler
+	// while the other three idle (ncu: 26 % of the stall samples were warps of the light chunks waiting for a stage).
+	const uint32_t rot = SELF ? (blockIdx.x / a.rot_div) % (T / 32u) : 0u;
+	const uint32_t t = SELF ? (((threadIdx.x >> 5) + rot) % (T / 32u)) * 32u + lane : threadIdx.x - grp * T;     // index inside the group = frame of iteration k = 0
 	// (making F a compile-time constant too was measured 5 % slower here: it tips the register allocation into spills)
 	// Batches of kBatch consecutive list entries are dealt to the CTAs round-robin (batch g -> CTA g % grid), so that a
 	// run of expensive sources (long ramps, occlusion, generic fetches) is spread over the whole grid.
@@ -683,7 +644,12 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 	if (threadIdx.x == 0) init_barriers<kStages>(hdr, T / 32);     // a batch is consumed by the T / 32 warps of ONE group
 	__syncthreads();
 	grid_dep_wait();     // everything above overlaps the tail of the previous kernel; K1's records are read from here on
-	if (threadIdx.x >= (uint32_t)G * T) { producer_warp<16, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+	if (!SELF && threadIdx.x >= (uint32_t)G * T) { issue_warp<16, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
+	if (SELF && threadIdx.x < 32) {     // (hardware warp 0, whatever chunk it owns)
+		// prologue of the self-service rings: the first record slots and window stages
+		for (uint32_t j = 0; j < (uint32_t)kRecStages; ++j) fill_record_slot<16, kStages, kBatch>(sm, a, s0, s1, nbatch, lane, j);
+		for (uint32_t j = 0; j < (uint32_t)kStages; ++j) fill_window_stage<16, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane, j);
+	}
 
 	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1) x frames t + k T
 #pragma unroll
@@ -705,7 +671,7 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 	};
 	// same for a frame inside a ramp: channel c's gain is konst + (i < nf ? stm + i inc : 0)  (ShRamps, sbm_core.h; GainProcessor in
 	// accumulate mode, gain.cc:25-92)
-	auto accumulate_ramped = [&](const float* gk, const ShRamps* rp, float yv, uint32_t, float fi, int k) {
+	auto accumulate_ramped = [&](const float* gk, const ShRamps* rp, float yv, float fi, int k) {
 		const float4* gk4 = reinterpret_cast<const float4*>(gk);
 #pragma unroll
 		for (int q = 0; q < NCH / 4; ++q) {
@@ -726,33 +692,35 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 		mbar_wait(&hdr->full_w[qw], ph_w);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
+		const MixRec* mrs = sm.recs + qr * kBatch;                         // this batch's records
+		const float* slots = sm.wring + (size_t)(qw * kBatch) * wslot;     // ... and stage slots (source b: slots + b * wslot)
 		// ---------------- whole-batch fast path ----------------
 		// A batch whose sources are all "simple" (window staged by TMA, native rate or one read head, no filter, every gain ramp
 		// over within the first T frames) runs in two straight-line passes:
 		//   1. constant pass -- all K frames of all sources with the constant gains: per source and thread 4 sample loads, the 16
 		//      gains as four LDS.128, 32 FFMA2; no branch depends on whether anything ramps;
 		//   2. fix-up pass -- only the warps whose k = 0 frames lie inside a ramp, only for the sources that ramp: adds
-		//      (gain(i) - konst) * y for the channel ramps, branch-free as konst + stm + inc * min(i, nf) (ShRamps), and
+		//      (gain(i) - konst) * y for the channel ramps, branch-free as stm + inc * min(i, nf) (ShRamps), and
 		//      konst * (y(i) - y_const) for a ramping direct gain.
 		bool batch_done = false;
 		if (EXACT && nb == (uint32_t)kBatch) {
-			const MathDesc* dsc = sm.descs + qr * kBatch;
 			uint32_t any = 0, ramps = 0;
 #pragma unroll
 			for (int b = 0; b < kBatch; ++b) {
-				const uint2 mn = *reinterpret_cast<const uint2*>(&dsc[b]);     // {mode, nramp}
-				any |= (mn.x & ~(kMdInterp | kMdRamp | kMdShRamp)) | (mn.y > (uint32_t)TMAX ? kMdGeneric : 0u);
+				const uint2 mn = *reinterpret_cast<const uint2*>(&mrs[b]);     // {mode, nramp}
+				any |= mn.x & ~(kMdInterp | kMdRamp | kMdShRamp);
 				ramps |= mn.x;
 			}
 			if (any == 0) {
 				// this thread's K samples of source b, before any gain
-				auto fetch = [&](int b, uint32_t w_idx, float* x) {
-					const float* wb = sm.wring + w_idx;
+				auto fetch = [&](int b, uint32_t w_off, float* x) {
+					const float* wb = slots + (size_t)b * wslot + w_off;
 					if (ramps & kMdInterp) {     // (batch-uniform test first: native-rate batches never look at the per-source mode)
-						const MathDesc& d = dsc[b];
-						if (d.mode & kMdInterp) {
-							unsigned long long p = d.x0 + (unsigned long long)t * d.step;
-							const unsigned long long stepT = d.step * (unsigned long long)T;
+						const MixRec& m = mrs[b];
+						if (m.mode & kMdInterp) {
+							const unsigned long long step = m.step;
+							unsigned long long p = m.x0 + (unsigned long long)t * step;
+							const unsigned long long stepT = step * (unsigned long long)T;
 #pragma unroll
 							for (int k = 0; k < K; ++k) {
 								const uint32_t di = (uint32_t)(p >> 32);
@@ -773,7 +741,7 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 					float gds[FUSE];
 #pragma unroll
 					for (int bb = 0; bb < FUSE; ++bb) {
-						const uint2 wg = reinterpret_cast<const uint2*>(&dsc[b0f + bb])[1];     // {w_idx, gd}
+						const uint2 wg = reinterpret_cast<const uint2*>(&mrs[b0f + bb])[1];     // {w_off, gd}
 						gds[bb] = __uint_as_float(wg.y);
 						fetch(b0f + bb, wg.x, xs[bb]);
 					}
@@ -794,41 +762,51 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 							}
 						}
 						// frame F - 1 = t + (K - 1) T of thread T - 1: the bypassed occlusion filter's memory (mono_pole_filter.cc:40-44)
-						if (t == T - 1) a.lpf_prev[dsc[b].slot] = yy[K - 1].x;
+						if (t == T - 1) a.lpf_prev[mrs[b].slot] = yy[K - 1].x;
 					}
 				}
 				if (ramps & kMdRamp) {
 #pragma unroll 1
 					for (int b = 0; b < kBatch; ++b) {
-						const MathDesc& d = dsc[b];
-						if (!(d.mode & kMdRamp) || warp_i0 >= d.nramp) continue;     // warp-uniform
-						const WorkRec& r = sm.recs[qr * kBatch + b];
+						const MixRec& m = mrs[b];
+						const uint32_t nramp = m.nramp;
+						if (!(m.mode & kMdRamp) || warp_i0 >= nramp) continue;     // warp-uniform
 						const float4* gk4 = reinterpret_cast<const float4*>(sm.shgs[qr * kBatch + b].konst);
+						const ShRamps* rp = (m.mode & kMdShRamp) ? &sm.shrs[qw * kBatch + b] : nullptr;
+						const bool dramp = (m.dn_nsrc & 0xffffu) != 0;
 						float x[K];
-						fetch(b, d.w_idx, x);     // (the window is still staged: re-reading frame t costs less than keeping it in a register)
-						const float y0 = x[0] * d.gd;
-						const float Y = (x[0] * d.mfx) * gain_at(r.direct, t);
-						if (r.direct.n) {
-							const float dl = Y - y0;
+						fetch(b, m.w_off, x);     // (the window is still staged: re-reading costs less than keeping the samples in registers)
 #pragma unroll
-							for (int q = 0; q < NCH / 4; ++q) {
-								const float4 g = gk4[q];
-								ffma2(acc[2 * q][0], make_float2(g.x, g.y), make_float2(dl, dl));
-								ffma2(acc[2 * q + 1][0], make_float2(g.z, g.w), make_float2(dl, dl));
-							}
-						}
-						if (d.mode & kMdShRamp) {
-							const ShRamps* rp = &sm.shrs[qw * kBatch + b];
+						for (int k = 0; k < K; ++k) {
+							// ramps usually end within the first T frames (k = 0 only); long ones (a volume change) reach further
+							if (k > 0 && warp_i0 + (uint32_t)k * T >= nramp) break;
+							const uint32_t i = t + (uint32_t)k * T;
+							const float fi = (float)i;
+							const float y0 = x[k] * m.gd;
+							const float Y = (x[k] * m.mfx) * direct_gain_at(m, i);
+							if (dramp) {
+								const float dl = Y - y0;
 #pragma unroll
-							for (int q = 0; q < NCH / 4; ++q) {
-								const float4 nn = reinterpret_cast<const float4*>(rp->nf)[q];
-								const float4 st = reinterpret_cast<const float4*>(rp->stm)[q], in = reinterpret_cast<const float4*>(rp->inc)[q];
-								float2 e0 = make_float2(st.x, st.y), e1 = make_float2(st.z, st.w);
-								ffma2(e0, make_float2(fminf(ft, nn.x), fminf(ft, nn.y)), make_float2(in.x, in.y));
-								ffma2(e1, make_float2(fminf(ft, nn.z), fminf(ft, nn.w)), make_float2(in.z, in.w));
-								ffma2(acc[2 * q][0], e0, make_float2(Y, Y));
-								ffma2(acc[2 * q + 1][0], e1, make_float2(Y, Y));
+								for (int q = 0; q < NCH / 4; ++q) {
+									const float4 g = gk4[q];
+									ffma2(acc[2 * q][k], make_float2(g.x, g.y), make_float2(dl, dl));
+									ffma2(acc[2 * q + 1][k], make_float2(g.z, g.w), make_float2(dl, dl));
+								}
 							}
+							if (rp) {
+#pragma unroll
+								for (int q = 0; q < NCH / 4; ++q) {
+									const float4 nn = reinterpret_cast<const float4*>(rp->nf)[q];
+									const float4 st = reinterpret_cast<const float4*>(rp->stm)[q], in = reinterpret_cast<const float4*>(rp->inc)[q];
+									float2 e0 = make_float2(st.x, st.y), e1 = make_float2(st.z, st.w);
+									ffma2(e0, make_float2(fminf(fi, nn.x), fminf(fi, nn.y)), make_float2(in.x, in.y));
+									ffma2(e1, make_float2(fminf(fi, nn.z), fminf(fi, nn.w)), make_float2(in.z, in.w));
+									ffma2(acc[2 * q][k], e0, make_float2(Y, Y));
+									ffma2(acc[2 * q + 1][k], e1, make_float2(Y, Y));
+								}
+							}
+							// (frame F - 1 inside a ramp: the constant pass stored y_const as the bypassed filter's memory)
+							if (k == K - 1 && t == T - 1) a.lpf_prev[m.slot] = Y;
 						}
 					}
 				}
@@ -836,12 +814,12 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 			}
 		}
 		for (uint32_t b = 0; b < nb && !batch_done; ++b) {
-			const MathDesc& d = sm.descs[qr * kBatch + b];
-			const WorkRec& r = sm.recs[qr * kBatch + b];
-			const uint32_t mode = d.mode;
+			const MixRec& m = mrs[b];
+			const uint32_t mode = m.mode;
 			if (mode & kMdSkip) {
 				// gain-skipped source: the feeder still consumed this buffer; carry the resampler history forward
-				if ((r.flags & kRecResample) && t == 0) {
+				if ((mode & kMdResample) && t == 0) {
+					const WorkRec& r = a.rec[b0 + b];
 					float p0, p1;
 					resampler_tail(r, &p0, &p1);
 					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
@@ -851,10 +829,11 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 			float x[K];          // engine-rate input samples of this thread's frames (before any gain)
 			float mf = 1.0f;     // MixSource::mix_factor where it is not already inside x
 			bool filtered = false;   // x already carries the direct gain and the occlusion low-pass
+			float* slot = sm.wring + (size_t)(qw * kBatch + b) * wslot;
 			if ((mode & (kMdGeneric | kMdLpf | kMdAdjust)) != 0) {
-				// ---------------- careful fetch (rare): every case, straightforward arithmetic ----------------
+				// ---------------- careful fetch (rare): every case, straightforward arithmetic, from the full record ----------------
+				const WorkRec& r = a.rec[b0 + b];
 				const WinPlan wp = plan_window(r, wslot);
-				float* slot = sm.wring + (size_t)(qw * kBatch + b) * wslot;
 				const float* w = slot + 4 + wp.off0;
 #pragma unroll
 				for (int k = 0; k < K; ++k) {
@@ -872,7 +851,7 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 					// direct gain, then the recurrence in the (now free) stage slot; x becomes the filtered, gained signal
 					math_sync_id(1u + grp, T);
 #pragma unroll
-					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) slot[i] = x[k] * gain_at(r.direct, i); }
+					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) slot[i] = x[k] * direct_gain_at(m, i); }
 					math_sync_id(1u + grp, T);
 					if (t < 32) { const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane); if (lane == 0) a.lpf_prev[r.slot] = carry; }
 					math_sync_id(1u + grp, T);
@@ -883,8 +862,8 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 				}
 			} else {
 				// ---------------- lean fetch: window staged in shared memory by the TMA ring ----------------
-				const float* wb = sm.wring + d.w_idx;
-				mf = d.mfx;
+				const float* wb = slot + m.w_off;
+				mf = m.mfx;
 				if (mode & kMdInterp) {
 					const bool rsmp = (mode & kMdResample) != 0;
 #pragma unroll
@@ -893,23 +872,21 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 						const uint32_t wi0 = warp_i0 + (uint32_t)k * T;
 						float v = 0.0f;
 						if (EXACT || i < F) {
-							const unsigned long long p = d.x0 + (unsigned long long)i * d.step;
+							const unsigned long long p = m.x0 + (unsigned long long)i * m.step;
 							const uint32_t di = (uint32_t)(p >> 32);
 							const float fr = frac_of(p);
 							float v0, v1;
 							// only the first frames (resampler history) and the last ones (index clamp) need the careful form
-							if (rsmp && (wi0 < 16u || wi0 + 32u > F - 1)) {
-								const WinPlan wp = plan_window(r, wslot);
-								v0 = staged_tmp(r, wb + 2, wp, (int)di); v1 = staged_tmp(r, wb + 2, wp, (int)di + 1);
-							} else { v0 = wb[di]; v1 = wb[di + 1]; }
+							if (rsmp && (wi0 < 16u || wi0 + 32u > F - 1)) { v0 = staged_tmp_m(m, wb, (int)di); v1 = staged_tmp_m(m, wb, (int)di + 1); }
+							else { v0 = wb[di]; v1 = wb[di + 1]; }
 							v = fmaf(fr, v1 - v0, v0);
 						}
 						x[k] = v;
 					}
 					if (rsmp && t == 0) {
-						const WinPlan wp = plan_window(r, wslot);
-						a.rs[d.slot].prev_samples[0] = staged_tmp(r, wb + 2, wp, (int)r.n_src);
-						a.rs[d.slot].prev_samples[1] = staged_tmp(r, wb + 2, wp, (int)r.n_src + 1);
+						const int ns = (int)(m.dn_nsrc >> 16);
+						a.rs[m.slot].prev_samples[0] = staged_tmp_m(m, wb, ns);
+						a.rs[m.slot].prev_samples[1] = staged_tmp_m(m, wb, ns + 1);
 					}
 				} else {
 #pragma unroll
@@ -921,27 +898,42 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 			}
 			// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
 			const float* gk = sm.shgs[qr * kBatch + b].konst;
-			const float gd = d.gd;
-			const uint32_t nramp = d.nramp;     // frames in which the direct gain or a channel gain still ramps
+			const float gd = m.gd;
+			const uint32_t nramp = m.nramp;     // frames in which the direct gain or a channel gain still ramps
 			const ShRamps* rp = (mode & kMdShRamp) ? &sm.shrs[qw * kBatch + b] : nullptr;
 #pragma unroll
 			for (int k = 0; k < K; ++k) {
 				const uint32_t i = t + (uint32_t)k * T;
 				if (warp_i0 + (uint32_t)k * T < nramp) {
 					// warp-uniform: only the warps whose frames lie inside a ramp evaluate ramps
-					const float yv = filtered ? x[k] : (x[k] * mf) * gain_at(r.direct, i);
-					if (!filtered && i == F - 1) a.lpf_prev[d.slot] = yv;
-					accumulate_ramped(gk, rp, yv, i, (float)i, k);
+					const float yv = filtered ? x[k] : (x[k] * mf) * direct_gain_at(m, i);
+					if (!filtered && i == F - 1) a.lpf_prev[m.slot] = yv;
+					accumulate_ramped(gk, rp, yv, (float)i, k);
 				} else {
 					const float yv = filtered ? x[k] : x[k] * gd;
-					if ((k == K - 1 || !EXACT) && !filtered && i == F - 1) a.lpf_prev[d.slot] = yv;
+					if ((k == K - 1 || !EXACT) && !filtered && i == F - 1) a.lpf_prev[m.slot] = yv;
 					accumulate_const(gk, yv, k);
 				}
 			}
 		}
-		// this warp is done with window stage qw and record slot qr: hand them back to the producer
+		// this warp is done with window stage qw and record slot qr
 		__syncwarp();
-		if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }
+		if (SELF) {
+			// the warp that finishes the batch last refills what it vacated: stage qw with batch jb + kStages, slot qr with the
+			// records of batch jb + kRecStages
+			uint32_t last = 0;
+			if (lane == 0) {
+				__threadfence_block();
+				last = atomicAdd(&hdr->done[qr], 1u) == T / 32u - 1u ? 1u : 0u;
+				if (last) hdr->done[qr] = 0u;
+				__threadfence_block();
+			}
+			last = __shfl_sync(0xffffffffu, last, 0);
+			if (last) {
+				fill_window_stage<16, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane, jb + (uint32_t)kStages);
+				fill_record_slot<16, kStages, kBatch>(sm, a, s0, s1, nbatch, lane, jb + (uint32_t)kRecStages);
+			}
+		} else if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }     // hand them back to the issue warp
 	}
 	float* out = partials + ((size_t)blockIdx.x * G + grp) * NCH * F;     // one partial bus per group
 #pragma unroll
@@ -953,24 +945,34 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 		}
 }
 
-// The two entry points of the ambisonic kernel: the register budget is set per shape (launch bounds for three 5-warp CTAs
-// per SM; an explicit cap for the one 17-warp CTA of the two-group shape, where the launch-bounds heuristic rounds the
-// CTA up to 20 warps and would allow only 96 registers).
-template <bool EXACT>
-__global__ void __launch_bounds__(128 + 32, 3) k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
-	ambisonic_body<128, kShK, 1, EXACT>(a, first, n, wslot, partials);
-}
-template <bool EXACT>
-#if SBM_SH_BIG_G == 1 && SBM_SH_BIG_CTAS == 1
-__global__ void __launch_bounds__(kShBigT + 32, 1)
-#elif SBM_SH_BIG_G == 1
-// two 288-thread CTAs per SM: 65536 / 576 = 113 registers per thread; the launch-bounds heuristic would settle on 96 and spill
-__global__ void __maxnreg__(112)
-#else
-__global__ void __maxnreg__(SBM_SH_BIG_MAXNREG)
+// Entry points of the ambisonic kernel.  frames 256 / 512 / 1024 (T = frames / 4 = 64 / 128 / 256 math threads, no per-frame bounds
+// checks): measured on B200 per shape --
+//   256:  all-math 2-warp CTAs with self-service rings (8 CTAs per SM): 0.030 ms per 33 792 sources vs 0.040 with an issue warp;
+//   512:  4 math warps + issue warp, 3 CTAs per SM: 0.22 ms per 262 144 sources.  The all-math form (4 CTAs x 4 warps = 16 math
+//         warps) measured 0.29: the warp that owns the first 32 frames does the ramp fix-ups of every source, finishes every
+//         batch last, and then also has to refill the rings while the other warps wait for it;
+//   1024: 8 math warps + issue warp, 1 CTA per SM (a 9-warp CTA at > 102 registers cannot be resident twice: the register file
+//         is per scheduler, 4 x 16 K): 0.150 ms per 65 536 sources; all-math 2 x 8 warps: 0.157.
+// Any other frame count: the issue-warp form with per-frame bounds checks.
+#ifndef SBM_STAGES_SELF
+#define SBM_STAGES_SELF 4
 #endif
-k2_mix_ambisonic_big_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
-	ambisonic_body<kShBigT, kShBigK, kShBigG, EXACT>(a, first, n, wslot, partials);
+#ifndef SBM_SH_SELF_MASK
+#define SBM_SH_SELF_MASK 64           // OR of the T values that use the self-service form (A/B: 64 | 128 | 256)
+#endif
+constexpr int kStagesSelf = SBM_STAGES_SELF, kStagesShX = 6;
+__host__ __device__ constexpr bool sh_self_shape(int T) { return (SBM_SH_SELF_MASK & T) != 0; }
+template <int TMAX>
+__global__ void __launch_bounds__(TMAX + (sh_self_shape(TMAX) ? 0 : 32), sh_self_shape(TMAX) ? 512 / TMAX : (TMAX == 256 ? 1 : (TMAX == 128 ? 3 : 5)))
+k2_mix_ambisonic_x_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+	constexpr bool kSelf = (SBM_SH_SELF_MASK & TMAX) != 0;
+	ambisonic_body<TMAX, kShK, 1, true, kSelf, kSelf ? kStagesSelf : kStagesShX>(a, first, n, wslot, partials);
+}
+__global__ void __launch_bounds__(128 + 32, 3) k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+	ambisonic_body<128, kShK, 1, false, false, kStagesSh>(a, first, n, wslot, partials);
+}
+__global__ void __launch_bounds__(kShBigT + 32, 1) k2_mix_ambisonic_big_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+	ambisonic_body<kShBigT, kShBigK, 1, false, false, kStagesShBig>(a, first, n, wslot, partials);
 }
 
 // K3: bus[row][f] = sum over CTAs of the partial buses; rows 0-15 from the ambisonic kernel's partials, rows 16-17 from
@@ -1097,16 +1099,13 @@ int sm_count() {
 	return device_cache_locked().sms;
 }
 
-// Stage slot per source, in floats: room for a window of frames * 1.25 (sample-rate ratios <= 1, doppler / pitch up
-// to +25 %) plus alignment slack; larger windows take the generic path.
-uint32_t window_slot(uint32_t F) { return (F + F / 4 + 24u + 3u) & ~3u; }
 uint32_t sh_frames_per_thread(uint32_t F) { return F <= 512 ? (uint32_t)kShK : (uint32_t)kShBigK; }
 uint32_t sh_threads(uint32_t F) { const uint32_t K = sh_frames_per_thread(F); return ((F + K - 1) / K + 31) / 32 * 32; }
-int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig); }
+bool sh_exact(uint32_t F) { return F == 256 || F == 512 || F == 1024; }     // the exact shapes (T = F / 4 = 64 / 128 / 256 math threads)
+int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_exact(F) ? (sh_self_shape((int)F / 4) ? kStagesSelf : kStagesShX) : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig)); }
 size_t mix_smem_bytes(uint32_t F, bool sh) {
 	const size_t st = (size_t)mix_stages(F, sh), rst = st + 2, kBatch = sh ? kBatchSh : kBatchPan;
-	return 512 + sizeof(WorkRec) * rst * kBatch + (sh ? sizeof(ShGains) * rst * kBatch + sizeof(ShRamps) * st * kBatch : 0) +
-	       sizeof(MathDesc) * rst * kBatch +
+	return 512 + sizeof(MixRec) * rst * kBatch + (sh ? sizeof(ShGains) * rst * kBatch + sizeof(ShRamps) * st * kBatch : 0) +
 	       sizeof(float) * st * kBatch * window_slot(F);
 }
 constexpr uint32_t kMinSourcesPerCta = 16;
@@ -1124,6 +1123,7 @@ int launch_one(Kernel kernel, const char* name, const MixArgs& a, uint32_t first
 	const uint32_t F = a.frames;
 	const size_t smem = mix_smem_bytes(F, sh);
 	uint32_t wave;
+	int sm_count_now = 148;
 	{
 		// cudaFuncSetAttribute and the occupancy query apply to the current device only: configured once per (device, kernel, size)
 		std::lock_guard<std::mutex> lk(g_cfg_mu);
@@ -1139,10 +1139,13 @@ int launch_one(Kernel kernel, const char* name, const MixArgs& a, uint32_t first
 			cfg->ctas_per_sm = per_sm > 0 ? per_sm : 1;
 		}
 		wave = (uint32_t)(dc.sms * cfg->ctas_per_sm);
+		sm_count_now = dc.sms;
 	}
 	if (wave > max_grid) wave = max_grid;
 	const uint32_t g = pick_grid(n, wave);
-	launch_pdl(kernel, dim3(g), dim3(threads), smem, st, a, first, n, window_slot(F), partials);
+	MixArgs a2 = a;
+	a2.rot_div = (uint32_t)sm_count_now;
+	launch_pdl(kernel, dim3(g), dim3(threads), smem, st, a2, first, n, window_slot(F), partials);
 	dev::note_launch();
 	*grid_out = g;
 	return dev::check_launch(name);
@@ -1169,7 +1172,7 @@ int num_mix_ctas(uint32_t frames, int sh) {
 }
 
 size_t partials_floats(uint32_t frames) {
-	const size_t groups = sh_threads(frames) <= 128 ? 1 : (size_t)kShBigG;
+	const size_t groups = 1;
 	return ((size_t)num_mix_ctas(frames, 0) * 2 + (size_t)num_mix_ctas(frames, 1) * groups * 16) * frames;
 }
 
@@ -1190,15 +1193,13 @@ int launch_mix(const MixArgs& a, void* stream) {
 	if (a.n_sh) {
 		const uint32_t tm = sh_threads(F);
 		const uint32_t mg = (uint32_t)num_mix_ctas(F, 1);
-		const bool exact = (tm == 128 || tm == (uint32_t)kShBigT) && F == tm * sh_frames_per_thread(F);     // the EXACT instantiations fix T = TMAX at compile time
 		int rc;
-		if (tm <= 128) rc = exact ? launch_one(k2_mix_ambisonic_kernel<true>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh)
-		                         : launch_one(k2_mix_ambisonic_kernel<false>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
-		else {
-			rc = exact ? launch_one(k2_mix_ambisonic_big_kernel<true>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm * kShBigG + 32, true, mg, part_sh, st, &g_sh)
-			           : launch_one(k2_mix_ambisonic_big_kernel<false>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm * kShBigG + 32, true, mg, part_sh, st, &g_sh);
-			g_sh *= (uint32_t)kShBigG;     // one partial bus per math group
-		}
+		if (sh_exact(F)) {
+			if (F == 256) rc = launch_one(k2_mix_ambisonic_x_kernel<64>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, 64 + (sh_self_shape(64) ? 0 : 32), true, mg, part_sh, st, &g_sh);
+			else if (F == 512) rc = launch_one(k2_mix_ambisonic_x_kernel<128>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, 128 + (sh_self_shape(128) ? 0 : 32), true, mg, part_sh, st, &g_sh);
+			else rc = launch_one(k2_mix_ambisonic_x_kernel<256>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, 256 + (sh_self_shape(256) ? 0 : 32), true, mg, part_sh, st, &g_sh);
+		} else if (tm <= 128) rc = launch_one(k2_mix_ambisonic_kernel, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
+		else rc = launch_one(k2_mix_ambisonic_big_kernel, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);

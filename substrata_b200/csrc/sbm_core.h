@@ -121,6 +121,36 @@ struct __attribute__((aligned(128))) WorkRec {   // 128 B, K1 -> K2, one per ent
 	uint32_t nz;                // 124 kRecMix: number of mix sources
 };
 
+// What the mix kernel needs to render one source on its lean paths, in final form (128 B, one per entry of the render lists,
+// written by K1 -- k1_params.cu, or the parameter warps of the fused kernel -- and streamed into K2's record ring by TMA).
+// The full WorkRec is only read back (from global memory) by the rarely taken careful paths.
+struct __attribute__((aligned(16))) MixRec {
+	uint32_t mode;              //   0  kMd*
+	uint32_t nramp;             //   4  frames from the start of the buffer in which some gain of this source still ramps
+	uint32_t w_off;             //   8  float offset, inside the source's stage slot, of element 0 of the array the read head indexes:
+	                            //      window sample 0, or two before it for the resampler's {prev0, prev1, window...}
+	float gd;                   //  12  direct gain * mix factor (constant part)
+	unsigned long long x0, step;   //  16  32.32 read head
+	float g0, g1;               //  32  stereo kernel: direct gain * mix factor * bus gain (constant parts)
+	uint32_t n1b;               //  40  index (same coordinates as w_off) from which `wadj` applies (loop wrap), 0xffffffff = never
+	uint32_t wadj;              //  44
+	uint32_t slot;              //  48
+	float mfx;                  //  52  MixSource::mix_factor where the lean paths must apply it to the samples themselves (ramping direct gain), else 1
+	float prev0, prev1;         //  56  AudioResampler::prev_samples
+	float d_konst, d_start, d_inc;   //  64  GainNode ramp
+	uint32_t dn_nsrc;           //  76  low 16 bits: ramp frames of the direct gain; high 16: window samples (n_src)
+	float c0_konst, c0_start, c0_inc;   //  80  stereo bus gain L
+	uint32_t cn;                //  92  low 16 bits: ramp frames of bus gain L; high 16: of bus gain R
+	float c1_konst, c1_start, c1_inc;   //  96  stereo bus gain R
+	uint32_t pad;               // 108
+	const float* pcm;           // 112  fetch plan: TMA segment 1 = pcm[a0 .. a0 + seg1), segment 2 = pcm[0 .. seg2)
+	uint32_t a0;                // 120
+	uint32_t segs;              // 124  low 16 bits: seg1 floats; high 16: seg2 floats; 0 = window not staged (careful path reads global memory)
+};
+static_assert(sizeof(MixRec) == 128, "MixRec is 128 bytes");
+constexpr uint32_t kMdSkip = 1, kMdGeneric = 2, kMdInterp = 4, kMdAdjust = 8, kMdResample = 16, kMdLpf = 32, kMdStereo = 64,
+                   kMdRamp = 128, kMdShRamp = 256;
+
 struct ShGains { float konst[kNumSh]; };                       // 64 B per HRTF source: effective constant gains
 // Channel ramps of an ambisonic source (read only when ch_ramp_mask != 0; all 48 entries are written then): the gain of bus
 // channel c at frame i is  konst[c] + (i < nf[c] ? stm[c] + i * inc[c] : 0)  with stm = ramp start - konst, nf = ramp frames in
@@ -177,6 +207,7 @@ struct SlotArrays {
 	double* mix_pos;
 	double* mix_pos0;
 	WorkRec* rec;               // [n_pan + n_sh] in render-list order (pan list first)
+	MixRec* mrec;               // indexed like rec (CUDA build; the host emulation mixes straight from rec)
 	ShGains* shg;               // indexed like rec
 	ShRamps* shr;               // indexed like rec
 	int* finished;              // list of public ids stopped by the feeder

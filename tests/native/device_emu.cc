@@ -77,7 +77,7 @@ int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const 
 	(void)n_slots;
 	for (uint32_t k = 0; k < g.n_pan + g.n_sh; ++k) {
 		uint32_t n_src = 0;
-		used |= update_source(g, A, flags, table, lists[k], k, &n_src);
+		used |= update_source(g, A, flags, table, lists[k], &A.rec[k], A.shg ? A.shg + k : nullptr, A.shr ? A.shr + k : nullptr, &n_src);
 		if (n_src) { flags->algo_bytes += 4ull * n_src; flags->n_rendered++; }
 	}
 	if (used & kUsedPan) flags->pan_used[g.parity] = 1;
