@@ -128,6 +128,10 @@ SBM_API int sbm_source_attach_mix1(sbm_engine* e, int n, const int* ids, const i
                                    const double* source_delta, const float* mix_factor);
 /* mix_sources[z].source_delta / mix_factor updates by the game thread (gui_client/BikePhysics.cpp:712-740). */
 SBM_API int sbm_source_set_mix_params(sbm_engine* e, int n, const int* ids, const int* z, const double* source_delta, const float* mix_factor);
+/* A streamed source whose decoder reports another sampling rate than the one it was attached with: `source->sampling_rate = hz;
+ * source->resampler.init(hz, engine rate)` (StreamerThread.cpp:98-105).  Ring- and buffer-fed sources; the AudioResampler state
+ * of the source starts over like AudioResampler::init (AudioResampler.cpp:24-36). */
+SBM_API int sbm_source_set_sampling_rate(sbm_engine* e, int id, int sampling_rate);
 /* AudioSource::EOF_marker_position (AudioEngine.h:120), AudioSource::looping. */
 SBM_API int sbm_source_set_eof_marker(sbm_engine* e, int id, int64_t samples_to_eof);
 SBM_API int sbm_source_set_looping(sbm_engine* e, int id, int looping);

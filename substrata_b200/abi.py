@@ -43,6 +43,7 @@ SIGNATURES = {
     "sbm_source_attach_mix": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sbm_source_attach_mix1": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sbm_source_set_mix_params": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "sbm_source_set_sampling_rate": (_i, [_vp, _i, _i]),
     "sbm_source_set_eof_marker": (_i, [_vp, _i, _i64]),
     "sbm_source_set_looping": (_i, [_vp, _i, _i]),
     "sbm_set_source_positions": (_i, [_vp, _i, _vp, _vp]),

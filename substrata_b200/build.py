@@ -96,7 +96,7 @@ HOST_DIR = os.path.join(HERE, "host")
 def build_host_library(objs_dir, lib, force=False, log=None):
     """libsubstrata_b200_host.so: the glare::AudioEngine / glare::AudioResampler mirror (host/*.cpp) above the C ABI."""
     out = os.path.join(os.path.dirname(lib), "libsubstrata_b200_host.so")
-    srcs = [os.path.join(HOST_DIR, f) for f in ("AudioEngine.cpp", "AudioResampler.cpp")]
+    srcs = [os.path.join(HOST_DIR, f) for f in ("AudioEngine.cpp", "AudioResampler.cpp", "StreamerThread.cpp")]
     deps = srcs + [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith(".h")] + [lib]
     if force or _newer(out, deps):
         cmd = ["g++"] + HOST_FLAGS + ["-fvisibility=default", "-shared", "-o", out] + srcs + [

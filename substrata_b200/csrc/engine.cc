@@ -780,6 +780,20 @@ SBM_API int sbm_source_attach_mix1(sbm_engine* e, int n, const int* ids, const i
 	return SBM_OK;
 }
 
+SBM_API int sbm_source_set_sampling_rate(sbm_engine* e, int id, int sampling_rate) {
+	if (!e) return SBM_ERR_INVALID_ARG;
+	if (sampling_rate < 8000 || sampling_rate > 48000) return fail(e, SBM_ERR_INVALID_ARG, "Unsupported sampling rate for audio source");
+	std::lock_guard<std::mutex> lk(e->mu);
+	const int slot = slot_for(e, id);
+	if (slot < 0) return SBM_ERR_UNKNOWN_ID;
+	SrcStatic& st = e->h_stat[(uint32_t)slot];
+	if (((st.flags >> kFlagFeedShift) & 3) == kFeedMix) return fail(e, SBM_ERR_UNSUPPORTED, "mix_sources at a rate other than the engine rate");
+	st.rate = sampling_rate;
+	e->d_stat.mark((uint32_t)slot);
+	add_patch(e, SlotPatch{(uint32_t)slot, kPatchResampler, 0ull, 0, sampling_rate, 0});
+	return SBM_OK;
+}
+
 SBM_API int sbm_source_set_eof_marker(sbm_engine* e, int id, int64_t samples_to_eof) {
 	if (!e) return SBM_ERR_INVALID_ARG;
 	std::lock_guard<std::mutex> lk(e->mu);

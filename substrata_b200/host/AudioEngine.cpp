@@ -2,6 +2,7 @@
 // the reference tree function by function; "AE.cpp:n" cites its lines.  No sample arithmetic happens here: the only
 // per-sample host work is the device-callback clamp (AE.cpp:215-216), which the reference also does on the host.
 #include "AudioEngine.h"
+#include "StreamerThread.h"
 
 #include <chrono>
 #include <limits>
@@ -18,7 +19,7 @@ AudioSource::AudioSource()
       type(SourceType_NonStreaming), spatial_type(SourceSpatialType_Spatial), paused(false), looping(true), remove_on_finish(false), volume(1.f),
       mute_volume_factor(1.f), mute_change_start_time(-2), mute_change_end_time(-1), mute_vol_fac_start(1.f), mute_vol_fac_end(1.f),
       doppler_factor(1), pos(0, 0, 0, 1), num_occlusions(0), userdata_1(0), smoothed_cur_level(0), feed_prev_dest_dst_coords(-1),
-      feed_prev_samples_0_src_coords(-2) {}
+      feed_prev_samples_0_src_coords(-2), device_sampling_rate(0), device_eof_marker(std::numeric_limits<int64>::max()) {}
 
 AudioSource::~AudioSource() {}
 
@@ -106,16 +107,30 @@ void AudioEngine::init() {
 	frames_mixed = 0;
 	die = false;
 	initialised = true;
-	if (options.start_mix_thread) mix_thread = std::thread(&AudioEngine::mixThreadMain, this);
+	// AE.cpp:711-726: the mixing thread (ResonanceThread in the reference) and the StreamerThread live under thread_manager
+	if (options.start_mix_thread) {
+		class MixThread : public MessageableThread {
+		public:
+			explicit MixThread(AudioEngine* e_) : e(e_) {}
+			void doRun() override { e->mixThreadMain(); }
+			void kill() override { e->die = true; }
+			AudioEngine* e;
+		};
+		thread_manager.addThread(Reference<MessageableThread>(new MixThread(this)));
+	}
+	if (options.start_streamer_thread) thread_manager.addThread(Reference<MessageableThread>(new StreamerThread(this)));
 }
 
 void AudioEngine::shutdown() {
-	if (mix_thread.joinable()) { die = true; mix_thread.join(); }   // thread_manager.killThreadsBlocking(), AE.cpp:816
+	die = true;
+	thread_manager.killThreadsBlocking();   // AE.cpp:816
 	{
 		Lock lock(mutex);
 		active_audio_sources.clear();
 		audio_sources.clear();
 		source_of_handle.clear();
+		unpaused_streams.clear();
+		stream_to_source_map.clear();
 	}
 	if (engine) { sbm_destroy(engine); engine = nullptr; }          // delete resonance, AE.cpp:837
 	device_buffers.clear();
@@ -175,6 +190,7 @@ void AudioEngine::createResonanceObAndResamplerForSource(AudioSource& source_) {
 	} else {
 		rc = sbm_source_attach_ring(engine, id, source->sampling_rate, 4 * 48000);
 		source->feed_prev_dest_dst_coords = -1; source->feed_prev_samples_0_src_coords = -2;
+		source->device_sampling_rate = source->sampling_rate;
 	}
 	if (rc != SBM_OK) {
 		const std::string msg = sbm_last_error(engine);
@@ -183,6 +199,8 @@ void AudioEngine::createResonanceObAndResamplerForSource(AudioSource& source_) {
 		throw glare::Exception("attaching audio data to the source failed: " + msg);
 	}
 	if (source->EOF_marker_position != std::numeric_limits<int64>::max()) sbm_source_set_eof_marker(engine, id, source->EOF_marker_position);
+	source->device_eof_marker = source->EOF_marker_position;
+	source->resampler.init(/*src rate=*/source->sampling_rate, (int)this->sample_rate, options.cuda_device);   // AE.cpp:875
 	if (source->num_occlusions != 0) sbm_set_source_occlusions(engine, 1, &id, &source->num_occlusions);
 }
 
@@ -211,15 +229,69 @@ void AudioEngine::removeSource(AudioSourceRef source) {
 	}
 	audio_sources.erase(source);
 	active_audio_sources.erase(source);
+	// Remove the source from the stream -> sources map; the last listener of a stream frees its decoder (AE.cpp:915-940).
+	Reference<MP3AudioStreamer> streamer_to_remove;
+	for (auto it = stream_to_source_map.begin(); it != stream_to_source_map.end(); ++it) {
+		it->second.erase(source);
+		if (it->second.empty()) streamer_to_remove = it->first;
+	}
+	if (streamer_to_remove) {
+		for (auto it = unpaused_streams.begin(); it != unpaused_streams.end(); ++it)
+			if (it->second == streamer_to_remove) { unpaused_streams.erase(it); break; }
+		stream_to_source_map.erase(streamer_to_remove);
+	}
 }
 
-// AE.cpp:946-956
+// AE.cpp:1081-1140
+AudioSourceRef AudioEngine::addSourceFromStreamingSoundFile(AddSourceFromStreamingSoundFileParams& params, const Vec4f& pos) {
+	Lock lock(mutex);
+	AudioSourceRef source = new AudioSource();
+	source->type = AudioSource::SourceType_Streaming;
+	source->remove_on_finish = false;
+	source->pos = pos;
+	source->volume = params.source_volume;
+	source->looping = params.looping;
+	source->paused = params.paused;
+	// A new decoder if the source is paused (a script may unpause it at any time, independently of the other listeners of the
+	// file) or if nobody streams this file yet; otherwise the running one is shared.
+	auto res = unpaused_streams.find(params.sound_file_path);
+	if ((res == unpaused_streams.end()) || params.paused) {
+		if (!make_streamer) throw glare::Exception("AudioEngine::make_streamer is not set: the mp3 decoder is supplied by the owner of the engine");
+		Reference<MP3AudioStreamer> streamer = make_streamer(params);
+		if (streamer.isNull()) throw glare::Exception("make_streamer returned no decoder for " + params.sound_file_path);
+		if (!params.paused) {   // if not paused, the stream can be shared with other sources
+			streamer->seekToApproxTimeWrapped(params.global_time);
+			unpaused_streams.insert(std::make_pair(params.sound_file_path, streamer));
+		}
+		stream_to_source_map[streamer].insert(source);
+	} else {
+		Reference<MP3AudioStreamer> streamer = res->second;
+		// another source already plays this stream: start from a copy of its backlog, so that both consume the stream in step
+		auto first_source_it = stream_to_source_map[streamer].begin();
+		if (first_source_it != stream_to_source_map[streamer].end()) {
+			AudioSourceRef first_source = *first_source_it;
+			source->buffer = first_source->buffer;
+		}
+		stream_to_source_map[streamer].insert(source);
+	}
+	addSource(source);
+	return source;
+}
+
+bool AudioEngine::needNewStreamerForPath(const std::string& sound_file_path, bool new_source_paused) {   // AE.cpp:1142-1146
+	auto res = unpaused_streams.find(sound_file_path);
+	return (res == unpaused_streams.end()) || new_source_paused;
+}
+
+// AE.cpp:946-956.  The notification only queues the new value; mixOneBuffer sends all queued ones as ONE sbm_set_source_positions
+// call (they take effect at the next buffer either way: Resonance queues its setters too, resonance_audio_api_impl.cc:305-317).
 void AudioEngine::sourcePositionUpdated(AudioSource& source) {
 	if (!initialised) return;
 	if (!source.pos.isFinite()) return;
 	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) {
-		const float xyz[3] = {source.pos[0], source.pos[1], source.pos[2]};
-		sbm_set_source_positions(engine, 1, &source.resonance_handle, xyz);
+		std::lock_guard<std::mutex> lk(pending_mutex);
+		pend_pos_ids.push_back(source.resonance_handle);
+		pend_pos.push_back(source.pos[0]); pend_pos.push_back(source.pos[1]); pend_pos.push_back(source.pos[2]);
 	}
 }
 
@@ -227,15 +299,61 @@ void AudioEngine::sourcePositionUpdated(AudioSource& source) {
 void AudioEngine::sourceVolumeUpdated(AudioSource& source) {
 	if (!initialised) return;
 	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) {
-		const float v = source.volume * source.getMuteVolumeFactor();
-		sbm_set_source_volumes(engine, 1, &source.resonance_handle, &v);
+		std::lock_guard<std::mutex> lk(pending_mutex);
+		pend_vol_ids.push_back(source.resonance_handle);
+		pend_vol.push_back(source.volume * source.getMuteVolumeFactor());
 	}
 }
 
 // AE.cpp:969-975
 void AudioEngine::sourceNumOcclusionsUpdated(AudioSource& source) {
 	if (!initialised) return;
-	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) sbm_set_source_occlusions(engine, 1, &source.resonance_handle, &source.num_occlusions);
+	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) {
+		std::lock_guard<std::mutex> lk(pending_mutex);
+		pend_occ_ids.push_back(source.resonance_handle);
+		pend_occ.push_back(source.num_occlusions);
+	}
+}
+
+// The client's per-frame loop over all sources (GUIClient.cpp:6979-7034) in batched form.
+void AudioEngine::sourcesPositionUpdated(AudioSource* const* sources, size_t n) {
+	if (!initialised) return;
+	std::lock_guard<std::mutex> lk(pending_mutex);
+	for (size_t i = 0; i < n; ++i) {
+		const AudioSource& s = *sources[i];
+		if (s.resonance_handle == INVALID_RESONANCE_HANDLE || !s.pos.isFinite()) continue;
+		pend_pos_ids.push_back(s.resonance_handle);
+		pend_pos.push_back(s.pos[0]); pend_pos.push_back(s.pos[1]); pend_pos.push_back(s.pos[2]);
+	}
+}
+void AudioEngine::sourcesVolumeUpdated(AudioSource* const* sources, size_t n) {
+	if (!initialised) return;
+	std::lock_guard<std::mutex> lk(pending_mutex);
+	for (size_t i = 0; i < n; ++i) {
+		const AudioSource& s = *sources[i];
+		if (s.resonance_handle == INVALID_RESONANCE_HANDLE) continue;
+		pend_vol_ids.push_back(s.resonance_handle);
+		pend_vol.push_back(s.volume * s.getMuteVolumeFactor());
+	}
+}
+void AudioEngine::sourcesNumOcclusionsUpdated(AudioSource* const* sources, size_t n) {
+	if (!initialised) return;
+	std::lock_guard<std::mutex> lk(pending_mutex);
+	for (size_t i = 0; i < n; ++i) {
+		const AudioSource& s = *sources[i];
+		if (s.resonance_handle == INVALID_RESONANCE_HANDLE) continue;
+		pend_occ_ids.push_back(s.resonance_handle);
+		pend_occ.push_back(s.num_occlusions);
+	}
+}
+
+// Everything the notifications queued since the last buffer: one C-ABI call per kind.
+void AudioEngine::flushPendingUpdates() {
+	std::lock_guard<std::mutex> lk(pending_mutex);
+	if (!pend_pos_ids.empty()) sbm_set_source_positions(engine, (int)pend_pos_ids.size(), pend_pos_ids.data(), pend_pos.data());
+	if (!pend_vol_ids.empty()) sbm_set_source_volumes(engine, (int)pend_vol_ids.size(), pend_vol_ids.data(), pend_vol.data());
+	if (!pend_occ_ids.empty()) sbm_set_source_occlusions(engine, (int)pend_occ_ids.size(), pend_occ_ids.data(), pend_occ.data());
+	pend_pos_ids.clear(); pend_pos.clear(); pend_vol_ids.clear(); pend_vol.clear(); pend_occ_ids.clear(); pend_occ.clear();
 }
 
 // AE.cpp:978-990
@@ -289,20 +407,27 @@ void AudioEngine::playOneShotSound(const std::string& sound_file_path, const Vec
 	}
 }
 
-// AE.cpp:1143-1159: (re)start a paused or finished source from the beginning.
+// AE.cpp:770-803: (re)start a paused or finished source from the beginning.
 void AudioEngine::seekToStartAndUnpauseAudio(AudioSource& source) {
 	if (!initialised) return;
 	Lock lock(mutex);
 	AudioSourceRef ref(&source);
+	source.cur_read_i = 0;
+	source.paused = false;
+	source.EOF_marker_position = std::numeric_limits<int64>::max();
+	source.buffer.clear();
+	for (MixSource& m : source.mix_sources) m.sound_file_i = 0;
+	// The device-side source holds the read index / ring / EOF state: recreate it (a fresh Resonance object in the reference only
+	// when there was none; re-creating is equivalent, the old one's filters start from silence either way after the seek).
 	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) {
 		sbm_source_destroy(engine, 1, &source.resonance_handle);
 		source_of_handle.erase(source.resonance_handle);
 		source.resonance_handle = INVALID_RESONANCE_HANDLE;
 	}
-	source.cur_read_i = 0;
-	source.paused = false;
-	for (MixSource& m : source.mix_sources) m.sound_file_i = 0;
 	createResonanceObAndResamplerForSource(source);
+	// If there is a streamer for this source, then restart the stream.
+	for (auto it = stream_to_source_map.begin(); it != stream_to_source_map.end(); ++it)
+		if (it->second.count(ref) != 0) it->first->seekToBeginningOfFile();
 	active_audio_sources.insert(ref);
 	source_of_handle[source.resonance_handle] = ref;
 }
@@ -312,6 +437,17 @@ void AudioEngine::seekToStartAndUnpauseAudio(AudioSource& source) {
 // StreamerThread relies on (StreamerThread.cpp:53).  numSrcSamplesNeeded is a pure function of two integer counters.
 void AudioEngine::feedStreamingSource(AudioSource& source) {
 	const int64 F = options.frames_per_buffer;
+	if (source.sampling_rate != source.device_sampling_rate) {
+		// StreamerThread found the stream's real rate (StreamerThread.cpp:98-105: source->resampler.init): same on the device
+		sbm_source_set_sampling_rate(engine, source.resonance_handle, source.sampling_rate);
+		source.device_sampling_rate = source.sampling_rate;
+		source.feed_prev_dest_dst_coords = -1; source.feed_prev_samples_0_src_coords = -2;
+	}
+	if (source.EOF_marker_position != source.device_eof_marker) {
+		// StreamerThread placed the EOF marker behind the samples it queued (StreamerThread.cpp:108-109)
+		sbm_source_set_eof_marker(engine, source.resonance_handle, source.EOF_marker_position);
+		source.device_eof_marker = source.EOF_marker_position;
+	}
 	size_t n_src = (size_t)F;
 	if (source.sampling_rate != (int)sample_rate) {
 		const int64 max_dest = source.feed_prev_dest_dst_coords + F;
@@ -328,6 +464,11 @@ void AudioEngine::feedStreamingSource(AudioSource& source) {
 		source.buffer.popFrontNItems(feed_payload.data() + at, have);
 		feed_ids.push_back(source.resonance_handle);
 		feed_offsets.push_back(feed_payload.size());
+	}
+	// AE.cpp:496: the marker counts down by the samples each buffer asks for -- on the device (K1) and here alike
+	if (source.EOF_marker_position != std::numeric_limits<int64>::max()) {
+		source.EOF_marker_position -= (int64)n_src;
+		source.device_eof_marker = source.EOF_marker_position;
 	}
 }
 
@@ -346,14 +487,19 @@ bool AudioEngine::mixOneBuffer() {
 			if (source.type == AudioSource::SourceType_Streaming) {
 				if (source.mix_sources.empty()) feedStreamingSource(source);
 				else {
-					// the game thread edits source_delta / mix_factor in place under `mutex` (BikePhysics.cpp:712-740)
+					// the game thread edits source_delta / mix_factor in place under `mutex` (BikePhysics.cpp:712-740): collected for one call
 					for (size_t z = 0; z < source.mix_sources.size(); ++z) {
-						const int zi = (int)z;
-						sbm_source_set_mix_params(engine, 1, &source.resonance_handle, &zi, &source.mix_sources[z].source_delta, &source.mix_sources[z].mix_factor);
+						mixp_ids.push_back(source.resonance_handle); mixp_z.push_back((int)z);
+						mixp_delta.push_back(source.mix_sources[z].source_delta); mixp_factor.push_back(source.mix_sources[z].mix_factor);
 					}
 				}
 			}
 		}
+		if (!mixp_ids.empty()) {
+			sbm_source_set_mix_params(engine, (int)mixp_ids.size(), mixp_ids.data(), mixp_z.data(), mixp_delta.data(), mixp_factor.data());
+			mixp_ids.clear(); mixp_z.clear(); mixp_delta.clear(); mixp_factor.clear();
+		}
+		flushPendingUpdates();
 		if (!feed_ids.empty() && sbm_source_ring_push_batch(engine, (int)feed_ids.size(), feed_ids.data(), feed_payload.data(), feed_offsets.data()) != SBM_OK)
 			throw glare::Exception(std::string("sbm_source_ring_push_batch failed: ") + sbm_last_error(engine));
 		const int rc = sbm_mix(engine, out.data(), &valid);

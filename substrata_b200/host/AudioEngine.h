@@ -6,12 +6,15 @@
 // buffer (include/sbm_audio.h); `resonance_handle` holds the sbm source id.
 //
 // Not carried over (out of the hot path): the OS audio device (miniaudio / RtAudio) -- the device
-// callback body is exposed as fillOutputBuffer() for whoever owns the device --, the MP3 streamer
-// (addSourceFromStreamingSoundFile) and the audio file readers (getOrLoadSoundFile only consults the cache).
+// callback body is exposed as fillOutputBuffer() for whoever owns the device --, the mp3 / audio file DECODERS (streams come in
+// through the MP3AudioStreamer interface, getOrLoadSoundFile only consults the cache).  The streaming feed itself is here:
+// addSourceFromStreamingSoundFile, needNewStreamerForPath, the stream maps, sync-start of sources that share a stream, and
+// StreamerThread (StreamerThread.h) -- all under thread_manager like the reference's.
 #pragma once
 #ifndef SBM_USE_GLARE_CORE
 #include "glare_core_min.h"
 #endif
+#include <functional>
 #include <map>
 #include <set>
 #include <string>
@@ -20,6 +23,7 @@
 
 #include "../../include/sbm_audio.h"
 #include "AudioResampler.h"
+#include "MP3AudioStreamer.h"
 
 namespace glare {
 
@@ -99,11 +103,15 @@ public:
 	std::string debugname;
 	float smoothed_cur_level;
 
+	AudioResampler resampler;   // AudioEngine.h:153.  (Sources are resampled inside the mix kernels; kept for callers such as StreamerThread that re-init it.)
+
 private:
 	friend class AudioEngine;
 	// Host mirror of the AudioResampler counters of a ring-fed source (AudioResampler.h:37-39): how many source samples
 	// the next buffer consumes is a pure function of these, so the feeder can move exactly that many to the device ring.
 	int64 feed_prev_dest_dst_coords, feed_prev_samples_0_src_coords;
+	int device_sampling_rate;      // the rate the device side was last told (StreamerThread may change sampling_rate mid-stream)
+	int64 device_eof_marker;       // the EOF marker the device side holds, as far as the host knows
 };
 typedef Reference<AudioSource> AudioSourceRef;
 
@@ -121,13 +129,14 @@ public:
 	// Extra knobs the reference hard-codes (AudioEngine.cpp:580-586,857) or gets from the device.  Set before init().
 	struct Options {
 		Options() : frames_per_buffer(256), sample_rate(48000), cuda_device(0), max_sources(65536), max_mix_sources(4096),
-		            binaural(true), start_mix_thread(true), initial_mute_frames(48000) {}
+		            binaural(true), start_mix_thread(true), start_streamer_thread(true), initial_mute_frames(48000) {}
 		int frames_per_buffer;   // device period (256; 1024 on Emscripten)
 		int sample_rate;
 		int cuda_device;
 		int max_sources, max_mix_sources;
 		bool binaural;           // true: kBinauralHighQuality for spatial sources as the reference; false: kStereoPanning
 		bool start_mix_thread;   // false: the owner calls mixOneBuffer() itself (tests, offline rendering)
+		bool start_streamer_thread;   // false: the owner pumps the streams itself (StreamerThread::streamOnce)
 		int initial_mute_frames; // the reference discards the first second of output (AudioEngine.cpp:532-533)
 		std::vector<float> sh_hrir;  // planar [16][taps] SH-HRIRs (CreateShHrirsFromAssets); required when binaural
 		int sh_hrir_taps = 0;
@@ -141,12 +150,37 @@ public:
 	void addSource(AudioSourceRef source);
 	void removeSource(AudioSourceRef source);
 
+	// sound_data_source may be null.  If non-null, read from it, otherwise read from disk from sound_file_path  (AudioEngine.h:193-206)
+	struct AddSourceFromStreamingSoundFileParams {
+		AddSourceFromStreamingSoundFileParams() : source_volume(1.f), global_time(0.0), looping(true), paused(false) {}
+		std::string sound_file_path;
+		Reference<SharedMemMappedFile> mem_mapped_sound_file;
+		Reference<MP3AudioStreamerDataSource> sound_data_source;
+		float source_volume;
+		double global_time;
+		bool looping;
+		bool paused;
+	};
+	// AudioEngine.cpp:1081-1140: a new streaming source; sources that play the same (unpaused) file share one decoder, and a
+	// source that joins a running stream starts from a copy of the first listener's backlog so that all of them stay in sync.
+	AudioSourceRef addSourceFromStreamingSoundFile(AddSourceFromStreamingSoundFileParams& params, const Vec4f& pos);
+	bool needNewStreamerForPath(const std::string& sound_file_path, bool new_source_paused);   // AudioEngine.cpp:1142-1146
+	// Where the reference constructs `new MP3AudioStreamer(data source | mem-mapped file)` (AudioEngine.cpp:1106-1110) this mirror
+	// asks the owner for the decoder: the codec is outside the accelerated path.  Must be set before the first streaming source.
+	std::function<Reference<MP3AudioStreamer>(const AddSourceFromStreamingSoundFileParams&)> make_streamer;
+
+	// Batched forms of the three per-frame notifications below for the O(N) per-frame loop of the client
+	// (gui_client/GUIClient.cpp:6979-7034): one C-ABI call for all of them instead of one per source.
+	void sourcesPositionUpdated(AudioSource* const* sources, size_t n);
+	void sourcesVolumeUpdated(AudioSource* const* sources, size_t n);
+	void sourcesNumOcclusionsUpdated(AudioSource* const* sources, size_t n);
+
 	void sourcePositionUpdated(AudioSource& source);
 	void sourceVolumeUpdated(AudioSource& source);
 	void sourceNumOcclusionsUpdated(AudioSource& source);
 	void setHeadTransform(const Vec4f& head_pos, const Quatf& head_rot);
 	void playOneShotSound(const std::string& sound_file_path, const Vec4f& pos);
-	void setRoomEffectsEnabled(bool enabled);                      // only `false` is on the accelerated path
+	void setRoomEffectsEnabled(bool enabled);                      // only `false` is on the accelerated path (next)
 	void setCurentRoomDimensions(const js::AABBox& room_aabb);     // accepted and ignored while room effects are off
 	uint32 getSampleRate() const { return sample_rate; }
 	void seekToStartAndUnpauseAudio(AudioSource& source);
@@ -171,11 +205,20 @@ private:
 	void feedStreamingSource(AudioSource& source);
 	void mixThreadMain();
 
+	void flushPendingUpdates();
+
 	sbm_engine* engine;
 	AudioCallbackData callback_data;
 	bool initialised;
-	std::thread mix_thread;
 	std::atomic<bool> die;
+	// The single-source notifications (sourcePositionUpdated ...) only append here; mixOneBuffer sends each kind as ONE batched
+	// sbm_set_* call per buffer.  They take effect at the same point as before: the next buffer.
+	std::mutex pending_mutex;
+	std::vector<int> pend_pos_ids, pend_vol_ids, pend_occ_ids;
+	std::vector<float> pend_pos, pend_vol, pend_occ;
+	std::vector<int> mixp_ids, mixp_z;
+	std::vector<double> mixp_delta;
+	std::vector<float> mixp_factor;
 	int64 frames_mixed;
 	std::map<const AudioBuffer*, int> device_buffers;   // AudioBuffer -> sbm buffer id (the buffer is kept alive below)
 	std::vector<AudioBufferRef> device_buffer_refs;
@@ -190,7 +233,14 @@ public:
 	Mutex mutex;  // Guards access to audio_sources
 	std::set<AudioSourceRef> active_audio_sources GUARDED_BY(mutex);
 	std::set<AudioSourceRef> audio_sources GUARDED_BY(mutex);
+
+	ThreadManager thread_manager;  // Manages: the mixing thread (ResonanceThread in the reference), StreamerThread
+
 	std::map<std::string, SoundFileRef> sound_files;
+
+	std::map<std::string, Reference<MP3AudioStreamer>> unpaused_streams;  // Map from mp3 file path to MP3AudioStreamer for that mp3.
+
+	std::map<Reference<MP3AudioStreamer>, std::set<AudioSourceRef>> stream_to_source_map;  // Map from MP3AudioStreamer to audio sources playing that stream.
 
 private:
 	uint32 sample_rate;

@@ -3,26 +3,34 @@
 
 namespace glare {
 
-AudioResampler::AudioResampler() : r(nullptr), src_rate(0), dest_rate(0) {}
+AudioResampler::AudioResampler() : r(nullptr), src_rate(0), dest_rate(0), device(0) {}
 
 AudioResampler::~AudioResampler() { if (r) sbm_resampler_destroy(r); }
 
-void AudioResampler::init(int src_rate_, int dest_rate_, int device) {
+// init only records the rates (and forgets the carried state, AudioResampler.cpp:24-36): every AudioSource owns an AudioResampler
+// (AudioEngine.h:153) that the accelerated engine never calls -- sources are resampled inside the mix kernels -- so the device
+// object is created by the first call that needs it.
+void AudioResampler::init(int src_rate_, int dest_rate_, int device_) {
 	if (r) { sbm_resampler_destroy(r); r = nullptr; }
-	src_rate = src_rate_; dest_rate = dest_rate_;
+	src_rate = src_rate_; dest_rate = dest_rate_; device = device_;
+}
+
+void AudioResampler::ensure() {
+	if (r) return;
+	if (src_rate <= 0 || dest_rate <= 0) throw glare::Exception("AudioResampler: init() has not been called");
 	const int rc = sbm_resampler_create(device, 1, &src_rate, dest_rate, &r);
-	if (rc != SBM_OK) throw glare::Exception("AudioResampler::init: sbm_resampler_create failed (" + std::to_string(rc) + ")");
+	if (rc != SBM_OK) throw glare::Exception("AudioResampler: sbm_resampler_create failed (" + std::to_string(rc) + ")");
 }
 
 size_t AudioResampler::numSrcSamplesNeeded(size_t dest_num_samples) {
-	if (!r) throw glare::Exception("AudioResampler::numSrcSamplesNeeded: init() has not been called");
+	ensure();
 	size_t n = 0;
 	sbm_resampler_num_src_needed(r, dest_num_samples, &n);
 	return n;
 }
 
 void AudioResampler::resample(float* dest_samples, size_t dest_samples_size, const float* src_samples, size_t src_samples_size, js::Vector<float, 16>& /*temp_buf*/) {
-	if (!r) throw glare::Exception("AudioResampler::resample: init() has not been called");
+	ensure();
 	if (src_samples_size != numSrcSamplesNeeded(dest_samples_size))
 		throw glare::Exception("AudioResampler::resample: src_samples_size must equal numSrcSamplesNeeded(dest_samples_size)");
 	const size_t off = 0;

@@ -28,8 +28,9 @@ public:
 	void resample(float* dest_samples, size_t dest_samples_size, const float* src_samples, size_t src_samples_size, js::Vector<float, 16>& temp_buf);
 
 private:
+	void ensure();
 	sbm_resampler* r;
-	int src_rate, dest_rate;
+	int src_rate, dest_rate, device;
 };
 
 }  // namespace glare

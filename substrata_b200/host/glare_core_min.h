@@ -13,6 +13,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 typedef uint32_t uint32;
@@ -156,13 +157,15 @@ private:
 	size_t head, count;
 };
 
-// utils/Mutex.h, utils/Lock.h
+// utils/Mutex.h, utils/Lock.h.  glare-core's Mutex is recursive (CRITICAL_SECTION / a recursive pthread mutex):
+// addSourceFromStreamingSoundFile holds AudioEngine::mutex while it calls addSource, which takes it again
+// (AudioEngine.cpp:1085,1137,892).
 class Mutex {
 public:
 	void lock() { m.lock(); }
 	void unlock() { m.unlock(); }
 private:
-	std::mutex m;
+	std::recursive_mutex m;
 };
 class Lock {
 public:
@@ -179,3 +182,49 @@ private:
 #ifndef GLARE_ALIGNED_16_NEW_DELETE
 #define GLARE_ALIGNED_16_NEW_DELETE
 #endif
+
+// utils/AtomicInt.h
+namespace glare {
+class AtomicInt {
+public:
+	AtomicInt(int64_t v = 0) : val(v) {}
+	operator int64_t() const { return val.load(); }
+	AtomicInt& operator=(int64_t v) { val.store(v); return *this; }
+	int64_t increment() { return val.fetch_add(1); }
+	int64_t decrement() { return val.fetch_sub(1); }
+private:
+	std::atomic<int64_t> val;
+};
+}  // namespace glare
+
+// utils/MessageableThread.h + utils/ThreadManager.h, as AudioEngine uses them (AudioEngine.cpp:340-345,557-560,711-726,816):
+// threads are objects with doRun() / kill(); the manager starts them and, on killThreadsBlocking(), asks each to stop and joins.
+class MessageableThread : public ThreadSafeRefCounted {
+public:
+	virtual ~MessageableThread() {}
+	virtual void doRun() = 0;
+	virtual void kill() = 0;
+};
+class ThreadManager {
+public:
+	~ThreadManager() { killThreadsBlocking(); }
+	void addThread(const Reference<MessageableThread>& t) {
+		objs.push_back(t);
+		MessageableThread* raw = t.ptr();
+		threads.emplace_back([raw]() { raw->doRun(); });
+	}
+	void killThreadsBlocking() {
+		for (auto& o : objs) o->kill();
+		for (auto& th : threads) if (th.joinable()) th.join();
+		threads.clear(); objs.clear();
+	}
+	size_t getNumThreads() const { return objs.size(); }
+private:
+	std::vector<Reference<MessageableThread>> objs;
+	std::vector<std::thread> threads;
+};
+
+// utils/MemMappedFile.h (SharedMemMappedFile) and audio/MP3AudioStreamer.h (MP3AudioStreamerDataSource): opaque here -- the
+// mp3 codec is outside the accelerated path; they only travel through AddSourceFromStreamingSoundFileParams.
+class SharedMemMappedFile : public ThreadSafeRefCounted {};
+class MP3AudioStreamerDataSource : public ThreadSafeRefCounted {};

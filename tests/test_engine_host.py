@@ -295,3 +295,15 @@ def test_partitioned_oracle_equals_single_oracle():
     assert va == vb
     for k in range(sc.nb):
         assert rel_rms(b[k], a[k]) <= 3e-6
+
+
+def test_streaming_boundary_of_the_audio_engine_mirror():
+    """SURVEY 8f row 1 through the glare::AudioEngine mirror on the emulated device (tests/native/test_streaming_host.cc):
+    addSourceFromStreamingSoundFile / needNewStreamerForPath / the stream maps, two sources sharing one decoder start in sync
+    (AudioEngine.cpp:1124-1131), a decoder-reported sampling rate (StreamerThread.cpp:98-105), a paused source with its own
+    decoder unpaused by seekToStartAndUnpauseAudio, removeSource freeing the decoder -- output against the oracle fed with
+    exactly the samples the synthetic decoder produced."""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR, "test_streaming_host"])
+    r = subprocess.run([os.path.join(EMU_DIR, "test_streaming_host")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rel_rms" in r.stdout
