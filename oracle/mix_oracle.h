@@ -41,6 +41,11 @@ void orc_set_source_occlusions(orc_engine* e, int n, const int* ids, const float
 void orc_set_head(orc_engine* e, const float* pos, const float* quat_xyzw);
 void orc_set_master_volume(orc_engine* e, float v);
 void orc_source_destroy(orc_engine* e, int id);
+/* Room effects as Substrata drives them (AudioEngine.cpp:738-768): early reflections in a shoebox room; off by default. */
+void orc_set_room_hrir(orc_engine* e, const float* sh_hrir_order1 /* [4][taps] */, int taps);
+void orc_enable_room_effects(orc_engine* e, int enable);
+void orc_set_reflection_properties(orc_engine* e, const float* room_position, const float* room_rotation_xyzw, const float* room_dimensions,
+                                   const float* coefficients6, float cutoff_frequency, float gain);
 int  orc_mix(orc_engine* e, float* out_interleaved);
 int  orc_get_ambisonic_bus(orc_engine* e, float* out16xF);
 int  orc_poll_finished(orc_engine* e, int* ids, int cap);

@@ -330,7 +330,31 @@ int ref_source_query(void* h, int id, uint64_t* cur_read_i, int64_t* eof_marker,
 	return 1;
 }
 
+// Room effects as Substrata drives them: setRoomEffectsEnabled -> EnableRoomEffects (AudioEngine.cpp:738-743),
+// setCurentRoomDimensions -> SetReflectionProperties (AudioEngine.cpp:746-768).
+void ref_enable_room_effects(void* h, int enable) { ((RefEngine*)h)->api->EnableRoomEffects(enable != 0); }
+void ref_set_reflection_properties(void* h, const float* room_position, const float* room_rotation_xyzw, const float* room_dimensions,
+                                   const float* coefficients6, float cutoff_frequency, float gain) {
+	vraudio::ReflectionProperties p;
+	for (int i = 0; i < 3; ++i) { p.room_position[i] = room_position[i]; p.room_dimensions[i] = room_dimensions[i]; }
+	for (int i = 0; i < 4; ++i) p.room_rotation[i] = room_rotation_xyzw[i];
+	for (int i = 0; i < 6; ++i) p.coefficients[i] = coefficients6[i];
+	p.cutoff_frequency = cutoff_frequency; p.gain = gain;
+	((RefEngine*)h)->api->SetReflectionProperties(p);
+}
+
 // ---- stage-level probes of the real reference, used to pin the oracle restatement -----------------------
+// The stock SH-HRIRs of ambisonic order 1 (the reflections' decoder) exactly as that decoder receives them.
+int ref_dump_sh_hrirs_order1(int sample_rate_hz, float* out, int cap_floats, int* channels) {
+	vraudio::Resampler resampler;
+	std::unique_ptr<vraudio::AudioBuffer> hr =
+		vraudio::CreateShHrirsFromAssets("WAV/Subject_002/SH/sh_hrir_order_1.wav", sample_rate_hz, &resampler);
+	const int C = (int)hr->num_channels(), T = (int)hr->num_frames();
+	*channels = C;
+	if (out && cap_floats >= C * T)
+		for (int c = 0; c < C; ++c) for (int t = 0; t < T; ++t) out[c * T + t] = (*hr)[(size_t)c][(size_t)t];
+	return T;
+}
 
 // The stock order-3 SH-HRIRs exactly as the decoder receives them (sh_hrir_creator.cc:60-70).  Returns taps.
 int ref_dump_sh_hrirs(int sample_rate_hz, float* out, int cap_floats, int* channels) {
