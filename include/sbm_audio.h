@@ -142,7 +142,20 @@ SBM_API int sbm_set_source_volumes(sbm_engine* e, int n, const int* ids, const f
 SBM_API int sbm_set_source_occlusions(sbm_engine* e, int n, const int* ids, const float* occ); /* SetSoundObjectOcclusionIntensity, :974 */
 SBM_API int sbm_set_head(sbm_engine* e, const float* pos_xyz, const float* quat_xyzw);          /* SetHeadPosition/Rotation, :987-988 */
 SBM_API int sbm_set_master_volume(sbm_engine* e, float volume);                                  /* SetMasterVolume, :810 */
-SBM_API int sbm_enable_room_effects(sbm_engine* e, int enable);                                  /* EnableRoomEffects, :742; only 0 supported */
+/* ---- room effects: early reflections of a shoebox room (AudioEngine.cpp:738-768; RA/graph/graph_manager.cc:106-107,144-151,182-198,
+ * RA/graph/reflections_node.cc, RA/dsp/reflections_processor.cc).  Every sound object additionally feeds a mono reflections bus
+ * through a ramped gain (room effects gain 1 * direct attenuation * ReflectionProperties::gain); once per buffer the bus goes through six
+ * delayed, gain-ramped wall reflections, a first-order ambisonic encode cross-faded whenever the room or the listener moved, the
+ * head rotation, and the order-1 SH-HRIR decoder.  The late-reverb send exists too but has gain 0 with Substrata's settings
+ * (AudioEngine never calls SetReverbProperties): it contributes zeros and only keeps *out_valid true while sources play. ---- */
+/* The order-1 SH-HRIRs the reflections are decoded with: planar [4][taps] (CreateShHrirsFromAssets("...sh_hrir_order_1.wav")).
+ * Once, before room effects are first enabled, with no buffer in flight. */
+SBM_API int sbm_set_room_sh_hrir(sbm_engine* e, const float* sh_hrir_order1, int taps);
+SBM_API int sbm_enable_room_effects(sbm_engine* e, int enable);                                  /* EnableRoomEffects, :742 */
+/* SetReflectionProperties, :767 (vraudio::ReflectionProperties, resonance_audio_api.h:73-105): centre, rotation (xyzw) and size of
+ * the room, the six wall reflection coefficients (-x +x -y +y -z +z), low-pass cut-off (0 = none) and the reflections gain. */
+SBM_API int sbm_set_reflection_properties(sbm_engine* e, const float* room_position, const float* room_rotation_xyzw, const float* room_dimensions,
+                                          const float* coefficients6, float cutoff_frequency, float gain);
 
 /* ---- the per-buffer call ---- */
 /* SetPlanarBuffer for every active source + FillInterleavedOutputBuffer(2, frames, out) (AudioEngine.cpp:370-526).
@@ -156,8 +169,9 @@ SBM_API int sbm_mix(sbm_engine* e, float* out_interleaved, int* out_valid);
  *   (caller may now sum the bus across ranks, e.g. ncclAllReduce on sbm_stream())
  *   sbm_mix_finish  launches SH decode + stereo mix + interleave, copies 2*frames floats to out_interleaved (host)
  *                   and synchronises.  Pass NULL to leave the result on the device (sbm_out_device()).
- * Bus layout: [18][frames] f32: rows 0-15 ambisonic (ACN), 16-17 the stereo bus (panned + non-spatial sources),
- * followed by 4 floats of flags {ambisonic bus used, stereo bus used, 0, 0} that sum across ranks like the audio. */
+ * Bus layout: [19][frames] f32: rows 0-15 ambisonic (ACN), 16-17 the stereo bus (panned + non-spatial sources), 18 the mono
+ * reflections send (room effects), followed by 4 floats of flags {ambisonic bus, stereo panner, stereo sources, reflections send
+ * fed} that sum across ranks like the audio. */
 SBM_API int sbm_mix_begin(sbm_engine* e);
 SBM_API int sbm_mix_finish(sbm_engine* e, float* out_interleaved, int* out_valid);
 /* Pipelined form of sbm_mix: sbm_mix_submit enqueues one whole buffer (uploads, kernels, the copy of the result into

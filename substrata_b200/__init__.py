@@ -19,6 +19,7 @@ from .abi import bind, SbmConfig, SbmSourceState, SbmStats, ERROR_NAMES
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsubstrata_b200.so")
 HRIR_PATH = os.path.join(HERE, "data", "sh_hrir_order3_48k.f32")
+HRIR1_PATH = os.path.join(HERE, "data", "sh_hrir_order1_48k.f32")
 
 KIND_PAN = 0        # vraudio::RenderingMode::kStereoPanning
 KIND_HRTF = 3       # vraudio::RenderingMode::kBinauralHighQuality (AudioEngine.cpp:857)
@@ -54,6 +55,11 @@ def load_sh_hrir(taps=None):
     (RA/dsp/sh_hrir_creator.cc:60-70; dumped by tests/golden/make_golden.py).  `taps` truncates (config C3: 128)."""
     a = np.fromfile(HRIR_PATH, dtype=np.float32).reshape(16, -1)
     return np.ascontiguousarray(a[:, :taps]) if taps else a
+
+
+def load_sh_hrir_order1():
+    """Order-1 SADIE SH-HRIRs [4][256] f32 at 48 kHz: what the reference's order-1 decoder (the reflections') receives."""
+    return np.fromfile(HRIR1_PATH, dtype=np.float32).reshape(4, -1)
 
 
 def _p(a):
@@ -224,6 +230,18 @@ class MixEngine:
 
     def set_master_volume(self, v):
         self._ck(self._l.sbm_set_master_volume(self.h, float(v)), "sbm_set_master_volume")
+
+    # -- room effects (AudioEngine.cpp:738-768) ------------------------------------------------------------------
+    def set_room_hrir(self, sh_hrir_order1):
+        h = _f32(sh_hrir_order1)
+        self._ck(self._l.sbm_set_room_sh_hrir(self.h, _p(h), int(h.shape[1])), "sbm_set_room_sh_hrir")
+
+    def enable_room_effects(self, on):
+        self._ck(self._l.sbm_enable_room_effects(self.h, int(bool(on))), "sbm_enable_room_effects")
+
+    def set_reflection_properties(self, room_position, room_rotation_xyzw, room_dimensions, coefficients6, cutoff_frequency=0.0, gain=0.0):
+        a, b, c, d = _f32(room_position), _f32(room_rotation_xyzw), _f32(room_dimensions), _f32(coefficients6)
+        self._ck(self._l.sbm_set_reflection_properties(self.h, _p(a), _p(b), _p(c), _p(d), float(cutoff_frequency), float(gain)), "sbm_set_reflection_properties")
 
     # -- the per-buffer call --------------------------------------------------------------------------------------
     def mix(self, out=None):

@@ -51,6 +51,8 @@ SIGNATURES = {
     "sbm_set_source_occlusions": (_i, [_vp, _i, _vp, _vp]),
     "sbm_set_head": (_i, [_vp, _vp, _vp]),
     "sbm_set_master_volume": (_i, [_vp, _f]),
+    "sbm_set_room_sh_hrir": (_i, [_vp, _vp, _i]),
+    "sbm_set_reflection_properties": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f]),
     "sbm_enable_room_effects": (_i, [_vp, _i]),
     "sbm_mix": (_i, [_vp, _vp, _vp]),
     "sbm_mix_submit": (_i, [_vp]),

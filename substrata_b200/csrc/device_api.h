@@ -7,6 +7,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include "sbm_core.h"
+#include "room_core.h"
 
 namespace sbm {
 
@@ -66,6 +67,7 @@ struct MixArgs {
 	const WorkRec* rec;         // indexed like mrec: the full records (the CUDA kernels read them on their careful paths only)
 	const ShGains* shg;         // indexed like rec
 	const ShRamps* shr;         // indexed like rec
+	const ReflSend* rfl;        // indexed like rec; null = room effects off (the kernels then carry no reflections row)
 	const MixZ* mixz;
 	const double* mix_pos0;
 	Resamp* rs;                 // K2 stores prev_samples of resampled sources
@@ -85,8 +87,18 @@ struct MixArgs {
 	uint32_t rot_div;           // set by the launcher: SM count (CTA index / rot_div = which resident CTA of its SM a CTA is, first wave)
 };
 
+struct RoomArgs {               // the room kernel (room_core.h): reflections bus -> first-order buffer
+	const float* bus;           // (possibly cross-rank summed) [19][frames] + 4 flags: row kRowRefl is the mono reflections send
+	const RoomParams* params;   // device copy of this buffer's RoomParams
+	RoomState* state;
+	float* delay_line;          // [delay_size] mono
+	float* foa;                 // [4][frames] out (ACN: W Y Z X)
+	DevFlags* flags;
+	uint32_t frames;
+};
+
 struct FinishArgs {
-	const float* bus;           // (possibly all-reduced) [18][frames] + 4 flags
+	const float* bus;           // (possibly all-reduced) [19][frames] + 4 flags
 	const float* hrir;          // [16][taps] or null
 	uint32_t taps;
 	float* hist;                // [16][taps-1] FIR history (the decoder's overlap state), updated in place
@@ -100,6 +112,13 @@ struct FinishArgs {
 	const unsigned long long* read_i;
 	const int* finished;        // this buffer's finished-id list (device); the first kInlineFinished ids are copied behind the ring counters
 	int hist_smem_all;          // set by launch_finish: K4b updates the FIR history of all 16 channels in one pass
+	// room effects: the reflections' first-order buffer and its order-1 SH-HRIR decoder (null hrir1: no room effects configured)
+	const float* foa;           // [4][frames]
+	const float* hrir1;         // [4][taps1]
+	uint32_t taps1;
+	float* hist1;               // [4][taps1-1]
+	float* dec1;                // [2][frames]
+	uint32_t room_enabled;
 };
 
 struct OutTail {                // follows the 2*frames output floats in the D2H staging buffer
@@ -134,6 +153,7 @@ int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, cons
 int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, const uint32_t* lists, uint32_t n_slots, void* stream);   // lists: [n_pan + n_sh] slots in render order
 int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void* stream);   // batched ring push: one CTA per packet
 int launch_mix(const MixArgs& a, void* stream);  // K2 (both lists) + K3 (partials -> bus)
+int launch_room(const RoomArgs& a, void* stream);   // ReflectionsNode for this buffer (room effects)
 int launch_finish(const FinishArgs& a, void* stream);
 // peer exchange (multi-GPU): IPC plumbing + the gather kernel
 int peer_export(void* device_ptr, void* handle_out64);             // cudaIpcGetMemHandle

@@ -34,28 +34,37 @@ constexpr int kDecFrames = 32;
 // DBL: taps and inputs are converted to double ONCE while they are staged (f32 -> f64 conversions run on the 16-lane XU
 // pipe: two per tap and thread made this kernel 16 us long); the float staging is the fall-back when 8-byte copies of
 // [16][taps] + [16][taps + 31] do not fit in shared memory (taps > ~430).
-template <bool DBL>
+// ORDER1: the same decode for the reflections' first-order buffer (4 channels, the order-1 SH-HRIRs, its own history and flush
+// counter) -- room effects.
+template <bool DBL, bool ORDER1>
 __global__ void __launch_bounds__(kNumSh * 32) k4a_decode_kernel(FinishArgs a) {
 	typedef typename std::conditional<DBL, double, float>::type stage_t;
 	extern __shared__ __align__(16) unsigned char smem_raw[];   // [16][taps] HRIRs | [16][taps - 1 + 32] inputs | [16][32] channel results (float)
-	const uint32_t F = a.frames, taps = a.taps;
+	constexpr int NCH = ORDER1 ? 4 : kNumSh;
+	const uint32_t F = a.frames, taps = ORDER1 ? a.taps1 : a.taps;
 	const int H = (int)taps - 1;
 	grid_dep_wait();
 	const float* bf = a.bus + (size_t)kBusRows * F;
-	if (!(bf[0] > 0.0f) && !(a.flags->sh_flush_frames < (int)F)) return;      // nothing to decode, no tail to flush
+	if (ORDER1) { if (!room_decode1_wanted(a.flags, F)) return; }
+	else if (!(bf[0] > 0.0f) && !(a.flags->sh_flush_frames < (int)F)) return;      // nothing to decode, no tail to flush
 	const uint32_t c = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 	const uint32_t i0 = blockIdx.x * kDecFrames;
 	const uint32_t span = (uint32_t)H + kDecFrames;
 	stage_t* sm = reinterpret_cast<stage_t*>(smem_raw);
 	stage_t* h = sm + (size_t)c * taps;
-	stage_t* x = sm + (size_t)kNumSh * taps + (size_t)c * span;
-	float* ys = reinterpret_cast<float*>(sm + (size_t)kNumSh * taps + (size_t)kNumSh * span);
-	const float* bus_c = a.bus + (size_t)c * F;
-	const float* hist_c = a.hist + (size_t)c * (size_t)(H > 0 ? H : 1);
-	for (uint32_t q = lane; q < taps; q += 32) h[q] = (stage_t)a.hrir[(size_t)c * taps + q];
+	stage_t* x = sm + (size_t)NCH * taps + (size_t)c * span;
+	float* ys = reinterpret_cast<float*>(sm + (size_t)NCH * taps + (size_t)NCH * span);
+	// order 1: the reflections' buffer -- all zeros while the decoder only flushes its tail (the node produced nothing)
+	const bool silent_in = ORDER1 && !a.flags->foa_valid;
+	const float* bus_c = (ORDER1 ? a.foa : a.bus) + (size_t)c * F;
+	const float* hist_c = (ORDER1 ? a.hist1 : a.hist) + (size_t)c * (size_t)(H > 0 ? H : 1);
+	const float* hrir = ORDER1 ? a.hrir1 : a.hrir;
+	for (uint32_t q = lane; q < taps; q += 32) h[q] = (stage_t)hrir[(size_t)c * taps + q];
 	for (uint32_t q = lane; q < span; q += 32) {
 		const int j = (int)i0 - H + (int)q;                        // input sample index; negative = history
-		x[q] = (stage_t)(j < (int)F ? decode_input(bus_c, hist_c, H, j) : 0.0f);
+		float v = 0.0f;
+		if (j < (int)F) v = (silent_in && j >= 0) ? 0.0f : decode_input(bus_c, hist_c, H, j);
+		x[q] = (stage_t)v;
 	}
 	__syncwarp();
 	// four interleaved partial sums break the taps' dependent DFMA chain; everything is accumulated in double, so the
@@ -75,12 +84,52 @@ __global__ void __launch_bounds__(kNumSh * 32) k4a_decode_kernel(FinishArgs a) {
 	if (c == 0 && i0 + lane < F) {
 		float l = 0.0f, r = 0.0f;
 #pragma unroll
-		for (int cc = 0; cc < kNumSh; ++cc) {
+		for (int cc = 0; cc < NCH; ++cc) {
 			const float y = ys[cc * kDecFrames + lane];
 			l += y;
 			r = sh_right_ear_negated(cc) ? r - y : r + y;
 		}
-		a.dec[i0 + lane] = l; a.dec[F + i0 + lane] = r;
+		float* dec = ORDER1 ? a.dec1 : a.dec;
+		dec[i0 + lane] = l; dec[F + i0 + lane] = r;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Room kernel: Resonance's ReflectionsNode for this buffer (room_core.h).  One CTA, thread i = frame i.  Thread 0 plans
+// (gain processors, crossfade, rotation mode, tail bookkeeping), then every frame is independent: insert the (low-passed)
+// reflections bus into the delay line, read six delayed copies, ramp, encode to first order, crossfade, rotate.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_room_kernel(RoomArgs a) {
+	__shared__ RoomPlan plan;
+	__shared__ float lp[kMaxFrames];
+	const uint32_t F = a.frames, i = threadIdx.x;
+	grid_dep_wait();
+	const float* in = a.bus + (size_t)kRowRefl * F;
+	if (i == 0) {
+		const RoomParams p = *a.params;
+		const bool have_input = p.enabled && a.bus[(size_t)kBusRows * F + 3] > 0.0f;
+		room_plan(p, a.state, have_input, F, &plan);
+		if (plan.process && !(plan.lp_coef < kEpsilonFloat)) {
+			// MonoPoleFilter: a serial recurrence over the buffer (only with a cut-off frequency set; Substrata sets none)
+			float prev = plan.lp_prev;
+			for (uint32_t n = 0; n < F; ++n) { prev = lpf_step(plan.lp_coef, prev, plan.silent_input ? 0.0f : in[n]); lp[n] = prev; }
+			a.state->lp_prev = prev;
+		} else if (plan.process) {
+			a.state->lp_prev = plan.silent_input ? 0.0f : in[F - 1];      // bypassed filter remembers its last input (mono_pole_filter.cc:40-44)
+		}
+		a.flags->foa_valid = plan.process ? 1 : 0;
+	}
+	__syncthreads();
+	if (!plan.process) return;
+	if (i < F) {
+		const float v = !(plan.lp_coef < kEpsilonFloat) ? lp[i] : (plan.silent_input ? 0.0f : in[i]);
+		a.delay_line[room_insert_index(plan, F, i)] = v;
+	}
+	__syncthreads();      // (one CTA: the inserted frames are visible to every thread's reads below)
+	if (i < F) {
+		float w, y, z, x;
+		room_frame(plan, a.delay_line, F, i, &w, &y, &z, &x);
+		a.foa[i] = w; a.foa[(size_t)F + i] = y; a.foa[(size_t)2 * F + i] = z; a.foa[(size_t)3 * F + i] = x;
 	}
 }
 
@@ -98,11 +147,29 @@ __global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
 	const uint32_t taps = a.hrir ? a.taps : 0;
 	const int H = (int)taps - 1;
 	grid_dep_wait();
-	if (i == 0) plan = plan_finish(a.bus + (size_t)kBusRows * F, a.hrir != nullptr, a.flags, a.parity, F);
+	const int foa_valid = a.hrir1 ? a.flags->foa_valid : 0;      // (read by every thread before thread 0's plan_finish clears it: barrier)
+	__syncthreads();
+	if (i == 0) plan = plan_finish(a.bus + (size_t)kBusRows * F, a.hrir != nullptr, a.hrir1 != nullptr, a.room_enabled != 0, a.flags, a.parity, F);
 	__syncthreads();
 	float l = 0.0f, r = 0.0f;
+	if (plan.decode1) {
+		// the reflections' order-1 decode (K4a<.., true>) + its FIR history: last taps1 - 1 samples of {history, buffer or silence}
+		if (i < F) { l = a.dec1[i]; r = a.dec1[F + i]; }
+		const int H1 = (int)a.taps1 - 1;
+		if (H1 > 0) {
+			const uint32_t n1 = 4u * (uint32_t)H1;      // <= 4 * 1023 floats: through shared memory (it may overlap the old history when frames < taps)
+			for (uint32_t q = i; q < n1; q += T) {
+				const uint32_t c = q / (uint32_t)H1, k = q - c * (uint32_t)H1;
+				const int j = (int)F - H1 + (int)k;
+				smem[q] = (j >= 0 && !foa_valid) ? 0.0f : decode_input(a.foa + (size_t)c * F, a.hist1 + (size_t)c * (size_t)H1, H1, j);
+			}
+			__syncthreads();
+			for (uint32_t q = i; q < n1; q += T) a.hist1[q] = smem[q];
+			__syncthreads();
+		}
+	}
 	if (plan.decode) {
-		if (i < F) { l = a.dec[i]; r = a.dec[F + i]; }
+		if (i < F) { l += a.dec[i]; r += a.dec[F + i]; }
 		if (H > 0 && a.hist_smem_all) {
 			// all 16 channels at once: the new history goes through shared memory (it may overlap the old one when frames < taps)
 			const uint32_t n = (uint32_t)kNumSh * (uint32_t)H;
@@ -293,6 +360,13 @@ int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage,
 	return check_launch("k_ring_scatter");
 }
 
+int launch_room(const RoomArgs& a, void* stream) {
+	const uint32_t threads = ((a.frames + 31) / 32) * 32;
+	launch_pdl(k_room_kernel, dim3(1), dim3(threads), 0, (cudaStream_t)stream, a);
+	note_launch();
+	return check_launch("k_room");
+}
+
 int launch_finish(const FinishArgs& a, void* stream) {
 	const uint32_t F = a.frames;
 	cudaStream_t st = (cudaStream_t)stream;
@@ -302,20 +376,29 @@ int launch_finish(const FinishArgs& a, void* stream) {
 		const size_t smem = (dbl ? sizeof(double) : sizeof(float)) * elems + sizeof(float) * (size_t)kNumSh * kDecFrames;
 		static size_t configured[2] = {48 * 1024, 48 * 1024};
 		if (smem > configured[dbl]) {
-			if (check(dbl ? cudaFuncSetAttribute(k4a_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-			              : cudaFuncSetAttribute(k4a_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k4a)")) return -1;
+			if (check(dbl ? cudaFuncSetAttribute(k4a_decode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+			              : cudaFuncSetAttribute(k4a_decode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(k4a)")) return -1;
 			configured[dbl] = smem;
 		}
-		if (dbl) launch_pdl(k4a_decode_kernel<true>, dim3((F + kDecFrames - 1) / kDecFrames), dim3(kNumSh * 32), smem, st, a);
-		else launch_pdl(k4a_decode_kernel<false>, dim3((F + kDecFrames - 1) / kDecFrames), dim3(kNumSh * 32), smem, st, a);
+		if (dbl) launch_pdl(k4a_decode_kernel<true, false>, dim3((F + kDecFrames - 1) / kDecFrames), dim3(kNumSh * 32), smem, st, a);
+		else launch_pdl(k4a_decode_kernel<false, false>, dim3((F + kDecFrames - 1) / kDecFrames), dim3(kNumSh * 32), smem, st, a);
 		note_launch();
 		if (check_launch("k4a_decode")) return -1;
+	}
+	if (a.hrir1) {
+		// the reflections' order-1 decode: 4 channels, float staging (4 x (2 taps + 31) floats <= 33 KB)
+		const size_t elems = (size_t)4 * a.taps1 + (size_t)4 * (a.taps1 - 1 + kDecFrames);
+		const size_t smem = sizeof(float) * elems + sizeof(float) * (size_t)4 * kDecFrames;
+		launch_pdl(k4a_decode_kernel<false, true>, dim3((F + kDecFrames - 1) / kDecFrames), dim3(4 * 32), smem, st, a);
+		note_launch();
+		if (check_launch("k4a_decode(order 1)")) return -1;
 	}
 	const uint32_t threads = ((F + 31) / 32) * 32;
 	const size_t h1 = a.hrir && a.taps > 1 ? a.taps - 1 : 1;
 	FinishArgs b = a;
 	b.hist_smem_all = sizeof(float) * h1 * kNumSh <= 48 * 1024 ? 1 : 0;      // 16 channels' history in one pass when it fits the default limit
-	const size_t smem = sizeof(float) * h1 * (b.hist_smem_all ? (size_t)kNumSh : 1);
+	size_t smem = sizeof(float) * h1 * (b.hist_smem_all ? (size_t)kNumSh : 1);
+	if (a.hrir1 && a.taps1 > 1) smem = smem > sizeof(float) * 4 * (a.taps1 - 1) ? smem : sizeof(float) * 4 * (a.taps1 - 1);
 	launch_pdl(k4b_finish_kernel, dim3(1), dim3(threads), smem, st, b);
 	note_launch();
 	return check_launch("k4b_finish");

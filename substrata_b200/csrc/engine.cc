@@ -161,7 +161,22 @@ struct sbm_engine {
 	unsigned long long buffer_index = 0;
 	bool begun = false;
 	int last_valid = 0;
-	int room_effects = 0;
+	// room effects (RA/graph/graph_manager.cc:106-107,144-151,182-198).  System settings as the setters left
+	// them, the ReflectionsNode's cached copy (what its Update compares against), and the device side of the node.
+	struct Room {
+		bool configured = false;             // sbm_set_room_sh_hrir was called: the room kernel and the order-1 decoder exist
+		bool enabled = false;
+		float pos[3] = {0, 0, 0}, rot[4] = {0, 0, 0, 1}, dims[3] = {0, 0, 0}, coeffs[6] = {0, 0, 0, 0, 0, 0}, cutoff = 0, gain = 0;   // ReflectionProperties()
+		float n_pos[3] = {0, 0, 0}, n_rot[4] = {0, 0, 0, 1}, n_dims[3] = {0, 0, 0}, n_coeffs[6] = {0, 0, 0, 0, 0, 0}, n_cutoff = 0, n_listener[3] = {0, 0, 0};
+		uint32_t tail_buffers = 0;           // buffers the node may still need to play out its delay line after the sends were muted
+		uint32_t taps1 = 0;
+		uint32_t delay_size = 0;
+		RoomParams* dv_params = nullptr;     // [2]: one per buffer parity
+		RoomState* dv_state = nullptr;
+		float* dv_delay = nullptr; float* dv_foa = nullptr; float* dv_hrir1 = nullptr; float* dv_hist1 = nullptr; float* dv_dec1 = nullptr;
+		RoomParams h_params;                 // this buffer's parameters (staged through the upload block)
+		bool run_this_buffer = false;
+	} room;
 
 	// stats
 	bool profiling = false;
@@ -422,7 +437,7 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	ok = ok && dalloc(e->dv_stat, cap) && dalloc(e->dv_posvol, cap) && dalloc(e->dv_occl, cap) && dalloc(e->dv_ring_write, cap) && dalloc(e->dv_mixz, mixcap);
 	A.stat = e->dv_stat; A.posvol = e->dv_posvol; A.occl = e->dv_occl; A.ring_write = e->dv_ring_write; A.mixz = e->dv_mixz;
 	ok = ok && dalloc(A.live, cap) && dalloc(A.read_i, cap) && dalloc(A.eof, cap) && dalloc(A.rs, cap) && dalloc(A.dgain, cap) &&
-	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.mrec, cap) && dalloc(A.finished, 2 * (size_t)cap) &&
+	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.mrec, cap) && dalloc(A.rfl, cap) && dalloc(A.rgain, cap) && dalloc(A.finished, 2 * (size_t)cap) &&
 	     dalloc(A.mix_pos, mixcap) && dalloc(A.mix_pos0, mixcap);
 	A.cstride = kNumSh;
 	ok = ok && dalloc(A.cgain, (size_t)cap * kNumSh);
@@ -450,7 +465,7 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	if (ok) ok = dev::h2d(e->dv_table, encoder_table(), sizeof(float) * kTableAz * kTableEl * kShRaw, e->stream) == 0;
 	if (ok) {
 		// AmbisonicBinauralDecoderNode starts with num_frames_processed_on_empty_input_ = frames (no flush pending).
-		DevFlags f; memset(&f, 0, sizeof(f)); f.sh_flush_frames = (int)F;
+		DevFlags f; memset(&f, 0, sizeof(f)); f.sh_flush_frames = (int)F; f.sh1_flush_frames = (int)F;
 		ok = dev::h2d(e->dv_flags, &f, sizeof(f), e->stream) == 0 && dev::sync(e->stream) == 0;
 	}
 	if (!ok) { fprintf(stderr, "sbm_create: %s\n", dev::last_error()); sbm_destroy(e); return SBM_ERR_CUDA; }
@@ -472,7 +487,8 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	for (SetterRec* l = e->setq.exchange(nullptr); l;) { SetterRec* nx = l->next; free(l); l = nx; }
 	SlotArrays& A = e->A;
 	void* ptrs[] = {e->dv_stat, e->dv_posvol, e->dv_occl, e->dv_ring_write, e->dv_mixz, A.live, A.read_i, A.eof, A.rs, A.dgain, A.occ_cur,
-	                A.lpf_prev, A.bits, A.rec, A.mrec, e->fl[0].dv_finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
+	                A.lpf_prev, A.bits, A.rec, A.mrec, A.rfl, A.rgain, e->room.dv_params, e->room.dv_state, e->room.dv_delay, e->room.dv_foa, e->room.dv_hrir1,
+	                e->room.dv_hist1, e->room.dv_dec1, e->fl[0].dv_finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
 	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
 	                e->dv_hist, e->dv_dec};
 	for (void* p : ptrs) if (p) dev::release(p);
@@ -867,9 +883,99 @@ SBM_API int sbm_set_master_volume(sbm_engine* e, float volume) {
 	return SBM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// room effects: early reflections of a shoebox room (what Substrata turns on inside every parcel, AudioEngine.cpp:738-768)
+// ---------------------------------------------------------------------------------------------------------------
+SBM_API int sbm_set_room_sh_hrir(sbm_engine* e, const float* sh_hrir_order1, int taps) {
+	if (!e || !sh_hrir_order1 || taps < 1 || taps > 1024) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	dev::use(e->cfg.device);
+	sbm_engine::Room& r = e->room;
+	if (r.configured) return fail(e, SBM_ERR_INVALID_ARG, "room SH-HRIRs already set");
+	if (e->begun || e->collected != e->buffer_index) return fail(e, SBM_ERR_INVALID_ARG, "sbm_set_room_sh_hrir with a buffer in flight");
+	const uint32_t F = e->g.frames;
+	r.taps1 = (uint32_t)taps;
+	r.delay_size = F + 2u * (uint32_t)e->cfg.sample_rate_hz;     // DelayFilter(max_delay = kMaxDelayTimeSeconds * rate, frames): reflections_processor.cc:54,67
+	bool ok = dalloc(r.dv_params, 2) && dalloc(r.dv_state, 1) && dalloc(r.dv_delay, r.delay_size) && dalloc(r.dv_foa, 4 * (size_t)F) &&
+	          dalloc(r.dv_hrir1, 4 * (size_t)taps) && dalloc(r.dv_hist1, 4 * (size_t)taps) && dalloc(r.dv_dec1, 2 * (size_t)F);
+	if (ok) {
+		RoomState st; memset(&st, 0, sizeof(st));
+		st.frames_processed_on_empty = F;      // reflections_node.cc:31-32
+		st.rot_cur[3] = 1.0f;
+		ok = dev::h2d(r.dv_hrir1, sh_hrir_order1, sizeof(float) * 4 * (size_t)taps, e->stream) == 0 && dev::h2d(r.dv_state, &st, sizeof(st), e->stream) == 0 &&
+		     dev::sync(e->stream) == 0;
+	}
+	if (!ok) return fail_cuda(e, "sbm_set_room_sh_hrir");
+	r.configured = true;
+	return SBM_OK;
+}
+
 SBM_API int sbm_enable_room_effects(sbm_engine* e, int enable) {
 	if (!e) return SBM_ERR_INVALID_ARG;
-	return enable ? fail(e, SBM_ERR_UNSUPPORTED, "room effects are not on the accelerated path (SURVEY.md 8f)") : SBM_OK;
+	std::lock_guard<std::mutex> lk(e->mu);
+	if (enable && !e->room.configured) return fail(e, SBM_ERR_INVALID_ARG, "room effects need the order-1 SH-HRIRs first (sbm_set_room_sh_hrir)");
+	if (e->room.enabled && !enable) {
+		// the sends are muted from the next buffer on; the ReflectionsNode plays out its delay line (2 s at most) on silence
+		e->room.tail_buffers = (2u * (uint32_t)e->cfg.sample_rate_hz + 2u * e->g.frames) / e->g.frames + 4u;
+	}
+	e->room.enabled = enable != 0;
+	return SBM_OK;
+}
+
+SBM_API int sbm_set_reflection_properties(sbm_engine* e, const float* room_position, const float* room_rotation_xyzw, const float* room_dimensions,
+                                          const float* coefficients6, float cutoff_frequency, float gain) {
+	if (!e || !room_position || !room_rotation_xyzw || !room_dimensions || !coefficients6) return SBM_ERR_INVALID_ARG;
+	std::lock_guard<std::mutex> lk(e->mu);
+	sbm_engine::Room& r = e->room;
+	memcpy(r.pos, room_position, 12); memcpy(r.rot, room_rotation_xyzw, 16); memcpy(r.dims, room_dimensions, 12); memcpy(r.coeffs, coefficients6, 24);
+	r.cutoff = cutoff_frequency; r.gain = gain;
+	return SBM_OK;
+}
+
+// What ResonanceAudioApiImpl::ProcessNextBuffer does for the room before the graph runs (resonance_audio_api_impl.cc:464-467):
+// ReflectionsNode::Update (reflections_node.cc:41-82) compares the properties and the listener position with its cached copies and,
+// on any change, has the ReflectionsProcessor recompute the six reflections (reflections_processor.cc:74-97,
+// RA/dsp/shoe_box_room.cc:23-61) and start a crossfade.  Float for float like the reference (this file is built without FMA
+// contraction); the result rides to the device as this buffer's RoomParams.
+static bool floats_differ(const float* a, const float* b, int n) { for (int i = 0; i < n; ++i) if (a[i] != b[i]) return true; return false; }
+static void room_update_host(sbm_engine* e) {
+	sbm_engine::Room& r = e->room;
+	RoomParams& p = r.h_params;
+	memset(&p, 0, sizeof(p));
+	p.enabled = r.enabled ? 1u : 0u;
+	p.delay_size = r.delay_size;
+	p.head_q_inv[0] = -e->g.head_q[0]; p.head_q_inv[1] = -e->g.head_q[1]; p.head_q_inv[2] = -e->g.head_q[2]; p.head_q_inv[3] = e->g.head_q[3];
+	if (!r.enabled) return;
+	const float* listener = e->g.head_pos;
+	const bool changed = floats_differ(r.n_pos, r.pos, 3) || floats_differ(r.n_rot, r.rot, 4) || floats_differ(r.n_dims, r.dims, 3) || r.n_cutoff != r.cutoff ||
+	                     floats_differ(r.n_coeffs, r.coeffs, 6) || floats_differ(r.n_listener, listener, 3);
+	if (!changed) return;
+	memcpy(r.n_pos, r.pos, 12); memcpy(r.n_rot, r.rot, 16); memcpy(r.n_dims, r.dims, 12); memcpy(r.n_coeffs, r.coeffs, 24);
+	r.n_cutoff = r.cutoff; memcpy(r.n_listener, listener, 12);
+	const float rate = (float)e->cfg.sample_rate_hz;
+	// ComputeLowPassMonoPoleCoefficient (RA/dsp/filter_coefficient_generators.cc:151-163) + MonoPoleFilter::SetCoefficient's clamp
+	float coef = 0.0f;
+	if (r.n_cutoff > 20.0f) { const float itc = 6.28318530717958647692f * r.n_cutoff; coef = rate / (itc + rate); }
+	p.lp_coef = std::max(std::min(coef, 1.0f), 0.0f);
+	// the listener in the room's frame: GetRelativeDirection(room position, conj(room rotation), listener)
+	const float conj[4] = {-r.n_rot[0], -r.n_rot[1], -r.n_rot[2], r.n_rot[3]};
+	float rel[3];
+	source_relative(r.n_pos, conj, r.n_listener, rel);
+	const bool inside = fabsf(rel[0] - 0.0f) <= 0.5f * r.n_dims[0] && fabsf(rel[1] - 0.0f) <= 0.5f * r.n_dims[1] && fabsf(rel[2] - 0.0f) <= 0.5f * r.n_dims[2];
+	float delay_s[6] = {0, 0, 0, 0, 0, 0}, mag[6] = {0, 0, 0, 0, 0, 0}, max_delay = 0.0f;
+	if (inside) {
+		const float off[3] = {0.5f * r.n_dims[0], 0.5f * r.n_dims[1], 0.5f * r.n_dims[2]};
+		const float dist[6] = {off[0] + rel[0] + 1.0f, off[0] - rel[0] + 1.0f, off[1] + rel[1] + 1.0f, off[1] - rel[1] + 1.0f, off[2] + rel[2] + 1.0f, off[2] - rel[2] + 1.0f};
+		for (int i = 0; i < 6; ++i) { delay_s[i] = dist[i] / 343.0f; mag[i] = r.n_coeffs[i] / dist[i]; }
+	}
+	const size_t max_delay_samples = 2u * (size_t)e->cfg.sample_rate_hz;
+	for (int i = 0; i < 6; ++i) {
+		max_delay = std::max(max_delay, delay_s[i]);
+		p.tgt_delay[i] = (uint32_t)std::min(max_delay_samples, (size_t)(delay_s[i] * rate));      // UpdateGainsAndDelays (reflections_processor.cc:123-132)
+		p.tgt_gain[i] = mag[i];
+	}
+	p.frames_to_process_on_empty = (uint32_t)((size_t)e->g.frames + (size_t)(max_delay * rate));
+	p.updated = 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -895,6 +1001,8 @@ static int upload_block_locked(sbm_engine* e, const SlotPatch** d_patches, const
 		if (!e->list_sh.empty()) plans.push_back(SegPlan{e->dv_lists + e->list_pan.size(), (const unsigned char*)e->list_sh.data(), nullptr, 4, false, (uint32_t)e->list_sh.size(), 0});
 		if (!e->list_ring.empty()) plans.push_back(SegPlan{e->dv_list_ring, (const unsigned char*)e->list_ring.data(), nullptr, 4, false, (uint32_t)e->list_ring.size(), 0});
 	}
+	if (e->room.run_this_buffer)      // this buffer's RoomParams -> the parity's device copy
+		plans.push_back(SegPlan{e->room.dv_params + (e->buffer_index & 1), (const unsigned char*)&e->room.h_params, nullptr, (uint32_t)sizeof(RoomParams), false, 1, 0});
 	*d_patches = nullptr; *d_mix_patches = nullptr;
 	if (plans.empty() && e->patches.empty() && e->mix_patches.empty()) return 0;
 	if (plans.size() > (size_t)kMaxUpSegs) return -1;
@@ -950,6 +1058,14 @@ static int mix_begin_locked(sbm_engine* e) {
 	void* st = e->stream;
 	// 1. queued setters -> mirrors; everything the host changed since the last buffer -> ONE block, one copy, one kernel
 	drain_setters(e);
+	// room effects: the ReflectionsNode runs while the sends are on and until its delay line has played out afterwards
+	e->room.run_this_buffer = e->room.configured && (e->room.enabled || e->room.tail_buffers > 0);
+	if (e->room.run_this_buffer) {
+		if (!e->room.enabled) e->room.tail_buffers--;
+		room_update_host(e);
+	}
+	e->g.room = e->room.enabled ? 1u : 0u;
+	e->g.refl_gain = e->room.gain;
 	const SlotPatch* d_patches; const MixPatch* d_mix_patches;
 	if (upload_block_locked(e, &d_patches, &d_mix_patches)) return fail_cuda(e, "sbm_mix_begin(upload)");
 	if (!e->patches.empty() || !e->mix_patches.empty()) {
@@ -967,6 +1083,7 @@ static int mix_begin_locked(sbm_engine* e) {
 	if (e->g.n_pan + e->g.n_sh && dev::launch_params(e->g, e->A, e->dv_flags, e->dv_table, e->dv_lists, e->n_slots, st)) return fail_cuda(e, "k1_params");
 	if (e->profiling) dev::event_record(fl.ev[1], st);
 	MixArgs m;
+	m.rfl = e->room.enabled ? e->A.rfl : nullptr;
 	m.mrec = e->A.mrec; m.rec = e->A.rec; m.shg = e->A.shg; m.shr = e->A.shr; m.mixz = e->dv_mixz; m.mix_pos0 = e->A.mix_pos0; m.rs = e->A.rs; m.lpf_prev = e->A.lpf_prev;
 	m.n_pan = (uint32_t)e->list_pan.size();
 	m.n_sh = (uint32_t)e->list_sh.size();
@@ -996,7 +1113,15 @@ static int mix_enqueue_finish_locked(sbm_engine* e) {
 		if (dev::launch_peer_gather(pa, e->dv_bus, e->dv_bus_sum, e->bus_floats, target, e->dv_flags, st)) return fail_cuda(e, "k_peer_gather");
 		e->peer_buffers++;
 	}
+	if (e->room.run_this_buffer) {
+		RoomArgs ra;
+		ra.bus = e->peer.world ? e->dv_bus_sum : e->dv_bus; ra.params = e->room.dv_params + parity; ra.state = e->room.dv_state;
+		ra.delay_line = e->room.dv_delay; ra.foa = e->room.dv_foa; ra.flags = e->dv_flags; ra.frames = F;
+		if (dev::launch_room(ra, st)) return fail_cuda(e, "k_room");
+	}
 	FinishArgs f;
+	f.foa = e->room.dv_foa; f.hrir1 = e->room.configured ? e->room.dv_hrir1 : nullptr; f.taps1 = e->room.taps1; f.hist1 = e->room.dv_hist1; f.dec1 = e->room.dv_dec1;
+	f.room_enabled = e->room.enabled ? 1u : 0u;
 	f.bus = e->peer.world ? e->dv_bus_sum : e->dv_bus; f.hrir = e->dv_hrir; f.taps = (uint32_t)e->cfg.sh_hrir_taps; f.hist = e->dv_hist; f.dec = e->dv_dec;
 	f.flags = e->dv_flags; f.parity = parity; f.frames = F; f.out = e->dv_out;
 	f.list_ring = e->dv_list_ring; f.n_ring = (uint32_t)e->list_ring.size(); f.read_i = e->A.read_i; f.finished = fl.dv_finished; f.hist_smem_all = 0;

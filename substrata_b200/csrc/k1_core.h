@@ -20,7 +20,7 @@ SBM_HD int finished_push(DevFlags* f) {
 #endif
 }
 // Bits returned by update_source (OR-reduced per block by the caller into DevFlags::*_used[parity]).
-constexpr uint32_t kUsedPan = 1, kUsedSh = 2, kUsedStereo = 4;
+constexpr uint32_t kUsedPan = 1, kUsedSh = 2, kUsedStereo = 4, kUsedRefl = 8;
 
 // StereoPanner gains straight from the relative direction r: with az = atan2(-r.x, -r.z) and el = atan2(r.y, |r.xz|),
 // cos(pi/2 - az) cos(el) = sin(az) cos(el) = -r.x / |r|, so  gL = 0.5 (1 - r.x/|r|),  gR = 0.5 (1 + r.x/|r|)  -- the same
@@ -83,7 +83,7 @@ constexpr uint32_t kMaxMix1Window = 4096;
 // `rec_out`, `shg_out`, `shr_out`: where this source's WorkRec / ShGains / ShRamps go (the arrays in HBM indexed by render-list
 // position, or -- fused kernel -- registers and the CTA's shared-memory rings).
 SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot, WorkRec* rec_out,
-                              ShGains* shg_out, ShRamps* shr_out, uint32_t* rendered_src) {
+                              ShGains* shg_out, ShRamps* shr_out, ReflSend* rfl_out, uint32_t* rendered_src) {
 	*rendered_src = 0;
 	// All per-slot state is loaded up front, unconditionally: the loads are independent of each other, so the memory
 	// system sees them as one batch instead of a chain of dependent round trips behind the branches below.
@@ -99,6 +99,8 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	const float lpf_prev0 = A.lpf_prev[slot];
 	uint8_t bits = A.bits[slot];
 	const int prev_used_sh = flags->sh_used[G.parity ^ 1], prev_used_pan = flags->pan_used[G.parity ^ 1];   // previous buffer's mixers (GainMixer sweep)
+	const int prev_used_refl = G.room ? flags->refl_used[G.parity ^ 1] : 0;
+	float rg = G.room ? A.rgain[slot] : 0.0f;
 	// stereo-pan bus gains (the first two of the slot's cstride floats), loaded with the rest: left where they are used,
 	// the compiler must keep them behind the state stores above them (possible aliasing) = one more DRAM round trip
 	const float cg_pan0 = A.cgain[(size_t)slot * (size_t)A.cstride], cg_pan1 = A.cgain[(size_t)slot * (size_t)A.cstride + 1];
@@ -221,6 +223,23 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	const float src_pos[3] = {pv.x, pv.y, pv.z};
 	const float input_gain = fmul(G.master, pv.w);
 	const bool hrtf = kind == kKindHrtf;
+	uint32_t used_refl = 0;
+	if (G.room && kind != kKindStereo) {
+		// The reflections send (graph_manager.cc:150, gain_mixer_node.cc:44-63): every fed sound object adds its RAW buffer to the
+		// mono reflections mixer through a ramped gain = room effects gain (1) * direct attenuation * ReflectionProperties::gain
+		// (distance_attenuation.cc:112-113), whatever the GainNode decides below.  Its GainMixer sweeps every buffer it had input.
+		if (prev_used_refl) {
+			if (bits & kBitReflActive) bits &= (uint8_t)~kBitReflActive;
+			else bits &= (uint8_t)~kBitReflExists;
+		}
+		const float direct_att = fmul(input_gain, log_distance_attenuation(G.head_pos, src_pos));
+		const float refl_target = fmul(fmul(1.0f, direct_att), G.refl_gain);
+		const RampDesc d = plan_gain(&rg, (bits & kBitReflExists) != 0, refl_target, F, /*accumulate=*/true);
+		bits |= kBitReflExists | kBitReflActive;
+		A.rgain[slot] = rg;
+		rfl_out->konst = d.konst; rfl_out->start = d.start; rfl_out->inc = d.inc; rfl_out->n = d.n;
+		used_refl = kUsedRefl;
+	}
 	if (kind != kKindStereo) {
 		// GainMixer::Reset sweep (gain_mixer.cc:80-96): it runs once between two non-empty buffers of that mixer and
 		// touches every source that owns processors, whether or not the source reaches the mixer this buffer.
@@ -239,7 +258,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		// K2 must still carry AudioResampler::prev_samples forward.
 		rec.flags = kRecSkip | (rflags & (kRecResample | kRecWrap));
 		*rec_out = rec;
-		return 0;
+		return used_refl;     // (its reflections send is below -60 dB too: K2 adds nothing for a skipped source, the mixer still counts as fed)
 	}
 	if (near_unity(target) && near_unity(dg)) {
 		dg = 1.0f;
@@ -340,7 +359,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	}
 	rec.flags = rflags;
 	*rec_out = rec;
-	return hrtf ? kUsedSh : kUsedPan;
+	return (hrtf ? kUsedSh : kUsedPan) | used_refl;
 }
 
 }  // namespace sbm

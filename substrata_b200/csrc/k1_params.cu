@@ -23,13 +23,20 @@ __global__ void __launch_bounds__(SBM_K1_THREADS, SBM_K1_MINB) k1_params_kernel(
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;    // position in the render lists
 	// whether this buffer's "mixer used" flags are already set: read NOW, so that the loads overlap the work below instead
 	// of being a dependent round trip at the end of every warp (a stale 0 only costs a redundant atomicOr)
-	const int set_pan = flags->pan_used[g.parity], set_sh = flags->sh_used[g.parity], set_st = flags->st_used[g.parity];
+	const int set_pan = flags->pan_used[g.parity], set_sh = flags->sh_used[g.parity], set_st = flags->st_used[g.parity], set_refl = flags->refl_used[g.parity];
 	uint32_t used = 0, n_src = 0;
 	if (k < g.n_pan + g.n_sh) {
 		WorkRec rec;
-		used = update_source(g, A, flags, table, lists[k], &rec, A.shg + k, A.shr + k, &n_src);
+		ReflSend rfl;
+		rfl.konst = 0.0f; rfl.start = 0.0f; rfl.inc = 0.0f; rfl.n = 0;
+		used = update_source(g, A, flags, table, lists[k], &rec, A.shg + k, A.shr + k, &rfl, &n_src);
 		// the record the mix kernel consumes, in final form (k2_rec.h); the full WorkRec only where a careful path will read it back
-		const MixRec m = make_mixrec(rec, wslot, k >= g.n_pan);
+		MixRec m = make_mixrec(rec, wslot, k >= g.n_pan);
+		if (g.room) {
+			// a ramping reflections send needs the per-frame gain path like any other ramp
+			A.rfl[k] = rfl;
+			if (rfl.n && !(m.mode & kMdSkip)) { if (rfl.n > m.nramp) m.nramp = rfl.n; m.mode |= kMdRamp; }
+		}
 		A.mrec[k] = m;
 		if (mixrec_needs_workrec(m.mode)) A.rec[k] = rec;
 	}
@@ -50,6 +57,7 @@ __global__ void __launch_bounds__(SBM_K1_THREADS, SBM_K1_MINB) k1_params_kernel(
 		if ((u & kUsedPan) && !set_pan) atomicOr(&flags->pan_used[g.parity], 1);
 		if ((u & kUsedSh) && !set_sh) atomicOr(&flags->sh_used[g.parity], 1);
 		if ((u & kUsedStereo) && !set_st) atomicOr(&flags->st_used[g.parity], 1);
+		if ((u & kUsedRefl) && !set_refl) atomicOr(&flags->refl_used[g.parity], 1);
 		if (rendered) {
 			const uint32_t part = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kStatParts;
 			atomicAdd(&flags->part_bytes[part][0], bytes);

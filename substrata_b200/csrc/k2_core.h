@@ -133,10 +133,10 @@ SBM_HD float decode_input(const float* bus_c, const float* hist_c, int H, int j)
 // form, double accumulation -- the reference's partitioned FFT computes the same convolution in f32), summed into L
 // and, sign by ACN degree, into R.
 SBM_HD void decode_frame(const float* bus, const float* hrir, const float* hist, uint32_t frames, uint32_t taps, uint32_t i,
-                         float* out_l, float* out_r) {
+                         float* out_l, float* out_r, int nch = kNumSh) {
 	const int H = (int)taps - 1;
 	float l = 0.0f, r = 0.0f;
-	for (int c = 0; c < kNumSh; ++c) {
+	for (int c = 0; c < nch; ++c) {
 		const float* h = hrir + (size_t)c * taps;
 		const float* x = bus + (size_t)c * frames;
 		const float* hc = hist + (size_t)c * (size_t)(H > 0 ? H : 1);
@@ -156,18 +156,27 @@ SBM_HD void decode_frame(const float* bus, const float* hrir, const float* hist,
 //   FillInterleavedOutputBuffer returns false when nothing reached the stereo mixer (resonance_audio_api_impl.cc:498-522).
 // Also publishes the global "mixer was used" bits for the next buffer's GainMixer sweep (k1_core.h) and clears the
 // other parity for K1's atomicOr.
-struct FinishPlan { int sh, stereo, decode, valid; };
-SBM_HD FinishPlan plan_finish(const float* bus_flags, bool have_hrir, DevFlags* f, uint32_t parity, uint32_t frames) {
+//   Room effects: the order-1 decoder of the reflections follows the same decode / flush rule on the ReflectionsNode's output
+//   (DevFlags::foa_valid, set by the room kernel); the ReverbNode -- gain 0 with Substrata's settings -- contributes an all-zero
+//   buffer whenever the reverb send mixer was fed, which only shows in `valid` (RA/graph/reverb_node.cc:118-145).
+struct FinishPlan { int sh, stereo, decode, decode1, valid; };
+SBM_HD bool room_decode1_wanted(const DevFlags* f, uint32_t frames) { return f->foa_valid || f->sh1_flush_frames < (int)frames; }
+SBM_HD FinishPlan plan_finish(const float* bus_flags, bool have_hrir, bool have_hrir1, bool room_enabled, DevFlags* f, uint32_t parity, uint32_t frames) {
 	FinishPlan p;
-	const int sh = bus_flags[0] > 0.0f, pan = bus_flags[1] > 0.0f, st = bus_flags[2] > 0.0f;
-	p.sh = sh; p.stereo = pan || st; p.decode = 0;
+	const int sh = bus_flags[0] > 0.0f, pan = bus_flags[1] > 0.0f, st = bus_flags[2] > 0.0f, refl = bus_flags[3] > 0.0f;
+	p.sh = sh; p.stereo = pan || st; p.decode = 0; p.decode1 = 0;
 	if (have_hrir) {
 		if (sh) { f->sh_flush_frames = 0; p.decode = 1; }
 		else if (f->sh_flush_frames < (int)frames) { f->sh_flush_frames += (int)frames; p.decode = 1; }
 	}
-	p.valid = p.stereo || p.decode;
-	f->sh_used[parity] = sh; f->pan_used[parity] = pan; f->st_used[parity] = st;
-	f->sh_used[parity ^ 1] = 0; f->pan_used[parity ^ 1] = 0; f->st_used[parity ^ 1] = 0;
+	if (have_hrir1) {
+		if (f->foa_valid) { f->sh1_flush_frames = 0; p.decode1 = 1; }
+		else if (f->sh1_flush_frames < (int)frames) { f->sh1_flush_frames += (int)frames; p.decode1 = 1; }
+	}
+	f->foa_valid = 0;
+	p.valid = p.stereo || p.decode || p.decode1 || (room_enabled && refl);
+	f->sh_used[parity] = sh; f->pan_used[parity] = pan; f->st_used[parity] = st; f->refl_used[parity] = refl;
+	f->sh_used[parity ^ 1] = 0; f->pan_used[parity ^ 1] = 0; f->st_used[parity ^ 1] = 0; f->refl_used[parity ^ 1] = 0;
 	return p;
 }
 

@@ -215,11 +215,13 @@ __device__ float lpf_warp(float* buf, uint32_t F, float coef, float prev, uint32
 template <int NCH, int kStages, int kBatch>
 struct SmemView {
 	static constexpr int kRecStages = kStages + 2;
-	MixSmemHdr* hdr; MixRec* recs; ShGains* shgs; ShRamps* shrs; float* wring;
-	__device__ explicit SmemView(unsigned char* raw) {
+	MixSmemHdr* hdr; MixRec* recs; ReflSend* rfls; ShGains* shgs; ShRamps* shrs; float* wring;
+	__device__ explicit SmemView(unsigned char* raw, bool room) {
 		hdr = reinterpret_cast<MixSmemHdr*>(raw);
 		recs = reinterpret_cast<MixRec*>(raw + 512);
 		unsigned char* p = reinterpret_cast<unsigned char*>(recs) + sizeof(MixRec) * kRecStages * kBatch;
+		rfls = reinterpret_cast<ReflSend*>(p);      // room effects: the reflections send ramps, staged with the records
+		if (room) p += sizeof(ReflSend) * kRecStages * kBatch;
 		shgs = reinterpret_cast<ShGains*>(p);
 		if (NCH == 16) p += sizeof(ShGains) * kRecStages * kBatch;
 		shrs = reinterpret_cast<ShRamps*>(p);       // channel ramps of the sources that have any, staged with the windows
@@ -243,10 +245,11 @@ __device__ void issue_warp(const SmemView<NCH, kStages, kBatch>& sm, const MixAr
 		if (lane == 0) {
 			const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 			const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
-			const uint32_t bytes = nb * (uint32_t)sizeof(MixRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u);
+			const uint32_t bytes = nb * (uint32_t)sizeof(MixRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u) + (a.rfl ? nb * (uint32_t)sizeof(ReflSend) : 0u);
 			mbar_expect_tx(&hdr->full_r[q], bytes);
 			bulk_g2s(sm.recs + q * kBatch, grec + b0, nb * (uint32_t)sizeof(MixRec), &hdr->full_r[q]);
 			if (NCH == 16) bulk_g2s(sm.shgs + q * kBatch, gshg + b0, nb * (uint32_t)sizeof(ShGains), &hdr->full_r[q]);
+			if (a.rfl) bulk_g2s(sm.rfls + q * kBatch, a.rfl + b0, nb * (uint32_t)sizeof(ReflSend), &hdr->full_r[q]);
 		}
 		__syncwarp();
 	};
@@ -303,10 +306,11 @@ __device__ __forceinline__ void fill_record_slot(const SmemView<NCH, kStages, kB
 		const uint32_t q = j % kRecStages;
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(j) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
-		const uint32_t bytes = nb * (uint32_t)sizeof(MixRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u);
+		const uint32_t bytes = nb * (uint32_t)sizeof(MixRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u) + (a.rfl ? nb * (uint32_t)sizeof(ReflSend) : 0u);
 		mbar_expect_tx(&sm.hdr->full_r[q], bytes);
 		bulk_g2s(sm.recs + q * kBatch, a.mrec + b0, nb * (uint32_t)sizeof(MixRec), &sm.hdr->full_r[q]);
 		if (NCH == 16) bulk_g2s(sm.shgs + q * kBatch, a.shg + b0, nb * (uint32_t)sizeof(ShGains), &sm.hdr->full_r[q]);
+		if (a.rfl) bulk_g2s(sm.rfls + q * kBatch, a.rfl + b0, nb * (uint32_t)sizeof(ReflSend), &sm.hdr->full_r[q]);
 	}
 	__syncwarp();
 }
@@ -357,7 +361,9 @@ __device__ __forceinline__ void init_barriers(MixSmemHdr* hdr, uint32_t n_consum
 // direct gain and the low-pass too when it returns true -- and does the feeder / filter bookkeeping; the caller then reads the
 // slot like a native-rate window.  Keeping this (large, rarely executed) code out of the kernel body shrinks the hot path's
 // instruction footprint; its staging array lives in local memory, which only this path touches.
-__device__ __noinline__ bool careful_source_to_slot(const MixArgs& a, const WorkRec& r, float* slot, uint32_t wslot, uint32_t lane) {
+// apply_lpf = false (room effects): the occlusion low-pass is left to direct_gain_and_lpf_in_slot, so that the caller can take
+// the RAW samples for the reflections send first.
+__device__ __noinline__ bool careful_source_to_slot(const MixArgs& a, const WorkRec& r, float* slot, uint32_t wslot, uint32_t lane, bool apply_lpf) {
 	const uint32_t F = a.frames;
 	const WinPlan wp = plan_window(r, wslot);
 	const float* w = slot + 4 + wp.off0;
@@ -375,7 +381,7 @@ __device__ __noinline__ bool careful_source_to_slot(const MixArgs& a, const Work
 		a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
 	}
 	__syncwarp();
-	const bool lpf = (r.flags & kRecLpf) != 0;
+	const bool lpf = apply_lpf && (r.flags & kRecLpf) != 0;
 #pragma unroll 1
 	for (uint32_t k = 0; k * 32u < F; ++k) {
 		const uint32_t i = lane + 32u * k;
@@ -392,7 +398,20 @@ __device__ __noinline__ bool careful_source_to_slot(const MixArgs& a, const Work
 	return lpf;
 }
 
+// Second half of the careful path for a low-passed source when the first half ran with apply_lpf = false: slot[i] holds the raw
+// samples; multiply by the direct gain and run the occlusion low-pass in place.
+__device__ __noinline__ void direct_gain_and_lpf_in_slot(const MixArgs& a, const WorkRec& r, float* slot, uint32_t lane) {
+	const uint32_t F = a.frames;
+	for (uint32_t i = lane; i < F; i += 32u) slot[i] = slot[i] * gain_at(r.direct, i);
+	__syncwarp();
+	const float carry = lpf_warp(slot, F, r.lpf_coef, r.lpf_prev, lane);
+	__syncwarp();
+	if (lane == 0) a.lpf_prev[r.slot] = carry;
+	fence_proxy_async();
+}
+
 template <int V> struct IntTag { static constexpr int value = V; };
+__device__ __forceinline__ float refl_gain_at(const ReflSend& s, uint32_t i) { return i < s.n ? fmaf((float)i, s.inc, s.start) : s.konst; }
 
 __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_as_float(0x3f800000u | ((uint32_t)p >> 9)) - 1.0f; }
 
@@ -400,11 +419,13 @@ __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_a
 // Stereo-bus kernel (panned + non-spatial sources): kBatch math warps, one source per warp, + the producer warp.
 // KF = frames / 32 rounded up to 8, 16 or 32; EXACT = (frames == 32 * KF): no per-frame bounds checks.
 // =====================================================================================================================
-template <int KF, bool EXACT>
-__global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CTAS) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
+// ROOM (room effects on): a third accumulator per frame collects the source's RAW signal through the ramped reflections send
+// gain (graph_manager.cc:150); the CTA's partial bus then has three rows.
+template <int KF, bool EXACT, bool ROOM>
+__global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : (ROOM ? 3 : SBM_MIN_CTAS)) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	constexpr int kStages = kStagesPan, kRecStages = kStages + 2, kBatch = kBatchPan;
-	const SmemView<2, kStages, kBatch> sm(smem_raw);
+	const SmemView<2, kStages, kBatch> sm(smem_raw, ROOM);
 	MixSmemHdr* hdr = sm.hdr;
 	// EXACT: the frame count is a compile-time constant (every "is this frame F - 1 / inside the buffer" test folds away)
 	const uint32_t F = EXACT ? 32u * (uint32_t)KF : a.frames, t = threadIdx.x, lane = t & 31u, warp = t >> 5;
@@ -424,8 +445,11 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 	if (warp == (uint32_t)kPanWarps) { issue_warp<2, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[KF];     // (L, R) of frame lane + 32 k: one FFMA2 (gain pair x broadcast sample) per frame on the constant-gain path
+	float acc3[ROOM ? KF : 1];     // the reflections send
 #pragma unroll
 	for (int k = 0; k < KF; ++k) acc[k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+	for (int k = 0; k < (ROOM ? KF : 1); ++k) acc3[k] = 0.0f;
 
 	uint32_t qr = 0, qw = 0, ph_w = 0;     // record slot / window stage of batch jb, parity of its full_w
 	for (uint32_t jb = 0; jb < nbatch; ++jb, qr = qr + 1 == (uint32_t)kRecStages ? 0u : qr + 1, ph_w ^= (qw + 1 == (uint32_t)kStages), qw = qw + 1 == (uint32_t)kStages ? 0u : qw + 1) {
@@ -473,9 +497,20 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 					}
 				} else if (mode & (kMdGeneric | kMdLpf | kMdAdjust)) {
 					// ---------------- careful fetch (rare, out of line): leaves the samples in this source's stage slot ----------------
-					filtered = careful_source_to_slot(a, a.rec[b0 + src], slot, wslot, lane);
+					filtered = careful_source_to_slot(a, a.rec[b0 + src], slot, wslot, lane, !ROOM);
 #pragma unroll
 					for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; x[k] = (EXACT || i < F) ? slot[i] : 0.0f; }
+					if (ROOM && (mode & kMdLpf)) {
+						// room effects: the reflections send takes the raw samples; then direct gain + low-pass, and read again
+						const ReflSend rs = sm.rfls[qr * kBatch + src];
+#pragma unroll
+						for (int k = 0; k < KF; ++k) acc3[k] = fmaf(refl_gain_at(rs, lane + 32u * k), x[k], acc3[k]);
+						__syncwarp();
+						direct_gain_and_lpf_in_slot(a, a.rec[b0 + src], slot, lane);
+#pragma unroll
+						for (int k = 0; k < KF; ++k) { const uint32_t i = lane + 32u * k; x[k] = (EXACT || i < F) ? slot[i] : 0.0f; }
+						filtered = true;
+					}
 				} else {
 					// ---------------- lean fetch: window staged in shared memory by the TMA ring ----------------
 					const float* wb = slot + m.w_off;
@@ -538,6 +573,11 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 				// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
 				const float2 g01 = make_float2(m.g0, m.g1);
 				const uint32_t nramp = filtered ? F : m.nramp;     // frames that need per-frame gain evaluation
+				const bool refl_here = ROOM && !(filtered && (mode & kMdLpf)) && !(mode & kMdStereo);     // (a low-passed source sent its raw samples above)
+				ReflSend rs;
+				rs.konst = 0.0f; rs.start = 0.0f; rs.inc = 0.0f; rs.n = 0;
+				if (refl_here) rs = sm.rfls[qr * kBatch + src];
+				const float gr = rs.konst * mf;     // constant part of the send gain, on the sample as x holds it
 				// RAMPS: 0 = no gain ramps in this buffer, 1 = ramps end within the first 32 frames (the usual case while the
 				// listener moves), 2 = anything (long ramps, filtered signal): per-iteration warp-uniform test.
 				auto gains = [&](auto ramps_tag) {
@@ -551,8 +591,10 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 							acc[k].x = fmaf(ch0_gain_at(m, i), yv, acc[k].x);
 							acc[k].y = fmaf(ch1_gain_at(m, i), yv, acc[k].y);
 							if (!filtered && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[m.slot] = yv;
+							if (ROOM && refl_here) acc3[k] = fmaf(refl_gain_at(rs, i), x[k] * mf, acc3[k]);
 						} else {
 							ffma2(acc[k], g01, make_float2(x[k], x[k]));
+							if (ROOM && refl_here) acc3[k] = fmaf(gr, x[k], acc3[k]);
 							// bypassed occlusion filter remembers the last input sample (mono_pole_filter.cc:40-44)
 							if ((k == KF - 1 || !EXACT) && !(mode & kMdStereo) && i == F - 1) a.lpf_prev[m.slot] = x[k] * m.gd;
 						}
@@ -569,18 +611,22 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : SBM_MIN_CT
 	}
 	// ---- combine the math warps' tiles (the window ring is idle now: every batch has been consumed) ----
 	math_sync(kPanWarps * 32);
-	float* tile = sm.wring;     // [kPanWarps][2][F]
+	constexpr uint32_t ROWS = ROOM ? 3u : 2u;     // L, R (+ the reflections send)
+	float* tile = sm.wring;     // [kPanWarps][ROWS][F]
 #pragma unroll
 	for (int k = 0; k < KF; ++k) {
 		const uint32_t i = lane + 32u * k;
-		if (EXACT || i < F) { tile[(warp * 2 + 0) * F + i] = acc[k].x; tile[(warp * 2 + 1) * F + i] = acc[k].y; }
+		if (EXACT || i < F) {
+			tile[(warp * ROWS + 0) * F + i] = acc[k].x; tile[(warp * ROWS + 1) * F + i] = acc[k].y;
+			if (ROOM) tile[(warp * ROWS + 2) * F + i] = acc3[k];
+		}
 	}
 	math_sync(kPanWarps * 32);
-	float* out = partials + (size_t)blockIdx.x * 2 * F;
-	for (uint32_t q = t; q < 2 * F; q += kPanWarps * 32) {
+	float* out = partials + (size_t)blockIdx.x * ROWS * F;
+	for (uint32_t q = t; q < ROWS * F; q += kPanWarps * 32) {
 		float s = 0.0f;
 #pragma unroll
-		for (int wv = 0; wv < kPanWarps; ++wv) s += tile[wv * 2 * F + q];
+		for (int wv = 0; wv < kPanWarps; ++wv) s += tile[wv * ROWS * F + q];
 		out[q] = s;
 	}
 }
@@ -612,13 +658,14 @@ constexpr int kShK = 4, kShBigK = SBM_SH_BIG_K, kShBigT = 1024 / kShBigK, kShBig
 // the CTA's slice; the groups share the producer warp and its rings.  Where the register file leaves room for only one CTA
 // per SM (frames > 512: 256 math threads x ~120 registers), two groups overlap each other's barrier waits and dependent
 // chains the way two resident CTAs would.
-template <int TMAX, int K, int G, bool EXACT, bool SELF, int kStages>     // TMAX math threads x K frames each; EXACT: frames == K * TMAX, no per-frame
-                                                                          // bounds checks; SELF: self-service rings (no issue warp; implies EXACT, G == 1)
+template <int TMAX, int K, int G, bool EXACT, bool SELF, int kStages, bool ROOM>     // TMAX math threads x K frames each; EXACT: frames == K * TMAX, no per-frame
+                                                                          // bounds checks; SELF: self-service rings (no issue warp; implies EXACT, G == 1);
+                                                                          // ROOM: a 17th accumulator row = the reflections send (room effects)
 __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	constexpr int kRecStages = kStages + 2, kBatch = kBatchSh;
-	const SmemView<16, kStages, kBatch> sm(smem_raw);
+	const SmemView<16, kStages, kBatch> sm(smem_raw, ROOM);
 	MixSmemHdr* hdr = sm.hdr;
 	// blockDim.x = T math threads (+ one issue warp, the last warp, unless SELF)
 	const uint32_t F = a.frames, T = EXACT ? (uint32_t)TMAX : (blockDim.x - 32) / G;   // EXACT: T is a compile-time constant
@@ -652,10 +699,13 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 	}
 
 	float2 acc[NCH / 2][K];      // channel pairs (2c, 2c+1) x frames t + k T
+	float acc17[ROOM ? K : 1];   // the reflections send
 #pragma unroll
 	for (int c = 0; c < NCH / 2; ++c)
 #pragma unroll
 		for (int k = 0; k < K; ++k) acc[c][k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+	for (int k = 0; k < (ROOM ? K : 1); ++k) acc17[k] = 0.0f;
 	const uint32_t warp_i0 = t & ~31u;     // first frame of this warp in iteration k = 0
 	const float ft = (float)t;
 
@@ -763,6 +813,12 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 						}
 						// frame F - 1 = t + (K - 1) T of thread T - 1: the bypassed occlusion filter's memory (mono_pole_filter.cc:40-44)
 						if (t == T - 1) a.lpf_prev[mrs[b].slot] = yy[K - 1].x;
+						if (ROOM) {
+							// the reflections send: the raw sample (mix factor applied) through the send gain's constant part
+							const float gr = sm.rfls[qr * kBatch + b].konst * mrs[b].mfx;
+#pragma unroll
+							for (int k = 0; k < K; ++k) acc17[k] = fmaf(gr, xs[bb][k], acc17[k]);
+						}
 					}
 				}
 				if (ramps & kMdRamp) {
@@ -807,6 +863,10 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 							}
 							// (frame F - 1 inside a ramp: the constant pass stored y_const as the bypassed filter's memory)
 							if (k == K - 1 && t == T - 1) a.lpf_prev[m.slot] = Y;
+							if (ROOM) {
+								const ReflSend rs = sm.rfls[qr * kBatch + b];
+								if (i < rs.n) acc17[k] = fmaf(fmaf(fi, rs.inc, rs.start) - rs.konst, x[k] * m.mfx, acc17[k]);
+							}
 						}
 					}
 				}
@@ -846,6 +906,12 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 					if (wp.fast) { p0 = staged_tmp(r, w, wp, (int)r.n_src); p1 = staged_tmp(r, w, wp, (int)r.n_src + 1); }
 					else resampler_tail(r, &p0, &p1);
 					a.rs[r.slot].prev_samples[0] = p0; a.rs[r.slot].prev_samples[1] = p1;
+				}
+				if (ROOM) {
+					// the reflections send takes the raw samples (mix factors are inside x on this path), before gain and filter
+					const ReflSend rs = sm.rfls[qr * kBatch + b];
+#pragma unroll
+					for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (i < F) acc17[k] = fmaf(refl_gain_at(rs, i), x[k], acc17[k]); }
 				}
 				if (mode & kMdLpf) {
 					// direct gain, then the recurrence in the (now free) stage slot; x becomes the filtered, gained signal
@@ -896,6 +962,11 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 					}
 				}
 			}
+			if (ROOM && (mode & (kMdGeneric | kMdLpf | kMdAdjust)) == 0) {
+				const ReflSend rs = sm.rfls[qr * kBatch + b];
+#pragma unroll
+				for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (EXACT || i < F) acc17[k] = fmaf(refl_gain_at(rs, i), x[k] * mf, acc17[k]); }
+			}
 			// ---------------- direct gain + bus gains (GainNode, GainMixer in accumulate mode) ----------------
 			const float* gk = sm.shgs[qr * kBatch + b].konst;
 			const float gd = m.gd;
@@ -935,7 +1006,8 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 			}
 		} else if (lane == 0) { mbar_arrive(&hdr->empty_w[qw]); mbar_arrive(&hdr->empty_r[qr]); }     // hand them back to the issue warp
 	}
-	float* out = partials + ((size_t)blockIdx.x * G + grp) * NCH * F;     // one partial bus per group
+	constexpr uint32_t ROWS = ROOM ? NCH + 1 : NCH;
+	float* out = partials + ((size_t)blockIdx.x * G + grp) * ROWS * F;     // one partial bus per group
 #pragma unroll
 	for (int c = 0; c < NCH / 2; ++c)
 #pragma unroll
@@ -943,6 +1015,10 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 			const uint32_t i = t + (uint32_t)k * T;
 			if (EXACT || i < F) { out[(size_t)(2 * c) * F + i] = acc[c][k].x; out[(size_t)(2 * c + 1) * F + i] = acc[c][k].y; }
 		}
+	if (ROOM) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) { const uint32_t i = t + (uint32_t)k * T; if (EXACT || i < F) out[(size_t)NCH * F + i] = acc17[k]; }
+	}
 }
 
 // Entry points of the ambisonic kernel.  frames 256 / 512 / 1024 (T = frames / 4 = 64 / 128 / 256 math threads, no per-frame bounds
@@ -962,17 +1038,19 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 #endif
 constexpr int kStagesSelf = SBM_STAGES_SELF, kStagesShX = 6;
 __host__ __device__ constexpr bool sh_self_shape(int T) { return (SBM_SH_SELF_MASK & T) != 0; }
-template <int TMAX>
+template <int TMAX, bool ROOM>
 __global__ void __launch_bounds__(TMAX + (sh_self_shape(TMAX) ? 0 : 32), sh_self_shape(TMAX) ? 512 / TMAX : (TMAX == 256 ? 1 : (TMAX == 128 ? 3 : 5)))
 k2_mix_ambisonic_x_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr bool kSelf = (SBM_SH_SELF_MASK & TMAX) != 0;
-	ambisonic_body<TMAX, kShK, 1, true, kSelf, kSelf ? kStagesSelf : kStagesShX>(a, first, n, wslot, partials);
+	ambisonic_body<TMAX, kShK, 1, true, kSelf, kSelf ? kStagesSelf : kStagesShX, ROOM>(a, first, n, wslot, partials);
 }
+template <bool ROOM>
 __global__ void __launch_bounds__(128 + 32, 3) k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
-	ambisonic_body<128, kShK, 1, false, false, kStagesSh>(a, first, n, wslot, partials);
+	ambisonic_body<128, kShK, 1, false, false, kStagesSh, ROOM>(a, first, n, wslot, partials);
 }
+template <bool ROOM>
 __global__ void __launch_bounds__(kShBigT + 32, 1) k2_mix_ambisonic_big_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
-	ambisonic_body<kShBigT, kShBigK, 1, false, false, kStagesShBig>(a, first, n, wslot, partials);
+	ambisonic_body<kShBigT, kShBigK, 1, false, false, kStagesShBig, ROOM>(a, first, n, wslot, partials);
 }
 
 // K3: bus[row][f] = sum over CTAs of the partial buses; rows 0-15 from the ambisonic kernel's partials, rows 16-17 from
@@ -982,15 +1060,16 @@ __global__ void __launch_bounds__(kShBigT + 32, 1) k2_mix_ambisonic_big_kernel(M
 constexpr uint32_t kK3Warps = 32;
 __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* __restrict__ part_pan, uint32_t g_pan, const float* __restrict__ part_sh,
                                                        uint32_t g_sh, float* __restrict__ bus, const DevFlags* __restrict__ flags,
-                                                       uint32_t parity, uint32_t F, PeerArgs pa, size_t bus_floats) {
+                                                       uint32_t parity, uint32_t F, PeerArgs pa, size_t bus_floats, uint32_t room) {
 	__shared__ float warp_sum[kK3Warps][32];
 	grid_dep_wait();
 	const uint32_t row = blockIdx.y, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	const uint32_t f = blockIdx.x * 32 + lane;
-	const float* part = row < 16 ? part_sh : part_pan;
-	const uint32_t g = row < 16 ? g_sh : g_pan, rows = row < 16 ? 16u : 2u, r = row < 16 ? row : row - 16;
+	// partial buses: [16 (+1)][F] per ambisonic CTA, [2 (+1)][F] per stereo-bus CTA; the extra row is the reflections send
+	// (room effects), whose bus row (kRowRefl) sums BOTH kernels' extra rows
+	const uint32_t rows_sh = room ? 17u : 16u, rows_pan = room ? 3u : 2u;
 	float s = 0.0f;
-	if (f < F) {
+	auto sum_partials = [&](const float* part, uint32_t g, uint32_t rows, uint32_t r) {
 		// four independent running sums (fixed assignment b -> sum, fixed combination order: still bit-stable) keep
 		// several loads in flight per lane instead of one dependent add chain
 		float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
@@ -1001,7 +1080,12 @@ __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* _
 			s0 += pp[(size_t)b * stride]; s1 += pp[(size_t)(b + kK3Warps) * stride]; s2 += pp[(size_t)(b + 2 * kK3Warps) * stride]; s3 += pp[(size_t)(b + 3 * kK3Warps) * stride];
 		}
 		for (; b < g; b += kK3Warps) s0 += pp[(size_t)b * stride];
-		s = (s0 + s1) + (s2 + s3);
+		return (s0 + s1) + (s2 + s3);
+	};
+	if (f < F) {
+		if (row < 16) s = sum_partials(part_sh, g_sh, rows_sh, row);
+		else if (row < 18) s = sum_partials(part_pan, g_pan, rows_pan, row - 16);
+		else if (room) s = sum_partials(part_sh, g_sh, rows_sh, 16) + sum_partials(part_pan, g_pan, rows_pan, 2);
 	}
 	warp_sum[w][lane] = s;
 	__syncthreads();
@@ -1019,7 +1103,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* _
 		bf[0] = flags->sh_used[parity] ? 1.0f : 0.0f;
 		bf[1] = flags->pan_used[parity] ? 1.0f : 0.0f;
 		bf[2] = flags->st_used[parity] ? 1.0f : 0.0f;
-		bf[3] = 0.0f;
+		bf[3] = flags->refl_used[parity] ? 1.0f : 0.0f;
 		for (int q = 0; q < 4; ++q) {
 			bus[(size_t)kBusRows * F + q] = bf[q];
 			for (uint32_t p = 0; p < pa.world; ++p) pa.gather[p][slot_off + (size_t)kBusRows * F + q] = bf[q];
@@ -1103,9 +1187,9 @@ uint32_t sh_frames_per_thread(uint32_t F) { return F <= 512 ? (uint32_t)kShK : (
 uint32_t sh_threads(uint32_t F) { const uint32_t K = sh_frames_per_thread(F); return ((F + K - 1) / K + 31) / 32 * 32; }
 bool sh_exact(uint32_t F) { return F == 256 || F == 512 || F == 1024; }     // the exact shapes (T = F / 4 = 64 / 128 / 256 math threads)
 int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_exact(F) ? (sh_self_shape((int)F / 4) ? kStagesSelf : kStagesShX) : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig)); }
-size_t mix_smem_bytes(uint32_t F, bool sh) {
+size_t mix_smem_bytes(uint32_t F, bool sh, bool room = false) {
 	const size_t st = (size_t)mix_stages(F, sh), rst = st + 2, kBatch = sh ? kBatchSh : kBatchPan;
-	return 512 + sizeof(MixRec) * rst * kBatch + (sh ? sizeof(ShGains) * rst * kBatch + sizeof(ShRamps) * st * kBatch : 0) +
+	return 512 + sizeof(MixRec) * rst * kBatch + (room ? sizeof(ReflSend) * rst * kBatch : 0) + (sh ? sizeof(ShGains) * rst * kBatch + sizeof(ShRamps) * st * kBatch : 0) +
 	       sizeof(float) * st * kBatch * window_slot(F);
 }
 constexpr uint32_t kMinSourcesPerCta = 16;
@@ -1121,7 +1205,7 @@ template <class Kernel>
 int launch_one(Kernel kernel, const char* name, const MixArgs& a, uint32_t first, uint32_t n, uint32_t threads, bool sh,
                uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
 	const uint32_t F = a.frames;
-	const size_t smem = mix_smem_bytes(F, sh);
+	const size_t smem = mix_smem_bytes(F, sh, a.rfl != nullptr);
 	uint32_t wave;
 	int sm_count_now = 148;
 	{
@@ -1154,8 +1238,12 @@ int launch_one(Kernel kernel, const char* name, const MixArgs& a, uint32_t first
 template <int KF>
 int launch_stereo(const MixArgs& a, uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
 	const uint32_t threads = kPanWarps * 32 + 32;
-	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
-	return launch_one(k2_mix_stereo_kernel<KF, false>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+	if (a.rfl) {
+		if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true, true>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+		return launch_one(k2_mix_stereo_kernel<KF, false, true>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+	}
+	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true, false>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+	return launch_one(k2_mix_stereo_kernel<KF, false, false>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
 }
 
 }  // namespace
@@ -1172,15 +1260,14 @@ int num_mix_ctas(uint32_t frames, int sh) {
 }
 
 size_t partials_floats(uint32_t frames) {
-	const size_t groups = 1;
-	return ((size_t)num_mix_ctas(frames, 0) * 2 + (size_t)num_mix_ctas(frames, 1) * groups * 16) * frames;
+	return ((size_t)num_mix_ctas(frames, 0) * 3 + (size_t)num_mix_ctas(frames, 1) * 17) * frames;     // (+1 row each: the reflections send, room effects)
 }
 
 int launch_mix(const MixArgs& a, void* stream) {
 	cudaStream_t st = (cudaStream_t)stream;
 	const uint32_t F = a.frames;
 	float* part_pan = a.partials;
-	float* part_sh = a.partials + (size_t)num_mix_ctas(F, 0) * 2 * F;
+	float* part_sh = a.partials + (size_t)num_mix_ctas(F, 0) * 3 * F;
 	uint32_t g_pan = 0, g_sh = 0;
 	if (a.n_pan) {
 		const uint32_t mg = (uint32_t)num_mix_ctas(F, 0);
@@ -1194,16 +1281,23 @@ int launch_mix(const MixArgs& a, void* stream) {
 		const uint32_t tm = sh_threads(F);
 		const uint32_t mg = (uint32_t)num_mix_ctas(F, 1);
 		int rc;
+		const bool room = a.rfl != nullptr;
+#define SBM_LAUNCH_SH(KERNEL, THREADS) (room ? launch_one(KERNEL<true>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, THREADS, true, mg, part_sh, st, &g_sh) \
+                                             : launch_one(KERNEL<false>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, THREADS, true, mg, part_sh, st, &g_sh))
+#define SBM_LAUNCH_SHX(TT) (room ? launch_one(k2_mix_ambisonic_x_kernel<TT, true>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, TT + (sh_self_shape(TT) ? 0 : 32), true, mg, part_sh, st, &g_sh) \
+                                 : launch_one(k2_mix_ambisonic_x_kernel<TT, false>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, TT + (sh_self_shape(TT) ? 0 : 32), true, mg, part_sh, st, &g_sh))
 		if (sh_exact(F)) {
-			if (F == 256) rc = launch_one(k2_mix_ambisonic_x_kernel<64>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, 64 + (sh_self_shape(64) ? 0 : 32), true, mg, part_sh, st, &g_sh);
-			else if (F == 512) rc = launch_one(k2_mix_ambisonic_x_kernel<128>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, 128 + (sh_self_shape(128) ? 0 : 32), true, mg, part_sh, st, &g_sh);
-			else rc = launch_one(k2_mix_ambisonic_x_kernel<256>, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, 256 + (sh_self_shape(256) ? 0 : 32), true, mg, part_sh, st, &g_sh);
-		} else if (tm <= 128) rc = launch_one(k2_mix_ambisonic_kernel, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
-		else rc = launch_one(k2_mix_ambisonic_big_kernel, "k2_mix_ambisonic", a, a.n_pan, a.n_sh, tm + 32, true, mg, part_sh, st, &g_sh);
+			if (F == 256) rc = SBM_LAUNCH_SHX(64);
+			else if (F == 512) rc = SBM_LAUNCH_SHX(128);
+			else rc = SBM_LAUNCH_SHX(256);
+		} else if (tm <= 128) rc = SBM_LAUNCH_SH(k2_mix_ambisonic_kernel, tm + 32);
+		else rc = SBM_LAUNCH_SH(k2_mix_ambisonic_big_kernel, tm + 32);
+#undef SBM_LAUNCH_SH
+#undef SBM_LAUNCH_SHX
 		if (rc) return -1;
 	}
 	if (a.ev_after_k2) cudaEventRecord((cudaEvent_t)a.ev_after_k2, st);
-	launch_pdl(k3_reduce_kernel, dim3((F + 31) / 32, kBusRows), dim3(kK3Warps * 32), 0, st, (const float*)part_pan, g_pan, (const float*)part_sh, g_sh, a.bus, a.flags, a.parity, F, a.peer, a.bus_floats);
+	launch_pdl(k3_reduce_kernel, dim3((F + 31) / 32, kBusRows), dim3(kK3Warps * 32), 0, st, (const float*)part_pan, g_pan, (const float*)part_sh, g_sh, a.bus, a.flags, a.parity, F, a.peer, a.bus_floats, a.rfl ? 1u : 0u);
 	note_launch();
 	return check_launch("k3_reduce");
 }

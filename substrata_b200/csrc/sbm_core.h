@@ -34,7 +34,8 @@ constexpr float kOcclusionSmoothing = 0.75f;       // RA/graph/occlusion_node.cc
 constexpr int kNumSh = 16;                         // 3rd-order ambisonics (RA/config/source_config.cc:54-63)
 constexpr int kShRaw = 15;
 constexpr int kTableAz = 91, kTableEl = 91;        // RA/ambisonics/ambisonic_lookup_table.cc:31-35
-constexpr int kBusRows = 18;                       // 16 ambisonic + stereo L/R
+constexpr int kBusRows = 19;                       // 16 ambisonic + stereo L/R + the mono reflections send (room effects)
+constexpr int kRowRefl = 18;
 constexpr int kMaxFrames = 1024;
 constexpr double kFx = 4294967296.0;               // 2^32: scale of the 32.32 fixed-point read-head coordinates
 
@@ -151,6 +152,10 @@ static_assert(sizeof(MixRec) == 128, "MixRec is 128 bytes");
 constexpr uint32_t kMdSkip = 1, kMdGeneric = 2, kMdInterp = 4, kMdAdjust = 8, kMdResample = 16, kMdLpf = 32, kMdStereo = 64,
                    kMdRamp = 128, kMdShRamp = 256;
 
+// Room effects (RA/graph/graph_manager.cc:144-151): the ramped gain of a sound object's send into the mono reflections mixer
+// (GainMixerNode of AttenuationType::kReflections), 16 B per source, written by K1 and read by K2 only while room effects are on.
+struct ReflSend { float konst, start, inc; uint32_t n; };
+
 struct ShGains { float konst[kNumSh]; };                       // 64 B per HRTF source: effective constant gains
 // Channel ramps of an ambisonic source (read only when ch_ramp_mask != 0; all 48 entries are written then): the gain of bus
 // channel c at frame i is  konst[c] + (i < nf[c] ? stm[c] + i * inc[c] : 0)  with stm = ramp start - konst, nf = ramp frames in
@@ -168,7 +173,8 @@ struct Globals {
 	uint32_t parity;            // buffer index & 1
 	uint32_t n_slots;
 	uint32_t n_pan, n_sh;       // render-list lengths
-	uint32_t pad[2];
+	uint32_t room;              // room effects enabled: sound objects also feed the reflections send
+	float refl_gain;            // ReflectionProperties::gain
 };
 
 // Device-side flags / counters.
@@ -177,6 +183,9 @@ struct DevFlags {
 	int sh_used[2];             // GainMixer of the ambisonic encoder
 	int st_used[2];             // a non-spatial source reached the stereo mixer
 	int sh_flush_frames;        // AmbisonicBinauralDecoderNode::num_frames_processed_on_empty_input_
+	int refl_used[2];           // the reflections send mixer received >= 1 input (by buffer parity)
+	int foa_valid;              // the ReflectionsNode produced a first-order buffer this cycle (room kernel -> decode / finish)
+	int sh1_flush_frames;       // the order-1 decoder's num_frames_processed_on_empty_input_
 	int n_finished;             // entries in the finished list
 	unsigned long long algo_bytes;  // accounting: sum of 4*n_src over rendered sources
 	unsigned int n_rendered;
@@ -210,11 +219,13 @@ struct SlotArrays {
 	MixRec* mrec;               // indexed like rec (CUDA build; the host emulation mixes straight from rec)
 	ShGains* shg;               // indexed like rec
 	ShRamps* shr;               // indexed like rec
+	ReflSend* rfl;              // indexed like rec (room effects)
+	float* rgain;               // [slot] the reflections mixer's processor gain of the source
 	int* finished;              // list of public ids stopped by the feeder
 	int cstride;                // 2 or 16
 };
 
-constexpr uint8_t kBitDirectInit = 1, kBitMixExists = 2, kBitMixActive = 4;
+constexpr uint8_t kBitDirectInit = 1, kBitMixExists = 2, kBitMixActive = 4, kBitReflExists = 8, kBitReflActive = 16;
 
 // ------------------------------------------------------------------------------------------------
 // Bit helpers.

@@ -103,6 +103,9 @@ void AudioEngine::init() {
 		engine = nullptr;
 		throw glare::Exception("Failed to initialise the B200 audio mixer (sbm_create returned " + std::to_string(rc) + "); there is no CPU fallback");
 	}
+	if (!options.sh_hrir_order1.empty() &&
+	    sbm_set_room_sh_hrir(engine, options.sh_hrir_order1.data(), options.sh_hrir_order1_taps) != SBM_OK)
+		throw glare::Exception(std::string("sbm_set_room_sh_hrir failed: ") + sbm_last_error(engine));
 	sbm_enable_room_effects(engine, 0);   // AE.cpp:742 / GUIClient.cpp:6896: room effects off outside parcels
 	frames_mixed = 0;
 	die = false;
@@ -373,11 +376,23 @@ void AudioEngine::setMasterVolume(float volume) {   // AE.cpp:806-811
 
 void AudioEngine::setRoomEffectsEnabled(bool enabled) {   // AE.cpp:738-743
 	if (!initialised) return;
-	if (enabled) throw glare::Exception("room effects are not on the accelerated path yet (SURVEY.md 8f)");
-	sbm_enable_room_effects(engine, 0);
+	if (enabled && options.sh_hrir_order1.empty()) throw glare::Exception("room effects need the order-1 SH-HRIR taps (Options::sh_hrir_order1)");
+	if (sbm_enable_room_effects(engine, enabled ? 1 : 0) != SBM_OK) throw glare::Exception(std::string("sbm_enable_room_effects failed: ") + sbm_last_error(engine));
 }
 
-void AudioEngine::setCurentRoomDimensions(const js::AABBox& /*room_aabb*/) {}   // AE.cpp:746-768: only meaningful with room effects on
+// AE.cpp:746-768: the parcel's bounding box as Resonance's shoebox room, with Substrata's fixed wall coefficients and gain.
+void AudioEngine::setCurentRoomDimensions(const js::AABBox& room_aabb) {
+	if (!initialised) return;
+	const float dims[3] = {room_aabb.axisLength(0), room_aabb.axisLength(1), room_aabb.axisLength(2)};
+	const Vec4f c = room_aabb.centroid();
+	const float pos[3] = {c[0], c[1], c[2]};
+	const float rot[4] = {0.f, 0.f, 0.f, 1.f};      // vraudio::ReflectionProperties(): room_rotation stays the identity
+	float coeffs[6];
+	for (int i = 0; i < 6; ++i) coeffs[i] = 0.8f;
+	coeffs[5] = 0.2f;
+	coeffs[2] = 0.3f;
+	sbm_set_reflection_properties(engine, pos, rot, dims, coeffs, /*cutoff_frequency=*/0.f, /*gain=*/0.7f);
+}
 
 void AudioEngine::insertSoundFile(const std::string& sound_file_path, SoundFileRef sound) { sound_files.insert(std::make_pair(sound_file_path, sound)); }   // AE.cpp:999-1002
 

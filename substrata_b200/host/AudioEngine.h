@@ -140,6 +140,8 @@ public:
 		int initial_mute_frames; // the reference discards the first second of output (AudioEngine.cpp:532-533)
 		std::vector<float> sh_hrir;  // planar [16][taps] SH-HRIRs (CreateShHrirsFromAssets); required when binaural
 		int sh_hrir_taps = 0;
+		std::vector<float> sh_hrir_order1;  // planar [4][taps] order-1 SH-HRIRs: the reflections' decoder; required for room effects
+		int sh_hrir_order1_taps = 0;
 	};
 	Options options;
 
@@ -180,8 +182,8 @@ public:
 	void sourceNumOcclusionsUpdated(AudioSource& source);
 	void setHeadTransform(const Vec4f& head_pos, const Quatf& head_rot);
 	void playOneShotSound(const std::string& sound_file_path, const Vec4f& pos);
-	void setRoomEffectsEnabled(bool enabled);                      // only `false` is on the accelerated path (next)
-	void setCurentRoomDimensions(const js::AABBox& room_aabb);     // accepted and ignored while room effects are off
+	void setRoomEffectsEnabled(bool enabled);                      // early reflections on the GPU (needs Options::sh_hrir_order1)
+	void setCurentRoomDimensions(const js::AABBox& room_aabb);
 	uint32 getSampleRate() const { return sample_rate; }
 	void seekToStartAndUnpauseAudio(AudioSource& source);
 	void setMasterVolume(float volume);

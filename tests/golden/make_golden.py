@@ -3,6 +3,7 @@
 Run here (where /root/reference exists):   make -C oracle ref && python tests/golden/make_golden.py
 
 Outputs
+  substrata_b200/data/sh_hrir_order1_48k.f32  order-1 SADIE SH-HRIRs [4][256] (the reflections' decoder, room effects), same source
   substrata_b200/data/sh_hrir_order3_48k.f32  order-3 SADIE SH-HRIRs [16][256] f32 exactly as the reference decoder
                                               receives them (CreateShHrirsFromAssets, RA/dsp/sh_hrir_creator.cc:60-70).
                                               This is input DATA of the path (the host passes the taps through the C ABI).
@@ -49,6 +50,16 @@ GOLDEN_SCENARIOS = {
     "special_positions_hq": (dict(n_sources=30, kind=KIND_HRTF, seed=114, positions_override=SPECIAL_POSITIONS, moving=False), 256, 6, 0),
     "special_positions_mixed": (dict(n_sources=45, mixed_kinds=True, seed=115, positions_override=SPECIAL_POSITIONS, feeder="resample"), 512, 8, 0),
     "bike_mix3_hq": (dict(n_sources=24, kind=KIND_HRTF, feeder="mix3", loop_len=4096, seed=112, n_shared_buffers=9, volume_toggle=True), 256, 10, 0),
+    # room effects as Substrata drives them inside a parcel (AudioEngine.cpp:738-768, GUIClient.cpp:6886-6896): reflections sends,
+    # six wall reflections cross-faded while the listener moves and when the room changes, head rotation, order-1 decode; enabled
+    # mid-stream, the room replaced, disabled again (the delay line and the decoder play out)
+    "room_hq": (dict(n_sources=40, kind=KIND_HRTF, loop_len=3000, seed=121, volume_toggle=True,
+                     room=dict(on=0, off=20, moves={9: ((0.0, 0.0, 0.0), (20.0, 6.0, 20.0))})), 256, 34, 0),
+    "room_pan_doppler": (dict(n_sources=48, kind=KIND_PAN, feeder="doppler", loop_len=4099, seed=122, room=dict(on=2)), 512, 10, 0),
+    # ... with occluded (low-passed) sources, a low-pass in the reflections (cut-off frequency) and a rotated room
+    "room_mixed_lpf": (dict(n_sources=60, mixed_kinds=True, occlusion_toggle=True, volume_toggle=True, feeder="resample", seed=123,
+                            room=dict(on=1, off=14, cutoff=800.0, rot=(0.0, 0.38268343, 0.0, 0.92387953), pos=(0.5, 0.0, -1.0), dims=(16.0, 5.0, 12.0))), 256, 20, 0),
+    "room_hq_1024": (dict(n_sources=48, kind=KIND_HRTF, feeder="doppler", loop_len=4096, seed=124, room=dict(on=1)), 1024, 6, 0),
 }
 
 RESAMPLER_PAIRS = [(8000, 48000), (12000, 48000), (16000, 48000), (24000, 48000), (44100, 48000), (48000, 48000),
@@ -68,6 +79,13 @@ def main():
     L.ref_dump_sh_hrirs(48000, hr.ctypes.data, hr.size, C.byref(ch))
     os.makedirs(os.path.join(ROOT, "substrata_b200", "data"), exist_ok=True)
     hr.tofile(os.path.join(ROOT, "substrata_b200", "data", "sh_hrir_order3_48k.f32"))
+    # ... and the order-1 set the reflections are decoded with (room effects)
+    L.ref_dump_sh_hrirs_order1.restype = C.c_int
+    L.ref_dump_sh_hrirs_order1.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    T1 = L.ref_dump_sh_hrirs_order1(48000, None, 0, C.byref(ch))
+    hr1 = np.zeros((ch.value, T1), np.float32)
+    L.ref_dump_sh_hrirs_order1(48000, hr1.ctypes.data, hr1.size, C.byref(ch))
+    hr1.tofile(os.path.join(ROOT, "substrata_b200", "data", "sh_hrir_order1_48k.f32"))
     # 2. encoder cells
     L.ref_encoding_coeffs.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
     # every cell of the stored quadrant (0..90 x 0..90) plus every 5th cell of the full sphere (symmetry flips)
@@ -96,7 +114,16 @@ def main():
     out["churn__valid"] = np.array(cv, np.int32)
     out["churn__fin_flat"] = np.array([i for f in cf for i in f], np.int32)
     out["churn__fin_off"] = np.cumsum([0] + [len(f) for f in cf]).astype(np.int32)
-    np.savez_compressed(os.path.join(HERE, "scenarios.npz"), **out)
+    # The reference sums its sources in unordered_map order (RA/node/node.h:163), i.e. in an order that depends on heap addresses:
+    # a regenerated scenario differs from the committed one by that f32 order noise (1e-7 .. 3e-7 relative).  Entries that already
+    # exist are therefore kept as committed unless --force is given; new scenarios are added.
+    path = os.path.join(HERE, "scenarios.npz")
+    if os.path.exists(path) and "--force" not in sys.argv:
+        old = dict(np.load(path))
+        for k, v in old.items():
+            if k in out and out[k].shape == v.shape:
+                out[k] = v
+    np.savez_compressed(path, **out)
     # 4. resampler (the reference's own test pattern: ramp src[i] = i, 4-sample chunks; AudioResampler.cpp:213-287)
     L.ref_resampler_create.restype = C.c_void_p
     L.ref_resampler_create.argtypes = [C.c_int, C.c_int]

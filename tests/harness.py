@@ -46,6 +46,11 @@ def ref_library_path():
     return p if os.path.exists(p) else None
 
 
+def load_sh_hrir_order1():
+    """Order-1 SADIE SH-HRIRs [4][256]: the reflections' decoder (room effects); dumped from the compiled reference."""
+    return np.fromfile(os.path.join(ROOT, "substrata_b200", "data", "sh_hrir_order1_48k.f32"), dtype=np.float32).reshape(4, -1)
+
+
 def load_sh_hrir():
     """Order-3 SADIE SH-HRIRs [16][256] as the reference decoder receives them (dumped by make_golden.py)."""
     a = np.fromfile(os.path.join(ROOT, "substrata_b200", "data", "sh_hrir_order3_48k.f32"), dtype=np.float32)
@@ -143,6 +148,24 @@ class _CBackend:
     def set_master_volume(self, v):
         self._fn["set_master_volume"](self.h, float(v))
 
+    # room effects (AudioEngine.cpp:738-768): bound lazily, the same three calls on every backend
+    def _room_fn(self, name, argtypes):
+        f = getattr(self._room_lib(), self.prefix + name)
+        f.restype, f.argtypes = None, argtypes
+        return f
+
+    def set_room_hrir(self, sh_hrir_order1):
+        if self.prefix == "orc_":           # (the compiled reference loads its own order-1 asset)
+            h = _f32(sh_hrir_order1)
+            self._room_fn("set_room_hrir", [_vp, _vp, _i])(self.h, _ptr(h), h.shape[1])
+
+    def enable_room_effects(self, on):
+        self._room_fn("enable_room_effects", [_vp, _i])(self.h, int(bool(on)))
+
+    def set_reflection_properties(self, room_position, room_rotation_xyzw, room_dimensions, coefficients6, cutoff_frequency=0.0, gain=0.0):
+        a, b, c, d = _f32(room_position), _f32(room_rotation_xyzw), _f32(room_dimensions), _f32(coefficients6)
+        self._room_fn("set_reflection_properties", [_vp, _vp, _vp, _vp, _vp, _f, _f])(self.h, _ptr(a), _ptr(b), _ptr(c), _ptr(d), float(cutoff_frequency), float(gain))
+
     def source_destroy(self, sid):
         self._fn["source_destroy"](self.h, sid)
 
@@ -205,6 +228,9 @@ class OracleBackend(_CBackend):
     prefix = "orc_"
     name = "oracle"
 
+    def _room_lib(self):
+        return oracle_lib()
+
     def __init__(self, frames, rate=48000, sh_hrir=None, double_bus=False):
         lib = oracle_lib()
         self._bind(lib)
@@ -247,6 +273,9 @@ class OracleBackend(_CBackend):
 class RefBackend(_CBackend):
     prefix = "ref_"
     name = "reference"
+
+    def _room_lib(self):
+        return ref_lib()
 
     def __init__(self, frames, rate=48000, hrir_taps=0):
         lib = ref_lib()
@@ -307,7 +336,7 @@ class Scenario:
     def __init__(self, n_sources, frames, seed=12345, kind=KIND_PAN, feeder="native", loop_len=16384, moving=True,
                  rates=(44100, 24000, 16000, 48000), rate_probs=(0.5, 0.2, 0.15, 0.15), boundary_safe=False,
                  volume_toggle=False, occlusion_toggle=False, mixed_kinds=False, n_shared_buffers=0, batched_ring_push=False,
-                 master_script=None, positions_override=None):
+                 master_script=None, positions_override=None, room=None):
         self.n, self.F, self.seed = n_sources, frames, seed
         rng = np.random.default_rng(seed)
         self.moving = moving
@@ -333,6 +362,9 @@ class Scenario:
         self.ring_rng_seed = seed + 1
         self.batched_ring_push = batched_ring_push
         self.master_script = master_script or {}      # buffer index -> master volume (AudioEngine::setMasterVolume, AudioEngine.cpp:805-811)
+        # room effects script (AudioEngine.cpp:738-768, GUIClient.cpp:6886-6896): {"on": buffer, "off": buffer or None, "moves": {buffer: (pos, dims)},
+        # "pos", "dims", "rot", "cutoff"} -- Substrata's fixed coefficients and gain unless given
+        self.room = room
 
     def build(self, be):
         bufs = [be.buffer_create(p) for p in self.pcm]
@@ -365,8 +397,29 @@ class Scenario:
     MIX3_PITCH = (1.0, 0.5, 1.87)
     MIX3_LEVEL = (0.6, 0.3, 0.45)
 
+    ROOM_COEFFS = (0.8, 0.8, 0.3, 0.8, 0.8, 0.2)      # AudioEngine.cpp:762-765
+    ROOM_GAIN = 0.7                                     # AudioEngine.cpp:766
+
+    def _room_events(self, be, b):
+        r = self.room
+        if b == 0:
+            be.set_room_hrir(load_sh_hrir_order1())
+        props = None
+        if b == r.get("on", 0):
+            be.enable_room_effects(True)
+            props = (r.get("pos", (1.0, 0.5, 2.0)), r.get("dims", (30.0, 8.0, 24.0)))
+        if b in r.get("moves", {}):
+            props = r["moves"][b]
+        if props is not None:
+            be.set_reflection_properties(props[0], r.get("rot", (0.0, 0.0, 0.0, 1.0)), props[1], r.get("coeffs", self.ROOM_COEFFS),
+                                         r.get("cutoff", 0.0), r.get("gain", self.ROOM_GAIN))
+        if r.get("off") is not None and b == r["off"]:
+            be.enable_room_effects(False)
+
     def step(self, be, b):
         """Events before buffer `b`."""
+        if self.room is not None:
+            self._room_events(be, b)
         if self.feeder == "mix3" and b > 0:
             # the game thread retunes the engine sound every frame: new source_delta / mix_factor for one of the three
             # mix sources of every other AudioSource

@@ -77,9 +77,12 @@ int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const 
 	(void)n_slots;
 	for (uint32_t k = 0; k < g.n_pan + g.n_sh; ++k) {
 		uint32_t n_src = 0;
-		used |= update_source(g, A, flags, table, lists[k], &A.rec[k], A.shg ? A.shg + k : nullptr, A.shr ? A.shr + k : nullptr, &n_src);
+		ReflSend rfl; rfl.konst = 0.0f; rfl.start = 0.0f; rfl.inc = 0.0f; rfl.n = 0;
+		used |= update_source(g, A, flags, table, lists[k], &A.rec[k], A.shg ? A.shg + k : nullptr, A.shr ? A.shr + k : nullptr, &rfl, &n_src);
+		if (g.room) A.rfl[k] = rfl;
 		if (n_src) { flags->algo_bytes += 4ull * n_src; flags->n_rendered++; }
 	}
+	if (used & kUsedRefl) flags->refl_used[g.parity] = 1;
 	if (used & kUsedPan) flags->pan_used[g.parity] = 1;
 	if (used & kUsedSh) flags->sh_used[g.parity] = 1;
 	if (used & kUsedStereo) flags->st_used[g.parity] = 1;
@@ -94,6 +97,12 @@ static void mix_list(const MixArgs& a, uint32_t first, uint32_t n, bool sh) {
 		if (r.flags & kRecSkip) {
 			if (r.flags & kRecResample) resampler_tail(r, &a.rs[r.slot].prev_samples[0], &a.rs[r.slot].prev_samples[1]);
 			continue;
+		}
+		if (a.rfl && !(r.flags & kRecStereo)) {
+			// room effects: the raw signal through the ramped reflections send (graph_manager.cc:150)
+			RampDesc d; d.konst = a.rfl[k].konst; d.start = a.rfl[k].start; d.inc = a.rfl[k].inc; d.n = a.rfl[k].n;
+			float* row = a.bus + (size_t)kRowRefl * F;
+			for (uint32_t i = 0; i < F; ++i) row[i] = fmaf(gain_at(d, i), source_sample(r, a.mixz, a.mix_pos0, i), row[i]);
 		}
 		for (uint32_t i = 0; i < F; ++i) y[i] = fmul(source_sample(r, a.mixz, a.mix_pos0, i), gain_at(r.direct, i));
 		if (r.flags & kRecResample) resampler_tail(r, &a.rs[r.slot].prev_samples[0], &a.rs[r.slot].prev_samples[1]);
@@ -132,7 +141,7 @@ int launch_mix(const MixArgs& a, void*) {
 	bf[0] = a.flags->sh_used[a.parity] ? 1.0f : 0.0f;
 	bf[1] = a.flags->pan_used[a.parity] ? 1.0f : 0.0f;
 	bf[2] = a.flags->st_used[a.parity] ? 1.0f : 0.0f;
-	bf[3] = 0.0f;
+	bf[3] = a.flags->refl_used[a.parity] ? 1.0f : 0.0f;
 	return 0;
 }
 
@@ -152,14 +161,49 @@ int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage,
 	return 0;
 }
 
+int launch_room(const RoomArgs& a, void*) {
+	++g_launches;
+	const uint32_t F = a.frames;
+	const float* in = a.bus + (size_t)kRowRefl * F;
+	RoomPlan plan;
+	const RoomParams p = *a.params;
+	room_plan(p, a.state, p.enabled && a.bus[(size_t)kBusRows * F + 3] > 0.0f, F, &plan);
+	a.flags->foa_valid = plan.process ? 1 : 0;
+	if (!plan.process) return 0;
+	std::vector<float> lp(F);
+	for (uint32_t i = 0; i < F; ++i) lp[i] = plan.silent_input ? 0.0f : in[i];
+	if (!(plan.lp_coef < kEpsilonFloat)) a.state->lp_prev = room_lowpass(plan.lp_coef, plan.lp_prev, lp.data(), lp.data(), F);
+	else a.state->lp_prev = lp[F - 1];
+	for (uint32_t i = 0; i < F; ++i) a.delay_line[room_insert_index(plan, F, i)] = lp[i];
+	for (uint32_t i = 0; i < F; ++i) room_frame(plan, a.delay_line, F, i, &a.foa[i], &a.foa[(size_t)F + i], &a.foa[(size_t)2 * F + i], &a.foa[(size_t)3 * F + i]);
+	return 0;
+}
+
 int launch_finish(const FinishArgs& a, void*) {
 	++g_launches;
 	const uint32_t F = a.frames;
-	const FinishPlan plan = plan_finish(a.bus + (size_t)kBusRows * F, a.hrir != nullptr, a.flags, a.parity, F);
+	const int foa_valid = a.hrir1 ? a.flags->foa_valid : 0;
+	const FinishPlan plan = plan_finish(a.bus + (size_t)kBusRows * F, a.hrir != nullptr, a.hrir1 != nullptr, a.room_enabled != 0, a.flags, a.parity, F);
 	std::vector<float> l(F, 0.0f), r(F, 0.0f);
+	if (plan.decode1) {
+		// the reflections' order-1 decode (silence in while the decoder only flushes its tail)
+		std::vector<float> foa(4 * (size_t)F, 0.0f);
+		if (foa_valid) memcpy(foa.data(), a.foa, sizeof(float) * 4 * F);
+		const int H1 = (int)a.taps1 - 1;
+		for (uint32_t i = 0; i < F; ++i) decode_frame(foa.data(), a.hrir1, a.hist1, F, a.taps1, i, &l[i], &r[i], 4);
+		if (H1 > 0) {
+			std::vector<float> nh((size_t)H1);
+			for (int c = 0; c < 4; ++c) {
+				float* hc = a.hist1 + (size_t)c * (size_t)H1;
+				for (int q = 0; q < H1; ++q) nh[(size_t)q] = decode_input(foa.data() + (size_t)c * F, hc, H1, (int)F - H1 + q);
+				memcpy(hc, nh.data(), sizeof(float) * (size_t)H1);
+			}
+		}
+	}
+	std::vector<float> l3(F, 0.0f), r3(F, 0.0f);
 	if (plan.decode) {
 		const int H = (int)a.taps - 1;
-		for (uint32_t i = 0; i < F; ++i) decode_frame(a.bus, a.hrir, a.hist, F, a.taps, i, &l[i], &r[i]);
+		for (uint32_t i = 0; i < F; ++i) { decode_frame(a.bus, a.hrir, a.hist, F, a.taps, i, &l3[i], &r3[i]); l[i] += l3[i]; r[i] += r3[i]; }
 		if (H > 0) {
 			std::vector<float> nh((size_t)H);
 			for (int c = 0; c < kNumSh; ++c) {

@@ -52,6 +52,14 @@ def test_cuda_matches_reference_golden(name):
     # three mix sources per AudioSource (the bike), retuned every buffer: the generic multi-read-head path
     (dict(n_sources=600, mixed_kinds=True, feeder="mix3", loop_len=4099, seed=38, n_shared_buffers=31, occlusion_toggle=True), 512, 8, 0),
     (dict(n_sources=200, kind=KIND_HRTF, feeder="mix3", loop_len=2048, seed=39, n_shared_buffers=17), 1024, 6, 0),
+    # room effects (reflections sends in the ROOM instantiations of both mix kernels, room kernel, order-1 decode) at sizes where
+    # every CTA works through several batches
+    (dict(n_sources=4096, kind=KIND_HRTF, loop_len=4096, seed=41, volume_toggle=True, room=dict(on=1, off=9, moves={5: ((2.0, 0.0, 1.0), (24.0, 7.0, 18.0))})), 512, 12, 0),
+    (dict(n_sources=8192, kind=KIND_PAN, feeder="doppler", loop_len=4096, seed=42, room=dict(on=0)), 512, 6, 0),
+    (dict(n_sources=900, mixed_kinds=True, occlusion_toggle=True, volume_toggle=True, feeder="resample", seed=43, loop_len=3001,
+          room=dict(on=2, cutoff=1200.0, rot=(0.0, 0.25881905, 0.0, 0.96592583))), 256, 12, 0),
+    (dict(n_sources=2048, kind=KIND_HRTF, feeder="doppler", loop_len=4098, seed=44, room=dict(on=1)), 1024, 5, 0),
+    (dict(n_sources=300, mixed_kinds=True, occlusion_toggle=True, seed=45, room=dict(on=0, off=4)), 480, 14, 0),
 ])
 def test_cuda_matches_oracle(kw, F, nb, taps):
     hr = load_sh_hrir()
