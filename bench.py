@@ -40,12 +40,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "source-samples/sec mixed @48kHz/512-frame buffers"
 UNIT = "source-samples/s"
-STATE_BYTES = {"pan": 88, "hq": 200}     # per-source state read+written per buffer
+STATE_BYTES = {"pan": 88, "hq": 200}     # per-source state read+written per buffer (+ 8 B with room effects: the send's gain)
 
 WORKLOADS = {
     # name: sources per GPU, frames, source kind, feeder, loop length, SH-HRIR taps, description
     "c4_1m_doppler_pan": dict(n=1048576, frames=512, kind="pan", feeder="doppler", loop=16384, taps=0,
                               desc="1 048 576 sources/GPU, doppler resample (delta in [0.92,1.10]) + distance atten + stereo pan, 512-frame @48kHz"),
+    "c4_1m_doppler_pan_room": dict(n=1048576, frames=512, kind="pan", feeder="doppler", loop=16384, taps=0, room=True,
+                                   desc="1 048 576 sources/GPU, doppler resample + atten + pan + ROOM EFFECTS (reflections send per source, Substrata's parcel settings), 512-frame @48kHz"),
+    "256k_hq_room": dict(n=262144, frames=512, kind="hq", feeder="native", loop=16384, taps=256, room=True,
+                         desc="262 144 sources/GPU, 3rd-order ambisonic encode + 256-tap SH-HRIR decode + ROOM EFFECTS, 512-frame @48kHz"),
     "c2_4096_resample_pan": dict(n=4096, frames=512, kind="pan", feeder="resample", loop=16384, taps=0,
                                  desc="4 096 sources, linear resample (44.1k/24k/16k/48k mix) + atten + pan, 512-frame @48kHz"),
     "c3_65536_hq_128tap": dict(n=65536, frames=1024, kind="hq", feeder="native", loop=16384, taps=128,
@@ -271,6 +275,11 @@ def build_engine(wl, device, seed):
         eng.sources_attach_buffer(ids, bufs, p["start"], p["rates"])
     eng.set_source_positions(ids, p["pos"])
     eng.set_source_volumes(ids, p["vol"])
+    if wl.get("room"):
+        # inside a parcel (GUIClient.cpp:6886-6896 -> AudioEngine.cpp:746-768): the parcel's box, Substrata's wall coefficients and gain
+        eng.set_room_hrir(sb.load_sh_hrir_order1())
+        eng.enable_room_effects(True)
+        eng.set_reflection_properties([0.0, 0.0, 0.0], [0, 0, 0, 1], [90.0, 24.0, 90.0], [0.8, 0.8, 0.3, 0.8, 0.8, 0.2], 0.0, 0.7)
     return eng, pcm, ids, p
 
 

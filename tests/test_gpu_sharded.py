@@ -21,11 +21,11 @@ sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests")
 import torch, torch.distributed as dist
 import substrata_b200 as sb
 from substrata_b200.sharding import ShardedMixer, shard_slice
-from harness import KIND_HRTF, KIND_PAN, OracleBackend, load_sh_hrir, positions, quat_yaw, rel_rms, synth_pcm
+from harness import KIND_HRTF, KIND_PAN, OracleBackend, load_sh_hrir, load_sh_hrir_order1, positions, quat_yaw, rel_rms, synth_pcm
 rank, world = int(sys.argv[1]), int(sys.argv[2])
 torch.cuda.set_device(rank)
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[3], rank=rank, world_size=world)
-F, N, NB = 512, 600, 9
+F, N, NB = 512, 600, 12
 rng = np.random.default_rng(78)
 pcm = [synth_pcm(rng, 3001) for _ in range(N)]
 pos = positions(rng, N); vol = rng.uniform(0.25, 1, N).astype(np.float32)
@@ -44,6 +44,13 @@ def build(be, sel):
 def script(be, ids_of, b):
     t = b * F / 48000.0
     be.set_head([t, 0, 0], quat_yaw(0.5 * t))
+    # room effects from buffer 3 on: the mono reflections send is one more row of the exchanged bus, its "fed" flag travels with
+    # the others, and every rank runs the (O(1)) room kernel on the summed send
+    if b == 0: be.set_room_hrir(load_sh_hrir_order1())
+    if b == 3:
+        be.enable_room_effects(True)
+        be.set_reflection_properties([0.5, 0.0, 1.0], [0, 0, 0, 1], [30.0, 8.0, 24.0], [0.8, 0.8, 0.3, 0.8, 0.8, 0.2], 0.0, 0.7)
+    if b == 7: be.enable_room_effects(False)
     last = np.arange(N - N // world, N)
     sel = [ids_of[s] for s in last if s in ids_of]
     if sel and b == 0: be.set_source_volumes(np.array(sel, np.int32), np.zeros(len(sel), np.float32))
