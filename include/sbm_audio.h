@@ -249,6 +249,24 @@ SBM_API int sbm_resampler_num_src_needed(sbm_resampler* r, size_t n_dst, size_t*
 /* resample(): stream k reads src + src_offsets[k] .. +needed[k], writes dst + k*n_dst (AudioResampler.cpp:89-113). */
 SBM_API int sbm_resampler_resample(sbm_resampler* r, float* dst, size_t n_dst, const float* src, const size_t* src_offsets, size_t src_total);
 
+/* ---- vraudio::Resampler drop-in: Resonance Audio's polyphase sample-rate converter (RA/dsp/resampler.h:27-130), which the AudioEngine
+ * path uses to bring the SH-HRIRs to a device rate other than 48 kHz (RA/dsp/sh_hrir_creator.cc:42-55).  Same methods, same
+ * argument meaning; audio is planar [channels][frames] in HOST memory; the filtering runs on the GPU and reproduces the reference
+ * bit for bit. ---- */
+typedef struct sbm_polyphase sbm_polyphase;
+SBM_API int sbm_polyphase_create(int device, sbm_polyphase** out);
+SBM_API void sbm_polyphase_destroy(sbm_polyphase* p);
+SBM_API int sbm_polyphase_rates_supported(int source_hz, int destination_hz);                         /* Resampler::AreSampleRatesSupported: 1 / 0 */
+SBM_API int sbm_polyphase_set_rate_and_channels(sbm_polyphase* p, int source_hz, int destination_hz, int num_channels);   /* SetRateAndNumChannels */
+SBM_API void sbm_polyphase_reset_state(sbm_polyphase* p);                                              /* ResetState */
+SBM_API size_t sbm_polyphase_max_output_length(const sbm_polyphase* p, size_t input_length);           /* GetMaxOutputLength */
+SBM_API size_t sbm_polyphase_next_output_length(const sbm_polyphase* p, size_t input_length);          /* GetNextOutputLength */
+/* Process: n_out must be sbm_polyphase_next_output_length(n_in). */
+SBM_API int sbm_polyphase_process(sbm_polyphase* p, const float* input, size_t n_in, float* output, size_t n_out);
+/* CreateShHrirsFromWav's resampling step: SH-HRIRs [channels][taps] at source_hz -> destination_hz.  out == NULL: only *out_taps. */
+SBM_API int sbm_resample_sh_hrir(int device, const float* sh_hrir, int channels, int taps, int source_hz, int destination_hz, float* out,
+                                 int out_cap_taps, int* out_taps);
+
 /* ---- debugging / test hooks (host-side exact-arithmetic helpers shared with the kernels) ---- */
 SBM_API float sbm_debug_ramp_advance(float g, float inc, uint32_t n);   /* value after n float adds g += inc, closed form */
 SBM_API float sbm_debug_atan2f(float y, float x);                        /* bit-exact restatement of glibc 2.39 atan2f */

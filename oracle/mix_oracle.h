@@ -74,6 +74,17 @@ size_t orc_resampler_num_src_needed(const orc_resampler* r, size_t n_dst);
 void   orc_resampler_resample(orc_resampler* r, float* dst, size_t n_dst, const float* src, size_t n_src);
 /* SH-domain binaural decode of one 16-channel buffer (direct-form FIR + tail carry). sh_hrir: [channels][taps]; bus: [channels][frames]; history: [channels][taps-1]. */
 void  orc_sh_decode(const float* sh_hrir, int channels, int taps, float* history, const float* bus, int frames, float* out_l, float* out_r);
+/* Resonance's polyphase resampler (RA/dsp/resampler.cc), SURVEY.md 8f row 4: planar [channels][frames] in and out. */
+typedef struct orc_polyphase orc_polyphase;
+orc_polyphase* orc_polyphase_create(void);
+void   orc_polyphase_destroy(orc_polyphase* p);
+int    orc_polyphase_rates_supported(int source_hz, int destination_hz);
+void   orc_polyphase_set_rate_and_channels(orc_polyphase* p, int source_hz, int destination_hz, int num_channels);
+void   orc_polyphase_reset_state(orc_polyphase* p);
+size_t orc_polyphase_max_output_length(const orc_polyphase* p, size_t input_length);
+size_t orc_polyphase_next_output_length(const orc_polyphase* p, size_t input_length);
+const float* orc_polyphase_coeffs(const orc_polyphase* p, size_t* coeffs_per_phase, size_t* up_rate);
+void   orc_polyphase_process(orc_polyphase* p, const float* input, size_t n_in, float* output, size_t n_out);
 #ifdef __cplusplus
 }
 #endif

@@ -387,4 +387,19 @@ void ref_resampler_resample(void* r, float* dst, size_t n_dst, const float* src,
 
 float ref_atan2f(float y, float x) { return std::atan2(y, x); }   // the libm the reference is linked against
 
+// vraudio::Resampler (the polyphase resampler, RA/dsp/resampler.h) driven stand-alone: planar [channels][frames] in and out.
+void* ref_polyphase_create() { return new vraudio::Resampler(); }
+void ref_polyphase_destroy(void* p) { delete (vraudio::Resampler*)p; }
+int ref_polyphase_rates_supported(int s, int d) { return vraudio::Resampler::AreSampleRatesSupported(s, d) ? 1 : 0; }
+void ref_polyphase_set_rate_and_channels(void* p, int s, int d, int nch) { ((vraudio::Resampler*)p)->SetRateAndNumChannels(s, d, (size_t)nch); }
+void ref_polyphase_reset_state(void* p) { ((vraudio::Resampler*)p)->ResetState(); }
+size_t ref_polyphase_max_output_length(void* p, size_t n) { return ((vraudio::Resampler*)p)->GetMaxOutputLength(n); }
+size_t ref_polyphase_next_output_length(void* p, size_t n) { return ((vraudio::Resampler*)p)->GetNextOutputLength(n); }
+void ref_polyphase_process(void* p, const float* input, size_t n_in, int nch, float* output, size_t n_out) {
+	vraudio::AudioBuffer in((size_t)nch, n_in), out((size_t)nch, n_out);
+	for (int c = 0; c < nch; ++c) for (size_t i = 0; i < n_in; ++i) in[(size_t)c][i] = input[(size_t)c * n_in + i];
+	((vraudio::Resampler*)p)->Process(in, &out);
+	for (int c = 0; c < nch; ++c) for (size_t i = 0; i < n_out; ++i) output[(size_t)c * n_out + i] = out[(size_t)c][i];
+}
+
 }  // extern "C"

@@ -367,3 +367,74 @@ class AudioResampler:
             self.close()
         except Exception:
             pass
+
+
+class PolyphaseResampler:
+    """vraudio::Resampler (RA/dsp/resampler.h:27-130): Resonance's polyphase sample-rate converter, bit-exact on the GPU.
+
+    Audio is planar [channels][frames] float32.  Method names follow the reference's."""
+
+    def __init__(self, device=0, _lib_path=None):
+        self._l = lib(_lib_path)
+        h = C.c_void_p()
+        rc = self._l.sbm_polyphase_create(int(device), C.byref(h))
+        if rc:
+            raise SbmError(rc, "sbm_polyphase_create")
+        self.h = h
+        self.channels = 0
+
+    @staticmethod
+    def are_sample_rates_supported(source_hz, destination_hz, _lib_path=None):
+        return bool(lib(_lib_path).sbm_polyphase_rates_supported(int(source_hz), int(destination_hz)))
+
+    def set_rate_and_num_channels(self, source_hz, destination_hz, num_channels):
+        rc = self._l.sbm_polyphase_set_rate_and_channels(self.h, int(source_hz), int(destination_hz), int(num_channels))
+        if rc:
+            raise SbmError(rc, "sbm_polyphase_set_rate_and_channels")
+        self.channels = int(num_channels)
+
+    def reset_state(self):
+        self._l.sbm_polyphase_reset_state(self.h)
+
+    def get_max_output_length(self, input_length):
+        return int(self._l.sbm_polyphase_max_output_length(self.h, int(input_length)))
+
+    def get_next_output_length(self, input_length):
+        return int(self._l.sbm_polyphase_next_output_length(self.h, int(input_length)))
+
+    def process(self, x):
+        x = _f32(np.atleast_2d(x))
+        if x.shape[0] != self.channels:
+            raise ValueError("expected [%d][frames]" % self.channels)
+        n_out = self.get_next_output_length(x.shape[1])
+        out = np.zeros((self.channels, max(n_out, 1)), dtype=np.float32)
+        rc = self._l.sbm_polyphase_process(self.h, _p(x), x.shape[1], _p(out), n_out)
+        if rc:
+            raise SbmError(rc, "sbm_polyphase_process")
+        return out[:, :n_out]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._l.sbm_polyphase_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def resample_sh_hrir(sh_hrir, source_hz, destination_hz, device=0, _lib_path=None):
+    """The resampling step of CreateShHrirsFromWav (RA/dsp/sh_hrir_creator.cc:42-55): [channels][taps] -> [channels][taps']."""
+    l = lib(_lib_path)
+    h = _f32(np.atleast_2d(sh_hrir))
+    n = C.c_int(0)
+    rc = l.sbm_resample_sh_hrir(int(device), _p(h), h.shape[0], h.shape[1], int(source_hz), int(destination_hz), None, 0, C.byref(n))
+    if rc:
+        raise SbmError(rc, "sbm_resample_sh_hrir")
+    out = np.zeros((h.shape[0], max(n.value, 1)), dtype=np.float32)
+    rc = l.sbm_resample_sh_hrir(int(device), _p(h), h.shape[0], h.shape[1], int(source_hz), int(destination_hz), _p(out), out.shape[1], C.byref(n))
+    if rc:
+        raise SbmError(rc, "sbm_resample_sh_hrir")
+    return out[:, :n.value]

@@ -74,6 +74,15 @@ SIGNATURES = {
     "sbm_resampler_destroy": (None, [_vp]),
     "sbm_resampler_num_src_needed": (_i, [_vp, _sz, _vp]),
     "sbm_resampler_resample": (_i, [_vp, _vp, _sz, _vp, _vp, _sz]),
+    "sbm_polyphase_create": (_i, [_i, _vp]),
+    "sbm_polyphase_destroy": (None, [_vp]),
+    "sbm_polyphase_rates_supported": (_i, [_i, _i]),
+    "sbm_polyphase_set_rate_and_channels": (_i, [_vp, _i, _i, _i]),
+    "sbm_polyphase_reset_state": (None, [_vp]),
+    "sbm_polyphase_max_output_length": (_sz, [_vp, _sz]),
+    "sbm_polyphase_next_output_length": (_sz, [_vp, _sz]),
+    "sbm_polyphase_process": (_i, [_vp, _vp, _sz, _vp, _sz]),
+    "sbm_resample_sh_hrir": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "sbm_debug_ramp_advance": (_f, [_f, _f, C.c_uint32]),
     "sbm_debug_atan2f": (_f, [_f, _f]),
     "sbm_debug_encoder_table": (_vp, []),

@@ -21,9 +21,10 @@ CUDA_UNITS = [
     ("k2_mix.cu", []),
     ("device_cuda.cu", []),
     ("k5_resampler.cu", []),
+    ("k6_polyphase.cu", []),
 ]
 # Host units: no FMA contraction -- sh_table.cc must evaluate the encoder table like the reference's SSE build.
-HOST_UNITS = ["engine.cc", "sh_table.cc"]
+HOST_UNITS = ["engine.cc", "sh_table.cc", "polyphase.cc"]
 HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-Wall", "-Wextra", "-Wno-unused-parameter"]
 
 

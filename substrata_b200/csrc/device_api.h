@@ -130,6 +130,14 @@ struct OutTail {                // follows the 2*frames output floats in the D2H
 };
 constexpr int kTailOk = 0, kTailPeerTimeout = 1;
 
+struct PolyphaseArgs {          // K6 (k6_polyphase.cu): Resonance's polyphase resampler, one launch per Process call
+	const float* in;            // [channels][ext]: per channel the carried state (hist = cpp - 1 samples) followed by the input
+	const float* coeffs;        // transposed_filter_coeffs_: [up][cpp], each phase flipped
+	float* out;                 // [channels][n_out]
+	uint32_t channels, ext, hist, n_out;
+	uint32_t up, down, time_modulo, last, cpp;
+};
+
 namespace dev {
 int init(int device, void** stream_out);
 void* stream_create();                           // another non-blocking stream on the current device
@@ -153,6 +161,7 @@ int launch_patch(const SlotArrays& A, const SlotPatch* patches, uint32_t n, cons
 int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const float* table, const uint32_t* lists, uint32_t n_slots, void* stream);   // lists: [n_pan + n_sh] slots in render order
 int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage, void* stream);   // batched ring push: one CTA per packet
 int launch_mix(const MixArgs& a, void* stream);  // K2 (both lists) + K3 (partials -> bus)
+int launch_polyphase(const PolyphaseArgs& a, void* stream);
 int launch_room(const RoomArgs& a, void* stream);   // ReflectionsNode for this buffer (room effects)
 int launch_finish(const FinishArgs& a, void* stream);
 // peer exchange (multi-GPU): IPC plumbing + the gather kernel

@@ -161,6 +161,21 @@ int launch_ring_scatter(const RingPush* packets, uint32_t n, const float* stage,
 	return 0;
 }
 
+int launch_polyphase(const PolyphaseArgs& a, void*) {
+	++g_launches;
+	for (uint32_t c = 0; c < a.channels; ++c)
+		for (uint32_t k = 0; k < a.n_out; ++k) {
+			const unsigned long long total = (unsigned long long)a.time_modulo + (unsigned long long)k * a.down;
+			const uint32_t input_sample = a.last + (uint32_t)(total / a.up), phase = (uint32_t)(total % a.up);
+			const float* x = a.in + (size_t)c * a.ext + (size_t)input_sample;
+			const float* h = a.coeffs + (size_t)phase * a.cpp;
+			float acc = 0.0f;
+			for (uint32_t j = 0; j < a.cpp; ++j) acc = fadd(acc, fmul(x[j], h[j]));
+			a.out[(size_t)c * a.n_out + k] = acc;
+		}
+	return 0;
+}
+
 int launch_room(const RoomArgs& a, void*) {
 	++g_launches;
 	const uint32_t F = a.frames;
