@@ -85,6 +85,8 @@ struct MixArgs {
 	PeerArgs peer;
 	size_t bus_floats;
 	uint32_t rot_div;           // set by the launcher: SM count (CTA index / rot_div = which resident CTA of its SM a CTA is, first wave)
+	const uint32_t* ready;      // non-null: K1 is still running beside the mix kernel; records of tile t are valid once ready[t] == epoch
+	uint32_t epoch;
 };
 
 struct RoomArgs {               // the room kernel (room_core.h): reflections bus -> first-order buffer
@@ -128,7 +130,7 @@ struct OutTail {                // follows the 2*frames output floats in the D2H
 	int status;                 // kTail*
 	unsigned long long algo_bytes;
 };
-constexpr int kTailOk = 0, kTailPeerTimeout = 1;
+constexpr int kTailOk = 0, kTailPeerTimeout = 1, kTailPipeTimeout = 2;
 
 struct PolyphaseArgs {          // K6 (k6_polyphase.cu): Resonance's polyphase resampler, one launch per Process call
 	const float* in;            // [channels][ext]: per channel the carried state (hist = cpp - 1 samples) followed by the input

@@ -209,9 +209,9 @@ __global__ void __launch_bounds__(1024) k4b_finish_kernel(FinishArgs a) {
 		tail->valid = plan.valid;
 		tail->n_finished = n_fin;
 		tail->n_rendered = a.flags->n_rendered + part_rendered;
-		tail->status = a.flags->peer_timeout ? kTailPeerTimeout : kTailOk;
+		tail->status = a.flags->pipe_timeout ? kTailPipeTimeout : (a.flags->peer_timeout ? kTailPeerTimeout : kTailOk);
 		tail->algo_bytes = a.flags->algo_bytes + part_bytes;
-		a.flags->n_finished = 0; a.flags->n_rendered = 0; a.flags->algo_bytes = 0; a.flags->peer_timeout = 0;
+		a.flags->n_finished = 0; a.flags->n_rendered = 0; a.flags->algo_bytes = 0; a.flags->peer_timeout = 0; a.flags->pipe_timeout = 0;
 	}
 	unsigned long long* reads = reinterpret_cast<unsigned long long*>(tail + 1);
 	for (uint32_t q = i; q < a.n_ring; q += T) reads[q] = a.read_i[a.list_ring[q]];

@@ -12,6 +12,7 @@ namespace dev {
 void note_launch(unsigned n = 1);            // bumps the library's kernel-launch counter
 int check(cudaError_t e, const char* what);  // records the error text; returns 0 on success, -1 otherwise
 int check_launch(const char* what);          // cudaGetLastError() after a launch
+int current_sm_count();                      // SM count of the current device (cached per device, k2_mix.cu)
 }  // namespace dev
 
 // Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may be set up -- and start running its
@@ -20,6 +21,9 @@ int check_launch(const char* what);          // cudaGetLastError() after a launc
 // [gather] -> K4a -> K4b is five short-lived launches; this takes their launch latencies off the critical path.
 #if defined(__CUDACC__)
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// The primary's side: "the next kernel of the stream may be set up now".  Its CTAs become resident as soon as EVERY CTA of this grid
+// has executed this (or exited) and resources allow.
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
 	cudaLaunchConfig_t cfg = {};

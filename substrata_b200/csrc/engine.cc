@@ -180,6 +180,8 @@ struct sbm_engine {
 
 	// stats
 	bool profiling = false;
+	int overlap_mode = 1;
+	bool overlap_allowed = false;   // K1 beside K2 for large stereo-bus scenes (mix_begin_locked): SBM_OVERLAP=1 in the environment turns it on
 	sbm_stats stats;
 };
 
@@ -192,6 +194,8 @@ int fail(sbm_engine* e, int code, const std::string& msg) {
 int fail_cuda(sbm_engine* e, const char* where) {
 	return fail(e, SBM_ERR_CUDA, std::string(where) + ": " + dev::last_error());
 }
+
+constexpr uint32_t kOverlapMinSources = 32768;     // below this K1 is a single wave: nothing to hide
 
 template <class T> bool dalloc(T*& p, size_t count) {
 	p = (T*)dev::alloc(sizeof(T) * (count ? count : 1));
@@ -413,6 +417,10 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	if (cfg->sample_rate_hz <= 0 || cfg->max_sources <= 0) return SBM_ERR_INVALID_ARG;
 	if (cfg->sh_hrir && (cfg->sh_hrir_taps < 1 || cfg->sh_hrir_taps > 1024)) return SBM_ERR_INVALID_ARG;
 	sbm_engine* e = new sbm_engine();
+	// K1 beside K2 (mix_begin_locked) is opt-in: measured on B200 at 2^20 sources it is SLOWER than one kernel after the other
+	// (0.56 vs 0.54 ms per buffer, DESIGN.md "K1 beside K2") -- kept, tested and selectable for the record and for further work.
+	if (const char* v = getenv("SBM_OVERLAP")) e->overlap_allowed = v[0] && v[0] != '0';
+	if (const char* v = getenv("SBM_OVERLAP_MODE")) e->overlap_mode = atoi(v);      // development: 2 = persistent K1, mix kernel waits for all of it
 	e->cfg = *cfg;
 	e->cfg.sh_hrir = nullptr;   // caller's pointer is not retained
 	memset(&e->stats, 0, sizeof(e->stats));
@@ -437,7 +445,7 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	ok = ok && dalloc(e->dv_stat, cap) && dalloc(e->dv_posvol, cap) && dalloc(e->dv_occl, cap) && dalloc(e->dv_ring_write, cap) && dalloc(e->dv_mixz, mixcap);
 	A.stat = e->dv_stat; A.posvol = e->dv_posvol; A.occl = e->dv_occl; A.ring_write = e->dv_ring_write; A.mixz = e->dv_mixz;
 	ok = ok && dalloc(A.live, cap) && dalloc(A.read_i, cap) && dalloc(A.eof, cap) && dalloc(A.rs, cap) && dalloc(A.dgain, cap) &&
-	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.mrec, cap) && dalloc(A.rfl, cap) && dalloc(A.rgain, cap) && dalloc(A.finished, 2 * (size_t)cap) &&
+	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.mrec, cap) && dalloc(A.rfl, cap) && dalloc(A.rgain, cap) && dalloc(A.ready, (size_t)cap / kK1Tile + 2) && dalloc(A.finished, 2 * (size_t)cap) &&
 	     dalloc(A.mix_pos, mixcap) && dalloc(A.mix_pos0, mixcap);
 	A.cstride = kNumSh;
 	ok = ok && dalloc(A.cgain, (size_t)cap * kNumSh);
@@ -487,7 +495,7 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	for (SetterRec* l = e->setq.exchange(nullptr); l;) { SetterRec* nx = l->next; free(l); l = nx; }
 	SlotArrays& A = e->A;
 	void* ptrs[] = {e->dv_stat, e->dv_posvol, e->dv_occl, e->dv_ring_write, e->dv_mixz, A.live, A.read_i, A.eof, A.rs, A.dgain, A.occ_cur,
-	                A.lpf_prev, A.bits, A.rec, A.mrec, A.rfl, A.rgain, e->room.dv_params, e->room.dv_state, e->room.dv_delay, e->room.dv_foa, e->room.dv_hrir1,
+	                A.lpf_prev, A.bits, A.rec, A.mrec, A.rfl, A.rgain, A.ready, e->room.dv_params, e->room.dv_state, e->room.dv_delay, e->room.dv_foa, e->room.dv_hrir1,
 	                e->room.dv_hist1, e->room.dv_dec1, e->fl[0].dv_finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
 	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
 	                e->dv_hist, e->dv_dec};
@@ -1079,10 +1087,17 @@ static int mix_begin_locked(sbm_engine* e) {
 	e->g.n_pan = (uint32_t)e->list_pan.size(); e->g.n_sh = (uint32_t)e->list_sh.size();
 	e->A.finished = fl.dv_finished;      // per-parity list: the previous buffer's may not have been collected yet
 	// 2. kernels
-	if (e->profiling) dev::event_record(fl.ev[0], st);
+	// Large stereo-bus scenes: K1 runs as a persistent grid BESIDE the mix kernel, which consumes its records tile by tile (k1_params.cu).
+	// (Not with ambisonic sources or room effects -- those mix kernels leave K1 no registers -- nor at 1024 frames, one CTA per SM.)
+	const bool overlap = e->overlap_allowed && e->g.n_sh == 0 && !e->room.enabled && e->g.n_pan >= kOverlapMinSources && e->g.frames <= 512;
+	e->g.overlap = overlap ? 1u : 0u;
+	e->g.epoch = (uint32_t)(e->buffer_index % 0xfffffffeull) + 1u;
+	// (an event between the two launches would serialise them: overlapped, the pair is timed as one span and reported as the mix kernel's)
+	if (e->profiling) { dev::event_record(fl.ev[0], st); if (overlap && e->overlap_mode != 2) dev::event_record(fl.ev[1], st); }
 	if (e->g.n_pan + e->g.n_sh && dev::launch_params(e->g, e->A, e->dv_flags, e->dv_table, e->dv_lists, e->n_slots, st)) return fail_cuda(e, "k1_params");
-	if (e->profiling) dev::event_record(fl.ev[1], st);
+	if (e->profiling && !(overlap && e->overlap_mode != 2)) dev::event_record(fl.ev[1], st);
 	MixArgs m;
+	m.ready = overlap && e->overlap_mode != 2 ? e->A.ready : nullptr; m.epoch = e->g.epoch;
 	m.rfl = e->room.enabled ? e->A.rfl : nullptr;
 	m.mrec = e->A.mrec; m.rec = e->A.rec; m.shg = e->A.shg; m.shr = e->A.shr; m.mixz = e->dv_mixz; m.mix_pos0 = e->A.mix_pos0; m.rs = e->A.rs; m.lpf_prev = e->A.lpf_prev;
 	m.n_pan = (uint32_t)e->list_pan.size();
@@ -1192,6 +1207,7 @@ static int mix_collect_locked(sbm_engine* e, std::unique_lock<std::mutex>& lk, f
 		e->stats.last_mix_kernel_ms = dev::event_elapsed_ms(fl.ev[1], fl.ev[2]);
 		e->stats.last_finish_kernel_ms = dev::event_elapsed_ms(fl.ev[2], fl.ev[3]);
 	}
+	if (tail.status == kTailPipeTimeout) return fail(e, SBM_ERR_CUDA, "the parameter kernel's records did not reach the mix kernel (overlapped K1 / K2): this buffer is not valid");
 	if (tail.status == kTailPeerTimeout) return fail(e, SBM_ERR_PEER_TIMEOUT, "a peer rank did not deliver its bus in time: this buffer holds the local sources only (see sbm_peer_resync)");
 	return SBM_OK;
 }

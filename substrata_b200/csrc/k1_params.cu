@@ -6,6 +6,8 @@
 // -60 dB rules, ramp lengths), so every float operation must round exactly like the reference's SSE build.
 // HBM traffic per slot: SrcStatic 32 B + pos/volume 16 B + ~60 B of state read-modify-write + 128 B MixRec write (k2_rec.h;
 // + the 128 B WorkRec only for sources a careful path of the mix kernel will read back).
+#include <atomic>
+
 #include "device_internal.h"
 #include "k1_core.h"
 #include "k2_rec.h"
@@ -18,50 +20,92 @@ namespace sbm {
 #ifndef SBM_K1_MINB
 #define SBM_K1_MINB (1024 / SBM_K1_THREADS)
 #endif
+// Overlapped mode (Globals::overlap; large stereo-bus scenes): the grid is PERSISTENT -- kK1OverlapCtas CTAs per SM, sized so that the
+// mix kernel's CTAs fit beside them -- and walks the render list tile by tile in the order the mix kernel consumes it (that kernel deals
+// batches to its CTAs round-robin, so the whole grid sweeps the list front to back).  Every CTA announces the dependent launch at once; the
+// mix kernel (k2_mix.cu: wait_records_ready) then polls SlotArrays::ready before it fetches a tile's records.  K1 never waits for K2 and is
+// fully resident before K2's first CTA can start, so the pair cannot deadlock.  K1 alone is latency-bound (3 dependent gathers per source)
+// and K2 is HBM-bound: side by side, K1's time disappears under K2's, and K2 finds the records K1 just wrote in L2.
+constexpr int kK1OverlapCtas = 2;
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+static_assert(SBM_K1_THREADS == (int)kK1Tile, "one thread per entry of a K1 tile");
+
+template <bool OVERLAP>
 __global__ void __launch_bounds__(SBM_K1_THREADS, SBM_K1_MINB) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table,
                                                        const uint32_t* __restrict__ lists, uint32_t wslot) {
-	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;    // position in the render lists
+	if (OVERLAP) grid_dep_launch_dependents();
+	const uint32_t n_list = g.n_pan + g.n_sh, n_tiles = (n_list + kK1Tile - 1) / kK1Tile;
 	// whether this buffer's "mixer used" flags are already set: read NOW, so that the loads overlap the work below instead
 	// of being a dependent round trip at the end of every warp (a stale 0 only costs a redundant atomicOr)
-	const int set_pan = flags->pan_used[g.parity], set_sh = flags->sh_used[g.parity], set_st = flags->st_used[g.parity], set_refl = flags->refl_used[g.parity];
-	uint32_t used = 0, n_src = 0;
-	if (k < g.n_pan + g.n_sh) {
-		WorkRec rec;
-		ReflSend rfl;
-		rfl.konst = 0.0f; rfl.start = 0.0f; rfl.inc = 0.0f; rfl.n = 0;
-		used = update_source(g, A, flags, table, lists[k], &rec, A.shg + k, A.shr + k, &rfl, &n_src);
-		// the record the mix kernel consumes, in final form (k2_rec.h); the full WorkRec only where a careful path will read it back
-		MixRec m = make_mixrec(rec, wslot, k >= g.n_pan);
-		if (g.room) {
-			// a ramping reflections send needs the per-frame gain path like any other ramp
-			A.rfl[k] = rfl;
-			if (rfl.n && !(m.mode & kMdSkip)) { if (rfl.n > m.nramp) m.nramp = rfl.n; m.mode |= kMdRamp; }
+	int set_pan = flags->pan_used[g.parity], set_sh = flags->sh_used[g.parity], set_st = flags->st_used[g.parity], set_refl = flags->refl_used[g.parity];
+	// Persistent grid: few threads per SM, so the chain  list entry -> slot -> a dozen per-slot arrays  is taken off the critical path by
+	// software: the list entry is read two tiles ahead and the slot's lines are prefetched into L2 one tile ahead.
+	const uint32_t stride = OVERLAP ? gridDim.x * kK1Tile : 0u;
+	uint32_t k0 = blockIdx.x * kK1Tile + threadIdx.x;
+	uint32_t slot_cur = k0 < n_list ? lists[k0] : 0u, slot_n1 = 0u;
+	if (OVERLAP && k0 + stride < n_list) slot_n1 = lists[k0 + stride];
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += OVERLAP ? gridDim.x : n_tiles) {      // (classic: one tile per CTA)
+		const uint32_t k = tile * kK1Tile + threadIdx.x;    // position in the render lists
+		uint32_t used = 0, n_src = 0;
+		uint32_t slot_n2 = 0u;
+		if (OVERLAP) {
+			if (k + 2u * stride < n_list) slot_n2 = lists[k + 2u * stride];
+			if (k + stride < n_list) {
+				const uint32_t sn = slot_n1;
+				prefetch_l2(A.stat + sn); prefetch_l2(A.posvol + sn); prefetch_l2(A.occl + sn); prefetch_l2(A.live + sn); prefetch_l2(A.read_i + sn);
+				prefetch_l2(A.eof + sn); prefetch_l2(A.rs + sn); prefetch_l2(A.dgain + sn); prefetch_l2(A.occ_cur + sn); prefetch_l2(A.lpf_prev + sn);
+				prefetch_l2(A.bits + sn); prefetch_l2(A.cgain + (size_t)sn * (size_t)A.cstride);
+			}
 		}
-		A.mrec[k] = m;
-		if (mixrec_needs_workrec(m.mode)) A.rec[k] = rec;
-	}
-	// Warp-level reduction of the "mixer used" bits and the accounting counters, then one lane publishes.  The flags are
-	// the same few words for the whole grid and same-address atomics serialise in L2 (one set per warp on ONE address cost
-	// ~100 us per million sources): a flag is only OR-ed by the warps that started while it still read 0, and the counters go to one of kStatParts
-	// padded slots chosen by the block index (K4b sums them).  No block-wide barrier: a finished warp leaves the SM.
-	const unsigned full = 0xffffffffu;
-	uint32_t u = used;
-	unsigned long long bytes = n_src ? 4ull * n_src : 0ull;
-	uint32_t rendered = n_src ? 1u : 0u;
-	for (int o = 16; o > 0; o >>= 1) {
-		u |= __shfl_xor_sync(full, u, o);
-		bytes += __shfl_xor_sync(full, bytes, o);
-		rendered += __shfl_xor_sync(full, rendered, o);
-	}
-	if ((threadIdx.x & 31) == 0) {
-		if ((u & kUsedPan) && !set_pan) atomicOr(&flags->pan_used[g.parity], 1);
-		if ((u & kUsedSh) && !set_sh) atomicOr(&flags->sh_used[g.parity], 1);
-		if ((u & kUsedStereo) && !set_st) atomicOr(&flags->st_used[g.parity], 1);
-		if ((u & kUsedRefl) && !set_refl) atomicOr(&flags->refl_used[g.parity], 1);
-		if (rendered) {
-			const uint32_t part = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kStatParts;
-			atomicAdd(&flags->part_bytes[part][0], bytes);
-			atomicAdd(&flags->part_rendered[part][0], rendered);
+		if (k < n_list) {
+			WorkRec rec;
+			ReflSend rfl;
+			rfl.konst = 0.0f; rfl.start = 0.0f; rfl.inc = 0.0f; rfl.n = 0;
+			used = update_source(g, A, flags, table, slot_cur, &rec, A.shg + k, A.shr + k, &rfl, &n_src);
+			// the record the mix kernel consumes, in final form (k2_rec.h); the full WorkRec only where a careful path will read it back
+			MixRec m = make_mixrec(rec, wslot, k >= g.n_pan);
+			if (g.room) {
+				// a ramping reflections send needs the per-frame gain path like any other ramp
+				A.rfl[k] = rfl;
+				if (rfl.n && !(m.mode & kMdSkip)) { if (rfl.n > m.nramp) m.nramp = rfl.n; m.mode |= kMdRamp; }
+			}
+			A.mrec[k] = m;
+			if (mixrec_needs_workrec(m.mode)) A.rec[k] = rec;
+		}
+		// Warp-level reduction of the "mixer used" bits and the accounting counters, then one lane publishes.  The flags are
+		// the same few words for the whole grid and same-address atomics serialise in L2 (one set per warp on ONE address cost
+		// ~100 us per million sources): a flag is only OR-ed by the warps that started while it still read 0, and the counters go to one of kStatParts
+		// padded slots chosen by the block index (K4b sums them).  No block-wide barrier (classic mode): a finished warp leaves the SM.
+		const unsigned full = 0xffffffffu;
+		uint32_t u = used;
+		unsigned long long bytes = n_src ? 4ull * n_src : 0ull;
+		uint32_t rendered = n_src ? 1u : 0u;
+		for (int o = 16; o > 0; o >>= 1) {
+			u |= __shfl_xor_sync(full, u, o);
+			bytes += __shfl_xor_sync(full, bytes, o);
+			rendered += __shfl_xor_sync(full, rendered, o);
+		}
+		if ((threadIdx.x & 31) == 0) {
+			if ((u & kUsedPan) && !set_pan) atomicOr(&flags->pan_used[g.parity], 1);
+			if ((u & kUsedSh) && !set_sh) atomicOr(&flags->sh_used[g.parity], 1);
+			if ((u & kUsedStereo) && !set_st) atomicOr(&flags->st_used[g.parity], 1);
+			if ((u & kUsedRefl) && !set_refl) atomicOr(&flags->refl_used[g.parity], 1);
+			if (rendered) {
+				const uint32_t part = (tile * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kStatParts;
+				atomicAdd(&flags->part_bytes[part][0], bytes);
+				atomicAdd(&flags->part_rendered[part][0], rendered);
+			}
+		}
+		// (a persistent warp sets each flag at most once)
+		if (OVERLAP) {
+			slot_cur = slot_n1; slot_n1 = slot_n2;
+			set_pan |= (int)(u & kUsedPan); set_sh |= (int)(u & kUsedSh); set_st |= (int)(u & kUsedStereo); set_refl |= (int)(u & kUsedRefl);
+			// publish the tile: every thread's stores (records, state, counters) ordered before the stamp -- also for the mix kernel's
+			// bulk copies, which read through the async proxy
+			__threadfence();
+			asm volatile("fence.proxy.async.global;" ::: "memory");
+			__syncthreads();
+			if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.ready + tile), "r"(g.epoch) : "memory");
 		}
 	}
 }
@@ -102,7 +146,25 @@ int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const 
 	(void)n_slots;
 	const uint32_t n = g.n_pan + g.n_sh;
 	if (!n) return 0;
-	k1_params_kernel<<<(n + SBM_K1_THREADS - 1) / SBM_K1_THREADS, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
+	uint32_t grid = (n + SBM_K1_THREADS - 1) / SBM_K1_THREADS;
+	if (g.overlap) {
+		const uint32_t resident = (uint32_t)(current_sm_count() * kK1OverlapCtas);
+		if (grid > resident) grid = resident;
+	}
+	if (g.overlap) {
+		// an SM holds ONE shared-memory carve-out at a time: K1 must ask for the mix kernel's (maximum shared memory), or that kernel's
+		// CTAs could not join K1's on the same SM before K1 has drained
+		static std::atomic<unsigned long long> configured{0};
+		int device = 0;
+		cudaGetDevice(&device);
+		const unsigned long long bit = 1ull << (device & 63);
+		if (!(configured.load(std::memory_order_acquire) & bit)) {
+			if (check(cudaFuncSetAttribute(k1_params_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(k1 carveout)")) return -1;
+			configured.fetch_or(bit, std::memory_order_release);
+		}
+	}
+	if (g.overlap) k1_params_kernel<true><<<grid, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
+	else k1_params_kernel<false><<<grid, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
 	note_launch();
 	return check_launch("k1_params");
 }

@@ -230,6 +230,27 @@ struct SmemView {
 	}
 };
 
+// Overlapped K1 / K2 (k1_params.cu): before the records of render-list entries [b0, b0 + nb) are fetched, wait until K1 has stamped their
+// tiles.  One lane polls (acquire, gpu scope); the bulk copies that follow read through the async proxy, hence the proxy fence.  K1 is
+// resident and never waits for this kernel, so the wait is bounded by K1's own progress; the spin limit (~2 s) only turns a lost K1
+// (a fault) into an error status instead of a hung stream.
+__device__ __forceinline__ void wait_records_ready(const MixArgs& a, uint32_t b0, uint32_t nb) {
+	const uint32_t t0 = b0 / kK1Tile, t1 = (b0 + nb - 1) / kK1Tile;
+	for (uint32_t t = t0; t <= t1; ++t) {
+		uint32_t spins = 0;
+		for (;;) {
+			uint32_t v;
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.ready + t) : "memory");
+			if (v == a.epoch) break;
+			__nanosleep(64);
+			++spins;
+			if ((spins & 1023u) == 0 && *reinterpret_cast<const volatile int*>(&a.flags->pipe_timeout)) break;      // somebody gave up already: drain
+			if (spins > (1u << 24)) { const_cast<DevFlags*>(a.flags)->pipe_timeout = 1; __threadfence(); break; }
+		}
+	}
+	asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 // ================= issue warp (both kernels): lane b looks after source b of each batch =================
 template <int NCH, int kStages, int kBatch>
 __device__ void issue_warp(const SmemView<NCH, kStages, kBatch>& sm, const MixArgs& a, uint32_t s0, uint32_t s1, uint32_t nbatch, uint32_t wslot, uint32_t lane) {
@@ -246,6 +267,7 @@ __device__ void issue_warp(const SmemView<NCH, kStages, kBatch>& sm, const MixAr
 			const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 			const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
 			const uint32_t bytes = nb * (uint32_t)sizeof(MixRec) + (NCH == 16 ? nb * (uint32_t)sizeof(ShGains) : 0u) + (a.rfl ? nb * (uint32_t)sizeof(ReflSend) : 0u);
+			if (a.ready) wait_records_ready(a, b0, nb);
 			mbar_expect_tx(&hdr->full_r[q], bytes);
 			bulk_g2s(sm.recs + q * kBatch, grec + b0, nb * (uint32_t)sizeof(MixRec), &hdr->full_r[q]);
 			if (NCH == 16) bulk_g2s(sm.shgs + q * kBatch, gshg + b0, nb * (uint32_t)sizeof(ShGains), &hdr->full_r[q]);
@@ -421,10 +443,14 @@ __device__ __forceinline__ float frac_of(unsigned long long p) { return __uint_a
 // =====================================================================================================================
 // ROOM (room effects on): a third accumulator per frame collects the source's RAW signal through the ramped reflections send
 // gain (graph_manager.cc:150); the CTA's partial bus then has three rows.
-template <int KF, bool EXACT, bool ROOM>
+// STAGES: window stages in flight per CTA.  kStagesPan with SBM_MIN_CTAS resident CTAs per SM is the stand-alone shape; the overlapped
+// shape (K1 resident beside this kernel, k1_params.cu) runs one CTA fewer per SM with one stage more -- the same bytes in flight -- which
+// leaves K1's CTAs their registers (the register file is per scheduler: 4 x 16 K).
+constexpr int kStagesPanOverlap = kStagesPan + 1;
+template <int KF, bool EXACT, bool ROOM, int STAGES>
 __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : (ROOM ? 3 : SBM_MIN_CTAS)) k2_mix_stereo_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	constexpr int kStages = kStagesPan, kRecStages = kStages + 2, kBatch = kBatchPan;
+	constexpr int kStages = STAGES, kRecStages = kStages + 2, kBatch = kBatchPan;
 	const SmemView<2, kStages, kBatch> sm(smem_raw, ROOM);
 	MixSmemHdr* hdr = sm.hdr;
 	// EXACT: the frame count is a compile-time constant (every "is this frame F - 1 / inside the buffer" test folds away)
@@ -441,7 +467,8 @@ __global__ void __launch_bounds__(kPanWarps * 32 + 32, KF == 32 ? 2 : (ROOM ? 3 
 #endif
 	if (t == 0) init_barriers<kStages>(hdr, kPanWarps);
 	__syncthreads();
-	grid_dep_wait();     // everything above overlaps the tail of K1; its records are read from here on
+	// everything above overlaps the tail of K1; its records are read from here on -- tile by tile as K1 stamps them when it runs beside us
+	if (!a.ready) grid_dep_wait();
 	if (warp == (uint32_t)kPanWarps) { issue_warp<2, kStages, kBatch>(sm, a, s0, s1, nbatch, wslot, lane); return; }
 
 	float2 acc[KF];     // (L, R) of frame lane + 32 k: one FFMA2 (gain pair x broadcast sample) per frame on the constant-gain path
@@ -1187,8 +1214,8 @@ uint32_t sh_frames_per_thread(uint32_t F) { return F <= 512 ? (uint32_t)kShK : (
 uint32_t sh_threads(uint32_t F) { const uint32_t K = sh_frames_per_thread(F); return ((F + K - 1) / K + 31) / 32 * 32; }
 bool sh_exact(uint32_t F) { return F == 256 || F == 512 || F == 1024; }     // the exact shapes (T = F / 4 = 64 / 128 / 256 math threads)
 int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_exact(F) ? (sh_self_shape((int)F / 4) ? kStagesSelf : kStagesShX) : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig)); }
-size_t mix_smem_bytes(uint32_t F, bool sh, bool room = false) {
-	const size_t st = (size_t)mix_stages(F, sh), rst = st + 2, kBatch = sh ? kBatchSh : kBatchPan;
+size_t mix_smem_bytes(uint32_t F, bool sh, bool room = false, int stages = 0) {
+	const size_t st = (size_t)(stages ? stages : mix_stages(F, sh)), rst = st + 2, kBatch = sh ? kBatchSh : kBatchPan;
 	return 512 + sizeof(MixRec) * rst * kBatch + (room ? sizeof(ReflSend) * rst * kBatch : 0) + (sh ? sizeof(ShGains) * rst * kBatch + sizeof(ShRamps) * st * kBatch : 0) +
 	       sizeof(float) * st * kBatch * window_slot(F);
 }
@@ -1203,9 +1230,9 @@ uint32_t pick_grid(uint32_t n, uint32_t max_grid) {
 // Launches one K2 kernel as a single wave: grid = SM count x resident CTAs per SM (never more than the sources warrant).
 template <class Kernel>
 int launch_one(Kernel kernel, const char* name, const MixArgs& a, uint32_t first, uint32_t n, uint32_t threads, bool sh,
-               uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
+               uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out, int stages = 0) {
 	const uint32_t F = a.frames;
-	const size_t smem = mix_smem_bytes(F, sh, a.rfl != nullptr);
+	const size_t smem = mix_smem_bytes(F, sh, a.rfl != nullptr, stages);
 	uint32_t wave;
 	int sm_count_now = 148;
 	{
@@ -1239,16 +1266,22 @@ template <int KF>
 int launch_stereo(const MixArgs& a, uint32_t max_grid, float* partials, cudaStream_t st, uint32_t* grid_out) {
 	const uint32_t threads = kPanWarps * 32 + 32;
 	if (a.rfl) {
-		if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true, true>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
-		return launch_one(k2_mix_stereo_kernel<KF, false, true>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+		if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true, true, kStagesPan>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+		return launch_one(k2_mix_stereo_kernel<KF, false, true, kStagesPan>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
 	}
-	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true, false>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
-	return launch_one(k2_mix_stereo_kernel<KF, false, false>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+	if (a.ready) {      // K1 is running beside this launch: the shape that leaves it room
+		if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true, false, kStagesPanOverlap>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out, kStagesPanOverlap);
+		return launch_one(k2_mix_stereo_kernel<KF, false, false, kStagesPanOverlap>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out, kStagesPanOverlap);
+	}
+	if (a.frames == 32u * KF) return launch_one(k2_mix_stereo_kernel<KF, true, false, kStagesPan>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
+	return launch_one(k2_mix_stereo_kernel<KF, false, false, kStagesPan>, "k2_mix_stereo", a, 0, a.n_pan, threads, false, max_grid, partials, st, grid_out);
 }
 
 }  // namespace
 
 namespace dev {
+
+int current_sm_count() { return sm_count(); }
 
 // Upper bound of the K2 grid (sizes the partial-bus scratch): SM count x the most CTAs that fit per SM.
 int num_mix_ctas(uint32_t frames, int sh) {

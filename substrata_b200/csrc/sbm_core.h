@@ -175,7 +175,11 @@ struct Globals {
 	uint32_t n_pan, n_sh;       // render-list lengths
 	uint32_t room;              // room effects enabled: sound objects also feed the reflections send
 	float refl_gain;            // ReflectionProperties::gain
+	uint32_t epoch;             // low 32 bits of buffer index + 1 (never 0): the value K1 stamps its finished tiles with
+	uint32_t overlap;           // K1 runs as a persistent grid beside the mix kernel and publishes SlotArrays::ready tile by tile
 };
+
+constexpr uint32_t kK1Tile = 128;       // render-list entries per K1 tile (one thread each)
 
 // Device-side flags / counters.
 struct DevFlags {
@@ -190,6 +194,7 @@ struct DevFlags {
 	unsigned long long algo_bytes;  // accounting: sum of 4*n_src over rendered sources
 	unsigned int n_rendered;
 	int peer_timeout;               // set by the gather kernel when a peer rank's bus did not arrive in time (reported and cleared by K4b)
+	int pipe_timeout;               // set by the mix kernel when K1's records of a tile did not appear in time (overlapped K1 / K2)
 	// K1 spreads its per-warp accounting atomics over kStatParts padded slots (same-address atomics serialise in L2;
 	// a block-wide reduction would hold every warp of a block until its slowest one is done); K4b folds them into the tail.
 	unsigned long long part_bytes[32][4];      // [part][0] used, rest = 32-byte padding
@@ -221,6 +226,7 @@ struct SlotArrays {
 	ShRamps* shr;               // indexed like rec
 	ReflSend* rfl;              // indexed like rec (room effects)
 	float* rgain;               // [slot] the reflections mixer's processor gain of the source
+	uint32_t* ready;            // [render-list index / kK1Tile] == Globals::epoch once K1 has written that tile's records
 	int* finished;              // list of public ids stopped by the feeder
 	int cstride;                // 2 or 16
 };
