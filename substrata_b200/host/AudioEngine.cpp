@@ -137,20 +137,37 @@ void AudioEngine::shutdown() {
 	}
 	if (engine) { sbm_destroy(engine); engine = nullptr; }          // delete resonance, AE.cpp:837
 	device_buffers.clear();
-	device_buffer_refs.clear();
+	buffers_of_handle.clear();
 	initialised = false;
 }
 
 // Uploads an AudioBuffer once; sources sharing it (sound_files cache, AE.h:122,253) share the device copy.
-int AudioEngine::deviceBufferFor(const AudioBufferRef& buf) {
-	auto it = device_buffers.find(buf.ptr());
-	if (it != device_buffers.end()) return it->second;
-	int id = -1;
-	const int rc = sbm_buffer_create(engine, buf->buffer.data(), buf->buffer.size(), &id);
-	if (rc != SBM_OK) throw glare::Exception(std::string("sbm_buffer_create failed: ") + sbm_last_error(engine));
-	device_buffers[buf.ptr()] = id;
-	device_buffer_refs.push_back(buf);
-	return id;
+int AudioEngine::deviceBufferFor(const AudioBufferRef& buf, int for_handle) {
+	DeviceBuffer& d = device_buffers[buf.ptr()];
+	if (d.id < 0) {
+		int id = -1;
+		const int rc = sbm_buffer_create(engine, buf->buffer.data(), buf->buffer.size(), &id);
+		if (rc != SBM_OK) { device_buffers.erase(buf.ptr()); throw glare::Exception(std::string("sbm_buffer_create failed: ") + sbm_last_error(engine)); }
+		d.id = id; d.keep = buf;
+	}
+	d.users++;
+	buffers_of_handle[for_handle].push_back(buf.ptr());
+	return d.id;
+}
+
+// A device source has gone (removeSource, or the feeder finished it): its buffers lose a user.
+void AudioEngine::releaseDeviceBuffersOf(int handle) {
+	auto f = buffers_of_handle.find(handle);
+	if (f == buffers_of_handle.end()) return;
+	for (const AudioBuffer* b : f->second) {
+		auto it = device_buffers.find(b);
+		if (it == device_buffers.end()) continue;
+		if (--it->second.users <= 0 && it->second.keep->getRefCount() == 1) {
+			sbm_buffer_destroy(engine, it->second.id);      // freed on the device once no submitted buffer can still read it
+			device_buffers.erase(it);
+		}
+	}
+	buffers_of_handle.erase(f);
 }
 
 // AE.cpp:848-876
@@ -179,14 +196,14 @@ void AudioEngine::createResonanceObAndResamplerForSource(AudioSource& source_) {
 	int rc = SBM_OK;
 	if (source->type == AudioSource::SourceType_NonStreaming) {
 		if (source->shared_buffer.isNull()) throw glare::Exception("AudioSource of type NonStreaming has no shared_buffer");
-		const int buf = deviceBufferFor(source->shared_buffer);
+		const int buf = deviceBufferFor(source->shared_buffer, id);
 		const uint64_t cur = source->cur_read_i;
 		const uint8_t looping = source->looping, rem = source->remove_on_finish;
 		rc = sbm_source_attach_buffer(engine, 1, &id, &buf, &cur, &source->sampling_rate, &looping, &rem);
 	} else if (!source->mix_sources.empty()) {
 		std::vector<int> bufs; std::vector<double> pos, delta; std::vector<float> mixf;
 		for (MixSource& m : source->mix_sources) {
-			bufs.push_back(deviceBufferFor(m.soundfile->buf));
+			bufs.push_back(deviceBufferFor(m.soundfile->buf, id));
 			pos.push_back(m.sound_file_i); delta.push_back(m.source_delta); mixf.push_back(m.mix_factor);
 		}
 		rc = sbm_source_attach_mix(engine, id, source->sampling_rate, (int)bufs.size(), bufs.data(), pos.data(), delta.data(), mixf.data());
@@ -198,6 +215,7 @@ void AudioEngine::createResonanceObAndResamplerForSource(AudioSource& source_) {
 	if (rc != SBM_OK) {
 		const std::string msg = sbm_last_error(engine);
 		sbm_source_destroy(engine, 1, &id);
+		releaseDeviceBuffersOf(id);
 		source->resonance_handle = INVALID_RESONANCE_HANDLE;
 		throw glare::Exception("attaching audio data to the source failed: " + msg);
 	}
@@ -227,6 +245,7 @@ void AudioEngine::removeSource(AudioSourceRef source) {
 	Lock lock(mutex);
 	if (source->resonance_handle != INVALID_RESONANCE_HANDLE) {
 		sbm_source_destroy(engine, 1, &source->resonance_handle);
+		releaseDeviceBuffersOf(source->resonance_handle);
 		source_of_handle.erase(source->resonance_handle);
 		source->resonance_handle = INVALID_RESONANCE_HANDLE;
 	}
@@ -436,6 +455,7 @@ void AudioEngine::seekToStartAndUnpauseAudio(AudioSource& source) {
 	// when there was none; re-creating is equivalent, the old one's filters start from silence either way after the seek).
 	if (source.resonance_handle != INVALID_RESONANCE_HANDLE) {
 		sbm_source_destroy(engine, 1, &source.resonance_handle);
+		releaseDeviceBuffersOf(source.resonance_handle);
 		source_of_handle.erase(source.resonance_handle);
 		source.resonance_handle = INVALID_RESONANCE_HANDLE;
 	}
@@ -528,6 +548,7 @@ bool AudioEngine::mixOneBuffer() {
 				if (f == source_of_handle.end()) continue;
 				AudioSourceRef s = f->second;
 				s->resonance_handle = INVALID_RESONANCE_HANDLE;
+				releaseDeviceBuffersOf(ids[i]);
 				active_audio_sources.erase(s);
 				if (s->remove_on_finish) audio_sources.erase(s);
 				source_of_handle.erase(f);

@@ -195,6 +195,7 @@ public:
 	// apply feeder bookkeeping (finished sources), push 2 * frames samples to the callback ring.  Returns false when
 	// nothing reached the mixer (nothing pushed), like FillInterleavedOutputBuffer.
 	bool mixOneBuffer();
+	size_t numDeviceBuffers() const { return device_buffers.size(); }   // AudioBuffers that currently have a device copy
 	// miniAudioCallBack (AudioEngine.cpp:191-226): pop, clamp to [-1, 1], zero-pad.
 	void fillOutputBuffer(float* output_buffer, size_t frame_count);
 	// Refreshes cur_read_i / EOF_marker_position / mix_sources[].sound_file_i of `source` from the device.
@@ -203,7 +204,7 @@ public:
 
 private:
 	void createResonanceObAndResamplerForSource(AudioSource& source);
-	int deviceBufferFor(const AudioBufferRef& buf);
+	int deviceBufferFor(const AudioBufferRef& buf, int for_handle);
 	void feedStreamingSource(AudioSource& source);
 	void mixThreadMain();
 
@@ -222,8 +223,13 @@ private:
 	std::vector<double> mixp_delta;
 	std::vector<float> mixp_factor;
 	int64 frames_mixed;
-	std::map<const AudioBuffer*, int> device_buffers;   // AudioBuffer -> sbm buffer id (the buffer is kept alive below)
-	std::vector<AudioBufferRef> device_buffer_refs;
+	// AudioBuffer -> its device copy.  `keep` holds the host buffer alive (so the key cannot be recycled for another buffer), `users` counts
+	// the live device sources reading it.  The device copy is dropped (sbm_buffer_destroy) when the last such source has gone AND nobody
+	// but this table still references the host buffer -- a SoundFile that stays in `sound_files` keeps its device copy for the next source.
+	struct DeviceBuffer { int id = -1; AudioBufferRef keep; int users = 0; };
+	std::map<const AudioBuffer*, DeviceBuffer> device_buffers;
+	std::map<int, std::vector<const AudioBuffer*> > buffers_of_handle;   // source handle -> the AudioBuffers it reads
+	void releaseDeviceBuffersOf(int handle);
 	std::map<int, AudioSourceRef> source_of_handle;
 	std::vector<float> temp_buf;
 	// this buffer's streaming feed, pushed to the device rings in one batched call (sbm_source_ring_push_batch)

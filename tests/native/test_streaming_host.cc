@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <limits>
 #include <vector>
 
 #include "AudioEngine.h"
@@ -149,6 +150,33 @@ int main() {
 	CHECK(engine.stream_to_source_map.size() == 2 && engine.stream_to_source_map.begin()->second.size() >= 1);
 	engine.removeSource(a2);
 	CHECK(engine.unpaused_streams.empty() && engine.stream_to_source_map.size() == 1);
+	// Device copies of AudioBuffers follow their users: a one-shot's private buffer goes with it (feeder-finished or removeSource), a
+	// buffer that something else still references (here `keep`, as `sound_files` would) stays for the next source.
+	{
+		const size_t base = engine.numDeviceBuffers();
+		AudioBufferRef keep = new AudioBuffer();
+		keep->buffer.resize(3 * F); for (size_t i = 0; i < keep->buffer.size(); ++i) keep->buffer[i] = 0.25f;
+		for (int round = 0; round < 2; ++round) {
+			AudioSourceRef one = new AudioSource();
+			one->type = AudioSource::SourceType_NonStreaming; one->looping = false; one->remove_on_finish = true;
+			one->shared_buffer = new AudioBuffer();
+			one->shared_buffer->buffer.resize(2 * F); for (size_t i = 0; i < one->shared_buffer->buffer.size(); ++i) one->shared_buffer->buffer[i] = 0.5f;
+			one->pos = Vec4f(1, 0, -2, 1);
+			AudioSourceRef cached = new AudioSource();
+			cached->type = AudioSource::SourceType_NonStreaming; cached->looping = true;
+			cached->shared_buffer = keep;
+			cached->pos = Vec4f(-1, 0, -2, 1);
+			engine.addSource(one); engine.addSource(cached);
+			CHECK(engine.numDeviceBuffers() == base + 2);
+			one->shared_buffer = AudioBufferRef();        // the source lets go of its own reference, as a finished one-shot's owner does
+			for (int b = 0; b < 4; ++b) engine.mixOneBuffer();      // 2 buffers of audio, then the feeder finishes it
+			CHECK(one->resonance_handle == std::numeric_limits<int>::max());      // INVALID_RESONANCE_HANDLE (AE.cpp:62)
+			CHECK(engine.numDeviceBuffers() == base + 1);         // the one-shot's buffer is gone, the cached one is not
+			engine.removeSource(cached);
+			CHECK(engine.numDeviceBuffers() == base + 1);         // still referenced by `keep`: kept for the next source
+		}
+		keep = AudioBufferRef();
+	}
 	const double err = rel_rms(got, want);
 	double energy = 0; for (float v : want) energy += (double)v * v;
 	printf("streaming host: %d buffers, rel_rms %.3g, energy %.3g, decoders %zu\n", NB, err, energy, made.size());
