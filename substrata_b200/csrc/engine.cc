@@ -21,6 +21,26 @@
 #include "../../include/sbm_audio.h"
 #include "device_api.h"
 
+// NVTX ranges around the host phases of a buffer (visible in Nsight Systems next to the kernels; no-ops without a tool attached).
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define SBM_HAVE_NVTX 1
+#endif
+#endif
+namespace {
+struct NvtxRange {
+#ifdef SBM_HAVE_NVTX
+	explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+#else
+	explicit NvtxRange(const char*) {}
+#endif
+	NvtxRange(const NvtxRange&) = delete;
+	NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace
+
 namespace sbm {
 const float* encoder_table();   // sh_table.cc
 }
@@ -996,6 +1016,7 @@ static void room_update_host(sbm_engine* e) {
 // latency hides behind the previous buffer's kernels -- the mixer thread of the reference also runs ahead of the device
 // callback (AudioEngine.cpp:540-545).
 static int upload_block_locked(sbm_engine* e, const SlotPatch** d_patches, const MixPatch** d_mix_patches) {
+	NvtxRange nvtx("sbm: upload block");
 	std::vector<SegPlan> plans;
 	plan_dirty(plans, e->dv_stat, e->h_stat, e->d_stat);
 	plan_dirty(plans, e->dv_posvol, e->h_posvol, e->d_posvol);
@@ -1057,6 +1078,7 @@ static int upload_block_locked(sbm_engine* e, const SlotPatch** d_patches, const
 }
 
 static int mix_begin_locked(sbm_engine* e) {
+	NvtxRange nvtx("sbm: mix begin (setters, upload, K1-K3)");
 	if (e->begun) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_begin called twice without sbm_mix_finish");
 	sbm_engine::InFlight& fl = e->fl[e->buffer_index & 1];
 	if (fl.pending) return fail(e, SBM_ERR_INVALID_ARG, "two buffers already in flight: call sbm_mix_collect first");
@@ -1115,6 +1137,7 @@ static int mix_begin_locked(sbm_engine* e) {
 
 // Enqueues the finish part of the buffer begun last; no host synchronisation.
 static int mix_enqueue_finish_locked(sbm_engine* e) {
+	NvtxRange nvtx("sbm: mix finish (exchange, room, K4, D2H)");
 	if (!e->begun) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_finish without sbm_mix_begin");
 	e->begun = false;
 	void* st = e->stream;
@@ -1154,6 +1177,7 @@ static int mix_enqueue_finish_locked(sbm_engine* e) {
 // Waits for the oldest buffer in flight -- with the engine lock RELEASED: source creation / destruction and ring pushes by
 // other threads go on meanwhile -- and hands it out.  `lk` holds e->mu on entry and on return.
 static int mix_collect_locked(sbm_engine* e, std::unique_lock<std::mutex>& lk, float* out_interleaved, int* out_valid) {
+	NvtxRange nvtx("sbm: mix collect (wait + copy out)");
 	sbm_engine::InFlight& fl = e->fl[e->collected & 1];
 	if (!fl.pending || fl.seq != e->collected) return fail(e, SBM_ERR_INVALID_ARG, "sbm_mix_collect: no buffer in flight");
 	void* st = e->stream;
