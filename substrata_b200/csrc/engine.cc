@@ -137,7 +137,7 @@ struct sbm_engine {
 	std::vector<int> patch_of_slot;          // slot -> index into patches, -1 = none pending
 	std::vector<MixPatch> mix_patches;
 	std::vector<RingInfo> rings;            // indexed by slot (storage == nullptr when not a ring source)
-	std::vector<uint32_t> list_pan, list_sh, list_ring;
+	std::vector<uint32_t> list_pan, list_sh, list_ring, list_mix_pan, list_mix_sh;     // list_mix_*: SrcStatic::mix_first per render-list entry (K1 hint)
 	bool lists_dirty = true;
 	std::vector<BufferInfo> buffers;
 	std::vector<int> finished_queue;
@@ -149,7 +149,7 @@ struct sbm_engine {
 	MixZ* dv_mixz = nullptr;
 	DevFlags* dv_flags = nullptr;
 	float* dv_table = nullptr;
-	uint32_t *dv_lists = nullptr, *dv_list_ring = nullptr;   // dv_lists: pan list followed by the ambisonic list
+	uint32_t *dv_lists = nullptr, *dv_list_ring = nullptr, *dv_list_mix = nullptr;   // dv_lists: pan list followed by the ambisonic list
 	float* dv_partials = nullptr; size_t partials_floats = 0;
 	float* dv_bus = nullptr; size_t bus_floats = 0;
 	float* dv_hrir = nullptr; float* dv_hist = nullptr; float* dv_dec = nullptr;
@@ -244,14 +244,28 @@ void add_patch(sbm_engine* e, const SlotPatch& p) {
 }
 
 void rebuild_lists(sbm_engine* e) {
-	e->list_pan.clear(); e->list_sh.clear(); e->list_ring.clear();
+	e->list_pan.clear(); e->list_sh.clear(); e->list_ring.clear(); e->list_mix_pan.clear(); e->list_mix_sh.clear();
 	for (uint32_t s = 0; s < e->n_slots; ++s) {
 		const SrcStatic& st = e->h_stat[s];
 		if (!(st.flags & kFlagAlive)) continue;
 		const uint32_t kind = (st.flags >> kFlagKindShift) & 0xff;
-		if (kind == kKindHrtf) e->list_sh.push_back(s); else e->list_pan.push_back(s);
+		const uint32_t mix = st.nz ? st.mix_first : 0xffffffffu;      // K1 requests the first MixZ together with the slot's state
+		if (kind == kKindHrtf) { e->list_sh.push_back(s); e->list_mix_sh.push_back(mix); } else { e->list_pan.push_back(s); e->list_mix_pan.push_back(mix); }
 		if (((st.flags >> kFlagFeedShift) & 3) == kFeedRing) e->list_ring.push_back(s);
 	}
+	// entry k of [pan list | ambisonic list] == slot k + base (one run of sources, nothing removed in between): K1 needs no list load
+	const size_t np = e->list_pan.size(), ns = e->list_sh.size();
+	bool ident = np + ns > 0;
+	const uint32_t base = np ? e->list_pan[0] : (ns ? e->list_sh[0] : 0u);
+	for (size_t k = 0; k < np && ident; ++k) ident = e->list_pan[k] == base + (uint32_t)k;
+	for (size_t k = 0; k < ns && ident; ++k) ident = e->list_sh[k] == base + (uint32_t)(np + k);
+	e->g.list_identity = ident ? 1u : 0u; e->g.list_base = base;
+	bool mident = np + ns > 0;
+	const uint32_t mbase = np ? e->list_mix_pan[0] : (ns ? e->list_mix_sh[0] : 0u);
+	if (mbase == 0xffffffffu) mident = false;
+	for (size_t k = 0; k < np && mident; ++k) mident = e->list_mix_pan[k] == mbase + (uint32_t)k;
+	for (size_t k = 0; k < ns && mident; ++k) mident = e->list_mix_sh[k] == mbase + (uint32_t)(np + k);
+	e->g.mix_identity = mident ? 1u : 0u; e->g.mix_base = mbase;
 	e->lists_dirty = false;
 }
 
@@ -467,12 +481,13 @@ SBM_API int sbm_create(const sbm_config* cfg, sbm_engine** out_engine) {
 	ok = ok && dalloc(A.live, cap) && dalloc(A.read_i, cap) && dalloc(A.eof, cap) && dalloc(A.rs, cap) && dalloc(A.dgain, cap) &&
 	     dalloc(A.occ_cur, cap) && dalloc(A.lpf_prev, cap) && dalloc(A.bits, cap) && dalloc(A.rec, cap) && dalloc(A.mrec, cap) && dalloc(A.rfl, cap) && dalloc(A.rgain, cap) && dalloc(A.ready, (size_t)cap / kK1Tile + 2) && dalloc(A.finished, 2 * (size_t)cap) &&
 	     dalloc(A.mix_pos, mixcap) && dalloc(A.mix_pos0, mixcap);
-	A.cstride = kNumSh;
+	A.cstride = (int)cap;      // cgain is quad-major: [kNumSh / 4][cap] x 16 bytes
 	ok = ok && dalloc(A.cgain, (size_t)cap * kNumSh);
 	const bool hrtf = cfg->sh_hrir != nullptr;
 	if (hrtf) ok = ok && dalloc(A.shg, cap) && dalloc(A.shr, cap); else { A.shg = nullptr; A.shr = nullptr; }
 	ok = ok && dalloc(e->dv_flags, 1) && dalloc(e->dv_table, (size_t)kTableAz * kTableEl * kShRaw);
-	ok = ok && dalloc(e->dv_lists, cap) && dalloc(e->dv_list_ring, cap);
+	ok = ok && dalloc(e->dv_lists, cap) && dalloc(e->dv_list_ring, cap) && dalloc(e->dv_list_mix, cap);
+	A.list_mix = e->dv_list_mix;
 	e->bus_floats = (size_t)kBusRows * F + 4;
 	ok = ok && dalloc(e->dv_bus, e->bus_floats);
 	e->partials_floats = dev::partials_floats(F);
@@ -517,7 +532,7 @@ SBM_API void sbm_destroy(sbm_engine* e) {
 	void* ptrs[] = {e->dv_stat, e->dv_posvol, e->dv_occl, e->dv_ring_write, e->dv_mixz, A.live, A.read_i, A.eof, A.rs, A.dgain, A.occ_cur,
 	                A.lpf_prev, A.bits, A.rec, A.mrec, A.rfl, A.rgain, A.ready, e->room.dv_params, e->room.dv_state, e->room.dv_delay, e->room.dv_foa, e->room.dv_hrir1,
 	                e->room.dv_hist1, e->room.dv_dec1, e->fl[0].dv_finished, A.mix_pos, A.mix_pos0, A.cgain, A.shg, A.shr, e->dv_flags,
-	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
+	                e->dv_table, e->dv_lists, e->dv_list_ring, e->dv_list_mix, e->dv_bus, e->dv_partials, e->dv_out, e->dv_hrir,
 	                e->dv_hist, e->dv_dec};
 	for (void* p : ptrs) if (p) dev::release(p);
 	for (auto& b : e->buffers) if (b.owned && b.dptr) dev::release(b.dptr);
@@ -1028,6 +1043,8 @@ static int upload_block_locked(sbm_engine* e, const SlotPatch** d_patches, const
 		// the render lists travel as plain contiguous segments
 		if (!e->list_pan.empty()) plans.push_back(SegPlan{e->dv_lists, (const unsigned char*)e->list_pan.data(), nullptr, 4, false, (uint32_t)e->list_pan.size(), 0});
 		if (!e->list_sh.empty()) plans.push_back(SegPlan{e->dv_lists + e->list_pan.size(), (const unsigned char*)e->list_sh.data(), nullptr, 4, false, (uint32_t)e->list_sh.size(), 0});
+		if (!e->list_mix_pan.empty()) plans.push_back(SegPlan{e->dv_list_mix, (const unsigned char*)e->list_mix_pan.data(), nullptr, 4, false, (uint32_t)e->list_mix_pan.size(), 0});
+		if (!e->list_mix_sh.empty()) plans.push_back(SegPlan{e->dv_list_mix + e->list_pan.size(), (const unsigned char*)e->list_mix_sh.data(), nullptr, 4, false, (uint32_t)e->list_mix_sh.size(), 0});
 		if (!e->list_ring.empty()) plans.push_back(SegPlan{e->dv_list_ring, (const unsigned char*)e->list_ring.data(), nullptr, 4, false, (uint32_t)e->list_ring.size(), 0});
 	}
 	if (e->room.run_this_buffer)      // this buffer's RoomParams -> the parity's device copy

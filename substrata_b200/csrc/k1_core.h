@@ -82,9 +82,14 @@ constexpr uint32_t kMaxMix1Window = 4096;
 // Returns kUsed* bits; *rendered_src = PCM samples a rendered source reads this buffer (0 when skipped / stopped).
 // `rec_out`, `shg_out`, `shr_out`: where this source's WorkRec / ShGains / ShRamps go (the arrays in HBM indexed by render-list
 // position, or -- fused kernel -- registers and the CTA's shared-memory rings).
-SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot, WorkRec* rec_out,
+// `mix_hint`: SrcStatic::mix_first of this slot as the render list knows it (SlotArrays::list_mix), or 0xffffffff.
+SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* flags, const float* table, uint32_t slot, uint32_t mix_hint, WorkRec* rec_out,
                               ShGains* shg_out, ShRamps* shr_out, ReflSend* rfl_out, uint32_t* rendered_src) {
 	*rendered_src = 0;
+	// (the first mix source's parameters and read head, requested together with the slot's state)
+	MixZ mz_hint; double pos_hint = 0.0;
+	mz_hint.pcm = nullptr; mz_hint.len = 0; mz_hint.delta = 0.0; mz_hint.mix_factor = 0.0f; mz_hint.pad = 0.0;
+	if (mix_hint != 0xffffffffu) { mz_hint = A.mixz[mix_hint]; pos_hint = A.mix_pos[mix_hint]; }
 	// All per-slot state is loaded up front, unconditionally: the loads are independent of each other, so the memory
 	// system sees them as one batch instead of a chain of dependent round trips behind the branches below.
 	const SrcStatic st = A.stat[slot];
@@ -103,7 +108,11 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	float rg = G.room ? A.rgain[slot] : 0.0f;
 	// stereo-pan bus gains (the first two of the slot's cstride floats), loaded with the rest: left where they are used,
 	// the compiler must keep them behind the state stores above them (possible aliasing) = one more DRAM round trip
-	const float cg_pan0 = A.cgain[(size_t)slot * (size_t)A.cstride], cg_pan1 = A.cgain[(size_t)slot * (size_t)A.cstride + 1];
+	// (quad-major layout: channels 4q .. 4q+3 of slot s are the F4 at cgain4[q * cstride + s], so a warp's slots are consecutive
+	// 16-byte elements; the pan gains are the first two floats of quad 0)
+	F4* cgain4 = reinterpret_cast<F4*>(A.cgain);
+	const F4 cg_q0 = cgain4[slot];
+	const float cg_pan0 = cg_q0.x, cg_pan1 = cg_q0.y;
 	WorkRec rec;
 	rec.pcm = st.pcm; rec.len = st.len; rec.start = 0; rec.n_src = 0; rec.avail = 0; rec.flags = kRecSkip;
 	rec.slot = slot; rec.x0_fx = 0; rec.step_fx = 0; rec.prev0 = 0.0f; rec.prev1 = 0.0f; rec.lpf_coef = 0.0f; rec.lpf_prev = 0.0f;
@@ -178,8 +187,9 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		bool fast = st.nz == 1;
 		for (uint32_t z = 0; z < st.nz; ++z) {
 			const uint32_t k = st.mix_first + z;
-			const MixZ mz = A.mixz[k];
-			const double p0 = A.mix_pos[k];
+			const bool hinted = z == 0 && mix_hint == st.mix_first;
+			const MixZ mz = hinted ? mz_hint : A.mixz[k];
+			const double p0 = hinted ? pos_hint : A.mix_pos[k];
 			A.mix_pos0[k] = p0;
 			// The reference adds delta n_src times in double; one fma differs by < n_src ulps of pos (continuous).
 			const double pend = fma((double)n_src, mz.delta, p0);
@@ -298,7 +308,6 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 	const bool chan_init = (bits & kBitMixExists) != 0;     // processors exist => already initialised by an ApplyGain
 	bits |= kBitMixExists | kBitMixActive;
 	A.bits[slot] = bits;
-	float* cg = A.cgain + (size_t)slot * (size_t)A.cstride;
 	if (!hrtf) {
 		float g[2];
 #if defined(__CUDA_ARCH__)
@@ -306,12 +315,14 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 #else
 		stereo_pan_gains(az, el, &g[0], &g[1]);
 #endif
+		float curs[2];
 		for (int c = 0; c < 2; ++c) {
 			float cur = c == 0 ? cg_pan0 : cg_pan1;
 			rec.ch[c] = plan_gain(&cur, chan_init, g[c], F, /*accumulate=*/true);
-			cg[c] = cur;
+			curs[c] = cur;
 			if (rec.ch[c].n) rec.ch_ramp_mask |= 1u << c;
 		}
+		cgain4[slot] = F4{curs[0], curs[1], cg_q0.z, cg_q0.w};
 	} else {
 		float g[kNumSh];
 		encoding_coeffs(table, az, el, g);
@@ -319,10 +330,10 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 		// effective constant gains leave as four 16-byte stores (read and written one float at a time, the 16 loads were
 		// 16 dependent round trips -- each sits behind the previous iteration's stores, which may alias as far as the compiler
 		// knows -- and the 4-byte stores of a warp scatter over 32 sectors each).
-		F4* cg4 = reinterpret_cast<F4*>(cg);                        // cstride == 16 floats: 64-byte aligned rows
 		F4* sg4 = reinterpret_cast<F4*>(shg_out->konst);
 		for (int q = 0; q < kNumSh / 4; ++q) {
-			const F4 v = cg4[q];
+			F4* cgq = cgain4 + (size_t)q * (size_t)A.cstride + slot;
+			const F4 v = q == 0 ? cg_q0 : *cgq;
 			float cur[4] = {v.x, v.y, v.z, v.w}, kon[4], stm[4], rin[4], rnf[4];
 			uint32_t gm = 0;
 			for (int j = 0; j < 4; ++j) {
@@ -338,7 +349,7 @@ SBM_HD uint32_t update_source(const Globals& G, const SlotArrays& A, DevFlags* f
 					if (d.n < F && d.konst != cur[j] && fabsf(cur[j]) > 1e-6f) rflags |= kRecRampCareful;
 				}
 			}
-			cg4[q] = F4{cur[0], cur[1], cur[2], cur[3]};
+			*cgq = F4{cur[0], cur[1], cur[2], cur[3]};
 			sg4[q] = F4{kon[0], kon[1], kon[2], kon[3]};
 			if (gm) {
 				// ramp parameters of the group, 16 bytes each (zeros for the channels of the group that do not ramp)

@@ -18,7 +18,7 @@ namespace sbm {
 #define SBM_K1_THREADS 128             // 64 .. 256 measure within 3 %; 512 is 5 % slower (one thread per source, latency-bound)
 #endif
 #ifndef SBM_K1_MINB
-#define SBM_K1_MINB (1024 / SBM_K1_THREADS)
+#define SBM_K1_MINB 6                  // 80 registers, no spills; K1 runs the same at 768 and 1024 resident threads (it is bound by its memory transactions)
 #endif
 // Overlapped mode (Globals::overlap; large stereo-bus scenes): the grid is PERSISTENT -- kK1OverlapCtas CTAs per SM, sized so that the
 // mix kernel's CTAs fit beside them -- and walks the render list tile by tile in the order the mix kernel consumes it (that kernel deals
@@ -30,9 +30,20 @@ constexpr int kK1OverlapCtas = 2;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 static_assert(SBM_K1_THREADS == (int)kK1Tile, "one thread per entry of a K1 tile");
 
-template <bool OVERLAP>
-__global__ void __launch_bounds__(SBM_K1_THREADS, SBM_K1_MINB) k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table,
+// Record stores.  One thread's 128-byte MixRec (or the 64 + 192 bytes of ShGains / ShRamps of an ambisonic source) written by that thread alone
+// is 8 (4 + 12) stores that each touch 32 different lines -- K1 was bound by those store transactions, not by its loads (it ran
+// the same at 768 and 1024 resident threads).  The records go to shared memory first and the WARP writes them out as consecutive
+// 16-byte stores (a warp's 32 list entries are 4 KB / 2 KB / 6 KB of contiguous global memory): 1 M panned sources 0.100 -> 0.083 ms.
+//   SH (the launch has ambisonic sources): a thread's staging slot is 272 bytes -- ShGains at 0, ShRamps at 64, padded so that the
+//   threads' 16-byte stores spread over the banks -- written by update_source itself, copied out, then reused for the MixRec.
+template <bool OVERLAP, bool SH>
+__global__ void __launch_bounds__(SBM_K1_THREADS, OVERLAP ? 8 : SBM_K1_MINB) k1_params_kernel(Globals g,      // (beside K2: 64 registers, or K2's CTAs do not fit) SlotArrays A, DevFlags* flags, const float* __restrict__ table,
                                                        const uint32_t* __restrict__ lists, uint32_t wslot) {
+	constexpr uint32_t kSlotBytes = SH ? 272u : 128u;
+	__shared__ __align__(16) unsigned char stage_raw[SBM_K1_THREADS * kSlotBytes];
+	unsigned char* wstage = stage_raw + (threadIdx.x >> 5) * 32u * kSlotBytes;      // this warp's staging region
+	const uint32_t lane = threadIdx.x & 31u;
+	const unsigned full = 0xffffffffu;
 	if (OVERLAP) grid_dep_launch_dependents();
 	const uint32_t n_list = g.n_pan + g.n_sh, n_tiles = (n_list + kK1Tile - 1) / kK1Tile;
 	// whether this buffer's "mixer used" flags are already set: read NOW, so that the loads overlap the work below instead
@@ -41,42 +52,92 @@ __global__ void __launch_bounds__(SBM_K1_THREADS, SBM_K1_MINB) k1_params_kernel(
 	// Persistent grid: few threads per SM, so the chain  list entry -> slot -> a dozen per-slot arrays  is taken off the critical path by
 	// software: the list entry is read two tiles ahead and the slot's lines are prefetched into L2 one tile ahead.
 	const uint32_t stride = OVERLAP ? gridDim.x * kK1Tile : 0u;
-	uint32_t k0 = blockIdx.x * kK1Tile + threadIdx.x;
-	uint32_t slot_cur = k0 < n_list ? lists[k0] : 0u, slot_n1 = 0u;
-	if (OVERLAP && k0 + stride < n_list) slot_n1 = lists[k0 + stride];
-	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += OVERLAP ? gridDim.x : n_tiles) {      // (classic: one tile per CTA)
+	// Classic mode walks the list BACK TO FRONT (CTAs are dispatched in index order): the records written last are the ones the mix kernel
+	// reads first, so the head of the list is still in L2 when it starts.
+	const uint32_t tile0 = OVERLAP ? blockIdx.x : n_tiles - 1u - blockIdx.x;
+	uint32_t k0 = tile0 * kK1Tile + threadIdx.x;
+	const bool ident = g.list_identity != 0;
+	uint32_t slot_cur = k0 < n_list ? (ident ? k0 + g.list_base : lists[k0]) : 0u, slot_n1 = 0u;
+	if (OVERLAP && k0 + stride < n_list) slot_n1 = ident ? k0 + stride + g.list_base : lists[k0 + stride];
+	for (uint32_t tile = tile0; tile < n_tiles; tile += OVERLAP ? gridDim.x : n_tiles) {      // (classic: one tile per CTA)
 		const uint32_t k = tile * kK1Tile + threadIdx.x;    // position in the render lists
+		const uint32_t kw = tile * kK1Tile + (threadIdx.x & ~31u);     // first list entry of this warp
 		uint32_t used = 0, n_src = 0;
 		uint32_t slot_n2 = 0u;
 		if (OVERLAP) {
-			if (k + 2u * stride < n_list) slot_n2 = lists[k + 2u * stride];
+			if (k + 2u * stride < n_list) slot_n2 = ident ? k + 2u * stride + g.list_base : lists[k + 2u * stride];
 			if (k + stride < n_list) {
 				const uint32_t sn = slot_n1;
 				prefetch_l2(A.stat + sn); prefetch_l2(A.posvol + sn); prefetch_l2(A.occl + sn); prefetch_l2(A.live + sn); prefetch_l2(A.read_i + sn);
 				prefetch_l2(A.eof + sn); prefetch_l2(A.rs + sn); prefetch_l2(A.dgain + sn); prefetch_l2(A.occ_cur + sn); prefetch_l2(A.lpf_prev + sn);
-				prefetch_l2(A.bits + sn); prefetch_l2(A.cgain + (size_t)sn * (size_t)A.cstride);
+				prefetch_l2(A.bits + sn); prefetch_l2(A.cgain + (size_t)sn * 4u);
 			}
 		}
-		if (k < n_list) {
+		const bool valid = k < n_list;
+		MixRec m;
+		bool sh_ramps = false;
+		if (valid) {
 			WorkRec rec;
 			ReflSend rfl;
 			rfl.konst = 0.0f; rfl.start = 0.0f; rfl.inc = 0.0f; rfl.n = 0;
-			used = update_source(g, A, flags, table, slot_cur, &rec, A.shg + k, A.shr + k, &rfl, &n_src);
+			const uint32_t mix_hint = g.mix_identity ? k + g.mix_base : (A.list_mix ? A.list_mix[k] : 0xffffffffu);
+			ShGains* shg_dst = SH ? reinterpret_cast<ShGains*>(wstage + lane * kSlotBytes) : A.shg + k;
+			ShRamps* shr_dst = SH ? reinterpret_cast<ShRamps*>(wstage + lane * kSlotBytes + 64u) : A.shr + k;
+			used = update_source(g, A, flags, table, slot_cur, mix_hint, &rec, shg_dst, shr_dst, &rfl, &n_src);
+			sh_ramps = (rec.flags & kRecHrtf) && rec.ch_ramp_mask != 0;
 			// the record the mix kernel consumes, in final form (k2_rec.h); the full WorkRec only where a careful path will read it back
-			MixRec m = make_mixrec(rec, wslot, k >= g.n_pan);
+			m = make_mixrec(rec, wslot, k >= g.n_pan);
 			if (g.room) {
 				// a ramping reflections send needs the per-frame gain path like any other ramp
 				A.rfl[k] = rfl;
 				if (rfl.n && !(m.mode & kMdSkip)) { if (rfl.n > m.nramp) m.nramp = rfl.n; m.mode |= kMdRamp; }
 			}
-			A.mrec[k] = m;
 			if (mixrec_needs_workrec(m.mode)) A.rec[k] = rec;
+		}
+		if (SH) {
+			// the warp's ShGains (4 chunks of 16 bytes per entry) and, for the entries with channel ramps, ShRamps (12 chunks)
+			__syncwarp();
+			const unsigned m_sh = __ballot_sync(full, valid && k >= g.n_pan), m_rp = __ballot_sync(full, sh_ramps);
+			if (m_sh) {
+				uint4* gg = reinterpret_cast<uint4*>(A.shg + kw);
+#pragma unroll
+				for (uint32_t i = 0; i < 4; ++i) {
+					const uint32_t idx = i * 32u + lane, r = idx >> 2, c = idx & 3u;
+					if ((m_sh >> r) & 1u) gg[idx] = *reinterpret_cast<const uint4*>(wstage + r * kSlotBytes + c * 16u);
+				}
+			}
+			if (m_rp) {
+				uint4* gr = reinterpret_cast<uint4*>(A.shr + kw);
+#pragma unroll
+				for (uint32_t i = 0; i < 12; ++i) {
+					const uint32_t idx = i * 32u + lane, r = idx / 12u, c = idx - r * 12u;
+					if ((m_rp >> r) & 1u) gr[idx] = *reinterpret_cast<const uint4*>(wstage + r * kSlotBytes + 64u + c * 16u);
+				}
+			}
+			__syncwarp();      // the region is reused for the MixRecs
+		}
+		{
+			// MixRec: 16-byte chunks swizzled by lane on the way in (4 wavefronts per store instead of 32), consecutive on the way out
+			uint4* my = reinterpret_cast<uint4*>(wstage);
+			if (valid) {
+				uint4 mv[8];
+				__builtin_memcpy(mv, &m, sizeof(MixRec));
+#pragma unroll
+				for (uint32_t j = 0; j < 8; ++j) my[lane * 8u + (j ^ (lane & 7u))] = mv[j];
+			}
+			__syncwarp();
+			uint4* gw = reinterpret_cast<uint4*>(A.mrec + kw);
+#pragma unroll
+			for (uint32_t i = 0; i < 8; ++i) {
+				const uint32_t idx = i * 32u + lane, r = idx >> 3, c = idx & 7u;
+				if (kw + r < n_list) gw[idx] = my[r * 8u + (c ^ (r & 7u))];
+			}
+			if (OVERLAP || SH) __syncwarp();      // (the stage is reused: by the next tile of a persistent grid)
 		}
 		// Warp-level reduction of the "mixer used" bits and the accounting counters, then one lane publishes.  The flags are
 		// the same few words for the whole grid and same-address atomics serialise in L2 (one set per warp on ONE address cost
 		// ~100 us per million sources): a flag is only OR-ed by the warps that started while it still read 0, and the counters go to one of kStatParts
 		// padded slots chosen by the block index (K4b sums them).  No block-wide barrier (classic mode): a finished warp leaves the SM.
-		const unsigned full = 0xffffffffu;
 		uint32_t u = used;
 		unsigned long long bytes = n_src ? 4ull * n_src : 0ull;
 		uint32_t rendered = n_src ? 1u : 0u;
@@ -159,12 +220,13 @@ int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const 
 		cudaGetDevice(&device);
 		const unsigned long long bit = 1ull << (device & 63);
 		if (!(configured.load(std::memory_order_acquire) & bit)) {
-			if (check(cudaFuncSetAttribute(k1_params_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(k1 carveout)")) return -1;
+			if (check(cudaFuncSetAttribute(k1_params_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute(k1 carveout)")) return -1;
 			configured.fetch_or(bit, std::memory_order_release);
 		}
 	}
-	if (g.overlap) k1_params_kernel<true><<<grid, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
-	else k1_params_kernel<false><<<grid, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
+	if (g.overlap) k1_params_kernel<true, false><<<grid, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
+	else if (g.n_sh) k1_params_kernel<false, true><<<grid, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
+	else k1_params_kernel<false, false><<<grid, SBM_K1_THREADS, 0, (cudaStream_t)stream>>>(g, A, flags, table, lists, window_slot(g.frames));
 	note_launch();
 	return check_launch("k1_params");
 }

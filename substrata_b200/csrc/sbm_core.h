@@ -175,6 +175,10 @@ struct Globals {
 	uint32_t n_pan, n_sh;       // render-list lengths
 	uint32_t room;              // room effects enabled: sound objects also feed the reflections send
 	float refl_gain;            // ReflectionProperties::gain
+	uint32_t list_identity;     // render-list entry k is slot k + list_base (sources created in one run, none removed): K1 skips the list load
+	uint32_t list_base;
+	uint32_t mix_identity;      // ... and its first mix source is MixZ k + mix_base (every listed source has mix sources, allocated in one run)
+	uint32_t mix_base;
 	uint32_t epoch;             // low 32 bits of buffer index + 1 (never 0): the value K1 stamps its finished tiles with
 	uint32_t overlap;           // K1 runs as a persistent grid beside the mix kernel and publishes SlotArrays::ready tile by tile
 };
@@ -215,7 +219,7 @@ struct SlotArrays {
 	float* dgain;               // GainNode current gain
 	float* occ_cur;
 	float* lpf_prev;
-	float* cgain;               // [slot][cstride] GainMixer processor gains
+	float* cgain;               // GainMixer processor gains, quad-major: channels 4q .. 4q+3 of slot s = 16 bytes at float index 4 * (q * cstride + s)
 	uint8_t* bits;              // bit0 direct-gain initialised, bit1 mixer processors exist, bit2 active
 	const MixZ* mixz;
 	double* mix_pos;
@@ -227,8 +231,10 @@ struct SlotArrays {
 	ReflSend* rfl;              // indexed like rec (room effects)
 	float* rgain;               // [slot] the reflections mixer's processor gain of the source
 	uint32_t* ready;            // [render-list index / kK1Tile] == Globals::epoch once K1 has written that tile's records
+	const uint32_t* list_mix;   // [render-list index] SrcStatic::mix_first of the entry's slot (0xffffffff: no mix sources): lets K1 fetch the
+	                            // first MixZ and read head together with the slot's state instead of one dependent round trip later
 	int* finished;              // list of public ids stopped by the feeder
-	int cstride;                // 2 or 16
+	int cstride;                // slots per quad plane of cgain (= the engine's slot capacity)
 };
 
 constexpr uint8_t kBitDirectInit = 1, kBitMixExists = 2, kBitMixActive = 4, kBitReflExists = 8, kBitReflActive = 16;

@@ -78,7 +78,8 @@ int launch_params(const Globals& g, const SlotArrays& A, DevFlags* flags, const 
 	for (uint32_t k = 0; k < g.n_pan + g.n_sh; ++k) {
 		uint32_t n_src = 0;
 		ReflSend rfl; rfl.konst = 0.0f; rfl.start = 0.0f; rfl.inc = 0.0f; rfl.n = 0;
-		used |= update_source(g, A, flags, table, lists[k], &A.rec[k], A.shg ? A.shg + k : nullptr, A.shr ? A.shr + k : nullptr, &rfl, &n_src);
+		const uint32_t slot = g.list_identity ? k + g.list_base : lists[k];
+		used |= update_source(g, A, flags, table, slot, g.mix_identity ? k + g.mix_base : (A.list_mix ? A.list_mix[k] : 0xffffffffu), &A.rec[k], A.shg ? A.shg + k : nullptr, A.shr ? A.shr + k : nullptr, &rfl, &n_src);
 		if (g.room) A.rfl[k] = rfl;
 		if (n_src) { flags->algo_bytes += 4ull * n_src; flags->n_rendered++; }
 	}
