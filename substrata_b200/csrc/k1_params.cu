@@ -37,7 +37,7 @@ static_assert(SBM_K1_THREADS == (int)kK1Tile, "one thread per entry of a K1 tile
 //   SH (the launch has ambisonic sources): a thread's staging slot is 272 bytes -- ShGains at 0, ShRamps at 64, padded so that the
 //   threads' 16-byte stores spread over the banks -- written by update_source itself, copied out, then reused for the MixRec.
 template <bool OVERLAP, bool SH>
-__global__ void __launch_bounds__(SBM_K1_THREADS, OVERLAP ? 8 : SBM_K1_MINB) k1_params_kernel(Globals g,      // (beside K2: 64 registers, or K2's CTAs do not fit) SlotArrays A, DevFlags* flags, const float* __restrict__ table,
+__global__ void __launch_bounds__(SBM_K1_THREADS, OVERLAP ? 8 : SBM_K1_MINB) /* beside K2: 64 registers, or K2's CTAs do not fit */ k1_params_kernel(Globals g, SlotArrays A, DevFlags* flags, const float* __restrict__ table,
                                                        const uint32_t* __restrict__ lists, uint32_t wslot) {
 	constexpr uint32_t kSlotBytes = SH ? 272u : 128u;
 	__shared__ __align__(16) unsigned char stage_raw[SBM_K1_THREADS * kSlotBytes];
