@@ -72,7 +72,15 @@ namespace {
 // Sources per pipeline stage.  The producer warp plans one source per LANE, so its (latency-bound, serial) cost per batch
 // is the same for 4 or 8 sources: the stereo kernel, whose math warps take a source each, uses batches of 8 (two rounds
 // of its four warps) to halve the producer's cost per source -- it was the producer, not HBM, the math warps waited for.
-constexpr int kBatchSh = 4, kBatchPan = SBM_BATCH_PAN, kPanWarps = 4;
+#ifndef SBM_BATCH_SH
+#define SBM_BATCH_SH 4
+#endif
+#ifndef SBM_BATCH_SH_BIG
+#define SBM_BATCH_SH_BIG 8            // sources per stage of the 1024-frame ambisonic shape.  It is alone on its SM (one issue warp, eight math warps): the per-batch
+#endif                                // costs -- the issue warp's serial chain, the math warps' barrier round trip and record scan -- are amortised over twice the
+                                      // sources: 0.150 -> 0.137 ms per 65 536 sources (0.108 -> 0.084 with the ramp fix-ups compiled out).  The 512-frame shape
+                                      // (three CTAs per SM) measures the same with 4 and 8
+constexpr int kBatchSh = SBM_BATCH_SH, kBatchPan = SBM_BATCH_PAN, kPanWarps = 4;
 // Window stages in flight per CTA (batches of kBatch sources); the record ring is two batches deeper.
 #ifndef SBM_STAGES_SH
 #define SBM_STAGES_SH 4
@@ -292,13 +300,18 @@ __device__ void issue_warp(const SmemView<NCH, kStages, kBatch>& sm, const MixAr
 			if (NCH == 16) want_ramps = (m.mode & (kMdShRamp | kMdSkip)) == kMdShRamp;
 		}
 		const uint32_t seg1 = pl.w & 0xffffu, seg2 = pl.w >> 16;
-		uint32_t bytes = 4u * (seg1 + seg2) + (want_ramps ? (uint32_t)sizeof(ShRamps) : 0u);
+		uint32_t bytes = 4u * (seg1 + seg2);
 		for (int o = kBatch / 2; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+		// channel ramps: ONE copy for the batch's ShRamps when any of its sources has some (the entries of sources without ramps are
+		// stale and never read) -- a copy per source costs this warp ~12 serial instructions each
+		const bool any_ramps = NCH == 16 && __ballot_sync(0xffffffffu, want_ramps) != 0u;
+		if (any_ramps) bytes += nb * (uint32_t)sizeof(ShRamps);
 		issue_recs(jb + 2, q2, ph_2 ^ 1u);
 		if (jb >= (uint32_t)kStages) mbar_wait_relaxed(&hdr->empty_w[qw], ph_w ^ 1u);
 		__syncwarp();
 		if (lane == 0) {
 			if (bytes) mbar_expect_tx(&hdr->full_w[qw], bytes); else mbar_arrive(&hdr->full_w[qw]);
+			if (any_ramps) bulk_g2s(sm.shrs + qw * kBatch, a.shr + b0, nb * (uint32_t)sizeof(ShRamps), &hdr->full_w[qw]);
 		}
 		__syncwarp();
 		if (seg1) {
@@ -307,7 +320,6 @@ __device__ void issue_warp(const SmemView<NCH, kStages, kBatch>& sm, const MixAr
 			bulk_g2s(dst, pcm + pl.z, 4u * seg1, &hdr->full_w[qw]);
 			if (seg2) bulk_g2s(dst + seg1, pcm, 4u * seg2, &hdr->full_w[qw]);
 		}
-		if (NCH == 16 && want_ramps) bulk_g2s(sm.shrs + qw * kBatch + lane, a.shr + (b0 + lane), (uint32_t)sizeof(ShRamps), &hdr->full_w[qw]);
 		__syncwarp();
 		if (++qr == (uint32_t)kRecStages) { qr = 0; ph_r ^= 1u; }
 		if (++qw == (uint32_t)kStages) { qw = 0; ph_w ^= 1u; }
@@ -685,13 +697,13 @@ constexpr int kShK = 4, kShBigK = SBM_SH_BIG_K, kShBigT = 1024 / kShBigK, kShBig
 // the CTA's slice; the groups share the producer warp and its rings.  Where the register file leaves room for only one CTA
 // per SM (frames > 512: 256 math threads x ~120 registers), two groups overlap each other's barrier waits and dependent
 // chains the way two resident CTAs would.
-template <int TMAX, int K, int G, bool EXACT, bool SELF, int kStages, bool ROOM>     // TMAX math threads x K frames each; EXACT: frames == K * TMAX, no per-frame
-                                                                          // bounds checks; SELF: self-service rings (no issue warp; implies EXACT, G == 1);
-                                                                          // ROOM: a 17th accumulator row = the reflections send (room effects)
+template <int TMAX, int K, int G, bool EXACT, bool SELF, int kStages, bool ROOM, int kBatch = kBatchSh>     // TMAX math threads x K frames each; EXACT: frames == K * TMAX,
+                                                                          // no per-frame bounds checks; SELF: self-service rings (no issue warp; implies EXACT, G == 1);
+                                                                          // ROOM: a 17th accumulator row = the reflections send (room effects); kBatch: sources per stage
 __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
 	constexpr int NCH = 16;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	constexpr int kRecStages = kStages + 2, kBatch = kBatchSh;
+	constexpr int kRecStages = kStages + 2;
 	const SmemView<16, kStages, kBatch> sm(smem_raw, ROOM);
 	MixSmemHdr* hdr = sm.hdr;
 	// blockDim.x = T math threads (+ one issue warp, the last warp, unless SELF)
@@ -764,8 +776,13 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 		}
 	};
 
+	uint32_t qr_c = 0, qw_c = 0, ph_c = 0;     // (G == 1: running counters instead of two divisions per batch)
 	for (uint32_t jb = grp; jb < nbatch; jb += G) {     // this group's batches
-		const uint32_t qr = jb % kRecStages, qw = jb % kStages, ph_w = (jb / kStages) & 1u;     // record slot / window stage of batch jb, parity of its full_w
+		const uint32_t qr = G == 1 ? qr_c : jb % kRecStages, qw = G == 1 ? qw_c : jb % kStages, ph_w = G == 1 ? ph_c : (jb / kStages) & 1u;     // record slot / window stage of batch jb, parity of its full_w
+		if (G == 1) {
+			if (++qr_c == (uint32_t)kRecStages) qr_c = 0;
+			if (++qw_c == (uint32_t)kStages) { qw_c = 0; ph_c ^= 1u; }
+		}
 		mbar_wait(&hdr->full_w[qw], ph_w);
 		const uint32_t b0 = s0 + SBM_GLOBAL_BATCH(jb) * kBatch;
 		const uint32_t nb = s1 - b0 < (uint32_t)kBatch ? s1 - b0 : (uint32_t)kBatch;
@@ -781,12 +798,13 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 		//      konst * (y(i) - y_const) for a ramping direct gain.
 		bool batch_done = false;
 		if (EXACT && nb == (uint32_t)kBatch) {
-			uint32_t any = 0, ramps = 0;
+			uint32_t any = 0, ramps = 0, nr_max = 0;
 #pragma unroll
 			for (int b = 0; b < kBatch; ++b) {
 				const uint2 mn = *reinterpret_cast<const uint2*>(&mrs[b]);     // {mode, nramp}
 				any |= mn.x & ~(kMdInterp | kMdRamp | kMdShRamp);
 				ramps |= mn.x;
+				nr_max = mn.y > nr_max ? mn.y : nr_max;     // the batch's longest ramp (nramp is 0 for a source without ramps)
 			}
 			if (any == 0) {
 				// this thread's K samples of source b, before any gain
@@ -839,7 +857,7 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 							}
 						}
 						// frame F - 1 = t + (K - 1) T of thread T - 1: the bypassed occlusion filter's memory (mono_pole_filter.cc:40-44)
-						if (t == T - 1) a.lpf_prev[mrs[b].slot] = yy[K - 1].x;
+						if (warp_i0 == T - 32u) { if (lane == 31u) a.lpf_prev[mrs[b].slot] = yy[K - 1].x; }     // (warp-uniform test first: only the last chunk's warp looks)
 						if (ROOM) {
 							// the reflections send: the raw sample (mix factor applied) through the send gain's constant part
 							const float gr = sm.rfls[qr * kBatch + b].konst * mrs[b].mfx;
@@ -848,7 +866,7 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 						}
 					}
 				}
-				if (ramps & kMdRamp) {
+				if (nr_max > warp_i0) {     // (a warp whose frames lie beyond every ramp of the batch does not even look at the sources)
 #pragma unroll 1
 					for (int b = 0; b < kBatch; ++b) {
 						const MixRec& m = mrs[b];
@@ -1063,13 +1081,21 @@ __device__ __forceinline__ void ambisonic_body(const MixArgs& a, uint32_t first,
 #ifndef SBM_SH_SELF_MASK
 #define SBM_SH_SELF_MASK 64           // OR of the T values that use the self-service form (A/B: 64 | 128 | 256)
 #endif
-constexpr int kStagesSelf = SBM_STAGES_SELF, kStagesShX = 6;
+#ifndef SBM_STAGES_SHX
+#define SBM_STAGES_SHX 6
+#endif
+#ifndef SBM_STAGES_SHX_BIG
+#define SBM_STAGES_SHX_BIG 3          // (x 8 sources per stage: the bytes in flight of 6 stages of 4)
+#endif
+constexpr int kStagesSelf = SBM_STAGES_SELF, kStagesShX = SBM_STAGES_SHX;
 __host__ __device__ constexpr bool sh_self_shape(int T) { return (SBM_SH_SELF_MASK & T) != 0; }
+// sources per stage / window stages of the exact shape with T math threads
+__host__ __device__ constexpr int shx_batch(int T) { return T == 256 && !sh_self_shape(T) ? SBM_BATCH_SH_BIG : kBatchSh; }
+__host__ __device__ constexpr int shx_stages(int T) { return sh_self_shape(T) ? kStagesSelf : (T == 256 ? SBM_STAGES_SHX_BIG : kStagesShX); }
 template <int TMAX, bool ROOM>
 __global__ void __launch_bounds__(TMAX + (sh_self_shape(TMAX) ? 0 : 32), sh_self_shape(TMAX) ? 512 / TMAX : (TMAX == 256 ? 1 : (TMAX == 128 ? 3 : 5)))
 k2_mix_ambisonic_x_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
-	constexpr bool kSelf = (SBM_SH_SELF_MASK & TMAX) != 0;
-	ambisonic_body<TMAX, kShK, 1, true, kSelf, kSelf ? kStagesSelf : kStagesShX, ROOM>(a, first, n, wslot, partials);
+	ambisonic_body<TMAX, kShK, 1, true, sh_self_shape(TMAX), shx_stages(TMAX), ROOM, shx_batch(TMAX)>(a, first, n, wslot, partials);
 }
 template <bool ROOM>
 __global__ void __launch_bounds__(128 + 32, 3) k2_mix_ambisonic_kernel(MixArgs a, uint32_t first, uint32_t n, uint32_t wslot, float* __restrict__ partials) {
@@ -1213,9 +1239,9 @@ int sm_count() {
 uint32_t sh_frames_per_thread(uint32_t F) { return F <= 512 ? (uint32_t)kShK : (uint32_t)kShBigK; }
 uint32_t sh_threads(uint32_t F) { const uint32_t K = sh_frames_per_thread(F); return ((F + K - 1) / K + 31) / 32 * 32; }
 bool sh_exact(uint32_t F) { return F == 256 || F == 512 || F == 1024; }     // the exact shapes (T = F / 4 = 64 / 128 / 256 math threads)
-int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_exact(F) ? (sh_self_shape((int)F / 4) ? kStagesSelf : kStagesShX) : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig)); }
+int mix_stages(uint32_t F, bool sh) { return !sh ? kStagesPan : (sh_exact(F) ? shx_stages((int)F / 4) : (sh_threads(F) <= 128 ? kStagesSh : kStagesShBig)); }
 size_t mix_smem_bytes(uint32_t F, bool sh, bool room = false, int stages = 0) {
-	const size_t st = (size_t)(stages ? stages : mix_stages(F, sh)), rst = st + 2, kBatch = sh ? kBatchSh : kBatchPan;
+	const size_t st = (size_t)(stages ? stages : mix_stages(F, sh)), rst = st + 2, kBatch = sh ? (size_t)(sh_exact(F) ? shx_batch((int)F / 4) : kBatchSh) : kBatchPan;
 	return 512 + sizeof(MixRec) * rst * kBatch + (room ? sizeof(ReflSend) * rst * kBatch : 0) + (sh ? sizeof(ShGains) * rst * kBatch + sizeof(ShRamps) * st * kBatch : 0) +
 	       sizeof(float) * st * kBatch * window_slot(F);
 }
