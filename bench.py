@@ -520,7 +520,16 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
             block_ms = [float(x) for x in tt.tolist()]
         K = steps * blocks
         med = statistics.median(block_ms)
-        return dict(ms=med / steps, block_ms_per_step=[round(x / steps, 5) for x in block_ms], k1=acc["k1"] / K, k2=acc["k2"] / K, k3=acc["k3"] / K,
+        per_rank = None
+        if world > 1:
+            # every rank's own K1 / K2 / tail: the buffer ends with all ranks waiting for the slowest one's K3 (the exchange), so the
+            # step is the SLOWEST rank's K1 + K2 -- and the faster ranks' wait shows up in their "tail"
+            mine = torch.tensor([acc["k1"] / K, acc["k2"] / K, acc["k3"] / K], device="cuda:%d" % local_rank, dtype=torch.float64)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = {"k1_params": [round(float(t[0]), 5) for t in allr], "k2_mix": [round(float(t[1]), 5) for t in allr],
+                        "k3_reduce+exchange(wait)+k4_finish": [round(float(t[2]), 5) for t in allr]}
+        return dict(ms=med / steps, per_rank=per_rank, block_ms_per_step=[round(x / steps, 5) for x in block_ms], k1=acc["k1"] / K, k2=acc["k2"] / K, k3=acc["k3"] / K,
                     algo=acc["algo"] / K, rendered=acc["rendered"] / K, h2d=acc["h2d"] / K, d2h=acc["d2h"] / K,
                     launches=(en.stats()["kernel_launches"] - l0) * steps // max(1, args.warmup + K), next_step=s)
 
@@ -579,7 +588,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
         tot = n_s * world
         strong = {"scaling": "strong", "sources_total": tot, "sources_per_gpu": n_s, "value": tot * F / (rs["ms"] * 1e-3), "unit": UNIT, "ms_per_step": rs["ms"],
                   "e2e_value": tot * F / (rs_e["ms"] * 1e-3), "e2e_ms_per_step": rs_e["ms"], "block_ms_per_step": rs["block_ms_per_step"],
-                  "kernels_ms": {"k1_params": rs["k1"], "k2_mix": rs["k2"], "k3_reduce+exchange+k4_finish": rs["k3"]},
+                  "kernels_ms": {"k1_params": rs["k1"], "k2_mix": rs["k2"], "k3_reduce+exchange+k4_finish": rs["k3"]}, "per_rank_kernels_ms": rs["per_rank"],
                   "what": "BASELINE config 4 as written: the first %d sources of every rank's set, %d in total; speed-up = this value / the 1-GPU line's value (same 1 048 576 sources)" % (n_s, tot)}
         eng_s.close()
 
@@ -629,7 +638,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "k2_mix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak if achieved else None) if not l2_resident else None, "l2_resident": l2_resident,
                          "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": res["k2"], "peak_source": peak_src,
-                         "other_kernels_ms": {"k1_params": res["k1"], "k3_reduce+collective+k4_finish": res["k3"]},
+                         "other_kernels_ms": {"k1_params": res["k1"], "k3_reduce+collective+k4_finish": res["k3"]}, "per_rank_kernels_ms": res["per_rank"],
                          "whole_step": {"achieved": algo_bytes / (res["ms"] * 1e-3) / 1e9, "frac": (algo_bytes / (res["ms"] * 1e-3) / 1e9 / peak) if not l2_resident else None,
                                         "what": "the same algorithmic bytes over the whole buffer time (K1 + K2 + K3 + K4 + launch gaps)"}},
             "clocks": clk,

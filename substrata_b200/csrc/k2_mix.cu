@@ -1142,38 +1142,44 @@ __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* _
 	}
 	warp_sum[w][lane] = s;
 	__syncthreads();
-	// multi-GPU: this rank's slot in rank p's gather area
-	const size_t slot_off = ((size_t)pa.parity * pa.world + pa.rank) * bus_floats;
 	if (w == 0 && f < F) {
 		float t = warp_sum[0][lane];
 #pragma unroll
 		for (int q = 1; q < (int)kK3Warps; ++q) t += warp_sum[q][lane];
 		bus[(size_t)row * F + f] = t;
-		for (uint32_t p = 0; p < pa.world; ++p) pa.gather[p][slot_off + (size_t)row * F + f] = t;     // NVLink peer stores (local for p == rank)
 	}
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-		float bf[4];
-		bf[0] = flags->sh_used[parity] ? 1.0f : 0.0f;
-		bf[1] = flags->pan_used[parity] ? 1.0f : 0.0f;
-		bf[2] = flags->st_used[parity] ? 1.0f : 0.0f;
-		bf[3] = flags->refl_used[parity] ? 1.0f : 0.0f;
-		for (int q = 0; q < 4; ++q) {
-			bus[(size_t)kBusRows * F + q] = bf[q];
-			for (uint32_t p = 0; p < pa.world; ++p) pa.gather[p][slot_off + (size_t)kBusRows * F + q] = bf[q];
-		}
+		bus[(size_t)kBusRows * F + 0] = flags->sh_used[parity] ? 1.0f : 0.0f;
+		bus[(size_t)kBusRows * F + 1] = flags->pan_used[parity] ? 1.0f : 0.0f;
+		bus[(size_t)kBusRows * F + 2] = flags->st_used[parity] ? 1.0f : 0.0f;
+		bus[(size_t)kBusRows * F + 3] = flags->refl_used[parity] ? 1.0f : 0.0f;
 	}
 	if (pa.world) {
-		// Last-CTA election: every CTA makes its peer stores visible system-wide, then counts itself; the CTA that completes
-		// the count signals one arrival to every rank (system-scope atomics on peer memory).
-		__threadfence_system();
+		// Multi-GPU exchange.  Every CTA publishes its piece of the bus device-wide and counts itself; the CTA that completes the count
+		// -- ONE CTA, all of its threads -- copies the whole bus (39 KB) into this rank's slot of every rank's gather area over NVLink,
+		// makes those stores visible system-wide with ONE fence, and signals one arrival per rank.  (Until the end of round 2 every CTA
+		// stored its own piece to the peers: 300 CTAs x a system-scope fence each, 0.031 ms per buffer on top of waiting for the
+		// slowest rank; now 0.017.  Folding the wait-and-sum of k_peer_gather into this CTA as well measured 0.003 ms slower: one CTA
+		// summing behind a spin is no match for 39 blocks that start under programmatic dependent launch.)
+		__shared__ int is_last;
+		__threadfence();
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			const unsigned int total = gridDim.x * gridDim.y;
-			if (atomicAdd(pa.done, 1u) == total - 1u) {
-				*pa.done = 0u;
-				__threadfence_system();
-				for (uint32_t p = 0; p < pa.world; ++p) atomicAdd_system(pa.arrive[p] + pa.parity, 1u);
+			const bool last = atomicAdd(pa.done, 1u) == total - 1u;
+			if (last) { *pa.done = 0u; __threadfence(); }
+			is_last = last ? 1 : 0;
+		}
+		__syncthreads();
+		if (is_last) {
+			const size_t slot_off = ((size_t)pa.parity * pa.world + pa.rank) * bus_floats;     // this rank's slot in rank p's gather area
+			for (size_t i = threadIdx.x; i < bus_floats; i += blockDim.x) {
+				const float v = __ldcg(bus + i);
+				for (uint32_t p = 0; p < pa.world; ++p) pa.gather[p][slot_off + i] = v;     // NVLink peer stores (local for p == rank)
 			}
+			__threadfence_system();
+			__syncthreads();
+			if (threadIdx.x < pa.world) atomicAdd_system(pa.arrive[threadIdx.x] + pa.parity, 1u);
 		}
 	}
 }
@@ -1192,14 +1198,17 @@ __global__ void __launch_bounds__(256) k_peer_gather_kernel(PeerArgs pa, const f
 	__shared__ int timed_out;
 	grid_dep_wait();
 	if (threadIdx.x == 0) {
-		const volatile unsigned int* cnt = pa.arrive[pa.rank] + pa.parity;
+		// (acquire at system scope on the counter the peers bump after their system-scope fence: no fence of our own)
+		const unsigned int* cnt = pa.arrive[pa.rank] + pa.parity;
 		const unsigned long long t0 = global_timer_ns();
 		int late = 0;
-		while ((int)(*cnt - target) < 0) {
-			__nanosleep(128);
+		for (;;) {
+			unsigned int v;
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+			if ((int)(v - target) >= 0) break;
+			__nanosleep(32);
 			if (global_timer_ns() - t0 > pa.timeout_ns) { late = 1; break; }
 		}
-		__threadfence_system();
 		timed_out = late;
 		if (late && blockIdx.x == 0) flags->peer_timeout = 1;
 	}
