@@ -175,6 +175,7 @@ int launch_peer_gather(const PeerArgs& pa, const float* own_bus, float* bus_sum,
 void* event_create();
 void event_destroy(void* ev);
 void event_record(void* ev, void* stream);
+int stream_wait_event(void* stream, void* ev);   // work queued on `stream` after this call waits (on the device) for the event
 int event_sync(void* ev);                        // blocks the host until the event has happened
 float event_elapsed_ms(void* a, void* b);
 unsigned long long launches();                   // kernels launched so far by this library

@@ -410,6 +410,7 @@ void* event_create() {
 }
 void event_destroy(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
 void event_record(void* ev, void* stream) { if (ev) cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream); }
+int stream_wait_event(void* stream, void* ev) { return ev ? check(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0), "cudaStreamWaitEvent") : 0; }
 int event_sync(void* ev) { return ev ? check(cudaEventSynchronize((cudaEvent_t)ev), "cudaEventSynchronize") : 0; }
 float event_elapsed_ms(void* a, void* b) {
 	float ms = 0.0f;

@@ -250,6 +250,7 @@ void* event_create() { return nullptr; }
 void event_destroy(void*) {}
 void event_record(void*, void*) {}
 int event_sync(void*) { return 0; }
+int stream_wait_event(void*, void*) { return 0; }
 float event_elapsed_ms(void*, void*) { return 0.0f; }
 unsigned long long launches() { return g_launches; }
 
