@@ -630,6 +630,7 @@ def run_gpu_arm(args, wl, rank, world, local_rank):
             "timing": {"blocks": B, "steps_per_block": args.steps, "reported": "median block", "value_block_ms_per_step": res["block_ms_per_step"],
                        "e2e_block_ms_per_step": e2e["block_ms_per_step"]},
             "e2e": {"value": total / (e2e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e2e["ms"], "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "kernels_ms": {"k1_params": e2e["k1"], "k2_mix": e2e["k2"], "k3_reduce+collective+k4_finish": e2e["k3"]},
                     "what": ("%d source positions for ids drawn at random over all %d sources + listener pose from host arrays per step, stereo buffer back to host, through sbm_set_*/sbm_mix" % (movers, n)) +
                             ("; %d voice packets of 480 samples per 10 ms of audio through sbm_source_ring_push_batch" % voices if voices else ""),
                     "all_move": {"value": total / (allmove["ms"] * 1e-3), "ms_per_step": allmove["ms"], "h2d_bytes_per_step": allmove["h2d"], "d2h_bytes_per_step": allmove["d2h"],
