@@ -1057,11 +1057,11 @@ constexpr size_t kSideCopyMinSources = 65536;
 static int upload_block_locked(sbm_engine* e, const SlotPatch** d_patches, const MixPatch** d_mix_patches) {
 	NvtxRange nvtx("sbm: upload block");
 	std::vector<SegPlan> plans;
+	// (what only K1 -- positions, volumes, occlusions -- or only this buffer's room kernel -- its parity's RoomParams -- reads)
+	const bool only_per_frame = !e->d_stat.any() && !e->d_ring.any() && !e->d_mixz.any() && !e->lists_dirty && (e->d_posvol.any() || e->d_occl.any());
 	plan_dirty(plans, e->dv_stat, e->h_stat, e->d_stat);
-	const size_t plans_before_pose = plans.size();
 	plan_dirty(plans, e->dv_posvol, e->h_posvol, e->d_posvol);
 	plan_dirty(plans, e->dv_occl, e->h_occl, e->d_occl);
-	const size_t plans_pose = plans.size() - plans_before_pose;
 	plan_dirty(plans, e->dv_ring_write, e->h_ring_write, e->d_ring);
 	plan_dirty(plans, e->dv_mixz, e->h_mixz, e->d_mixz);
 	if (e->lists_dirty) {
@@ -1112,14 +1112,14 @@ static int upload_block_locked(sbm_engine* e, const SlotPatch** d_patches, const
 	}
 	if (!e->patches.empty()) memcpy(hs + patch_off, e->patches.data(), sizeof(SlotPatch) * e->patches.size());
 	if (!e->mix_patches.empty()) memcpy(hs + mpatch_off, e->mix_patches.data(), sizeof(MixPatch) * e->mix_patches.size());
-	// The per-frame case -- nothing but source positions / volumes / occlusions changed, the previous buffer still in flight (the caller
-	// pipelines): K1 is the only kernel that reads those arrays, so the block crosses PCIe and is scattered on a stream of its own as
+	// The per-frame case -- nothing but source positions / volumes / occlusions (and the room parameters) changed, the previous buffer still
+	// in flight (the caller pipelines): K1 is the only kernel that reads those arrays (the room kernel its own parity's parameters), so the block crosses PCIe and is scattered on a stream of its own as
 	// soon as the previous buffer's K1 is done, i.e. beside that buffer's mix kernel, and this buffer's K1 finds it applied.  Measured on
 	// B200: 1 M sources with 4 096 scattered movers per buffer 0.036 -> 0.023 ms on top of the resident time, 262 144 ambisonic sources 0.026 -> 0.006.  Everything
-	// else (attach / detach, mix parameters, rings, lists, room parameters, state patches) stays in the mixer's stream, in order.
+	// else (attach / detach, mix parameters, rings, lists, state patches) stays in the mixer's stream, in order.
 	// (large scenes only, like the result's copy stream: a small scene pays more for the hop between streams than the upload holds up --
 	// C2 end to end 0.072 -> 0.085 ms with it)
-	const bool early = plans_pose > 0 && plans.size() == plans_pose && e->patches.empty() && e->mix_patches.empty() && e->k1_event_valid &&
+	const bool early = only_per_frame && e->patches.empty() && e->mix_patches.empty() && e->k1_event_valid &&
 	                   e->fl[(e->buffer_index + 1) & 1].pending && e->list_pan.size() + e->list_sh.size() >= kSideCopyMinSources;
 	void* up = early ? e->early_stream : e->stream;
 	if (early && dev::stream_wait_event(up, e->ev_k1_done)) return -1;
