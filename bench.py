@@ -8,8 +8,9 @@ One "step" = one output buffer: every active source's window gathered, resampled
 (or ambisonic-encoded + SH-HRIR decoded) and summed to interleaved stereo.  Default workload: the configuration
 BASELINE.json's target is quoted on -- 1 048 576 concurrent doppler-resampled, distance-attenuated, panned sources,
 512-frame buffers at 48 kHz, on ONE B200 (config 4's source set, which fits a single GPU: 64 GiB of private 16 384-sample
-loops); with --gpus N every rank mixes its own 1 048 576 sources (weak scaling) and the 18 x 512 bus is summed across
-ranks by one NCCL all-reduce on the engine stream before the finish kernel.
+loops); with --gpus N every rank mixes its own 1 048 576 sources (weak scaling) and the 19 x 512 bus is summed across
+ranks inside the kernels over NVLink peer memory (K3's last CTA pushes, k_peer_gather sums; --exchange allreduce: one NCCL
+all-reduce on the engine stream before the finish kernel, the comparison arm).
 
 Timed legs (each W warm-up steps, then BLOCKS blocks of exactly K timed steps; every block is bracketed by CUDA events on
 the engine stream with barrier + synchronize on both sides and reduced with MAX over ranks; the line reports the MEDIAN block,
@@ -20,7 +21,9 @@ all block times are listed under "timing"):
           upload block + scatter kernel inside sbm_mix) and the interleaved stereo buffer is copied back to host memory.
   e2e.all_move : the same with EVERY source's position sent every step (16 B per source of H2D).
 With --gpus N the line also carries "strong_scaling": BASELINE config 4 as written -- 1 048 576 sources IN TOTAL sharded over
-the N ranks -- and "parity": the sharded mix through the peer exchange against the oracle (all ranks bit-identical).
+the N ranks --, "parity": the sharded mix through the peer exchange against the oracle (all ranks bit-identical), and
+"per_rank_kernels_ms": every rank's own K1 / K2 / tail (a buffer ends with all ranks waiting for the slowest one).
+"e2e.kernels_ms": the kernel times of the e2e leg (its movers ramp: K2 differs from the resident leg's).
 Per-buffer PCM windows of the default workload total 2.2 GB >> 126 MB L2, so every step streams from HBM (no L2 flush needed;
 config says so); workloads whose per-step windows fit in L2 are marked L2-resident and carry no HBM roofline fraction.
 """

@@ -46,7 +46,7 @@ def test_gpu_arm_line():
     for k in REQUIRED + ["e2e", "gpu_launches", "roofline", "clocks", "cpu_baseline", "parity"]:
         assert k in d, k
     assert d["n_gpus"] == 1 and d["gpu_launches"] > 0 and d["value"] > 0
-    assert set(["value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"]) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(["value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "kernels_ms"]) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert set(["bound", "achieved", "peak", "unit", "frac", "traffic"]) <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
     assert set(["value", "unit", "cores", "kind", "sample"]) <= set(d["cpu_baseline"])
     assert set(["sm_mhz", "sm_max_mhz", "reasons"]) <= set(d["clocks"])
