@@ -184,8 +184,9 @@ SBM_API int sbm_mix_submit(sbm_engine* e);
 SBM_API int sbm_mix_collect(sbm_engine* e, float* out_interleaved, int* out_valid);
 
 /* Multi-GPU (one engine per GPU, one process per GPU, sources sharded by the caller): the only exchange of
- * the path -- the sum of the ranks' [18][frames] buses -- runs over NVLink peer memory inside the kernels: K3 stores
- * its bus into every rank's gather area and signals, a gather kernel in front of K4 waits and sums in rank order.
+ * the path -- the sum of the ranks' [19][frames] buses -- runs over NVLink peer memory inside the kernels: the CTA of K3
+ * that finishes last copies this rank's bus into every rank's gather area and signals, a gather kernel in front of K4 waits
+ * and sums in rank order.
  *   sbm_peer_export : allocates this engine's gather area and returns its 64-byte CUDA IPC handle;
  *   sbm_peer_connect: after the ranks exchanged their handles (any host transport; handles + p * handle_stride is rank
  *                     p's), maps the peers.  From then on every sbm_mix / sbm_mix_begin+finish is a collective: all
@@ -202,6 +203,9 @@ SBM_API int sbm_peer_connect(sbm_engine* e, int rank, int world, const void* han
 SBM_API int sbm_set_peer_timeout_ms(sbm_engine* e, int timeout_ms);
 SBM_API int sbm_peer_resync(sbm_engine* e);
 SBM_API int sbm_bus_device(sbm_engine* e, float** out_device_ptr, size_t* out_num_floats);
+/* The interleaved result (2*frames floats) of the buffer finished or submitted LAST, on the device: the engine keeps one result
+ * block per buffer in flight, so the pointer alternates from buffer to buffer -- ask again after every sbm_mix_finish /
+ * sbm_mix_submit, and order reads behind that buffer on sbm_stream(). */
 SBM_API int sbm_out_device(sbm_engine* e, float** out_device_ptr);
 SBM_API void* sbm_stream(sbm_engine* e);   /* cudaStream_t */
 

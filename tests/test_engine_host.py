@@ -307,3 +307,24 @@ def test_streaming_boundary_of_the_audio_engine_mirror():
     r = subprocess.run([os.path.join(EMU_DIR, "test_streaming_host")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rel_rms" in r.stdout
+
+
+def test_out_device_names_the_block_of_the_last_buffer():
+    """sbm_out_device: the engine keeps one result block per buffer in flight; the pointer it returns must name the block of the
+    buffer finished (or submitted) LAST -- on the emulated device that block is plain host memory and can be read back."""
+    import ctypes
+    F = 128
+    e = emu_engine(F)
+    rng = np.random.default_rng(5)
+    buf = e.buffer_create((0.5 * rng.uniform(-1, 1, 4000)).astype(np.float32))
+    s = e.source_create(KIND_PAN); e.source_attach_buffer(s, buf, 0, 48000, True, False)
+    e.set_source_positions(np.array([s], np.int32), np.array([[1.0, 0.0, -2.0]], np.float32))
+    seen = set()
+    for k in range(5):
+        _, o = e.mix()
+        ptr = ctypes.c_void_p()
+        assert sb.lib(EMU).sbm_out_device(e.h, ctypes.byref(ptr)) == 0
+        seen.add(ptr.value)
+        dev = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(2 * F,))
+        assert np.array_equal(dev, np.asarray(o).reshape(-1))
+    assert len(seen) == 2          # two blocks, used alternately
