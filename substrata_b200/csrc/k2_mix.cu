@@ -1159,7 +1159,7 @@ __global__ void __launch_bounds__(kK3Warps * 32) k3_reduce_kernel(const float* _
 		// -- ONE CTA, all of its threads -- copies the whole bus (39 KB) into this rank's slot of every rank's gather area over NVLink,
 		// makes those stores visible system-wide with ONE fence, and signals one arrival per rank.  (Until the end of round 2 every CTA
 		// stored its own piece to the peers: 300 CTAs x a system-scope fence each, 0.031 ms per buffer on top of waiting for the
-		// slowest rank; now 0.017.  Folding the wait-and-sum of k_peer_gather into this CTA as well measured 0.003 ms slower: one CTA
+		// slowest rank; now 0.014 with the acquire loads of k_peer_gather.  Folding the wait-and-sum of k_peer_gather into this CTA as well measured 0.003 ms slower: one CTA
 		// summing behind a spin is no match for 39 blocks that start under programmatic dependent launch.)
 		__shared__ int is_last;
 		__threadfence();
